@@ -1,0 +1,389 @@
+#!/usr/bin/env python
+"""Benchmark of the sc.solve hot path on BASELINE.json configs[1] (C2): a single square film,
+~20k-vertex mesh, uniform applied field; one "step" = mesh operators + Q row sums + system
+assembly + LU + solve (the north-star "Q assembly + LU + solve").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+Prints ONE JSON line (see the task contract).  `value` is the device-resident wall time per
+solve, `e2e` the same through the public API with host buffers, `roofline` the LU's fp64
+TFLOP/s against the measured DMMA peak, `cpu_baseline` the oracle port on the host cores.
+Under torchrun every rank solves its own 20k film (weak scaling, no data-path collective).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "sc.solve wall time at 20k vertices (Q assembly + LU + solve)"
+FP64_DMMA_PEAK_TFLOPS = 37.0  # measured on this pool's B200 (profiles/r01_fp64_peaks.txt)
+N_VERTICES = 20164
+SIDE = 10.0
+LAMBDA = 0.1
+
+
+def make_workload(seed: int, n_vertices: int = N_VERTICES):
+    from superscreen_b200.synthetic import square_mesh
+
+    return square_mesh(SIDE, n_vertices, seed=seed)
+
+
+# ------------------------------------------------------------------------------------------
+# clocks sampling during the timed region
+# ------------------------------------------------------------------------------------------
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu_index = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.gpu_index)], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.proc is None:
+            return out
+        try:
+            self.proc.terminate()
+            self.proc.wait(timeout=5)
+            rows = [r.strip().split(", ") for r in open(self.path) if r.strip()]
+            sm = [float(r[1]) for r in rows if len(r) >= 9]
+            if sm:
+                out["sm_mhz"] = float(np.median(sm))
+                out["sm_max_mhz"] = float(rows[0][2])
+                out["samples"] = len(sm)
+                out["power_w_max"] = max(float(r[3]) for r in rows if len(r) >= 9)
+                names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+                reasons = set()
+                for r in rows:
+                    for k, nm in enumerate(names):
+                        if len(r) >= 9 and r[5 + k].strip().lower().startswith("active"):
+                            reasons.add(nm)
+                out["reasons"] = sorted(reasons)
+        except Exception:
+            pass
+        finally:
+            try:
+                os.unlink(self.path)
+            except Exception:
+                pass
+        return out
+
+
+# ------------------------------------------------------------------------------------------
+# CPU arm: the oracle port (the reference is pure Python and cannot travel to the GPU box)
+# ------------------------------------------------------------------------------------------
+def cpu_reference_solve(sites, elements):
+    """One full reference-path solve on the host: MeshOperators.from_mesh -> make_film_info
+    (dense casts) -> factorize_linear_systems -> solve_film, as restated in oracle/port.py.
+    Returns (seconds per stage dict, solution)."""
+    from oracle import port
+
+    t = {}
+    t0 = time.perf_counter()
+    mesh = port.build_mesh(sites, elements, with_Q=False)
+    t["mesh_operators"] = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    mesh.Q = port.Q_matrix(sites, mesh.vertex_areas)
+    t["Q_matrix"] = time.perf_counter() - t0
+    interior = np.setdiff1d(np.arange(len(sites)), mesh.boundary_indices)
+    film = port.OracleFilm(name="film", mesh=mesh, z0=0.0, Lambda=np.full(len(sites), LAMBDA),
+                           interior_indices=interior, hole_indices={})
+    t0 = time.perf_counter()
+    w = mesh.vertex_areas
+    lap = mesh.laplacian.toarray()
+    t["laplacian_toarray"] = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    A = port.build_system_2d(mesh.Q, w, film.Lambda, lap, 0, interior)
+    t["build_system_2d"] = time.perf_counter() - t0
+    del lap
+    import scipy.linalg as la
+
+    t0 = time.perf_counter()
+    film.lu_piv = la.lu_factor(-A)
+    t["lu_factor"] = time.perf_counter() - t0
+    film.indices, film.A = interior, None
+    del A
+    conv = port.field_conversion_mT_to_uA_per_um()
+    t0 = time.perf_counter()
+    sol = port.solve_film(film, np.full(len(sites), conv), {}, conv)
+    t["solve_film"] = time.perf_counter() - t0
+    return t, sol, len(interior)
+
+
+STAGE_EXPONENT = {"mesh_operators": 1.0, "Q_matrix": 2.0, "laplacian_toarray": 2.0, "build_system_2d": 2.0,
+                  "lu_factor": 3.0, "solve_film": 2.0}
+
+
+def cpu_threads():
+    try:
+        import numba
+
+        nt = numba.get_num_threads()
+    except Exception:
+        nt = os.cpu_count()
+    return int(nt)
+
+
+def warm_numba():
+    from oracle import port
+
+    p = np.random.default_rng(0).random((64, 2))
+    port.q_matrix(p)
+
+
+def run_reference_arm(args):
+    """--impl reference: bounded sample (smaller mesh of the same family), each stage scaled to
+    the full C2 size by its complexity exponent."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n_sample = 8000
+    sites, elements = make_workload(seed=0, n_vertices=n_sample)
+    warm_numba()
+    full_sites, _ = make_workload(seed=0)
+    scale_n = len(full_sites) / len(sites)
+    times = []
+    for it in range(args.warmup + args.steps):
+        st, _, n_int = cpu_reference_solve(sites, elements)
+        scaled = sum(v * scale_n ** STAGE_EXPONENT[k] for k, v in st.items())
+        if it >= args.warmup:
+            times.append(scaled)
+    value = float(np.mean(times))
+    sample = (f"{len(sites)}-vertex square of the same mesh family per step; every stage time scaled to "
+              f"{len(full_sites)} vertices by (n/n_s)^p, p=3 LU, 2 dense n^2 stages, 1 sparse operators")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": value * 1e3, "higher_is_better": False,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "C2: single square film, ~20k-vertex mesh, uniform 1 mT, Lambda=0.1 (oracle port of "
+                               "the reference CPU path; reference is pure Python and does not travel)",
+                   "n_vertices": int(len(full_sites))},
+        "cpu_baseline": {"value": value, "unit": "s", "cores": cpu_threads(), "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------
+# B200 arm
+# ------------------------------------------------------------------------------------------
+def run_b200_arm(args):
+    import torch
+    import torch.distributed as dist
+
+    import superscreen_b200 as sc
+    from superscreen_b200 import _lib
+    from superscreen_b200.geometry import box
+    from superscreen_b200.mesh import DeviceMeshData
+    from superscreen_b200.solver.solve_film import LinearSystem, assemble_negA, solve_film_device
+    from superscreen_b200.solver.utils import FilmInfo, LambdaInfo
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device(f"cuda:{local_rank}")
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    L = _lib.lib()
+
+    # each rank owns one independent 20k-vertex film (weak scaling; no data-path collective)
+    sites, elements = make_workload(seed=rank)
+    n, m = len(sites), len(elements)
+    conv = sc.field_conversion_factor("mT", "uA", "um").magnitude
+
+    # ---- device-resident leg: inputs already in HBM ----
+    sites_d = torch.as_tensor(sites).to(dev)
+    elements_d = torch.as_tensor(elements).to(dev)
+    H_d = torch.full((n,), conv, dtype=torch.float64, device=dev)
+    Lambda_d = torch.full((n,), LAMBDA, dtype=torch.float64, device=dev)
+    # index sets are inputs of the path (host polygon tests): mesh boundary excluded
+    probe = DeviceMeshData(sites_d, elements_d)
+    interior = np.setdiff1d(np.arange(n), probe.host("boundary_indices")).astype(np.int64)
+    ix_d = torch.as_tensor(interior).to(dev)
+    n_int = len(interior)
+    n_pad = -(-n_int // 128) * 128
+    del probe
+    lu_ws = torch.empty(n_pad, n_pad, dtype=torch.float64, device=dev)
+    dinv = torch.empty(int(L.scb_getrf_dinv_bytes(n_pad)) // 8, dtype=torch.float64, device=dev)
+    lu_info = torch.zeros(1, dtype=torch.int32, device=dev)
+    l2_flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device=dev)  # > 126 MB L2
+
+    ev = {k: (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+          for k in ("mesh", "assemble", "getrf", "solve")}
+
+    class _Mesh:  # minimal holder so FilmInfo can reach the device arrays
+        def __init__(self, data):
+            self._data = data
+            self.sites = None
+
+    def resident_step(record: bool):
+        stream = torch.cuda.current_stream()
+        if record: ev["mesh"][0].record(stream)
+        data = DeviceMeshData(sites_d, elements_d)
+        if record: ev["mesh"][1].record(stream)
+        info = FilmInfo(name="film", layer="layer", lambda_info=None, vortices=(), interior_indices=interior,
+                        boundary_indices=None, hole_indices={}, in_hole=None, circulating_currents={},
+                        mesh=_Mesh(data))
+        info.dev["Lambda"] = Lambda_d
+        info.dev["T"] = None
+        if record: ev["assemble"][0].record(stream)
+        assemble_negA(info, ix_d, n_int, n_pad, None, out=lu_ws)
+        if record: ev["assemble"][1].record(stream)
+        if record: ev["getrf"][0].record(stream)
+        _lib.check(L.scb_getrf_nopiv(n_pad, _lib.ptr(lu_ws), _lib.ptr(dinv), _lib.ptr(lu_info), _lib.stream_ptr()))
+        if record: ev["getrf"][1].record(stream)
+        system = LinearSystem(indices=interior, film_info=info, n_pad=n_pad, lu=lu_ws, dinv=dinv, indices_dev=ix_d)
+        if record: ev["solve"][0].record(stream)
+        out = solve_film_device(film_info=info, film_system=system, hole_systems={}, applied_field=H_d,
+                                vortex_flux=0.0)
+        if record: ev["solve"][1].record(stream)
+        return out
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        l2_flush.zero_()
+        resident_step(False)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = _lib.launch_count()
+    stage_ms = {k: [] for k in ev}
+    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    flush_ms = 0.0
+    total_ms = 0.0
+    for _ in range(args.steps):
+        l2_flush.zero_()  # flush L2 between timed iterations (untimed)
+        torch.cuda.synchronize()
+        t_start.record()
+        g, J, self_field = resident_step(True)
+        t_end.record()
+        torch.cuda.synchronize()
+        total_ms += t_start.elapsed_time(t_end)
+        for k in ev:
+            stage_ms[k].append(ev[k][0].elapsed_time(ev[k][1]))
+    barrier()
+    launches = _lib.launch_count() - launches0
+    clocks = sampler.stop()
+    ms_per_step = total_ms / args.steps
+    assert int(lu_info.item()) == 0, "LU reported a bad pivot"
+    getrf_ms = float(np.mean(stage_ms["getrf"]))
+
+    # ---- end-to-end leg: public API, host buffers in, host arrays out ----
+    pinned_sites = torch.as_tensor(sites).pin_memory()
+    pinned_elems = torch.as_tensor(elements).pin_memory()
+    film_poly = box(SIDE, points=4)
+
+    def e2e_step():
+        device = sc.Device("c2", layers=[sc.Layer("layer", Lambda=LAMBDA, z0=0.0)],
+                           films=[sc.Polygon("film", layer="layer", points=film_poly)])
+        device.set_meshes({"film": (pinned_sites.numpy(), pinned_elems.numpy())})
+        sol = sc.solve(device, applied_field=sc.ConstantField(1.0), field_units="mT", current_units="uA")[0]
+        return sol.film_solutions["film"]
+
+    for _ in range(min(args.warmup, 2)):
+        e2e_step()
+    barrier()
+    e2e_times = []
+    for _ in range(args.steps):
+        l2_flush.zero_()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        fs = e2e_step()
+        torch.cuda.synchronize()
+        e2e_times.append(time.perf_counter() - t0)
+    barrier()
+    e2e_s = float(np.mean(e2e_times))
+    h2d = sites.nbytes + elements.nbytes + interior.nbytes + 8 * n + 8 * n  # + ix, Lambda, applied field
+    d2h = fs.stream.nbytes + fs.current_density.nbytes + fs.self_field.nbytes + fs.applied_field.nbytes + 8 * 5 \
+        + 8 * (n - n_int)  # + counts/flags + boundary_indices
+
+    # max over ranks
+    vals = torch.tensor([ms_per_step, e2e_s, getrf_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(vals, op=dist.ReduceOp.MAX)
+    ms_per_step, e2e_s, getrf_ms = (float(v) for v in vals.cpu())
+
+    lu_flops = (2.0 / 3.0) * float(n_int) ** 3
+    lu_tflops = lu_flops / (getrf_ms * 1e-3) * 1e-12
+    line = {
+        "metric": METRIC, "value": ms_per_step * 1e-3, "unit": "s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": False, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "C2: single square film box(10 um), ~20k-vertex jittered-hex Delaunay mesh, "
+                               "Lambda=0.1 um, uniform 1 mT; one independent film per GPU",
+                   "n_vertices": int(n), "n_triangles": int(m), "n_interior": int(n_int), "n_pad": int(n_pad),
+                   "l2": "256 MiB buffer written between timed iterations (flushes the 126 MB L2)"},
+        "stages_ms": {k: float(np.mean(v)) for k, v in stage_ms.items()},
+        "lu_tflops": lu_tflops, "films_per_s": world / (ms_per_step * 1e-3),
+        "roofline": {"bound": "tensor", "achieved": lu_tflops, "peak": FP64_DMMA_PEAK_TFLOPS, "unit": "TFLOP/s",
+                     "frac": lu_tflops / FP64_DMMA_PEAK_TFLOPS, "traffic": None,
+                     "kernel": "scb_getrf_nopiv (update_kernel DMMA trailing updates + panel kernels)",
+                     "work": "2/3 * n_int^3 fp64 flop per factorization",
+                     "peak_source": "measured DMMA.8x8x4 issue rate on this pool's B200, "
+                                    "profiles/r01_fp64_peaks.txt (MEASURED_PEAKS.json has no fp64 entry)"},
+        "e2e": {"value": e2e_s, "unit": "s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        warm_numba()
+        st, ref_sol, _ = cpu_reference_solve(sites, elements)
+        cpu_s = float(sum(st.values()))
+        rel = float(np.linalg.norm(fs.stream - ref_sol.stream) / np.linalg.norm(ref_sol.stream))
+        line["cpu_baseline"] = {"value": cpu_s, "unit": "s", "cores": cpu_threads(), "kind": "port",
+                                "sample": "the full C2 workload (same mesh), one repetition after numba warm-up",
+                                "stages_s": {k: float(v) for k, v in st.items()},
+                                "rel_l2_stream_gpu_vs_cpu": rel}
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_b200_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,200 @@
+/*
+ * scb.h -- C ABI of libsc_b200.so: the B200 (sm_100a) implementation of SuperScreen's
+ * solve hot path.
+ *
+ * The reference (loganbvh/superscreen 0.13.0) is pure Python and has no FFI of its own;
+ * its seam for this path is the set of module-level callables listed in SURVEY.md 8(a).
+ * Each entry point below names the reference callable (file:line under
+ * /root/reference/superscreen/) whose arithmetic it replaces.  INTEGRATION.md shows the
+ * ctypes binding a SuperScreen maintainer would add.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer owned by the caller unless the name ends in _host;
+ *  - matrices are row-major (C order), fp64; index arrays are int64 where the reference
+ *    exposes int64 (elements, index sets, edges) and int32 for CSR indptr/indices
+ *    (scipy's native index dtype);
+ *  - one call == stream-ordered work on `stream` (a cudaStream_t passed as void*); no call
+ *    synchronises the device unless documented;
+ *  - return value 0 on success, negative on error (scb_last_error() gives the message);
+ *    no exceptions cross the boundary;
+ *  - there is no CPU fallback anywhere in this library.
+ */
+#ifndef SCB_H
+#define SCB_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* scb_stream_t;
+
+#define SCB_OK 0
+#define SCB_ERR_INVALID (-1)
+#define SCB_ERR_CUDA (-2)
+#define SCB_ERR_SINGULAR (-3)
+
+#define SCB_LU_BLOCK 128 /* LU panel width; LU workspaces are padded to a multiple of it */
+
+int scb_version(void);
+const char* scb_last_error(void);
+/* number of kernels launched by this library since load (bench.py's gpu_launches) */
+int64_t scb_launch_count(void);
+
+/* ------------------------------------------------------------------------------------
+ * Mesh topology + FEM operators  (K4-K7, rows a4-a8)
+ *   device/utils.py:139-152 get_edges, :230-273 triangle_areas/vertex_areas
+ *   device/mesh.py:157-170 find_boundary_indices, :400-432 C_vector
+ *   device/edge_mesh.py:38-63, fem.py:70-121 adjacency / directed-edge map
+ *   fem.py:124-296 weights + laplace_operator, :299-402 gradient_triangles/_vertices
+ * ------------------------------------------------------------------------------------ */
+
+/* int32 workspace elements needed by scb_mesh_analyze/scb_mesh_build for n vertices, m triangles */
+int64_t scb_mesh_workspace_elems(int64_t n, int64_t m);
+
+/* Phase 1: vertex stars, neighbour sets, edge / boundary counts.
+ * counts (device, int64[4]) <- { nnz of adjacency (=2E), E, #boundary vertices, #boundary edges }.
+ * flags  (device, int32[1]) <- nonzero if the mesh is not a consistently oriented manifold
+ *                              (an undirected edge shared by >2 triangles or a duplicated
+ *                              directed edge). */
+int scb_mesh_analyze(int64_t n, int64_t m, const int64_t* elements, int32_t* workspace,
+                     int64_t* counts, int32_t* flags, scb_stream_t stream);
+
+typedef struct scb_mesh_out {
+  /* per triangle / vertex floats */
+  double* triangle_areas;   /* [m]   device/utils.py:230-248 */
+  double* vertex_areas;     /* [n]   device/utils.py:251-273 (sum over the star in triangle order) */
+  double* centroids;        /* [m,2] device/mesh.py:144 */
+  double* C;                /* [n]   device/mesh.py:400-432 */
+  /* integer structures (bit-exact contract) */
+  int32_t* adj_indptr;      /* [n+1] fem.py:70-98 (symmetric 0/1 adjacency, sorted rows) */
+  int32_t* adj_indices;     /* [2E] */
+  int64_t* edges;           /* [E,2] device/utils.py:149-151, i<j, lexicographic */
+  uint8_t* edge_is_boundary;/* [E]   device/utils.py:152 */
+  int64_t* boundary_indices;/* [nb]  device/mesh.py:167-170 ascending */
+  int32_t* star_indptr;     /* [n+1] fem.py:101-121 in LIL (row) form: */
+  int32_t* star_heads;      /* [3m]  head vertex j of directed edge i->j, ascending per row */
+  int32_t* star_tris;       /* [3m]  triangle owning that edge */
+  /* edge mesh floats, device/edge_mesh.py:49-56 */
+  double* edge_centers;     /* [E,2] */
+  double* edge_directions;  /* [E,2] */
+  double* edge_lengths;     /* [E] */
+  /* operators; laplacian / gradient_x / gradient_y share the pattern adjacency + I */
+  int32_t* op_indptr;       /* [n+1] */
+  int32_t* op_indices;      /* [2E+n] sorted per row */
+  double* laplacian;        /* [2E+n] fem.py:259-296 */
+  double* gradient_x;       /* [2E+n] fem.py:350-402 */
+  double* gradient_y;       /* [2E+n] */
+  int32_t* gtri_indices;    /* [3m]  fem.py:299-347, 3 sorted columns per row */
+  double* gtri_x;           /* [3m] */
+  double* gtri_y;           /* [3m] */
+} scb_mesh_out;
+
+/* weight_method: 0 = half_cotangent, 1 = uniform, 2 = inv_euclidean (fem.py:225-256).
+ * Needs the workspace filled by scb_mesh_analyze for the same (n, m, elements). */
+int scb_mesh_build(int64_t n, int64_t m, const double* sites, const int64_t* elements,
+                   const int32_t* workspace, int weight_method, const scb_mesh_out* out,
+                   scb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * Kernel matrix pieces and system assembly  (K1-K3, K8-K10, K19, rows a1-a3, a9-a11)
+ *   distance.py:87-115 q_matrix, device/mesh.py:434-458 Q_matrix,
+ *   solver/utils.py:290-297 (dense casts, never materialised here),
+ *   solver/solve_film.py:181-185 grad_Lambda_term, :285-305 _build_system_1d/_2d
+ * ------------------------------------------------------------------------------------ */
+
+/* qdw[i] = C[i] + sum_{j != i} q_ij w_j  ( == Q_ii * w_i, device/mesh.py:456 ) */
+int scb_kernel_diagonal(int64_t n, const double* sites, const double* weights, const double* C,
+                        double* qdw, scb_stream_t stream);
+
+/* grad-Lambda term on the operator pattern (solve_film.py:181-185):
+ * T[k] = gLx[row] * gradient_x[k] + gLy[row] * gradient_y[k],  gL = gradient @ Lambda */
+int scb_grad_lambda_term(int64_t n, const int32_t* op_indptr, const int32_t* op_indices,
+                         const double* gradient_x, const double* gradient_y,
+                         const double* Lambda, double* T, scb_stream_t stream);
+
+/* Writes M = -A  (A of solve_film.py:296-305 restricted to rows/cols `ix`) into the padded
+ * row-major LU workspace negA[n_pad, n_pad] (n_pad = multiple of SCB_LU_BLOCK >= n_int;
+ * the padding block is the identity).  pos_scratch is int32[n].
+ *   M[r,c] = q(ix_r, ix_c) w[ix_c] + Lambda[ix_c] lap[ix_r, ix_c] + T[ix_r, ix_c]   (r != c)
+ *   M[r,r] = -qdw[ix_r]           + Lambda[ix_r] lap[ix_r, ix_r] + T[ix_r, ix_r]
+ * T may be NULL (homogeneous Lambda).  margin (may be NULL; needs C) receives a lower bound
+ * of the row-dominance margin |M_rr| - sum_{c != r} |M_rc| (exact when ix covers every vertex)
+ * used to validate the unpivoted LU. */
+int scb_system_assemble(int64_t n, const double* sites, const double* weights, const double* qdw,
+                        const double* C, const double* Lambda, const int32_t* op_indptr,
+                        const int32_t* op_indices,
+                        const double* laplacian, const double* T, int64_t n_int, const int64_t* ix,
+                        int32_t* pos_scratch, int64_t n_pad, double* negA, double* margin,
+                        scb_stream_t stream);
+
+/* Matrix-free action of the FULL (n x n) operator A on nrhs vectors, sources restricted
+ * to `src_idx` (NULL = all vertices):
+ *   out[i,:] (+)= sum_{j in src} A_ij v[j,:],  A_ij = Q_ij w_j - Lambda_j lap_ij - T_ij
+ * with Q_ij w_j = -q_ij w_j (i != j), Q_ii w_i = qdw_i.  v, out are [n, nrhs] row-major.
+ * Replaces the hole slabs `_build_system_1d` @ g[hole] (solve_film.py:285-293,498-503),
+ * `Q @ (weights * g)` (solve_film.py:565, with Lambda == NULL: kernel part only) and the
+ * check_inversion product (solve_film.py:533-540). */
+int scb_apply_operator(int64_t n, const double* sites, const double* weights, const double* qdw,
+                       const double* Lambda, const int32_t* op_indptr, const int32_t* op_indices,
+                       const double* laplacian, const double* T, int64_t n_src,
+                       const int64_t* src_idx, int64_t nrhs, const double* v, double* out,
+                       int accumulate, scb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * Dense LU  (K11, K12, row a12/a13): scipy.linalg.lu_factor / lu_solve at
+ *   solver/solve_film.py:232,253,279 and :367,388,530,545
+ * ------------------------------------------------------------------------------------ */
+
+/* bytes of the block-inverse store `dinv` for an n_pad x n_pad system */
+int64_t scb_getrf_dinv_bytes(int64_t n_pad);
+
+/* In-place blocked right-looking LU of the row-major matrix M[n_pad, n_pad] WITHOUT pivoting
+ * (valid for the row-diagonally-dominant systems of this path; the caller
+ * checks `margin` from scb_system_assemble).  On return M holds L (unit lower) and U; dinv
+ * holds inv(L_kk), inv(U_kk) of every 128x128 diagonal block (used by scb_getrs).
+ * info (device int32[1]) <- 0, or 1 + index of the first zero/non-finite pivot. */
+int scb_getrf_nopiv(int64_t n_pad, double* M, double* dinv, int32_t* info, scb_stream_t stream);
+
+/* Solves M X = B in place for nrhs right-hand sides, B[n_pad, nrhs] row-major. */
+int scb_getrs_nopiv(int64_t n_pad, const double* LU, const double* dinv, int64_t nrhs, double* B,
+                    scb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * Sparse mat-vec (K14): grad_y @ g, grad_x @ g  (solver/solve_film.py:556-559)
+ *   y[nrows, nrhs] = alpha * CSR @ x[ncols, nrhs] + beta * y
+ * ------------------------------------------------------------------------------------ */
+int scb_spmv(int64_t nrows, const int32_t* indptr, const int32_t* indices, const double* data,
+             int64_t nrhs, const double* x, double alpha, double beta, double* y,
+             scb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * Biot-Savart family (K15-K18, rows a14, a15, a17, a18)
+ * ------------------------------------------------------------------------------------ */
+enum scb_bs_kind {
+  /* solver/solve.py:28-73 biot_savart_film_to_film; also _biot_savart_within_film
+   * (solve_film.py:415-437) with dz = 0.  tgt [m,2], src [n,2], scalar dz, out [m] */
+  SCB_BS_FILM_TO_FILM = 0,
+  /* sources/current.py:13-57 _biot_savart_2d_z: tgt [m,3], src [n,3], out [m] */
+  SCB_BS_Z = 1,
+  /* sources/current.py:60-110 _biot_savart_2d_vector: out [m,3] */
+  SCB_BS_VECTOR = 2,
+  /* solution.py:917-928 vector potential: tgt [m,3], src [n,3], out [m,2] */
+  SCB_BS_VECTOR_POTENTIAL = 3,
+  /* solve_film.py:393-412 _get_boundary_effective_field: tgt [m,2], src = edge centres [n,2],
+   * J = edge normals [n,2], area = stream * length [n], out [m] */
+  SCB_BS_BOUNDARY = 4
+};
+
+/* out = prefactor * sum_j area_j * kernel(tgt_i, src_j, J_j).  nsets > 1 evaluates `nsets`
+ * current-density sets J[nsets, n, 2] against the same geometry, out[nsets, m(, c)]. */
+int scb_biot_savart(int kind, int64_t m, const double* tgt, int64_t n, const double* src,
+                    const double* area, const double* J, double dz, double prefactor,
+                    int64_t nsets, double* out, scb_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SCB_H */

@@ -1,0 +1,114 @@
+"""ctypes binding of libsc_b200.so (include/scb.h).
+
+The shared library is the product: if it is missing, cannot be loaded, or no CUDA device is
+present, every compute entry point raises -- there is no CPU fallback.  PyTorch is used only to
+own device buffers and streams; raw device pointers cross the C ABI.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, Structure, c_char_p, c_double, c_int, c_int32, c_int64, c_uint8, c_void_p
+from typing import Optional
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsc_b200.so")
+
+_lib = None
+
+
+class SCBError(RuntimeError):
+    pass
+
+
+class MeshOut(Structure):
+    """Mirror of ``struct scb_mesh_out`` (include/scb.h)."""
+
+    _fields_ = [
+        (name, c_void_p)
+        for name in (
+            "triangle_areas", "vertex_areas", "centroids", "C",
+            "adj_indptr", "adj_indices", "edges", "edge_is_boundary", "boundary_indices",
+            "star_indptr", "star_heads", "star_tris",
+            "edge_centers", "edge_directions", "edge_lengths",
+            "op_indptr", "op_indices", "laplacian", "gradient_x", "gradient_y",
+            "gtri_indices", "gtri_x", "gtri_y",
+        )
+    ]
+
+
+EXPORTS = {
+    # name: (restype, argtypes)
+    "scb_version": (c_int, []),
+    "scb_last_error": (c_char_p, []),
+    "scb_launch_count": (c_int64, []),
+    "scb_mesh_workspace_elems": (c_int64, [c_int64, c_int64]),
+    "scb_mesh_analyze": (c_int, [c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "scb_mesh_build": (c_int, [c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_int, POINTER(MeshOut), c_void_p]),
+    "scb_kernel_diagonal": (c_int, [c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "scb_grad_lambda_term": (c_int, [c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "scb_system_assemble": (c_int, [c_int64] + [c_void_p] * 9 + [c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
+    "scb_apply_operator": (c_int, [c_int64] + [c_void_p] * 8 + [c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int, c_void_p]),
+    "scb_getrf_dinv_bytes": (c_int64, [c_int64]),
+    "scb_getrf_nopiv": (c_int, [c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "scb_getrs_nopiv": (c_int, [c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
+    "scb_spmv": (c_int, [c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_double, c_double, c_void_p, c_void_p]),
+    "scb_biot_savart": (c_int, [c_int, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_double, c_double, c_int64, c_void_p, c_void_p]),
+}
+
+
+def load_library(path: Optional[str] = None) -> ctypes.CDLL:
+    """Loads libsc_b200.so and declares every prototype of include/scb.h.  Does not need a GPU."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = path or LIB_PATH
+    if not os.path.exists(p):
+        raise SCBError(
+            f"{p} not found: the CUDA library has not been built. Run "
+            "`python -c 'import __graft_entry__ as g; g.build()'` (needs nvcc). "
+            "superscreen_b200 has no CPU fallback."
+        )
+    lib = ctypes.CDLL(p)
+    for name, (restype, argtypes) in EXPORTS.items():
+        fn = getattr(lib, name)
+        fn.restype = restype
+        fn.argtypes = argtypes
+    if path is None:
+        _lib = lib
+    return lib
+
+
+def lib() -> ctypes.CDLL:
+    """The loaded library, after checking that a CUDA device is usable (fails loudly otherwise)."""
+    import torch
+
+    if not torch.cuda.is_available():
+        raise SCBError(
+            "superscreen_b200 needs a CUDA device (B200, sm_100a); no CPU fallback exists."
+        )
+    return load_library()
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        msg = load_library().scb_last_error()
+        raise SCBError(f"libsc_b200 error {rc}: {msg.decode() if msg else ''}")
+
+
+def ptr(t) -> Optional[int]:
+    """Device pointer of a torch tensor (None -> NULL)."""
+    if t is None:
+        return None
+    assert t.is_cuda and t.is_contiguous(), "tensor must be a contiguous CUDA tensor"
+    return t.data_ptr()
+
+
+def stream_ptr() -> int:
+    import torch
+
+    return torch.cuda.current_stream().cuda_stream
+
+
+def launch_count() -> int:
+    return int(load_library().scb_launch_count())

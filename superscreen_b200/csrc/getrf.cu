@@ -1,0 +1,418 @@
+// Blocked right-looking fp64 LU without pivoting (K11) for the row-diagonally-dominant systems
+// of this path, row-major, padded to a multiple of NB = 128.
+//
+// Per block step k (offset o = 128 k, trailing size rem):
+//   1. diag_kernel   (1 CTA)        LU of the 128x128 diagonal block in shared memory and the
+//                                   explicit inverses inv(L_kk), inv(U_kk) (kept for getrs);
+//   2. trsm_kernel   (2*rem/128 CTAs) L21 = A21 inv(U_kk), U12 = inv(L_kk) A12 as DMMA GEMMs;
+//                                   results are written in place AND as "fragment-major"
+//                                   packed copies (-L21 and U12) laid out exactly as the
+//                                   mma.sync m8n8k4 A/B register fragments;
+//   3. update_kernel (rem/128 x rem/64 CTAs, 2 per SM) A22 += (-L21) U12: the only O(n^3)
+//                                   contraction.  Operand chunks arrive by TMA bulk copies
+//                                   (cp.async.bulk + mbarrier, one 32 KB + one 16 KB copy per
+//                                   stage) and are consumed with conflict-free LDS.64 straight
+//                                   into DMMA.8x8x4; C tiles are read into the accumulators and
+//                                   written back with 128-bit accesses.  Two resident CTAs per
+//                                   SM overlap one CTA's C traffic with the other's DMMA work.
+//
+// Reference semantics: scipy.linalg.lu_factor(-A) at solver/solve_film.py:232,253,279 (LAPACK
+// dgetrf).  Pivoting is unnecessary here; parity is on the solution (1e-8 rel-L2), see DESIGN.md.
+#include "scb_common.cuh"
+
+namespace scb {
+
+constexpr int NB = SCB_LU_BLOCK;  // 128
+constexpr int BM = 128;           // update tile rows
+constexpr int BN = 64;            // update tile cols
+constexpr int KC = 32;            // k chunk
+constexpr int NCHUNK = NB / KC;   // 4
+constexpr int A_CHUNK = BM * KC;  // doubles per packed A chunk (32 KB)
+constexpr int B_CHUNK = KC * BN;  // doubles per packed B chunk (16 KB)
+
+// ---------------------------------------------------------------------------------------
+// PTX helpers
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void dmma(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(d0), "+d"(d1)
+               : "d"(a), "d"(b));
+}
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+// TMA bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+          smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+}
+
+// ---------------------------------------------------------------------------------------
+// packed ("fragment-major") operand layouts
+//   Lpack tile (128 rows x 128 k):  [chunk c(4)][row block rb(16)][k4 step s(8)][lane(32)]
+//        lane = (row%8)*4 + k%4 holds  -L[rb*8 + row%8][c*32 + s*4 + k%4]
+//   Upack tile (128 k x 64 cols):   [chunk c(4)][k4 step s(8)][col block nb(8)][lane(32)]
+//        lane = (col%8)*4 + k%4 holds   U[c*32 + s*4 + k%4][nb*8 + col%8]
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ int64_t lpack_index(int r /*0..127*/, int k /*0..127*/) {
+  return (int64_t)(k >> 5) * A_CHUNK + (((r >> 3) * 8 + ((k & 31) >> 2)) * 32 + (r & 7) * 4 + (k & 3));
+}
+__device__ __forceinline__ int64_t upack_index(int k /*0..127*/, int c /*0..63*/) {
+  return (int64_t)(k >> 5) * B_CHUNK + ((((k & 31) >> 2) * 8 + (c >> 3)) * 32 + (c & 7) * 4 + (k & 3));
+}
+
+// ---------------------------------------------------------------------------------------
+// 3. trailing update
+// ---------------------------------------------------------------------------------------
+struct __align__(128) UpdateStage {
+  double a[A_CHUNK];
+  double b[B_CHUNK];
+};
+
+__global__ void __launch_bounds__(256, 2)
+update_kernel(double* __restrict__ M, int64_t ld, int64_t o2, const double* __restrict__ Lpack,
+              const double* __restrict__ Upack) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  UpdateStage* stage = reinterpret_cast<UpdateStage*>(smem_raw);
+  __shared__ uint64_t bars[2];
+
+  const int tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5;
+  const int wm = warp >> 1, wn = warp & 1;  // 4 x 2 warps, 32x32 warp tiles
+  const int g = lane >> 2, t = lane & 3;
+
+  const double* Ltile = Lpack + (int64_t)blockIdx.y * (NB * BM);
+  const double* Utile = Upack + (int64_t)blockIdx.x * (NB * BN);
+  constexpr uint32_t kStageBytes = (A_CHUNK + B_CHUNK) * sizeof(double);
+
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  if (tid == 0) {
+#pragma unroll
+    for (int c = 0; c < 2; c++) {
+      mbar_expect_tx(&bars[c], kStageBytes);
+      bulk_g2s(stage[c].a, Ltile + (int64_t)c * A_CHUNK, A_CHUNK * sizeof(double), &bars[c]);
+      bulk_g2s(stage[c].b, Utile + (int64_t)c * B_CHUNK, B_CHUNK * sizeof(double), &bars[c]);
+    }
+  }
+
+  // accumulators start as the C tile
+  double acc[4][4][2];
+  double* Cbase = M + (o2 + (int64_t)blockIdx.y * BM + wm * 32 + g) * ld + o2 + (int64_t)blockIdx.x * BN +
+                  wn * 32 + 2 * t;
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const double2 v = *reinterpret_cast<const double2*>(Cbase + (int64_t)(i * 8) * ld + j * 8);
+      acc[i][j][0] = v.x;
+      acc[i][j][1] = v.y;
+    }
+
+#pragma unroll 1
+  for (int c = 0; c < NCHUNK; c++) {
+    const int st = c & 1;
+    mbar_wait(&bars[st], (c >> 1) & 1);
+    const double* As = stage[st].a + (wm * 4 * 8) * 32 + lane;
+    const double* Bs = stage[st].b + (wn * 4) * 32 + lane;
+#pragma unroll
+    for (int s = 0; s < 8; s++) {
+      double a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; i++) a[i] = As[(i * 8 + s) * 32];
+#pragma unroll
+      for (int j = 0; j < 4; j++) b[j] = Bs[(s * 8 + j) * 32];
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) dmma(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+    }
+    __syncthreads();
+    if (tid == 0 && c + 2 < NCHUNK) {
+      mbar_expect_tx(&bars[st], kStageBytes);
+      bulk_g2s(stage[st].a, Ltile + (int64_t)(c + 2) * A_CHUNK, A_CHUNK * sizeof(double), &bars[st]);
+      bulk_g2s(stage[st].b, Utile + (int64_t)(c + 2) * B_CHUNK, B_CHUNK * sizeof(double), &bars[st]);
+    }
+  }
+
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+      *reinterpret_cast<double2*>(Cbase + (int64_t)(i * 8) * ld + j * 8) =
+          make_double2(acc[i][j][0], acc[i][j][1]);
+}
+
+// ---------------------------------------------------------------------------------------
+// 2. panel solves as GEMMs with the explicit block inverses (K = 128, one pass per CTA)
+//    blockIdx.x <  ncol : L21 tile (64 rows x 128)  = A21 tile * invU      warps 2 x 4
+//    blockIdx.x >= ncol : U12 tile (128 x 64 cols)  = invL * A12 tile      warps 4 x 2
+//    Each CTA reads only the rows (col panel) / columns (row panel) it overwrites, so the
+//    in-place update is race-free.
+// ---------------------------------------------------------------------------------------
+constexpr int TA_LD = KC + 4;  // 36: A chunk [TM][36]   (ld % 16 == 4 -> conflict-free fragments)
+
+template <int TM, int TN, int WMW, int WNW>
+__device__ __forceinline__ void gemm_k128(const double* __restrict__ A, int64_t lda,
+                                          const double* __restrict__ B, int64_t ldb, double* As,
+                                          double* Bs, double (&acc)[4][4][2]) {
+  constexpr int TB_LD = TN + 4;
+  const int tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5;
+  const int wm = warp / WNW, wn = warp % WNW;
+  const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+#pragma unroll 1
+  for (int c = 0; c < NCHUNK; c++) {
+    __syncthreads();
+    // A chunk: TM rows x 32 k  (16 double2 per row)
+#pragma unroll
+    for (int q = 0; q < TM * 16 / 256; q++) {
+      const int idx = q * 256 + tid;
+      const int r = idx >> 4, kk = (idx & 15) * 2;
+      *reinterpret_cast<double2*>(&As[r * TA_LD + kk]) =
+          *reinterpret_cast<const double2*>(A + (int64_t)r * lda + c * KC + kk);
+    }
+    // B chunk: 32 k rows x TN cols  (TN/2 double2 per row)
+#pragma unroll
+    for (int q = 0; q < KC * (TN / 2) / 256; q++) {
+      const int idx = q * 256 + tid;
+      const int kr = idx / (TN / 2), cc = (idx % (TN / 2)) * 2;
+      *reinterpret_cast<double2*>(&Bs[kr * TB_LD + cc]) =
+          *reinterpret_cast<const double2*>(B + (int64_t)(c * KC + kr) * ldb + cc);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int s = 0; s < 8; s++) {
+      double a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; i++) a[i] = As[(wm * 32 + i * 8 + g) * TA_LD + s * 4 + t];
+#pragma unroll
+      for (int j = 0; j < 4; j++) b[j] = Bs[(s * 4 + t) * TB_LD + wn * 32 + j * 8 + g];
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) dmma(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+    }
+  }
+}
+
+constexpr int kTrsmSmemDoubles = 128 * TA_LD + KC * (64 + 4) > 64 * TA_LD + KC * (128 + 4)
+                                     ? 128 * TA_LD + KC * (64 + 4)
+                                     : 64 * TA_LD + KC * (128 + 4);
+
+__global__ void __launch_bounds__(256)
+trsm_kernel(double* __restrict__ M, int64_t ld, int64_t o, int ncol, const double* __restrict__ invL,
+            const double* __restrict__ invU, double* __restrict__ Lpack, double* __restrict__ Upack) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* As = reinterpret_cast<double*>(smem_raw);
+  const int tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int64_t o2 = o + NB;
+  double acc[4][4][2];
+  if ((int)blockIdx.x < ncol) {
+    // ---- column panel: 64 rows of L21 ----
+    const int tile = blockIdx.x;
+    double* Atile = M + (o2 + (int64_t)tile * 64) * ld + o;
+    double* Bs = As + 64 * TA_LD;
+    gemm_k128<64, 128, 2, 4>(Atile, ld, invU, NB, As, Bs, acc);
+    const int wm = warp / 4, wn = warp % 4;
+    double* P = Lpack + (int64_t)(tile >> 1) * (NB * BM);
+    const int rbase = (tile & 1) * 64;
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const int r = wm * 32 + i * 8 + g;
+        const int cc = wn * 32 + j * 8 + 2 * t;
+        *reinterpret_cast<double2*>(Atile + (int64_t)r * ld + cc) = make_double2(acc[i][j][0], acc[i][j][1]);
+        P[lpack_index(rbase + r, cc)] = -acc[i][j][0];
+        P[lpack_index(rbase + r, cc + 1)] = -acc[i][j][1];
+      }
+  } else {
+    // ---- row panel: 64 columns of U12 ----
+    const int tile = blockIdx.x - ncol;
+    double* Btile = M + o * ld + o2 + (int64_t)tile * 64;
+    double* Bs = As + 128 * TA_LD;
+    gemm_k128<128, 64, 4, 2>(invL, NB, Btile, ld, As, Bs, acc);
+    const int wm = warp / 2, wn = warp % 2;
+    double* P = Upack + (int64_t)tile * (NB * BN);
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const int r = wm * 32 + i * 8 + g;
+        const int cc = wn * 32 + j * 8 + 2 * t;
+        *reinterpret_cast<double2*>(Btile + (int64_t)r * ld + cc) = make_double2(acc[i][j][0], acc[i][j][1]);
+        P[upack_index(r, cc)] = acc[i][j][0];
+        P[upack_index(r, cc + 1)] = acc[i][j][1];
+      }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// 1. diagonal block: LU (no pivoting) + explicit triangular inverses, all in shared memory.
+//    The inverses are computed IN PLACE over the LU block (after it has been written back):
+//    inv(L) row by row downwards in the strict lower part (threads 0..255), inv(U) row by row
+//    upwards in the upper part (threads 256..511), concurrently.
+// ---------------------------------------------------------------------------------------
+constexpr int DLD = NB + 1;  // padded row stride
+
+__global__ void __launch_bounds__(512, 1)
+diag_kernel(double* __restrict__ M, int64_t ld, int64_t o, double* __restrict__ invL,
+            double* __restrict__ invU, int32_t* __restrict__ info, int block_index) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* D = reinterpret_cast<double*>(smem_raw);  // [128][129]
+  __shared__ double part[4][NB];
+  __shared__ int bad;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  double* blk = M + o * ld + o;
+  if (tid == 0) bad = 0;
+  for (int idx = tid; idx < NB * NB; idx += nt) {
+    const int r = idx >> 7, c = idx & 127;
+    D[r * DLD + c] = blk[(int64_t)r * ld + c];
+  }
+  __syncthreads();
+  // right-looking LU, one column per step
+  for (int j = 0; j < NB; j++) {
+    const double piv = D[j * DLD + j];
+    if (tid == 0 && !(fabs(piv) > 0.0 && isfinite(piv)) && bad == 0) bad = j + 1;
+    const double rp = 1.0 / piv;
+    for (int i = j + 1 + tid; i < NB; i += nt) D[i * DLD + j] *= rp;
+    __syncthreads();
+    const int rem = NB - 1 - j;
+    for (int idx = tid; idx < rem * rem; idx += nt) {
+      const int i = j + 1 + idx / rem, c = j + 1 + idx % rem;
+      D[i * DLD + c] -= D[i * DLD + j] * D[j * DLD + c];
+    }
+    __syncthreads();
+  }
+  for (int idx = tid; idx < NB * NB; idx += nt) {
+    const int r = idx >> 7, c = idx & 127;
+    blk[(int64_t)r * ld + c] = D[r * DLD + c];
+  }
+  if (tid == 0 && bad) atomicCAS(info, 0, block_index * NB + bad);
+  __syncthreads();
+
+  const int half = tid >> 8;        // 0: inv(L), 1: inv(U)
+  const int c = tid & 127;          // column
+  const int kg = (tid >> 7) & 1;    // 2 k-groups per half
+  for (int step = 0; step < NB; step++) {
+    double s = 0.0;
+    if (half == 0) {
+      // X[i][c] = -( L[i][c] + sum_{k=c+1}^{i-1} L[i][k] X[k][c] ),  c < i   (X[c][c] = 1 implicit)
+      const int i = step;
+      if (c < i) {
+        for (int k = c + 1 + kg; k < i; k += 2) s += D[i * DLD + k] * D[k * DLD + c];
+        if (kg == 0) s += D[i * DLD + c];
+      }
+    } else {
+      // X[i][c] = -( sum_{k=i+1}^{c} U[i][k] X[k][c] ) / U[i][i],  c > i ;  X[i][i] = 1/U[i][i]
+      const int i = NB - 1 - step;
+      if (c > i)
+        for (int k = i + 1 + kg; k <= c; k += 2) s += D[i * DLD + k] * D[k * DLD + c];
+    }
+    part[half * 2 + kg][c] = s;
+    __syncthreads();
+    if (kg == 0) {
+      if (half == 0) {
+        const int i = step;
+        if (c < i) D[i * DLD + c] = -(part[0][c] + part[1][c]);
+      } else {
+        const int i = NB - 1 - step;
+        const double rp = 1.0 / D[i * DLD + i];
+        if (c > i) D[i * DLD + c] = -(part[2][c] + part[3][c]) * rp;
+        else if (c == i) D[i * DLD + c] = rp;
+      }
+    }
+    __syncthreads();
+  }
+  for (int idx = tid; idx < NB * NB; idx += nt) {
+    const int r = idx >> 7, cc = idx & 127;
+    const double v = D[r * DLD + cc];
+    invL[idx] = cc < r ? v : (cc == r ? 1.0 : 0.0);
+    invU[idx] = cc >= r ? v : 0.0;
+  }
+}
+
+static bool g_attr_set = false;
+
+}  // namespace scb
+
+using namespace scb;
+
+extern "C" int64_t scb_getrf_dinv_bytes(int64_t n_pad) {
+  const int64_t nb = n_pad / NB;
+  // [nb][2][128][128] block inverses + Lpack [n_pad x 128] + Upack [128 x n_pad]
+  return (nb * 2 * NB * NB + 2 * n_pad * NB) * (int64_t)sizeof(double);
+}
+
+extern "C" int scb_getrf_nopiv(int64_t n_pad, double* M, double* dinv, int32_t* info,
+                               scb_stream_t stream) {
+  SCB_CHECK_ARG(n_pad > 0 && n_pad % NB == 0, "n_pad must be a positive multiple of 128");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int64_t nb = n_pad / NB;
+  double* Lpack = dinv + nb * 2 * NB * NB;
+  double* Upack = Lpack + n_pad * NB;
+  const int diag_smem = NB * DLD * sizeof(double);
+  const int trsm_smem = kTrsmSmemDoubles * sizeof(double);
+  const int upd_smem = 2 * sizeof(UpdateStage);
+  if (!g_attr_set) {
+    SCB_CUDA(cudaFuncSetAttribute(diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, diag_smem));
+    SCB_CUDA(cudaFuncSetAttribute(update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, upd_smem));
+    SCB_CUDA(cudaFuncSetAttribute(trsm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, trsm_smem));
+    SCB_CUDA(cudaFuncSetAttribute(update_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    g_attr_set = true;
+  }
+  SCB_CUDA(cudaMemsetAsync(info, 0, sizeof(int32_t), s));
+  for (int64_t k = 0; k < nb; k++) {
+    const int64_t o = k * NB;
+    double* invL = dinv + k * 2 * NB * NB;
+    double* invU = invL + NB * NB;
+    diag_kernel<<<1, 512, diag_smem, s>>>(M, n_pad, o, invL, invU, info, (int)k);
+    SCB_LAUNCH_CHECK();
+    const int ntiles = (int)(nb - k - 1);
+    if (ntiles == 0) break;
+    trsm_kernel<<<4 * ntiles, 256, trsm_smem, s>>>(M, n_pad, o, 2 * ntiles, invL, invU, Lpack, Upack);
+    SCB_LAUNCH_CHECK();
+    dim3 grid(2 * ntiles, ntiles);
+    update_kernel<<<grid, 256, upd_smem, s>>>(M, n_pad, o + NB, Lpack, Upack);
+    SCB_LAUNCH_CHECK();
+  }
+  return SCB_OK;
+}

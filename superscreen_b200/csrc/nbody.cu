@@ -1,0 +1,240 @@
+// Tiled fp64 N-body style pair sums (K13, K15-K18 and the row sums of the kernel matrix).
+//
+// One templated kernel: a CTA owns 256/SL targets; its threads are laid out as
+// (target, source-lane) with SL source lanes per target inside one warp.  Sources are staged
+// through shared memory in tiles of 256; each thread walks the tile entries congruent to its
+// source lane and the SL partial sums of a target are combined with a fixed-order warp-shuffle
+// butterfly, so results are deterministic and no float atomics are used.  SL is chosen from the
+// number of targets so that small target sets (film-to-film, row sums at 2k-60k vertices) still
+// fill 148 SMs, while million-point field evaluations run one target per thread.
+//
+// fp64 CUDA-core bound: ~20 DFMA-class operations per pair.
+//
+// Reference kernels restated (file:line under /root/reference/superscreen):
+//   distance.py:87-115 + device/mesh.py:454-458 (row sums / Q @ (w*g))
+//   solver/solve.py:28-73 biot_savart_film_to_film, solver/solve_film.py:393-437
+//   sources/current.py:13-110 _biot_savart_2d_z/_vector, solution.py:917-928 vector potential
+#include "scb_common.cuh"
+
+namespace scb {
+
+enum : int {
+  NB_FILM_TO_FILM = SCB_BS_FILM_TO_FILM,
+  NB_Z = SCB_BS_Z,
+  NB_VECTOR = SCB_BS_VECTOR,
+  NB_VECPOT = SCB_BS_VECTOR_POTENTIAL,
+  NB_BOUNDARY = SCB_BS_BOUNDARY,
+  NB_KERNEL = 16,  // sum_{j != i} q_ij * payload_j[r], r < NR   (in-plane, 1/r^3)
+};
+
+constexpr int kTile = 256;
+constexpr int kMaxNR = 4;
+
+struct NbodyParams {
+  int64_t m;              // targets
+  const double* tgt;      // [m,2] or [m,3]
+  int64_t n;              // sources
+  const double* src;      // [*,2] or [*,3] (indexed through src_idx when given)
+  const int64_t* src_idx; // optional gather list for NB_KERNEL
+  const double* area;     // [*] per-source weight
+  const double* J;        // [*,2] (biot-savart) or v [*, ldv] (NB_KERNEL)
+  int64_t ldv;            // row stride of v / out for NB_KERNEL
+  int64_t rhs0;           // first rhs column handled by this launch (NB_KERNEL)
+  double dz2;             // film-to-film
+  double prefactor;
+  double* out;
+  int accumulate;
+};
+
+template <int KIND>
+struct Traits {
+  static constexpr int tdim = (KIND == NB_Z || KIND == NB_VECTOR || KIND == NB_VECPOT) ? 3 : 2;
+  static constexpr int nacc = KIND == NB_VECTOR ? 4 : (KIND == NB_VECPOT ? 2 : (KIND == NB_Z ? 2 : 1));
+};
+
+template <int KIND, int SL, int NR>
+__global__ void __launch_bounds__(256) nbody_kernel(NbodyParams p) {
+  constexpr int TD = Traits<KIND>::tdim;
+  constexpr int NACC = KIND == NB_KERNEL ? NR : Traits<KIND>::nacc;
+  constexpr int NPAY = KIND == NB_KERNEL ? NR : 2;
+  __shared__ double sx[kTile], sy[kTile], sz[TD == 3 ? kTile : 1];
+  __shared__ double spay[NPAY][kTile];
+
+  const int tid = threadIdx.x;
+  const int sl = tid % SL;
+  const int64_t i = blockIdx.x * (int64_t)(256 / SL) + tid / SL;
+  const bool active = i < p.m;
+  double tx = 0, ty = 0, tz = 0;
+  if (active) {
+    tx = p.tgt[TD * i];
+    ty = p.tgt[TD * i + 1];
+    if (TD == 3) tz = p.tgt[TD * i + 2];
+  }
+  double acc[NACC];
+#pragma unroll
+  for (int a = 0; a < NACC; a++) acc[a] = 0.0;
+
+  for (int64_t base = 0; base < p.n; base += kTile) {
+    const int64_t j = base + tid;
+    __syncthreads();
+    if (j < p.n) {
+      const int64_t js = p.src_idx ? p.src_idx[j] : j;
+      sx[tid] = p.src[TD * js];
+      sy[tid] = p.src[TD * js + 1];
+      if (TD == 3) sz[tid] = p.src[TD * js + 2];
+      const double w = p.area[js];
+      if (KIND == NB_KERNEL) {
+#pragma unroll
+        for (int r = 0; r < NR; r++) spay[r][tid] = p.J ? w * p.J[js * p.ldv + p.rhs0 + r] : w;
+      } else {
+        spay[0][tid] = w * p.J[2 * js];
+        spay[1][tid] = w * p.J[2 * js + 1];
+      }
+    }
+    __syncthreads();
+    const int cnt = (int)((p.n - base) < kTile ? (p.n - base) : kTile);
+#pragma unroll 4
+    for (int jj = sl; jj < cnt; jj += SL) {
+      const double dx = tx - sx[jj];
+      const double dy = ty - sy[jj];
+      double r2 = dx * dx + dy * dy;
+      double dzv = 0.0;
+      if (TD == 3) {
+        dzv = tz - sz[jj];
+        r2 += dzv * dzv;
+      } else if (KIND == NB_FILM_TO_FILM) {
+        r2 += p.dz2;
+      }
+      if (KIND == NB_VECPOT) {
+        const double inv = rsqrt(r2);
+        acc[0] += spay[0][jj] * inv;
+        acc[1] += spay[1][jj] * inv;
+      } else {
+        double k3 = inv_r3(r2);
+        if (KIND == NB_KERNEL) {
+          k3 = r2 > 0.0 ? k3 : 0.0;  // q_ii = 0 (distance.py:104-105)
+#pragma unroll
+          for (int r = 0; r < NR; r++) acc[r] += spay[r][jj] * k3;
+        } else if (KIND == NB_FILM_TO_FILM) {
+          acc[0] += (spay[0][jj] * dy - spay[1][jj] * dx) * k3;
+        } else if (KIND == NB_BOUNDARY) {
+          acc[0] -= (spay[0][jj] * dx + spay[1][jj] * dy) * k3;
+        } else if (KIND == NB_Z) {
+          acc[0] += k3 * spay[0][jj] * dy;  // Jx_dy
+          acc[1] += k3 * spay[1][jj] * dx;  // Jy_dx
+        } else {                            // NB_VECTOR
+          const double px = k3 * spay[0][jj], py = k3 * spay[1][jj];
+          acc[0] += px * dy;   // Jx_dy
+          acc[1] += py * dx;   // Jy_dx
+          acc[2] += px * dzv;  // Jx_dz
+          acc[3] += py * dzv;  // Jy_dz
+        }
+      }
+    }
+  }
+  // fixed-order butterfly over the SL source lanes
+#pragma unroll
+  for (int off = SL / 2; off > 0; off >>= 1) {
+#pragma unroll
+    for (int a = 0; a < NACC; a++) acc[a] += __shfl_xor_sync(0xffffffffu, acc[a], off);
+  }
+  if (!active || sl != 0) return;
+  const double pf = p.prefactor;
+  if (KIND == NB_KERNEL) {
+#pragma unroll
+    for (int r = 0; r < NR; r++) {
+      double* o = p.out + i * p.ldv + p.rhs0 + r;
+      *o = p.accumulate ? *o + pf * acc[r] : pf * acc[r];
+    }
+  } else if (KIND == NB_Z) {
+    p.out[i] = pf * (acc[0] - acc[1]);
+  } else if (KIND == NB_VECTOR) {
+    p.out[3 * i] = pf * acc[3];
+    p.out[3 * i + 1] = -(pf * acc[2]);
+    p.out[3 * i + 2] = pf * (acc[0] - acc[1]);
+  } else if (KIND == NB_VECPOT) {
+    p.out[2 * i] = pf * acc[0];
+    p.out[2 * i + 1] = pf * acc[1];
+  } else {
+    p.out[i] = pf * acc[0];
+  }
+}
+
+template <int KIND, int NR>
+static int launch_nbody(const NbodyParams& p, cudaStream_t s) {
+  if (p.m == 0) return SCB_OK;
+  // enough CTAs for >= ~4 waves of 148 SMs when possible
+  const int64_t want = 148 * 4;
+  if (p.m * 32 / 256 <= want && p.n >= 32) {
+    nbody_kernel<KIND, 32, NR><<<(unsigned)ceil_div(p.m, 8), 256, 0, s>>>(p);
+  } else if (p.m * 8 / 256 <= want * 2 && p.n >= 8) {
+    nbody_kernel<KIND, 8, NR><<<(unsigned)ceil_div(p.m, 32), 256, 0, s>>>(p);
+  } else {
+    nbody_kernel<KIND, 1, NR><<<(unsigned)ceil_div(p.m, 256), 256, 0, s>>>(p);
+  }
+  SCB_LAUNCH_CHECK();
+  return SCB_OK;
+}
+
+// out[i, rhs0..] (+)= prefactor * sum_{j in src, r_ij > 0} q_ij w_j v[j, rhs0..]
+int nbody_kernel_sum(int64_t m, const double* tgt, int64_t n, const double* src,
+                     const int64_t* src_idx, const double* w, const double* v, int64_t ldv,
+                     int64_t nrhs, double prefactor, double* out, int accumulate, cudaStream_t s) {
+  NbodyParams p{};
+  p.m = m; p.tgt = tgt; p.n = n; p.src = src; p.src_idx = src_idx; p.area = w; p.J = v;
+  p.ldv = ldv; p.prefactor = prefactor; p.out = out; p.accumulate = accumulate;
+  int64_t r = 0;
+  while (r < nrhs) {
+    p.rhs0 = r;
+    int rc;
+    if (nrhs - r >= 4) { rc = launch_nbody<NB_KERNEL, 4>(p, s); r += 4; }
+    else if (nrhs - r >= 2) { rc = launch_nbody<NB_KERNEL, 2>(p, s); r += 2; }
+    else { rc = launch_nbody<NB_KERNEL, 1>(p, s); r += 1; }
+    if (rc) return rc;
+  }
+  return SCB_OK;
+}
+
+__global__ void qdw_finish_kernel(int64_t n, const double* __restrict__ C, double* qdw) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) qdw[i] = C[i] + qdw[i];
+}
+
+}  // namespace scb
+
+using namespace scb;
+
+extern "C" int scb_kernel_diagonal(int64_t n, const double* sites, const double* weights,
+                                   const double* C, double* qdw, scb_stream_t stream) {
+  SCB_CHECK_ARG(n > 0, "n must be positive");
+  cudaStream_t s = (cudaStream_t)stream;
+  int rc = nbody_kernel_sum(n, sites, n, sites, nullptr, weights, nullptr, 1, 1, kOneOver4Pi, qdw, 0, s);
+  if (rc) return rc;
+  qdw_finish_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, s>>>(n, C, qdw);
+  SCB_LAUNCH_CHECK();
+  return SCB_OK;
+}
+
+extern "C" int scb_biot_savart(int kind, int64_t m, const double* tgt, int64_t n, const double* src,
+                               const double* area, const double* J, double dz, double prefactor,
+                               int64_t nsets, double* out, scb_stream_t stream) {
+  SCB_CHECK_ARG(m >= 0 && n >= 0 && nsets >= 1, "bad sizes");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int64_t ocomp = kind == SCB_BS_VECTOR ? 3 : (kind == SCB_BS_VECTOR_POTENTIAL ? 2 : 1);
+  for (int64_t k = 0; k < nsets; k++) {
+    NbodyParams p{};
+    p.m = m; p.tgt = tgt; p.n = n; p.src = src; p.area = area; p.J = J + k * n * 2;
+    p.dz2 = dz * dz; p.prefactor = prefactor; p.out = out + k * m * ocomp;
+    int rc;
+    switch (kind) {
+      case SCB_BS_FILM_TO_FILM: rc = launch_nbody<NB_FILM_TO_FILM, 1>(p, s); break;
+      case SCB_BS_Z: rc = launch_nbody<NB_Z, 1>(p, s); break;
+      case SCB_BS_VECTOR: rc = launch_nbody<NB_VECTOR, 1>(p, s); break;
+      case SCB_BS_VECTOR_POTENTIAL: rc = launch_nbody<NB_VECPOT, 1>(p, s); break;
+      case SCB_BS_BOUNDARY: rc = launch_nbody<NB_BOUNDARY, 1>(p, s); break;
+      default: set_error("scb_biot_savart: unknown kind %d", kind); return SCB_ERR_INVALID;
+    }
+    if (rc) return rc;
+  }
+  return SCB_OK;
+}

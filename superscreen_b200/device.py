@@ -1,0 +1,267 @@
+"""Thin Device / Layer / Polygon model: exactly the attributes the solve hot path reads
+(reference solver/solve.py:391-409, solver/utils.py:241-304; the full shapely/matplotlib
+geometry subsystem of superscreen/device/*.py is out of scope).
+"""
+from __future__ import annotations
+
+import logging
+import numbers
+from typing import Callable, Dict, List, Optional, Sequence, Tuple, Union
+
+import numpy as np
+
+from . import units as _u
+from .geometry import close_curve, orient_ccw, points_in_polygon
+from .mesh import Mesh
+
+logger = logging.getLogger("device")
+
+
+class Layer:
+    """reference device/layer.py: name, Lambda or (london_lambda, thickness), z0."""
+
+    def __init__(self, name: str, Lambda=None, london_lambda=None, thickness=None, z0: float = 0):
+        self.name = name
+        self.thickness = thickness
+        self.london_lambda = london_lambda
+        self.z0 = z0
+        if Lambda is None:
+            if london_lambda is None or thickness is None:
+                raise ValueError("Either Lambda or both london_lambda and thickness must be given.")
+            self._Lambda = None
+        else:
+            if london_lambda is not None or thickness is not None:
+                raise ValueError("Either Lambda or both london_lambda and thickness must be given (not both).")
+            self._Lambda = Lambda
+
+    @property
+    def Lambda(self):
+        if self._Lambda is not None:
+            return self._Lambda
+        if callable(self.london_lambda):
+            ll, d = self.london_lambda, self.thickness
+            return lambda x, y: ll(x, y) ** 2 / d
+        return self.london_lambda**2 / self.thickness
+
+    @Lambda.setter
+    def Lambda(self, value):
+        self._Lambda = value
+        self.london_lambda = None
+        self.thickness = None
+
+    def copy(self) -> "Layer":
+        if self._Lambda is not None:
+            return Layer(self.name, Lambda=self._Lambda, z0=self.z0)
+        return Layer(self.name, london_lambda=self.london_lambda, thickness=self.thickness, z0=self.z0)
+
+
+class Polygon:
+    """A simply connected polygon in a layer (reference device/polygon.py:28-162).  Points are
+    stored closed and counter-clockwise, as the reference does (polygon.py:67-77)."""
+
+    def __init__(self, name: Optional[str] = None, *, layer: Optional[str] = None, points):
+        self.name = name
+        self.layer = layer
+        if isinstance(points, Polygon):
+            points = points.points
+        pts = np.asarray(points, dtype=float)
+        if pts.ndim != 2 or pts.shape[-1] != 2:
+            raise ValueError(f"Expected shape (n, 2), but got {pts.shape}.")
+        self._points = close_curve(orient_ccw(pts))
+
+    @property
+    def points(self) -> np.ndarray:
+        return self._points
+
+    @property
+    def is_valid(self) -> bool:
+        return len(self._points) >= 4
+
+    @property
+    def extents(self) -> Tuple[float, float]:
+        return tuple(np.ptp(self._points, axis=0))
+
+    def contains_points(self, points, index: bool = False, radius: float = 0):
+        mask = points_in_polygon(self._points, np.atleast_2d(points))
+        if index:
+            return np.where(mask)[0]
+        return mask
+
+    def copy(self) -> "Polygon":
+        return Polygon(self.name, layer=self.layer, points=self._points.copy())
+
+    def __repr__(self):
+        return f"Polygon(name={self.name!r}, layer={self.layer!r}, points=<{len(self._points)} x 2>)"
+
+
+def _as_dict(items):
+    if items is None:
+        return {}
+    if isinstance(items, dict):
+        items = list(items.values())
+    return {it.name: it for it in items}
+
+
+class Device:
+    """reference device/device.py:40-127 (constructor), :157-240 (layer/film queries, copy)."""
+
+    def __init__(self, name: str, *, layers, films, holes=None, terminals=None, abstract_regions=None,
+                 length_units: str = "um", solve_dtype="float64"):
+        self.name = name
+        self.layers: Dict[str, Layer] = _as_dict(layers)
+        self.films: Dict[str, Polygon] = _as_dict(films)
+        self.holes: Dict[str, Polygon] = _as_dict(holes)
+        self.terminals: Dict[str, List[Polygon]] = terminals or {}
+        if not set(self.terminals).issubset(self.films):
+            raise ValueError(f"terminals.keys() must be a subset of films.keys() ({list(self.films)!r}).")
+        self.abstract_regions: Dict[str, Polygon] = _as_dict(abstract_regions)
+        for polygons, label in [(self.films.values(), "film"), (self.holes.values(), "hole")]:
+            for polygon in polygons:
+                if not polygon.is_valid:
+                    raise ValueError(f"The following {label} is not valid: {polygon}.")
+                if polygon.layer not in self.layers:
+                    raise ValueError(
+                        f"The following {label} is assigned to a layer that doesn not "
+                        f"exist in the device: {polygon}."
+                    )
+        self._length_units = length_units
+        self.solve_dtype = solve_dtype
+        self.meshes: Optional[Dict[str, Mesh]] = None
+
+    ureg = _u  # the module plays the role of the reference's pint registry
+
+    @property
+    def length_units(self) -> str:
+        return self._length_units
+
+    @property
+    def solve_dtype(self) -> np.dtype:
+        return self._solve_dtype
+
+    @solve_dtype.setter
+    def solve_dtype(self, dtype) -> None:
+        try:
+            _ = np.finfo(dtype)
+        except ValueError as e:
+            raise ValueError(f"Invalid float dtype: {dtype}") from e
+        if np.dtype(dtype) != np.float64:
+            logger.info("superscreen_b200 computes in float64; solve_dtype only sets output dtype.")
+        self._solve_dtype = np.dtype(dtype)
+
+    def polygons_by_layer(self, polygon_type: Optional[str] = None) -> Dict[str, List[Polygon]]:
+        polygon_type = (polygon_type or "all").lower()
+        if polygon_type == "film":
+            polys = list(self.films.values())
+        elif polygon_type == "hole":
+            polys = list(self.holes.values())
+        elif polygon_type == "abstract":
+            polys = list(self.abstract_regions.values())
+        elif polygon_type == "all":
+            polys = list(self.films.values()) + list(self.holes.values()) + list(self.abstract_regions.values())
+        else:
+            raise ValueError(f"Invalid polygon type ({polygon_type}).")
+        out = {name: [] for name in self.layers}
+        for p in polys:
+            out[p.layer].append(p)
+        return out
+
+    def holes_by_film(self) -> Dict[str, List[Polygon]]:
+        by_layer = self.polygons_by_layer("hole")
+        out = {}
+        for film in self.films.values():
+            out[film.name] = [h for h in by_layer[film.layer] if film.contains_points(h.points).all()]
+        return out
+
+    def copy(self, with_mesh: bool = True, copy_mesh: bool = False) -> "Device":
+        d = Device(
+            self.name,
+            layers=[l.copy() for l in self.layers.values()],
+            films=[f.copy() for f in self.films.values()],
+            holes=[h.copy() for h in self.holes.values()],
+            terminals={k: [t.copy() for t in v] for k, v in self.terminals.items()},
+            abstract_regions=[r.copy() for r in self.abstract_regions.values()],
+            length_units=self.length_units,
+            solve_dtype=self.solve_dtype,  # the reference drops this; we keep fp64
+        )
+        if with_mesh and self.meshes is not None:
+            d.meshes = self.meshes
+        return d
+
+    # ---- meshes are inputs (mesh generation is out of scope) ----
+    def set_meshes(self, meshes: Dict[str, Union[Mesh, Tuple[np.ndarray, np.ndarray]]]) -> None:
+        """Attach one triangulation per film: ``{film: Mesh | (sites, elements)}``."""
+        out = {}
+        for name in self.films:
+            if name not in meshes:
+                raise ValueError(f"No mesh given for film {name!r}.")
+            m = meshes[name]
+            out[name] = m if isinstance(m, Mesh) else Mesh.from_triangulation(*m)
+        self.meshes = out
+
+    def make_mesh(self, target_vertices: Union[int, Dict[str, int]] = 2000, buffer_factor: float = 0.05,
+                  seed: int = 0) -> None:
+        """Synthetic stand-in for ``Device.make_mesh`` (reference device/device.py:383-471): meshes
+        the bounding disk/box of each film (convex outlines only) with ``synthetic.make_mesh``."""
+        from .synthetic import make_mesh
+
+        holes_by_film = self.holes_by_film()
+        meshes = {}
+        for k, (name, film) in enumerate(self.films.items()):
+            nv = target_vertices[name] if isinstance(target_vertices, dict) else target_vertices
+            pts = film.points[:-1]
+            embedded = [h.points[:-1] for h in holes_by_film[name]]
+            if buffer_factor:
+                c = pts.mean(axis=0)
+                outline = c + (pts - c) * (1.0 + 2 * buffer_factor)
+                embedded = [pts] + embedded
+            else:
+                outline = pts
+            meshes[name] = make_mesh(outline, target_vertices=nv, embedded=embedded, seed=seed + k)
+        self.set_meshes(meshes)
+
+    def mutual_inductance_matrix(self, hole_polygon_mapping: Dict[str, np.ndarray], units: str = "pH",
+                                 all_iterations: bool = False, **solve_kwargs):
+        """reference device/device.py:538-648.  ``hole_polygon_mapping`` is required (the default
+        shapely-buffered polygons of fluxoid.py:12-52 are out of scope).  All columns share one
+        factorization."""
+        from .solver import factorize_model, solve
+
+        holes = self.holes
+        hole_names = list(holes)
+        for hole_name, polygon in hole_polygon_mapping.items():
+            if hole_name not in holes:
+                raise ValueError(f"Hole '{hole_name}' does not exist in the device.")
+            if not points_in_polygon(polygon, holes[hole_name].points).all():
+                raise ValueError(f"Hole '{hole_name}' is not completely contained within the given polygon.")
+        n_holes = len(hole_polygon_mapping)
+        solve_kwargs = dict(solve_kwargs)
+        iterations = solve_kwargs.get("iterations", 1)
+        solve_kwargs["current_units"] = None
+        solve_kwargs["progress_bar"] = False
+        I_circ_A = _u.to_quantity("1 mA", "A").to("A").magnitude
+        if all_iterations:
+            n_iter = 1 if len(self.layers) == 1 else iterations + 1
+            sl = slice(None)
+        else:
+            n_iter = 1
+            sl = slice(-1, None)
+        M = np.zeros((n_iter, n_holes, n_holes))
+        films_by_hole = {h.name: film for film, hs in self.holes_by_film().items() for h in hs}
+        model = None
+        for j, hole_name in enumerate(hole_names):
+            if model is None:
+                model = factorize_model(device=self, current_units="mA", circulating_currents={hole_name: "1 mA"})
+                I_val = model.circulating_currents[hole_name]
+            else:
+                model.set_circulating_currents({hole_name: I_val})
+            solutions = solve(model=model, **solve_kwargs)[sl]
+            for nn, solution in enumerate(solutions):
+                for i, name in enumerate(hole_names):
+                    fluxoid = solution.polygon_fluxoid(hole_polygon_mapping[name], film=films_by_hole[name],
+                                                       units="Phi_0", with_units=False)
+                    phi = sum(fluxoid) * _u.PHI_0  # Wb
+                    M[nn, i, j] = phi / I_circ_A * _u.conversion_factor("H", units)
+        result = [m for m in M]
+        if not all_iterations:
+            result = result[0]
+        return result

@@ -1,0 +1,388 @@
+"""Solution containers and post-processing (reference superscreen/solution.py).
+
+The O(m*n) field evaluations (``field_at_position``, ``screening_field_at_position``,
+``vector_potential_at_position``; reference solution.py:611-934 and sources/current.py:13-196)
+run as tiled fp64 pair sums on the device (``scb_biot_savart``); fluxoids and interpolation are
+O(n + polygon points) host work (reference solution.py:278-319,484-609).
+"""
+from __future__ import annotations
+
+import datetime as dt
+import logging
+from dataclasses import dataclass
+from typing import Any, Callable, Dict, List, NamedTuple, Optional, Sequence, Tuple, Union
+
+import numpy as np
+
+from . import _lib
+from . import units as _u
+from .device import Device, Polygon
+from .geometry import points_in_polygon
+
+try:  # the reference's Biot-Savart uses scipy.constants.mu_0
+    from scipy.constants import mu_0 as _MU0_BIOT_SAVART
+except Exception:  # pragma: no cover
+    _MU0_BIOT_SAVART = _u.MU_0
+
+logger = logging.getLogger("solution")
+
+
+class Fluxoid(NamedTuple):
+    """flux part + supercurrent part (reference solution.py:39-59)."""
+
+    flux_part: Union[float, _u.Quantity]
+    supercurrent_part: Union[float, _u.Quantity]
+
+
+@dataclass
+class Vortex:
+    """reference solution.py:62-92"""
+
+    x: float
+    y: float
+    film: str
+    nPhi0: float = 1
+
+
+class FilmSolution:
+    """Raw solution data for a single film (reference solution.py:95-130)."""
+
+    def __init__(self, stream, current_density, applied_field, self_field, field_from_other_films=None):
+        self.stream = np.asarray(stream)
+        self.current_density = np.asarray(current_density)
+        self.applied_field = np.asarray(applied_field)
+        self.self_field = np.asarray(self_field)
+        if field_from_other_films is not None:
+            field_from_other_films = np.asarray(field_from_other_films)
+        self.field_from_other_films = field_from_other_films
+        self._total_field: Optional[np.ndarray] = None
+
+    @property
+    def total_field(self) -> np.ndarray:
+        if self._total_field is None:
+            self._total_field = self.applied_field + self.self_field
+            if self.field_from_other_films is not None:
+                self._total_field = self._total_field + self.field_from_other_films
+        return self._total_field
+
+
+def linear_tri_interpolate(sites: np.ndarray, elements: np.ndarray, values: np.ndarray, xy: np.ndarray,
+                           chunk: int = 256) -> np.ndarray:
+    """Piecewise-linear interpolation on a triangulation; NaN outside the mesh.  Stands in for
+    ``matplotlib.tri.LinearTriInterpolator`` (reference solution.py:272-276,310-312)."""
+    xy = np.atleast_2d(np.asarray(xy, dtype=float))
+    values = np.asarray(values, dtype=float)
+    p = sites[elements]
+    a, b, c = p[:, 0], p[:, 1], p[:, 2]
+    det = (b[:, 1] - c[:, 1]) * (a[:, 0] - c[:, 0]) + (c[:, 0] - b[:, 0]) * (a[:, 1] - c[:, 1])
+    out = np.full((len(xy),) + values.shape[1:], np.nan)
+    for s in range(0, len(xy), chunk):
+        q = xy[s:s + chunk]
+        dx = q[:, 0][:, None] - c[None, :, 0]
+        dy = q[:, 1][:, None] - c[None, :, 1]
+        l1 = ((b[:, 1] - c[:, 1])[None] * dx + (c[:, 0] - b[:, 0])[None] * dy) / det[None]
+        l2 = ((c[:, 1] - a[:, 1])[None] * dx + (a[:, 0] - c[:, 0])[None] * dy) / det[None]
+        l3 = 1.0 - l1 - l2
+        mn = np.minimum(np.minimum(l1, l2), l3)
+        t = np.argmax(mn, axis=1)
+        r = np.arange(len(q))
+        ok = mn[r, t] >= -1e-12
+        v = values[elements[t]]  # (q, 3, ...)
+        w = np.stack([l1[r, t], l2[r, t], l3[r, t]], axis=1)
+        res = np.einsum("qk,qk...->q...", w, v)
+        res[~ok] = np.nan
+        out[s:s + chunk] = res
+    return out
+
+
+def _normalize_positions(positions, zs, dtype):
+    """Shared argument handling of the *_at_position methods (reference solution.py:660-676)."""
+    positions = np.atleast_2d(positions)
+    if positions.shape[1] == 3:
+        if zs is not None:
+            raise ValueError("If positions has shape (m, 3) then zs cannot be specified.")
+        zs = positions[:, 2]
+        positions = positions[:, :2]
+    else:
+        zs = np.squeeze(zs)
+        if zs.ndim == 0:
+            zs = zs.item() * np.ones(positions.shape[0], dtype=dtype)
+    if not isinstance(zs, np.ndarray):
+        raise ValueError(f"Expected zs to be an ndarray, but got {type(zs)}.")
+    return np.ascontiguousarray(positions, dtype=np.float64), np.ascontiguousarray(zs, dtype=np.float64)
+
+
+def biot_savart_2d(x, y, z, *, positions, current_densities, z0: float = 0, areas=None, length_units: str = "um",
+                   current_units: str = "uA", vector: bool = True, device_tensors: Optional[dict] = None):
+    """Field (tesla) of a current sheet at ``(x, y, z)`` (reference sources/current.py:113-196).
+    ``areas`` is required (the Delaunay fallback of the reference, current.py:186-189, is host-side
+    meshing and out of scope)."""
+    import torch
+
+    L = _lib.lib()
+    if areas is None:
+        raise ValueError("areas (vertex areas of the current sheet) must be given.")
+    to_meter = _u.conversion_factor(length_units, "m")
+    to_amp_per_meter = _u.conversion_factor(f"({current_units}) / ({length_units})", "A / m")
+    x, y, z = np.atleast_1d(x, y, z)
+    if z.shape[0] == 1:
+        z = z * np.ones_like(x)
+    dev = torch.device(f"cuda:{torch.cuda.current_device()}")
+    ev = np.ascontiguousarray(np.array([x, y, z], dtype=np.float64).T * to_meter)
+    positions, current_densities = np.atleast_2d(positions, current_densities)
+    J = np.ascontiguousarray(current_densities * to_amp_per_meter, dtype=np.float64)
+    pos = positions * to_meter
+    zz = z0 * np.ones(len(pos)) * to_meter
+    ar = np.ascontiguousarray(np.asarray(areas) * to_meter**2, dtype=np.float64)
+    pos3 = np.ascontiguousarray(np.concatenate([pos, zz[:, None]], axis=1), dtype=np.float64)
+    m, n = len(ev), len(pos3)
+    with torch.cuda.device(dev):
+        t = lambda a: torch.as_tensor(a).to(dev)
+        out = torch.empty((m, 3) if vector else (m,), dtype=torch.float64, device=dev)
+        _lib.check(L.scb_biot_savart(2 if vector else 1, m, _lib.ptr(t(ev)), n, _lib.ptr(t(pos3)), _lib.ptr(t(ar)),
+                                     _lib.ptr(t(J)), 0.0, _MU0_BIOT_SAVART / (4 * np.pi), 1, _lib.ptr(out),
+                                     _lib.stream_ptr()))
+        return out.cpu().numpy()
+
+
+class Solution:
+    """reference solution.py:201-260 (container) + post-processing methods."""
+
+    def __init__(self, *, device: Device, film_solutions: Dict[str, FilmSolution], applied_field_func: Callable,
+                 field_units: str, current_units: str, circulating_currents: Optional[Dict[str, float]] = None,
+                 terminal_currents: Optional[Dict[str, float]] = None, vortices=None,
+                 solver: str = "superscreen_b200.solve"):
+        self.device = device.copy(with_mesh=True, copy_mesh=False)
+        self.film_solutions = film_solutions
+        self.applied_field_func = applied_field_func
+        self.circulating_currents = circulating_currents or {}
+        self.terminal_currents = terminal_currents or {}
+        self.vortices = vortices or []
+        self._field_units = field_units
+        self._current_units = current_units
+        self._solver = solver
+        self._time_created = dt.datetime.now()
+
+    field_units = property(lambda self: self._field_units)
+    current_units = property(lambda self: self._current_units)
+    solver = property(lambda self: self._solver)
+    time_created = property(lambda self: self._time_created)
+
+    # ---------------------------------------------------------------- interpolation
+    def interp_field(self, positions, *, film: str, dataset: str = "total_field", method: str = "linear",
+                     units: Optional[str] = None, with_units: bool = False):
+        """reference solution.py:357-420 (linear only)."""
+        from .solver.utils import convert_field
+
+        valid = ("total_field", "applied_field", "self_field", "field_from_other_films")
+        if dataset not in valid:
+            raise ValueError(f"Unexpected dataset: {dataset}.")
+        if method != "linear":
+            raise NotImplementedError("Only linear interpolation is available.")
+        positions = np.atleast_2d(positions)
+        mesh = self.device.meshes[film]
+        values = getattr(self.film_solutions[film], dataset)
+        if values is None:
+            return np.zeros(len(positions))
+        out = linear_tri_interpolate(mesh.sites, mesh.elements, values, positions)
+        out[~np.isfinite(out)] = 0
+        if units is None or units == self.field_units:
+            return _u.Quantity(out, self.field_units) if with_units else out
+        return convert_field(out, units, old_units=self.field_units, with_units=with_units)
+
+    def interp_current_density(self, positions, *, film: str, method: str = "linear", units: Optional[str] = None,
+                               with_units: bool = False):
+        """reference solution.py:278-319"""
+        if method != "linear":
+            raise NotImplementedError("Only linear interpolation is available.")
+        device = self.device
+        default_units = f"({self.current_units}) / ({device.length_units})"
+        positions = np.atleast_2d(positions)
+        mesh = device.meshes[film]
+        J = linear_tri_interpolate(mesh.sites, mesh.elements, self.film_solutions[film].current_density, positions)
+        in_film = device.films[film].contains_points(positions)
+        J[~in_film] = 0
+        J[~np.isfinite(J).all(axis=1)] = 0
+        if units is not None and units != default_units:
+            J = J * _u.conversion_factor(default_units, units)
+        if with_units:
+            return _u.Quantity(J, units or default_units)
+        return J
+
+    def current_through_path(self, path_coords: np.ndarray, *, film: str, interp_method: str = "linear",
+                             units: Optional[str] = None, with_units: bool = True):
+        """reference solution.py:321-355"""
+        from .geometry import path_vectors
+
+        units = units or self.current_units
+        path_coords = np.asarray(path_coords, dtype=float)
+        edge_lengths, unit_normals = path_vectors(path_coords)
+        edge_centers = (path_coords[:-1] + path_coords[1:]) / 2
+        J = self.interp_current_density(edge_centers, film=film, method=interp_method)
+        total = np.sum(np.sum(J * unit_normals, axis=1) * edge_lengths)
+        total = total * _u.conversion_factor(self.current_units, units)
+        return _u.Quantity(total, units) if with_units else total
+
+    # ---------------------------------------------------------------- fluxoid
+    def polygon_fluxoid(self, polygon_coords, *, film: str, interp_method: str = "linear",
+                        units: Optional[str] = "Phi_0", with_units: bool = True) -> Fluxoid:
+        """reference solution.py:484-563"""
+        device = self.device
+        if units is None:
+            units = f"({self.field_units}) * ({device.length_units}) ** 2"
+        polygon = polygon_coords if isinstance(polygon_coords, Polygon) else Polygon(points=polygon_coords)
+        points = polygon.points
+        if not device.films[film].contains_points(points).all():
+            raise ValueError(f"The polygon is not contained within the film ({film!r}).")
+        mesh = device.meshes[film]
+        ix = polygon.contains_points(mesh.sites)
+        flux = np.einsum("i, i ->", self.film_solutions[film].total_field[ix], mesh.vertex_areas[ix])
+        flux_units = f"({self.field_units}) * ({device.length_units}) ** 2"
+        flux_part = flux * _flux_conversion(flux_units, units)
+        J_units = f"({self.current_units}) / ({device.length_units})"
+        J_poly = self.interp_current_density(points, film=film, method=interp_method, units=J_units)
+        Lambda = device.layers[device.films[film].layer].Lambda
+        if callable(Lambda):
+            Lambda_poly = np.asarray(Lambda(points[:, 0], points[:, 1]), dtype=float) * np.ones(len(points))
+        else:
+            Lambda_poly = float(Lambda) * np.ones(len(points))
+        dl = np.diff(points, axis=0)
+        int_J = np.trapezoid(Lambda_poly[:-1] * np.sum(J_poly[:-1] * dl, axis=1))
+        # mu_0 * [J_units * length^2]
+        si = _u.MU_0 * int_J * _u.conversion_factor(f"({J_units}) * ({device.length_units}) ** 2", "A * m")
+        supercurrent_part = si * _u.conversion_factor("Wb", units)
+        if with_units:
+            return Fluxoid(_u.Quantity(flux_part, units), _u.Quantity(supercurrent_part, units))
+        return Fluxoid(flux_part, supercurrent_part)
+
+    def hole_fluxoid(self, hole_name: str, points: Optional[np.ndarray] = None, interp_method: str = "linear",
+                     units: Optional[str] = "Phi_0", with_units: bool = True) -> Fluxoid:
+        """reference solution.py:565-609 (an explicit polygon is required)."""
+        if points is None:
+            from .fluxoid import make_fluxoid_polygons
+
+            points = make_fluxoid_polygons(self.device, holes=hole_name)[hole_name]
+        device = self.device
+        hole = device.holes[hole_name]
+        if not points_in_polygon(points, hole.points).all():
+            raise ValueError(f"Hole {hole.name} is not completely enclosed by the given polygon.")
+        film_name = None
+        for film_name, holes in device.holes_by_film().items():
+            if hole.name in [h.name for h in holes]:
+                break
+        return self.polygon_fluxoid(points, film=film_name, interp_method=interp_method, units=units,
+                                    with_units=with_units)
+
+    # ---------------------------------------------------------------- fields in space
+    def screening_field_at_position(self, positions, *, zs=None, vector: bool = False, interp_method: str = "linear",
+                                    units: Optional[str] = None, with_units: bool = True, return_sum: bool = True):
+        """reference solution.py:611-723"""
+        from .solver.utils import convert_field
+
+        device = self.device
+        dtype = np.float64  # the reference allocates float32 here after Device.copy
+        units = units or self.field_units
+        positions, zs = _normalize_positions(positions, zs, dtype)
+        fields = {}
+        for name, film in device.films.items():
+            layer = device.layers[film.layer]
+            mesh = device.meshes[name]
+            shape = (len(positions), 3) if vector else (len(positions),)
+            field_from_film = np.zeros(shape, dtype=dtype)
+            in_film = np.zeros(len(positions), dtype=bool)
+            if np.all(zs == layer.z0):
+                in_film[film.contains_points(positions)] = True
+                fin = self.interp_field(positions[in_film], film=name, dataset="self_field", method=interp_method,
+                                        units="tesla", with_units=False)
+                if vector:
+                    zeros = np.zeros_like(fin)
+                    fin = np.array([zeros, zeros, fin]).T
+                field_from_film[in_film] = fin
+            out = ~in_film
+            if out.any():
+                field_from_film[out] = biot_savart_2d(
+                    positions[out, 0], positions[out, 1], zs[out], positions=mesh.sites, areas=mesh.vertex_areas,
+                    current_densities=self.film_solutions[name].current_density, z0=layer.z0,
+                    length_units=device.length_units, current_units=self.current_units, vector=vector)
+            fields[name] = convert_field(field_from_film, units, old_units="tesla", with_units=with_units)
+        if return_sum:
+            return sum(fields.values())
+        return fields
+
+    def field_at_position(self, positions, *, zs=None, interp_method: str = "linear", units: Optional[str] = None,
+                          with_units: bool = True, return_sum: bool = True):
+        """reference solution.py:725-831"""
+        from .solver.utils import convert_field
+
+        device = self.device
+        dtype = np.float64
+        units = units or self.field_units
+        positions, zs = _normalize_positions(positions, zs, dtype)
+        fields = self.screening_field_at_position(positions, zs=zs, vector=False, interp_method=interp_method,
+                                                  units=self.field_units, with_units=False, return_sum=False)
+        films_by_layer = device.polygons_by_layer("film")
+        Hz_applied = np.zeros(len(positions), dtype=dtype)
+        in_film = np.zeros(len(positions), dtype=bool)
+        for name, layer in device.layers.items():
+            if np.all(zs == layer.z0):
+                for film in films_by_layer[name]:
+                    ix = film.contains_points(positions)
+                    in_film[ix] = True
+                    Hz_applied[ix] = self.interp_field(positions[ix], film=film.name, dataset="applied_field",
+                                                       method=interp_method, units=self.field_units)
+                    Hz_applied[ix] += self.interp_field(positions[ix], film=film.name,
+                                                        dataset="field_from_other_films", method=interp_method,
+                                                        units=self.field_units)
+                break
+        mask = ~in_film
+        if mask.any():
+            Hz_applied[mask] = np.squeeze(
+                self.applied_field_func(positions[mask, 0], positions[mask, 1], zs[mask, np.newaxis]))
+        fields["applied_field"] = np.atleast_1d(Hz_applied).squeeze()
+        for key, f in fields.items():
+            fields[key] = convert_field(f, units, old_units=self.field_units, with_units=with_units)
+        if return_sum:
+            return sum(fields.values())
+        return fields
+
+    def vector_potential_at_position(self, positions, *, zs=None, units: Optional[str] = None,
+                                     with_units: bool = True, return_sum: bool = True):
+        """reference solution.py:833-934; the (m x n x 2) temporary of the reference becomes a tiled
+        pair sum on the device."""
+        import torch
+
+        L = _lib.lib()
+        device = self.device
+        dtype = np.float64
+        units = units or f"({self.field_units}) * ({device.length_units})"
+        positions, zs = _normalize_positions(positions, zs, dtype)
+        dev = torch.device(f"cuda:{torch.cuda.current_device()}")
+        tgt = torch.as_tensor(np.ascontiguousarray(np.column_stack([positions, zs]))).to(dev)
+        # result in [current_units] * mu_0/4pi -> convert (A * mu_0 = T m) to the requested units
+        scale = _u.MU_0 / (4 * np.pi) * _u.conversion_factor(self.current_units, "A") * _u.conversion_factor("T * m", units)
+        out = {}
+        for name, film in device.films.items():
+            layer = device.layers[film.layer]
+            dz = zs - layer.z0
+            if np.all(dz == 0) and film.contains_points(positions).all():
+                raise ValueError(f"Cannot evaluate vector potential inside the film ({name!r}).")
+            d = device.meshes[name]._data
+            n = d.n
+            with torch.cuda.device(dev):
+                src3 = torch.cat([d.sites.to(dev), torch.full((n, 1), float(layer.z0), dtype=torch.float64, device=dev)], 1).contiguous()
+                J = torch.as_tensor(np.ascontiguousarray(self.film_solutions[name].current_density, dtype=np.float64)).to(dev)
+                A2 = torch.empty(len(positions), 2, dtype=torch.float64, device=dev)
+                _lib.check(L.scb_biot_savart(3, len(positions), _lib.ptr(tgt), n, _lib.ptr(src3),
+                                             _lib.ptr(d.t["vertex_areas"].to(dev)), _lib.ptr(J), 0.0, scale, 1,
+                                             _lib.ptr(A2), _lib.stream_ptr()))
+                Axy = A2.cpu().numpy()
+            A = np.concatenate([Axy, np.zeros_like(Axy[:, :1])], axis=1)
+            out[name] = _u.Quantity(A, units) if with_units else A
+        if return_sum:
+            return sum(out.values())
+        return out
+
+
+def _flux_conversion(old: str, new: str) -> float:
+    """Flux units may be given as B*area (e.g. mT*um**2) or H*area; only B*area <-> Wb-like is needed."""
+    return _u.conversion_factor(old, new)

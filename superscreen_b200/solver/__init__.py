@@ -1,0 +1,8 @@
+from .solve import FactorizedModel, biot_savart_film_to_film, factorize_model, solve
+from .solve_film import LinearSystem, factorize_linear_systems, solve_film
+from .utils import (
+    FilmInfo,
+    LambdaInfo,
+    convert_field,
+    field_conversion_factor,
+)

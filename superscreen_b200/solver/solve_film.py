@@ -1,0 +1,265 @@
+"""Per-film linear systems on the B200 (reference solver/solve_film.py).
+
+``factorize_linear_systems`` assembles ``-A`` for every film straight into its LU workspace
+(``scb_system_assemble``: fused Q / Laplacian / grad-Lambda terms, one HBM write) and factors it
+in place (``scb_getrf_nopiv``).  The hole slabs of ``_build_system_1d`` are never formed: their
+only use, ``A_hole @ g[hole]`` (solve_film.py:498-503), is evaluated matrix-free by
+``scb_apply_operator``.  ``solve_film`` runs getrs, the CSR gradients and the matrix-free
+self-field ``Q @ (w*g)`` on the device and downloads only O(n) vectors.
+"""
+from __future__ import annotations
+
+import logging
+from dataclasses import dataclass, field
+from typing import Dict, Optional, Tuple, Union
+
+import numpy as np
+
+from .. import _lib
+from ..device import Device
+from ..solution import FilmSolution
+from .utils import FilmInfo
+
+logger = logging.getLogger("solve")
+
+LU_BLOCK = 128
+
+
+def _torch():
+    import torch
+
+    return torch
+
+
+@dataclass
+class LinearSystem:
+    """reference solver/solve_film.py:18-35.  ``indices`` is a host int64 array; the factorization
+    lives on the device (``lu``: padded row-major LU of ``-A`` without pivoting, ``dinv``: inverses
+    of its diagonal blocks).  ``A`` and ``lu_piv`` are lazy host views for API compatibility."""
+
+    indices: np.ndarray
+    film_info: FilmInfo = field(repr=False, default=None)
+    grad_Lambda_term: Union[float, object] = 0.0  # device CSR data on the operator pattern, or 0
+    n_pad: int = 0
+    lu: object = field(repr=False, default=None)      # torch (n_pad, n_pad) f64
+    dinv: object = field(repr=False, default=None)    # torch f64
+    indices_dev: object = field(repr=False, default=None)
+    margin: object = field(repr=False, default=None)  # torch (n_int,) row-dominance lower bound
+
+    @property
+    def A(self) -> np.ndarray:
+        """Dense A (n_int, n_int), re-assembled on demand (the LU overwrote the workspace)."""
+        torch = _torch()
+        M = assemble_negA(self.film_info, self.indices_dev, len(self.indices), self.n_pad,
+                          self.grad_Lambda_term if not isinstance(self.grad_Lambda_term, float) else None)[0]
+        n = len(self.indices)
+        return (-M[:n, :n]).cpu().numpy()
+
+    @property
+    def lu_piv(self) -> Tuple[np.ndarray, np.ndarray]:
+        """(lu, piv) in scipy.linalg.lu_factor layout; piv is the identity (no pivoting)."""
+        n = len(self.indices)
+        return self.lu[:n, :n].cpu().numpy(), np.arange(n, dtype=np.int32)
+
+
+def assemble_negA(info: FilmInfo, ix_dev, n_int: int, n_pad: int, T=None, out=None, want_margin=False):
+    """-A restricted to ``ix`` in a padded workspace (reference solve_film.py:296-305)."""
+    torch = _torch()
+    L = _lib.lib()
+    d = info.mesh._data
+    with torch.cuda.device(d.device):
+        M = out if out is not None else torch.empty(n_pad, n_pad, dtype=torch.float64, device=d.device)
+        pos = torch.empty(d.n, dtype=torch.int32, device=d.device)
+        margin = torch.empty(n_int, dtype=torch.float64, device=d.device) if want_margin else None
+        _lib.check(L.scb_system_assemble(
+            d.n, _lib.ptr(d.sites), _lib.ptr(d.t["vertex_areas"]), _lib.ptr(d.qdw), _lib.ptr(d.t["C"]),
+            _lib.ptr(info.dev["Lambda"]), _lib.ptr(d.t["op_indptr"]), _lib.ptr(d.t["op_indices"]),
+            _lib.ptr(d.t["laplacian"]), _lib.ptr(T), n_int, _lib.ptr(ix_dev), _lib.ptr(pos), n_pad,
+            _lib.ptr(M), _lib.ptr(margin), _lib.stream_ptr()))
+    return M, margin
+
+
+def factorize_linear_systems(device: Device, film_info_dict: Dict[str, FilmInfo]):
+    """reference solver/solve_film.py:151-282 (films without terminals)."""
+    torch = _torch()
+    L = _lib.lib()
+    film_systems: Dict[str, LinearSystem] = {}
+    hole_systems: Dict[str, Dict[str, LinearSystem]] = {}
+    terminal_systems: Dict[str, object] = {}
+    for film_name, info in film_info_dict.items():
+        d = info.mesh._data
+        with torch.cuda.device(d.device):
+            T = None
+            if info.lambda_info.inhomogeneous:
+                T = torch.empty_like(d.t["laplacian"])
+                _lib.check(L.scb_grad_lambda_term(
+                    d.n, _lib.ptr(d.t["op_indptr"]), _lib.ptr(d.t["op_indices"]), _lib.ptr(d.t["gradient_x"]),
+                    _lib.ptr(d.t["gradient_y"]), _lib.ptr(info.dev["Lambda"]), _lib.ptr(T), _lib.stream_ptr()))
+            info.dev["T"] = T
+            hole_systems[film_name] = {}
+            for hole_name, indices in info.hole_indices.items():
+                hole_systems[film_name][hole_name] = LinearSystem(
+                    indices=indices, film_info=info, grad_Lambda_term=T if T is not None else 0.0,
+                    indices_dev=torch.as_tensor(indices).to(d.device))
+            interior = info.interior_indices
+            if info.hole_indices:
+                interior = np.setdiff1d(interior, np.concatenate(list(info.hole_indices.values())))
+            interior = np.ascontiguousarray(interior, dtype=np.int64)
+            n_int = len(interior)
+            if n_int == 0:
+                raise ValueError(f"Film {film_name!r} has no interior mesh vertices.")
+            n_pad = -(-n_int // LU_BLOCK) * LU_BLOCK
+            ix_dev = torch.as_tensor(interior).to(d.device)
+            M, margin = assemble_negA(info, ix_dev, n_int, n_pad, T, want_margin=True)
+            dinv = torch.empty(int(L.scb_getrf_dinv_bytes(n_pad)) // 8, dtype=torch.float64, device=d.device)
+            lu_info = torch.zeros(1, dtype=torch.int32, device=d.device)
+            _lib.check(L.scb_getrf_nopiv(n_pad, _lib.ptr(M), _lib.ptr(dinv), _lib.ptr(lu_info), _lib.stream_ptr()))
+            system = LinearSystem(indices=interior, film_info=info, grad_Lambda_term=T if T is not None else 0.0,
+                                  n_pad=n_pad, lu=M, dinv=dinv, indices_dev=ix_dev, margin=margin)
+            info.dev["lu_info"] = lu_info
+            info.dev["margin_min"] = margin.min()
+            film_systems[film_name] = system
+    # one synchronising read per model: singularity flag + dominance margin of every film
+    for film_name, info in film_info_dict.items():
+        flag = int(info.dev["lu_info"].item())
+        mm = float(info.dev["margin_min"].item())
+        if flag != 0:
+            raise np.linalg.LinAlgError(
+                f"Film {film_name!r}: zero or non-finite pivot at row {flag - 1} in the unpivoted LU."
+            )
+        if mm <= 0:
+            logger.warning(
+                f"Film {film_name!r}: system matrix is not provably row-diagonally dominant "
+                f"(margin lower bound {mm:.3e}); the unpivoted LU may lose accuracy. "
+                f"Use check_inversion=True to verify."
+            )
+    return film_systems, hole_systems, terminal_systems
+
+
+def apply_operator(info: FilmInfo, v, src_idx=None, with_sparse: bool = True, out=None, accumulate: bool = False):
+    """out[n, nrhs] (+)= A_full[:, src] @ v[src]  (matrix-free; v must vanish outside src)."""
+    torch = _torch()
+    L = _lib.lib()
+    d = info.mesh._data
+    v2 = v if v.dim() == 2 else v[:, None]
+    v2 = v2.contiguous()
+    nrhs = v2.shape[1]
+    with torch.cuda.device(d.device):
+        if out is None:
+            out = torch.empty(d.n, nrhs, dtype=torch.float64, device=d.device)
+            accumulate = False
+        _lib.check(L.scb_apply_operator(
+            d.n, _lib.ptr(d.sites), _lib.ptr(d.t["vertex_areas"]), _lib.ptr(d.qdw),
+            _lib.ptr(info.dev["Lambda"]) if with_sparse else None, _lib.ptr(d.t["op_indptr"]),
+            _lib.ptr(d.t["op_indices"]), _lib.ptr(d.t["laplacian"]),
+            _lib.ptr(info.dev.get("T")) if with_sparse else None,
+            0 if src_idx is None else int(src_idx.numel()), _lib.ptr(src_idx), nrhs, _lib.ptr(v2), _lib.ptr(out),
+            1 if accumulate else 0, _lib.stream_ptr()))
+    return out if v.dim() == 2 else out[:, 0]
+
+
+def lu_solve(system: LinearSystem, h):
+    """x with (-A) x = h for h of shape (n_int,) or (n_int, nrhs) (device tensors)."""
+    torch = _torch()
+    L = _lib.lib()
+    n_int = len(system.indices)
+    h2 = h if h.dim() == 2 else h[:, None]
+    nrhs = h2.shape[1]
+    with torch.cuda.device(system.lu.device):
+        B = torch.zeros(system.n_pad, nrhs, dtype=torch.float64, device=system.lu.device)
+        B[:n_int] = h2
+        _lib.check(L.scb_getrs_nopiv(system.n_pad, _lib.ptr(system.lu), _lib.ptr(system.dinv), nrhs, _lib.ptr(B),
+                                     _lib.stream_ptr()))
+    x = B[:n_int]
+    return x if h.dim() == 2 else x[:, 0]
+
+
+def spmv(d, key: str, x, alpha: float = 1.0):
+    """alpha * (operator @ x) for a vertex operator ('gradient_x' ...) or a triangle gradient."""
+    torch = _torch()
+    L = _lib.lib()
+    x2 = (x if x.dim() == 2 else x[:, None]).contiguous()
+    nrhs = x2.shape[1]
+    if key in ("gtri_x", "gtri_y"):
+        nrows, indptr, indices = d.m, d.gtri_indptr, d.t["gtri_indices"]
+    else:
+        nrows, indptr, indices = d.n, d.t["op_indptr"], d.t["op_indices"]
+    with torch.cuda.device(d.device):
+        y = torch.empty(nrows, nrhs, dtype=torch.float64, device=d.device)
+        _lib.check(L.scb_spmv(nrows, _lib.ptr(indptr), _lib.ptr(indices), _lib.ptr(d.t[key]), nrhs, _lib.ptr(x2),
+                              float(alpha), 0.0, _lib.ptr(y), _lib.stream_ptr()))
+    return y if x.dim() == 2 else y[:, 0]
+
+
+def solve_film_device(*, film_info: FilmInfo, film_system: LinearSystem, hole_systems: Dict[str, LinearSystem],
+                      applied_field, vortex_flux: float, field_from_other_films=None,
+                      check_inversion: bool = False):
+    """Device-side body of ``solve_film`` (reference solve_film.py:483-565): all arguments and
+    results are device tensors in solver units.  Returns (g, J, self_field)."""
+    torch = _torch()
+    info = film_info
+    d = info.mesh._data
+    with torch.cuda.device(d.device):
+        Hz = applied_field if field_from_other_films is None else applied_field + field_from_other_films
+        g = torch.zeros_like(Hz)
+        Ha_eff = None
+        # hole boundary conditions: g[hole] = I_circ; Ha_eff = -sum_k A[:, hole_k] @ g[hole_k]
+        if hole_systems:
+            src = torch.cat([s.indices_dev for s in hole_systems.values()])
+            for name, s in hole_systems.items():
+                g[s.indices_dev] += float(info.circulating_currents.get(name, 0))
+            if any(info.circulating_currents.get(name, 0) for name in hole_systems):
+                Ha_eff = -apply_operator(info, g, src_idx=src)
+        ix = film_system.indices_dev
+        h = Hz[ix] if Ha_eff is None else Hz[ix] - Ha_eff[ix]
+        gf = lu_solve(film_system, h)
+        if check_inversion:
+            full = torch.zeros_like(Hz)
+            full[ix] = gf
+            hsim = -apply_operator(info, full, src_idx=ix)[ix]
+            if not torch.allclose(hsim, h):
+                logger.warning(
+                    f"Unable to solve for stream function in {info.name!r}), "
+                    f"maximum error {(hsim - h).abs().max().item():.3e}."
+                )
+        g[ix] += gf
+        for vortex in info.vortices:
+            # K[:, j] = -lu_solve(lu(-A), e_j): one right-hand side instead of eye(n)
+            # (reference solve_film.py:541-554)
+            xy = torch.tensor([vortex.x, vortex.y], dtype=torch.float64, device=d.device)
+            j_film = int(torch.argmin(torch.linalg.norm(d.sites[ix] - xy, dim=1)).item())
+            j_device = int(torch.argmin(torch.linalg.norm(d.sites - xy, dim=1)).item())
+            e = torch.zeros(len(film_system.indices), dtype=torch.float64, device=d.device)
+            e[j_film] = 1.0
+            Kj = -lu_solve(film_system, e)
+            g[ix] += vortex_flux * vortex.nPhi0 * Kj / d.t["vertex_areas"][j_device]
+        # J = curl(g z) = [dg/dy, -dg/dx]
+        J = torch.stack([spmv(d, "gradient_y", g), spmv(d, "gradient_x", g, alpha=-1.0)], dim=1)
+        # Q @ (w * g), matrix-free
+        self_field = apply_operator(info, g, src_idx=None, with_sparse=False)
+    return g, J, self_field
+
+
+def solve_film(*, device: Device, applied_field: np.ndarray, film_info: FilmInfo, film_system: LinearSystem,
+               hole_systems: Dict[str, LinearSystem], field_conversion: float, vortex_flux: float,
+               terminal_systems=None, field_from_other_films: Optional[np.ndarray] = None,
+               check_inversion: bool = False) -> FilmSolution:
+    """reference solver/solve_film.py:440-574 (host arrays in, FilmSolution out)."""
+    torch = _torch()
+    dev = film_info.mesh._data.device
+    H = torch.as_tensor(np.ascontiguousarray(applied_field, dtype=np.float64)).to(dev)
+    other = None
+    if field_from_other_films is not None:
+        other = torch.as_tensor(np.ascontiguousarray(field_from_other_films, dtype=np.float64)).to(dev)
+    g, J, self_field = solve_film_device(
+        film_info=film_info, film_system=film_system, hole_systems=hole_systems, applied_field=H,
+        vortex_flux=vortex_flux, field_from_other_films=other, check_inversion=check_inversion)
+    if field_from_other_films is not None:
+        field_from_other_films = np.asarray(field_from_other_films) / field_conversion
+    return FilmSolution(
+        stream=g.cpu().numpy(),
+        current_density=J.cpu().numpy(),
+        applied_field=np.asarray(applied_field) / field_conversion,
+        self_field=(self_field / field_conversion).cpu().numpy(),
+        field_from_other_films=field_from_other_films,
+    )

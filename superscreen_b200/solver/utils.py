@@ -1,0 +1,215 @@
+"""FilmInfo / LambdaInfo / unit helpers (reference solver/utils.py).
+
+Index sets are computed on the host with the package's point-in-polygon test and handed to the
+C ABI as inputs.  The dense ``kernel`` / ``laplacian`` / ``gradient`` arrays the
+reference stores eagerly (solver/utils.py:290-297) are lazy properties here: the solve path
+never densifies them.
+"""
+from __future__ import annotations
+
+import logging
+import numbers
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence, Tuple, Union
+
+import numpy as np
+
+from .. import units as _u
+from ..device import Device, Polygon
+from ..mesh import Mesh
+
+logger = logging.getLogger("solve")
+
+
+class LambdaInfo:
+    """reference solver/utils.py:19-58"""
+
+    lambda_str = "λ"
+    Lambda_str = "Λ"
+
+    def __init__(self, *, film: str, Lambda: np.ndarray, london_lambda: Optional[np.ndarray] = None,
+                 thickness: Optional[float] = None):
+        self.film = film
+        self.Lambda = Lambda
+        self.london_lambda = london_lambda
+        self.thickness = thickness
+        self.inhomogeneous = bool(
+            np.ptp(self.Lambda) / max(np.min(np.abs(self.Lambda)), np.finfo(float).eps) > 1e-6
+        )
+        if self.inhomogeneous:
+            logger.info(
+                f"Inhomogeneous {LambdaInfo.Lambda_str} in film {self.film!r}, "
+                f"which violates the assumptions of the London model. "
+                f"Results may not be reliable."
+            )
+        if self.london_lambda is not None:
+            assert self.thickness is not None
+            assert np.allclose(self.Lambda, self.london_lambda**2 / self.thickness)
+        if np.any(self.Lambda < 0):
+            raise ValueError(f"Negative Lambda in film {film!r}.")
+
+
+@dataclass
+class FilmInfo:
+    """reference solver/utils.py:96-132; dense members are lazy."""
+
+    name: str
+    layer: str
+    lambda_info: LambdaInfo
+    vortices: Tuple
+    interior_indices: np.ndarray
+    boundary_indices: np.ndarray
+    hole_indices: Dict[str, np.ndarray]
+    in_hole: np.ndarray
+    circulating_currents: Dict[str, float]
+    mesh: Mesh = field(repr=False, default=None)
+    terminal_currents: Optional[Dict[str, float]] = None
+    # device-resident state (torch tensors), filled by make_film_info
+    dev: Dict[str, object] = field(repr=False, default_factory=dict)
+
+    @property
+    def weights(self) -> np.ndarray:
+        return self.mesh.operators.weights
+
+    @property
+    def kernel(self) -> np.ndarray:
+        """Dense Q (n, n); materialised on demand only."""
+        return self.mesh.operators.Q
+
+    @property
+    def laplacian(self) -> np.ndarray:
+        return self.mesh.operators.laplacian.toarray()
+
+    @property
+    def gradient(self) -> Optional[np.ndarray]:
+        if not self.lambda_info.inhomogeneous:
+            return None
+        ops = self.mesh.operators
+        return np.array([ops.gradient_x.toarray(), ops.gradient_y.toarray()])
+
+
+def get_holes_and_vortices_by_film(device: Device, vortices: Sequence):
+    """reference solver/utils.py:214-231"""
+    from ..solution import Vortex
+
+    vortices_by_film = {film_name: [] for film_name in device.films}
+    holes_by_film = device.holes_by_film()
+    for vortex in vortices:
+        if not isinstance(vortex, Vortex):
+            raise TypeError(f"Expected a Vortex, but got {type(vortex)}.")
+        if not device.films[vortex.film].contains_points((vortex.x, vortex.y)).all():
+            raise ValueError(f"Vortex {vortex!r} is not located in film {vortex.film!r}.")
+        for hole in holes_by_film[vortex.film]:
+            if hole.contains_points((vortex.x, vortex.y)).all():
+                raise ValueError(f"Vortex {vortex} is located in hole {hole.name!r}.")
+        vortices_by_film[vortex.film].append(vortex)
+    return holes_by_film, vortices_by_film
+
+
+def _evaluate(param, x, y):
+    if isinstance(param, numbers.Real):
+        return float(param) * np.ones_like(x)
+    return np.asarray(param(x, y), dtype=np.float64) * np.ones_like(x)
+
+
+def make_film_info(*, device: Device, vortices: Sequence, circulating_currents: Dict[str, float],
+                   terminal_currents: Dict[str, Dict[str, float]]) -> Dict[str, FilmInfo]:
+    """reference solver/utils.py:234-324"""
+    import torch
+
+    holes_by_film, vortices_by_film = get_holes_and_vortices_by_film(device, vortices)
+    film_info = {}
+    for name, film in device.films.items():
+        if name in device.terminals and device.terminals[name]:
+            raise NotImplementedError(
+                "Transport terminals are a 'next' row of the hot-path scope (SURVEY.md 8f.1)."
+            )
+        mesh = device.meshes[name]
+        layer = device.layers[film.layer]
+        london_lambda = layer.london_lambda
+        d = layer.thickness
+        x, y = mesh.sites[:, 0], mesh.sites[:, 1]
+        Lambda = _evaluate(layer.Lambda, x, y).astype(np.float64)[:, np.newaxis]
+        if london_lambda is not None:
+            if isinstance(london_lambda, numbers.Real) and london_lambda <= d:
+                logger.info(
+                    f"Layer {name!r}: The film thickness, d = {d:.4f}, is greater than or equal to the "
+                    f"London penetration depth; the thin-film assumption may not be valid."
+                )
+            london_lambda = _evaluate(london_lambda, x, y)[:, np.newaxis]
+        hole_indices = {
+            hole.name: hole.contains_points(mesh.sites, index=True).astype(np.int64)
+            for hole in holes_by_film[name]
+        }
+        in_hole = np.zeros(len(mesh.sites), dtype=bool)
+        if hole_indices:
+            in_hole[np.concatenate(list(hole_indices.values()))] = True
+        circ = {h: c for h, c in circulating_currents.items() if h in hole_indices}
+        lambda_info = LambdaInfo(film=name, Lambda=Lambda, london_lambda=london_lambda, thickness=layer.thickness)
+        boundary_indices = mesh.boundary_indices
+        interior_indices = np.setdiff1d(film.contains_points(mesh.sites, index=True), boundary_indices).astype(np.int64)
+        info = FilmInfo(
+            name=name, layer=layer.name, lambda_info=lambda_info, vortices=tuple(vortices_by_film[name]),
+            interior_indices=interior_indices, boundary_indices=boundary_indices, hole_indices=hole_indices,
+            in_hole=in_hole, circulating_currents=circ, mesh=mesh,
+            terminal_currents=terminal_currents.get(name),
+        )
+        dev = mesh._data.device
+        info.dev["Lambda"] = torch.as_tensor(np.ascontiguousarray(Lambda[:, 0])).to(dev)
+        film_info[name] = info
+    return film_info
+
+
+def current_to_float(value, ureg, current_units: str) -> float:
+    """reference solver/utils.py:327-335"""
+    if isinstance(value, (str, _u.Quantity)):
+        return float(_u.to_quantity(value, current_units).to(current_units).magnitude)
+    return value
+
+
+def currents_to_floats(currents: Dict[str, Union[float, str]], ureg, current_units: str) -> Dict[str, float]:
+    return {k: current_to_float(v, ureg, current_units) for k, v in currents.items()}
+
+
+def convert_field(value, new_units: str, old_units: Optional[str] = None, ureg=None, with_units: bool = True):
+    """reference solver/utils.py:350-404: converts between H ([current]/[length]) and B = mu0 H."""
+    if isinstance(value, str):
+        value = _u.to_quantity(value, old_units or "dimensionless")
+    if isinstance(value, _u.Quantity):
+        old_units = value.units
+        value = value.magnitude
+    if old_units is None:
+        raise ValueError("Old units must be specified if value is not a string or pint.Quantity.")
+    so, do = _u.parse(old_units)
+    sn, dn = _u.parse(new_units)
+    if np.allclose(do, dn):
+        factor = so / sn
+    elif do[0] != 0:  # old is H (has [length]); want B = mu0 * H
+        s_mu, d_mu = _u.parse("mu_0")
+        if not np.allclose(do + d_mu, dn):
+            raise _u.DimensionalityError(f"Cannot convert {old_units!r} to {new_units!r}")
+        factor = so * s_mu / sn
+    else:
+        s_mu, d_mu = _u.parse("mu_0")
+        if not np.allclose(do - d_mu, dn):
+            raise _u.DimensionalityError(f"Cannot convert {old_units!r} to {new_units!r}")
+        factor = so / s_mu / sn
+    out = value * factor
+    if with_units:
+        return _u.Quantity(out, new_units)
+    return out
+
+
+def field_conversion_factor(field_units: str, current_units: str, length_units: str = "m", ureg=None) -> _u.Quantity:
+    """reference solver/utils.py:407-437"""
+    target = f"({current_units}) / ({length_units})"
+    s, d = _u.parse(field_units)
+    st, dt = _u.parse(target)
+    if np.allclose(d, dt):
+        mag = s / st
+    else:
+        s_mu, d_mu = _u.parse("mu_0")
+        if not np.allclose(d - d_mu, dt):
+            raise _u.DimensionalityError(f"Cannot convert {field_units!r} to {target!r}")
+        mag = s / s_mu / st
+    return _u.Quantity(mag, f"({target}) / ({field_units})")

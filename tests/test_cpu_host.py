@@ -1,0 +1,87 @@
+"""CPU-only tests: host logic, units, geometry, and the C-ABI surface (no compute calls)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import superscreen_b200 as sc
+from superscreen_b200 import _lib, units
+from superscreen_b200.geometry import box, circle, points_in_polygon
+from superscreen_b200.synthetic import disk_mesh, square_mesh
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    import __graft_entry__ as g
+
+    g.build()
+    lib = _lib.load_library()
+    header = open(os.path.join(ROOT, "include", "scb.h")).read()
+    declared = set(re.findall(r"\b(scb_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no prototypes found in include/scb.h"
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in scb.h but not exported"
+    assert set(_lib.EXPORTS) == declared
+    assert lib.scb_version() >= 100
+    assert lib.scb_getrf_dinv_bytes(256) == (2 * 2 * 128 * 128 + 2 * 256 * 128) * 8
+    assert lib.scb_mesh_workspace_elems(10, 20) > 0
+
+
+def test_compute_fails_loudly_without_gpu():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    sites, elements = square_mesh(4.0, 200)
+    with pytest.raises(_lib.SCBError):
+        sc.Mesh.from_triangulation(sites, elements)
+
+
+def test_units():
+    assert np.isclose(units.conversion_factor("mT", "T"), 1e-3)
+    assert np.isclose(units.conversion_factor("uA / um", "A / m"), 1.0)
+    assert np.isclose(units.conversion_factor("mT * um ** 2", "Phi_0"), 1e-15 / units.PHI_0)
+    assert np.isclose(units.conversion_factor("Phi_0 / A", "pH"), units.PHI_0 * 1e12)
+    assert np.isclose(sc.field_conversion_factor("mT", "uA", "um").magnitude, 1e-3 / units.MU_0)
+    assert np.isclose(sc.field_conversion_factor("A / m", "uA", "um").magnitude, 1.0)
+    assert np.isclose(sc.convert_field(1.0, "mT", old_units="uA / um", with_units=False), units.MU_0 * 1e3)
+    assert np.isclose(sc.convert_field(np.ones(3), "uT", old_units="mT", with_units=False)[0], 1e3)
+    assert np.isclose(units.to_quantity("1 mA", "uA").to("uA").magnitude, 1000.0)
+    with pytest.raises(units.DimensionalityError):
+        units.conversion_factor("mT", "um")
+
+
+def test_point_in_polygon_and_mesh_generators():
+    sq = box(2.0, points=4)
+    q = np.array([[0, 0], [0.99, 0.99], [1.01, 0], [5, 5]])
+    assert points_in_polygon(sq, q).tolist() == [True, True, False, False]
+    sites, elements = disk_mesh(4.4, 1200, embedded=[circle(4, 64), circle(2, 40)], seed=0)
+    p = sites[elements]
+    cross = (p[:, 1, 0] - p[:, 0, 0]) * (p[:, 2, 1] - p[:, 0, 1]) - (p[:, 1, 1] - p[:, 0, 1]) * (p[:, 2, 0] - p[:, 0, 0])
+    assert (cross > 0).all(), "all triangles must be CCW"
+    assert np.unique(elements).size == len(sites)
+    s2, e2 = disk_mesh(4.4, 1200, embedded=[circle(4, 64), circle(2, 40)], seed=0)
+    assert np.array_equal(sites, s2) and np.array_equal(elements, e2), "generator must be deterministic"
+
+
+def test_device_model_and_error_paths():
+    layer = sc.Layer("base", london_lambda=0.5, thickness=0.05, z0=0.5)
+    assert np.isclose(layer.Lambda, 5.0)
+    film = sc.Polygon("ring", layer="base", points=circle(4, 64))
+    hole = sc.Polygon("hole", layer="base", points=circle(2, 40))
+    dev = sc.Device("d", layers=[layer], films=[film], holes=[hole])
+    assert [h.name for h in dev.holes_by_film()["ring"]] == ["hole"]
+    assert dev.solve_dtype == np.float64
+    with pytest.raises(ValueError):
+        sc.solve()  # neither model nor device
+    with pytest.raises(ValueError):
+        sc.solve(dev)  # no mesh
+    with pytest.raises(TypeError):
+        sc.solve(model=object())
+    with pytest.raises(ValueError):
+        sc.Device("bad", layers=[layer], films=[sc.Polygon("f", layer="nope", points=circle(1, 16))])
+    with pytest.raises(ValueError):
+        sc.Layer("x")

@@ -1,0 +1,48 @@
+"""Runs one stage of the hot path in isolation (for ncu): python tools/run_stage.py --stage getrf --n 20164"""
+import argparse, os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+import superscreen_b200 as sc
+from superscreen_b200 import _lib
+from superscreen_b200.geometry import box
+from superscreen_b200.synthetic import square_mesh
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--stage", default="getrf")
+ap.add_argument("--n", type=int, default=20164)
+ap.add_argument("--reps", type=int, default=1)
+ap.add_argument("--nrhs", type=int, default=1)
+args = ap.parse_args()
+L = _lib.lib()
+sites, elements = square_mesh(10.0, args.n, seed=0)
+device = sc.Device("c2", layers=[sc.Layer("layer", Lambda=0.1, z0=0.0)],
+                   films=[sc.Polygon("film", layer="layer", points=box(10.0, points=4))])
+device.set_meshes({"film": (sites, elements)})
+torch.cuda.synchronize()
+if args.stage == "mesh":
+    for _ in range(args.reps):
+        sc.Mesh.from_triangulation(sites, elements)
+    torch.cuda.synchronize(); sys.exit(0)
+info = sc.solver.utils.make_film_info(device=device, vortices=[], circulating_currents={}, terminal_currents={})["film"]
+info.dev["T"] = None
+from superscreen_b200.solver.solve_film import assemble_negA, lu_solve, LinearSystem
+ix = torch.as_tensor(info.interior_indices).cuda()
+n_int = len(info.interior_indices); n_pad = -(-n_int // 128) * 128
+M = torch.empty(n_pad, n_pad, dtype=torch.float64, device="cuda")
+dinv = torch.empty(int(L.scb_getrf_dinv_bytes(n_pad)) // 8, dtype=torch.float64, device="cuda")
+flag = torch.zeros(1, dtype=torch.int32, device="cuda")
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+for rep in range(args.reps):
+    assemble_negA(info, ix, n_int, n_pad, None, out=M)
+    torch.cuda.synchronize()
+    e0.record()
+    _lib.check(L.scb_getrf_nopiv(n_pad, _lib.ptr(M), _lib.ptr(dinv), _lib.ptr(flag), _lib.stream_ptr()))
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    print(f"getrf n_int={n_int} n_pad={n_pad}: {ms:.2f} ms  {(2/3)*n_int**3/ms*1e-9:.2f} TFLOP/s  info={int(flag.item())}")
+if args.stage == "getrs":
+    system = LinearSystem(indices=info.interior_indices, film_info=info, n_pad=n_pad, lu=M, dinv=dinv, indices_dev=ix)
+    h = torch.randn(n_int, args.nrhs, dtype=torch.float64, device="cuda")
+    for rep in range(args.reps + 1):
+        e0.record(); x = lu_solve(system, h); e1.record(); torch.cuda.synchronize()
+        print(f"getrs nrhs={args.nrhs}: {e0.elapsed_time(e1):.3f} ms")
