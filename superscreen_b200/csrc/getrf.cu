@@ -286,88 +286,216 @@ trsm_kernel(double* __restrict__ M, int64_t ld, int64_t o, int ncol, const doubl
 }
 
 // ---------------------------------------------------------------------------------------
-// 1. diagonal block: LU (no pivoting) + explicit triangular inverses, all in shared memory.
-//    The inverses are computed IN PLACE over the LU block (after it has been written back):
-//    inv(L) row by row downwards in the strict lower part (threads 0..255), inv(U) row by row
-//    upwards in the upper part (threads 256..511), concurrently.
+// 1. diagonal block: LU (no pivoting) + explicit triangular inverses.
+//    The 128x128 block lives in REGISTERS, distributed 2-D cyclically over 512 threads
+//    (thread (ti, tj) = (warp, lane) owns rows ti + 16a, a < 8, and columns tj + 32b, b < 4).
+//    Every elimination step is a rank-1 update; the pivot row and pivot column are broadcast
+//    through double-buffered shared-memory vectors, so a step costs one __syncthreads.
+//    Row conditions are warp-uniform (ti is the warp id) and skip whole register rows.
+//    Phase 2 computes inv(L) (forward sweep, strict lower part) and inv(U) (backward sweep,
+//    upper part) simultaneously in the same register array, reading L/U columns from a shared
+//    copy of the factors.
 // ---------------------------------------------------------------------------------------
-constexpr int DLD = NB + 1;  // padded row stride
+constexpr int DLD = NB + 1;  // padded row stride of the shared copy
 
 __global__ void __launch_bounds__(512, 1)
 diag_kernel(double* __restrict__ M, int64_t ld, int64_t o, double* __restrict__ invL,
             double* __restrict__ invU, int32_t* __restrict__ info, int block_index) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  double* D = reinterpret_cast<double*>(smem_raw);  // [128][129]
-  __shared__ double part[4][NB];
-  __shared__ int bad;
-  const int tid = threadIdx.x, nt = blockDim.x;
+  double* D = reinterpret_cast<double*>(smem_raw);  // [128][129] copy of the LU factors
+  __shared__ double rowb[2][NB];                    // LU: pivot row      | inverse: row of inv(L)
+  __shared__ double colb[2][NB];                    // LU: pivot column   | inverse: row of inv(U)
+  const int tid = threadIdx.x;
+  const int ti = tid >> 5, tj = tid & 31;
   double* blk = M + o * ld + o;
-  if (tid == 0) bad = 0;
-  for (int idx = tid; idx < NB * NB; idx += nt) {
-    const int r = idx >> 7, c = idx & 127;
-    D[r * DLD + c] = blk[(int64_t)r * ld + c];
+  double x[8][4];
+#pragma unroll
+  for (int a = 0; a < 8; a++)
+#pragma unroll
+    for (int b = 0; b < 4; b++) x[a][b] = blk[(int64_t)(ti + 16 * a) * ld + tj + 32 * b];
+  if (ti == 0) {
+#pragma unroll
+    for (int b = 0; b < 4; b++) rowb[0][tj + 32 * b] = x[0][b];
+  }
+  if (tj == 0) {
+#pragma unroll
+    for (int a = 0; a < 8; a++) colb[0][ti + 16 * a] = x[a][0];
   }
   __syncthreads();
-  // right-looking LU, one column per step
-  for (int j = 0; j < NB; j++) {
-    const double piv = D[j * DLD + j];
-    if (tid == 0 && !(fabs(piv) > 0.0 && isfinite(piv)) && bad == 0) bad = j + 1;
-    const double rp = 1.0 / piv;
-    for (int i = j + 1 + tid; i < NB; i += nt) D[i * DLD + j] *= rp;
-    __syncthreads();
-    const int rem = NB - 1 - j;
-    for (int idx = tid; idx < rem * rem; idx += nt) {
-      const int i = j + 1 + idx / rem, c = j + 1 + idx % rem;
-      D[i * DLD + c] -= D[i * DLD + j] * D[j * DLD + c];
+  int bad = 0;
+  // The step loop is split as j = 16*ap + jj with the outer index unrolled, so that every
+  // register-array index below is a compile-time constant (dynamic indexing would push the
+  // block into local memory).
+#pragma unroll
+  for (int ap = 0; ap < 8; ap++) {
+#pragma unroll 1
+    for (int jj = 0; jj < 16; jj++) {
+      const int j = 16 * ap + jj;
+      const int cur = j & 1, nxt = cur ^ 1;
+      const double piv = rowb[cur][j];
+      if (bad == 0 && !(fabs(piv) > 0.0 && isfinite(piv))) bad = j + 1;
+      const double rp = 1.0 / piv;
+      constexpr int kDummy = 0;
+      (void)kDummy;
+      const int bj = ap >> 1;  // column block of column j (compile-time after unrolling)
+      double u[4];
+#pragma unroll
+      for (int b = 0; b < 4; b++) u[b] = (b >= bj) ? rowb[cur][tj + 32 * b] : 0.0;
+      const bool own_col = tj == (j & 31);
+#pragma unroll
+      for (int a = 0; a < 8; a++) {
+        if (a < ap) continue;                 // rows above the pivot block: done (static)
+        const int r = ti + 16 * a;
+        if (a > ap || r > j) {                // warp-uniform
+          const double l = colb[cur][r] * rp;
+#pragma unroll
+          for (int b = 0; b < 4; b++) {
+            if (b < bj) continue;             // columns left of the pivot block: done (static)
+            if (b > bj || tj + 32 * b > j) x[a][b] = fma(-l, u[b], x[a][b]);
+            if (b == bj && own_col) x[a][b] = l;
+          }
+        }
+      }
+      const int jn = j + 1;
+      if (jn < NB) {
+        if (ti == (jn & 15)) {
+          if (jj < 15) {
+#pragma unroll
+            for (int b = 0; b < 4; b++) rowb[nxt][tj + 32 * b] = x[ap][b];
+          } else if (ap + 1 < 8) {
+#pragma unroll
+            for (int b = 0; b < 4; b++) rowb[nxt][tj + 32 * b] = x[ap + 1 < 8 ? ap + 1 : 7][b];
+          }
+        }
+        if (tj == (jn & 31)) {
+          // column block of jn: ap>>1, or (ap+1)>>1 when jj == 15
+          if (jj < 15 || ((ap + 1) >> 1) == bj) {
+#pragma unroll
+            for (int a = 0; a < 8; a++) colb[nxt][ti + 16 * a] = x[a][bj];
+          } else {
+#pragma unroll
+            for (int a = 0; a < 8; a++) colb[nxt][ti + 16 * a] = x[a][bj + 1 < 4 ? bj + 1 : 3];
+          }
+        }
+      }
+      __syncthreads();
     }
-    __syncthreads();
-  }
-  for (int idx = tid; idx < NB * NB; idx += nt) {
-    const int r = idx >> 7, c = idx & 127;
-    blk[(int64_t)r * ld + c] = D[r * DLD + c];
   }
   if (tid == 0 && bad) atomicCAS(info, 0, block_index * NB + bad);
+  // factors -> global (in place) and shared
+#pragma unroll
+  for (int a = 0; a < 8; a++)
+#pragma unroll
+    for (int b = 0; b < 4; b++) {
+      const int r = ti + 16 * a, c = tj + 32 * b;
+      blk[(int64_t)r * ld + c] = x[a][b];
+      D[r * DLD + c] = x[a][b];
+      x[a][b] = (r == c) ? 1.0 : 0.0;  // identity: strict lower -> inv(L), upper incl. diag -> inv(U)
+    }
   __syncthreads();
-
-  const int half = tid >> 8;        // 0: inv(L), 1: inv(U)
-  const int c = tid & 127;          // column
-  const int kg = (tid >> 7) & 1;    // 2 k-groups per half
-  for (int step = 0; step < NB; step++) {
-    double s = 0.0;
-    if (half == 0) {
-      // X[i][c] = -( L[i][c] + sum_{k=c+1}^{i-1} L[i][k] X[k][c] ),  c < i   (X[c][c] = 1 implicit)
-      const int i = step;
-      if (c < i) {
-        for (int k = c + 1 + kg; k < i; k += 2) s += D[i * DLD + k] * D[k * DLD + c];
-        if (kg == 0) s += D[i * DLD + c];
-      }
-    } else {
-      // X[i][c] = -( sum_{k=i+1}^{c} U[i][k] X[k][c] ) / U[i][i],  c > i ;  X[i][i] = 1/U[i][i]
-      const int i = NB - 1 - step;
-      if (c > i)
-        for (int k = i + 1 + kg; k <= c; k += 2) s += D[i * DLD + k] * D[k * DLD + c];
+  // initial broadcasts: row 0 of inv(L) = e_0 ; row 127 of inv(U) = e_127 / u_127,127
+  {
+    const double rpu = 1.0 / D[(NB - 1) * DLD + NB - 1];
+    if (ti == 0) {
+#pragma unroll
+      for (int b = 0; b < 4; b++) rowb[0][tj + 32 * b] = (tj + 32 * b == 0) ? 1.0 : 0.0;
     }
-    part[half * 2 + kg][c] = s;
-    __syncthreads();
-    if (kg == 0) {
-      if (half == 0) {
-        const int i = step;
-        if (c < i) D[i * DLD + c] = -(part[0][c] + part[1][c]);
-      } else {
-        const int i = NB - 1 - step;
-        const double rp = 1.0 / D[i * DLD + i];
-        if (c > i) D[i * DLD + c] = -(part[2][c] + part[3][c]) * rp;
-        else if (c == i) D[i * DLD + c] = rp;
+    if (ti == ((NB - 1) & 15)) {
+#pragma unroll
+      for (int b = 0; b < 4; b++) {
+        const int c = tj + 32 * b;
+        if (c == NB - 1) x[7][b] = rpu;
+        colb[0][c] = (c == NB - 1) ? rpu : 0.0;
       }
     }
-    __syncthreads();
   }
-  for (int idx = tid; idx < NB * NB; idx += nt) {
-    const int r = idx >> 7, cc = idx & 127;
-    const double v = D[r * DLD + cc];
-    invL[idx] = cc < r ? v : (cc == r ? 1.0 : 0.0);
-    invU[idx] = cc >= r ? v : 0.0;
+  __syncthreads();
+  // step s = 16*sp + ss: jL = s (row block sp), jU = 127 - s (row block 7 - sp); outer index
+  // unrolled so that all register indices are compile-time constants
+#pragma unroll
+  for (int sp = 0; sp < 8; sp++) {
+#pragma unroll 1
+    for (int ss = 0; ss < 16; ss++) {
+      const int s = 16 * sp + ss;
+      if (s >= NB - 1) break;
+      const int cur = s & 1, nxt = cur ^ 1;
+      const int jL = s, jU = NB - 1 - s;
+      const int bL = sp >> 1;        // column block of jL
+      const int bU = (7 - sp) >> 1;  // column block of jU
+      double xl[4], xu[4];
+#pragma unroll
+      for (int b = 0; b < 4; b++) {
+        xl[b] = (b <= bL) ? rowb[cur][tj + 32 * b] : 0.0;
+        xu[b] = (b >= bU) ? colb[cur][tj + 32 * b] : 0.0;
+      }
+#pragma unroll
+      for (int a = 0; a < 8; a++) {
+        const int r = ti + 16 * a;
+        if (a >= sp && (a > sp || r > jL)) {  // inv(L):  X[r][c] -= L[r][jL] * X[jL][c],  c <= jL
+          const double l = D[r * DLD + jL];
+#pragma unroll
+          for (int b = 0; b < 4; b++) {
+            if (b > bL) continue;
+            if (b < bL || tj + 32 * b <= jL) x[a][b] = fma(-l, xl[b], x[a][b]);
+          }
+        }
+        if (a <= 7 - sp && (a < 7 - sp || r < jU)) {  // inv(U):  X[r][c] -= U[r][jU] * X[jU][c],  c >= jU
+          const double uu = D[r * DLD + jU];
+#pragma unroll
+          for (int b = 0; b < 4; b++) {
+            if (b < bU) continue;
+            if (b > bU || tj + 32 * b >= jU) x[a][b] = fma(-uu, xu[b], x[a][b]);
+          }
+        }
+      }
+      const int jLn = s + 1, jUn = NB - 2 - s;
+      if (ti == (jLn & 15)) {
+        // row block of jLn: sp, or sp + 1 when ss == 15
+        if (ss < 15) {
+#pragma unroll
+          for (int b = 0; b < 4; b++) {
+            const int c = tj + 32 * b;
+            rowb[nxt][c] = c < jLn ? x[sp][b] : (c == jLn ? 1.0 : 0.0);
+          }
+        } else {
+#pragma unroll
+          for (int b = 0; b < 4; b++) {
+            const int c = tj + 32 * b;
+            rowb[nxt][c] = c < jLn ? x[sp + 1 < 8 ? sp + 1 : 7][b] : (c == jLn ? 1.0 : 0.0);
+          }
+        }
+      }
+      if (ti == (jUn & 15)) {
+        const double rpu = 1.0 / D[jUn * DLD + jUn];
+        // row block of jUn: 7 - sp, or 6 - sp when ss == 15
+        if (ss < 15) {
+#pragma unroll
+          for (int b = 0; b < 4; b++) {
+            const int c = tj + 32 * b;
+            if (c >= jUn) x[7 - sp][b] *= rpu;
+            colb[nxt][c] = c >= jUn ? x[7 - sp][b] : 0.0;
+          }
+        } else {
+#pragma unroll
+          for (int b = 0; b < 4; b++) {
+            const int c = tj + 32 * b;
+            if (c >= jUn) x[6 - sp >= 0 ? 6 - sp : 0][b] *= rpu;
+            colb[nxt][c] = c >= jUn ? x[6 - sp >= 0 ? 6 - sp : 0][b] : 0.0;
+          }
+        }
+      }
+      __syncthreads();
+    }
   }
+#pragma unroll
+  for (int a = 0; a < 8; a++)
+#pragma unroll
+    for (int b = 0; b < 4; b++) {
+      const int r = ti + 16 * a, c = tj + 32 * b;
+      const double v = x[a][b];
+      invL[r * NB + c] = c < r ? v : (c == r ? 1.0 : 0.0);
+      invU[r * NB + c] = c >= r ? v : 0.0;
+    }
 }
 
 static bool g_attr_set = false;

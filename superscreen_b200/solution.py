@@ -137,10 +137,11 @@ def biot_savart_2d(x, y, z, *, positions, current_densities, z0: float = 0, area
     pos3 = np.ascontiguousarray(np.concatenate([pos, zz[:, None]], axis=1), dtype=np.float64)
     m, n = len(ev), len(pos3)
     with torch.cuda.device(dev):
-        t = lambda a: torch.as_tensor(a).to(dev)
+        # keep the uploads referenced until the result has been read back (stream-ordered use)
+        ev_d, pos_d, ar_d, J_d = (torch.as_tensor(a).to(dev) for a in (ev, pos3, ar, J))
         out = torch.empty((m, 3) if vector else (m,), dtype=torch.float64, device=dev)
-        _lib.check(L.scb_biot_savart(2 if vector else 1, m, _lib.ptr(t(ev)), n, _lib.ptr(t(pos3)), _lib.ptr(t(ar)),
-                                     _lib.ptr(t(J)), 0.0, _MU0_BIOT_SAVART / (4 * np.pi), 1, _lib.ptr(out),
+        _lib.check(L.scb_biot_savart(2 if vector else 1, m, _lib.ptr(ev_d), n, _lib.ptr(pos_d), _lib.ptr(ar_d),
+                                     _lib.ptr(J_d), 0.0, _MU0_BIOT_SAVART / (4 * np.pi), 1, _lib.ptr(out),
                                      _lib.stream_ptr()))
         return out.cpu().numpy()
 
@@ -372,8 +373,9 @@ class Solution:
                 src3 = torch.cat([d.sites.to(dev), torch.full((n, 1), float(layer.z0), dtype=torch.float64, device=dev)], 1).contiguous()
                 J = torch.as_tensor(np.ascontiguousarray(self.film_solutions[name].current_density, dtype=np.float64)).to(dev)
                 A2 = torch.empty(len(positions), 2, dtype=torch.float64, device=dev)
+                areas_d = d.t["vertex_areas"].to(dev)
                 _lib.check(L.scb_biot_savart(3, len(positions), _lib.ptr(tgt), n, _lib.ptr(src3),
-                                             _lib.ptr(d.t["vertex_areas"].to(dev)), _lib.ptr(J), 0.0, scale, 1,
+                                             _lib.ptr(areas_d), _lib.ptr(J), 0.0, scale, 1,
                                              _lib.ptr(A2), _lib.stream_ptr()))
                 Axy = A2.cpu().numpy()
             A = np.concatenate([Axy, np.zeros_like(Axy[:, :1])], axis=1)
