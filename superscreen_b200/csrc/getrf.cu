@@ -1,23 +1,26 @@
-// Blocked right-looking fp64 LU without pivoting (K11) for the row-diagonally-dominant systems
-// of this path, row-major, padded to a multiple of NB = 128.
+// Two-level blocked right-looking fp64 LU without pivoting (K11) for the row-diagonally-dominant
+// systems of this path, row-major, padded to a multiple of NB = 128.
 //
-// Per block step k (offset o = 128 k, trailing size rem):
-//   1. diag_kernel   (1 CTA)        LU of the 128x128 diagonal block in shared memory and the
-//                                   explicit inverses inv(L_kk), inv(U_kk) (kept for getrs);
-//   2. trsm_kernel   (2*rem/128 CTAs) L21 = A21 inv(U_kk), U12 = inv(L_kk) A12 as DMMA GEMMs;
-//                                   results are written in place AND as "fragment-major"
-//                                   packed copies (-L21 and U12) laid out exactly as the
-//                                   mma.sync m8n8k4 A/B register fragments;
-//   3. update_kernel (rem/128 x rem/64 CTAs, 2 per SM) A22 += (-L21) U12: the only O(n^3)
-//                                   contraction.  Operand chunks arrive by TMA bulk copies
-//                                   (cp.async.bulk + mbarrier, one 32 KB + one 16 KB copy per
-//                                   stage) and are consumed with conflict-free LDS.64 straight
-//                                   into DMMA.8x8x4; C tiles are read into the accumulators and
-//                                   written back with 128-bit accesses.  Two resident CTAs per
-//                                   SM overlap one CTA's C traffic with the other's DMMA work.
+// Outer panels of KB = q*128 columns (q = 8 by default); inside an outer panel, per inner block
+// step k (offset o = 128 k):
+//   1. diag_kernel   (1 CTA)        LU of the 128x128 diagonal block held in registers, fused with
+//                                   the explicit inverses inv(L_kk), inv(U_kk) (kept for getrs);
+//   2. trsm_kernel   (4*rem/128 CTAs) L21 = A21 inv(U_kk), U12 = inv(L_kk) A12 as DMMA GEMMs;
+//                                   results are written in place AND as "fragment-major" packed
+//                                   copies (-L21 and U12) laid out exactly as the mma.sync m8n8k4
+//                                   A/B register fragments, into chunk slot k of the outer panel;
+//   3. update_kernel on the L-shaped strip of the outer panel only (K = 128).
+// Once per outer panel: update_kernel on the big trailing block with K = KB -- the only O(n^3)
+// contraction.  Operand chunks arrive by TMA bulk copies (cp.async.bulk + mbarrier, one 32 KB +
+// one 16 KB copy per stage) and are consumed with conflict-free LDS.64 straight into DMMA.8x8x4;
+// C tiles are read into the accumulators and written back with 128-bit accesses.  Two resident
+// CTAs per SM overlap one CTA's C traffic with the other's DMMA work; K = KB amortises the C
+// traffic and CTA prologue/epilogue over q times more math than a plain rank-128 update.
 //
 // Reference semantics: scipy.linalg.lu_factor(-A) at solver/solve_film.py:232,253,279 (LAPACK
 // dgetrf).  Pivoting is unnecessary here; parity is on the solution (1e-8 rel-L2), see DESIGN.md.
+#include <stdlib.h>
+
 #include "scb_common.cuh"
 
 namespace scb {
@@ -97,8 +100,9 @@ struct __align__(128) UpdateStage {
 };
 
 __global__ void __launch_bounds__(256, 2)
-update_kernel(double* __restrict__ M, int64_t ld, int64_t o2, const double* __restrict__ Lpack,
-              const double* __restrict__ Upack) {
+update_kernel(double* __restrict__ M, int64_t ld, int64_t row0, int64_t col0,
+              const double* __restrict__ Lpack, const double* __restrict__ Upack, int tile_chunks,
+              int chunk0, int nchunks, unsigned stagger_ns) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   UpdateStage* stage = reinterpret_cast<UpdateStage*>(smem_raw);
   __shared__ uint64_t bars[2];
@@ -108,14 +112,23 @@ update_kernel(double* __restrict__ M, int64_t ld, int64_t o2, const double* __re
   const int wm = warp >> 1, wn = warp & 1;  // 4 x 2 warps, 32x32 warp tiles
   const int g = lane >> 2, t = lane & 3;
 
-  const double* Ltile = Lpack + (int64_t)blockIdx.y * (NB * BM);
-  const double* Utile = Upack + (int64_t)blockIdx.x * (NB * BN);
+  // packed operands are indexed by ABSOLUTE 128-row / 64-column tile and by chunk slot
+  const double* Ltile = Lpack + ((row0 >> 7) + blockIdx.y) * ((int64_t)tile_chunks * A_CHUNK) + (int64_t)chunk0 * A_CHUNK;
+  const double* Utile = Upack + ((col0 >> 6) + blockIdx.x) * ((int64_t)tile_chunks * B_CHUNK) + (int64_t)chunk0 * B_CHUNK;
   constexpr uint32_t kStageBytes = (A_CHUNK + B_CHUNK) * sizeof(double);
 
   if (tid == 0) {
     mbar_init(&bars[0], 1);
     mbar_init(&bars[1], 1);
     fence_barrier_init();
+  }
+  // The two CTAs resident on an SM would otherwise run in lock-step (same start, same length),
+  // so their C-tile load/store phases would coincide and leave the DMMA pipe idle.  Delay the
+  // second first-wave resident of every SM by about half a tile time once; later CTAs inherit
+  // the phase shift because each starts when its predecessor on that slot exits.
+  if (stagger_ns) {
+    const unsigned bid = blockIdx.y * gridDim.x + blockIdx.x;
+    if (bid >= 148u && bid < 296u) __nanosleep(stagger_ns);
   }
   __syncthreads();
   if (tid == 0) {
@@ -129,7 +142,7 @@ update_kernel(double* __restrict__ M, int64_t ld, int64_t o2, const double* __re
 
   // accumulators start as the C tile
   double acc[4][4][2];
-  double* Cbase = M + (o2 + (int64_t)blockIdx.y * BM + wm * 32 + g) * ld + o2 + (int64_t)blockIdx.x * BN +
+  double* Cbase = M + (row0 + (int64_t)blockIdx.y * BM + wm * 32 + g) * ld + col0 + (int64_t)blockIdx.x * BN +
                   wn * 32 + 2 * t;
 #pragma unroll
   for (int i = 0; i < 4; i++)
@@ -141,7 +154,7 @@ update_kernel(double* __restrict__ M, int64_t ld, int64_t o2, const double* __re
     }
 
 #pragma unroll 1
-  for (int c = 0; c < NCHUNK; c++) {
+  for (int c = 0; c < nchunks; c++) {
     const int st = c & 1;
     mbar_wait(&bars[st], (c >> 1) & 1);
     const double* As = stage[st].a + (wm * 4 * 8) * 32 + lane;
@@ -159,7 +172,7 @@ update_kernel(double* __restrict__ M, int64_t ld, int64_t o2, const double* __re
         for (int j = 0; j < 4; j++) dmma(acc[i][j][0], acc[i][j][1], a[i], b[j]);
     }
     __syncthreads();
-    if (tid == 0 && c + 2 < NCHUNK) {
+    if (tid == 0 && c + 2 < nchunks) {
       mbar_expect_tx(&bars[st], kStageBytes);
       bulk_g2s(stage[st].a, Ltile + (int64_t)(c + 2) * A_CHUNK, A_CHUNK * sizeof(double), &bars[st]);
       bulk_g2s(stage[st].b, Utile + (int64_t)(c + 2) * B_CHUNK, B_CHUNK * sizeof(double), &bars[st]);
@@ -237,7 +250,8 @@ constexpr int kTrsmSmemDoubles = 128 * TA_LD + KC * (64 + 4) > 64 * TA_LD + KC *
 
 __global__ void __launch_bounds__(256)
 trsm_kernel(double* __restrict__ M, int64_t ld, int64_t o, int ncol, const double* __restrict__ invL,
-            const double* __restrict__ invU, double* __restrict__ Lpack, double* __restrict__ Upack) {
+            const double* __restrict__ invU, double* __restrict__ Lpack, double* __restrict__ Upack,
+            int tile_chunks, int chunk0) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* As = reinterpret_cast<double*>(smem_raw);
   const int tid = threadIdx.x;
@@ -252,7 +266,7 @@ trsm_kernel(double* __restrict__ M, int64_t ld, int64_t o, int ncol, const doubl
     double* Bs = As + 64 * TA_LD;
     gemm_k128<64, 128, 2, 4>(Atile, ld, invU, NB, As, Bs, acc);
     const int wm = warp / 4, wn = warp % 4;
-    double* P = Lpack + (int64_t)(tile >> 1) * (NB * BM);
+    double* P = Lpack + ((o2 >> 7) + (tile >> 1)) * ((int64_t)tile_chunks * A_CHUNK) + (int64_t)chunk0 * A_CHUNK;
     const int rbase = (tile & 1) * 64;
 #pragma unroll
     for (int i = 0; i < 4; i++)
@@ -271,7 +285,7 @@ trsm_kernel(double* __restrict__ M, int64_t ld, int64_t o, int ncol, const doubl
     double* Bs = As + 128 * TA_LD;
     gemm_k128<128, 64, 4, 2>(invL, NB, Btile, ld, As, Bs, acc);
     const int wm = warp / 2, wn = warp % 2;
-    double* P = Upack + (int64_t)tile * (NB * BN);
+    double* P = Upack + ((o2 >> 6) + tile) * ((int64_t)tile_chunks * B_CHUNK) + (int64_t)chunk0 * B_CHUNK;
 #pragma unroll
     for (int i = 0; i < 4; i++)
 #pragma unroll
@@ -286,25 +300,39 @@ trsm_kernel(double* __restrict__ M, int64_t ld, int64_t o, int ncol, const doubl
 }
 
 // ---------------------------------------------------------------------------------------
-// 1. diagonal block: LU (no pivoting) + explicit triangular inverses.
+// 1. diagonal block: LU (no pivoting) + explicit inverses of both factors in ONE sweep.
 //    The 128x128 block lives in REGISTERS, distributed 2-D cyclically over 512 threads
 //    (thread (ti, tj) = (warp, lane) owns rows ti + 16a, a < 8, and columns tj + 32b, b < 4).
-//    Every elimination step is a rank-1 update; the pivot row and pivot column are broadcast
-//    through double-buffered shared-memory vectors, so a step costs one __syncthreads.
-//    Row conditions are warp-uniform (ti is the warp id) and skip whole register rows.
-//    Phase 2 computes inv(L) (forward sweep, strict lower part) and inv(U) (backward sweep,
-//    upper part) simultaneously in the same register array, reading L/U columns from a shared
-//    copy of the factors.
+//    Step j broadcasts register row j and register column j through double-buffered shared
+//    vectors (one __syncthreads per step) and applies rank-1 updates.  Register slots are
+//    re-used as soon as their LU value is final:
+//      slot (r, c), r > c : A -> L[r][c] (final at step c, copied out) -> inv(L)[r][c]
+//      slot (r, c), r < c : A -> U[r][c] (final at step r, copied out) -> Z[c][r], where Z is
+//                           the unit lower factor of U^T = Z^-1 D, so inv(U) = Z^T D^-1.
+//    Forward elimination applied to the identity yields inv(L); the same elimination applied
+//    to U^T (multipliers U[j][c] / U[j][j], i.e. the pivot row already being broadcast) yields Z.
 // ---------------------------------------------------------------------------------------
-constexpr int DLD = NB + 1;  // padded row stride of the shared copy
+constexpr int DLD = NB + 1;  // padded row stride of the shared copy of the factors
+
+__device__ __forceinline__ double fast_rcp(double a) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(a));
+  double e = fma(-a, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-a, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-a, r, 1.0);
+  return fma(r, e, r);
+}
 
 __global__ void __launch_bounds__(512, 1)
 diag_kernel(double* __restrict__ M, int64_t ld, int64_t o, double* __restrict__ invL,
             double* __restrict__ invU, int32_t* __restrict__ info, int block_index) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  double* D = reinterpret_cast<double*>(smem_raw);  // [128][129] copy of the LU factors
-  __shared__ double rowb[2][NB];                    // LU: pivot row      | inverse: row of inv(L)
-  __shared__ double colb[2][NB];                    // LU: pivot column   | inverse: row of inv(U)
+  double* D = reinterpret_cast<double*>(smem_raw);  // [128][129] finished L / U entries
+  __shared__ double rowb[2][NB];                    // register row j
+  __shared__ double colb[2][NB];                    // register column j
+  __shared__ double rdiag[NB];                      // 1 / U[j][j]
   const int tid = threadIdx.x;
   const int ti = tid >> 5, tj = tid & 31;
   double* blk = M + o * ld + o;
@@ -323,9 +351,8 @@ diag_kernel(double* __restrict__ M, int64_t ld, int64_t o, double* __restrict__ 
   }
   __syncthreads();
   int bad = 0;
-  // The step loop is split as j = 16*ap + jj with the outer index unrolled, so that every
-  // register-array index below is a compile-time constant (dynamic indexing would push the
-  // block into local memory).
+  // j = 16*ap + jj with the outer index unrolled: every register-array index below is a
+  // compile-time constant (dynamic indexing would push the block into local memory).
 #pragma unroll
   for (int ap = 0; ap < 8; ap++) {
 #pragma unroll 1
@@ -334,25 +361,47 @@ diag_kernel(double* __restrict__ M, int64_t ld, int64_t o, double* __restrict__ 
       const int cur = j & 1, nxt = cur ^ 1;
       const double piv = rowb[cur][j];
       if (bad == 0 && !(fabs(piv) > 0.0 && isfinite(piv))) bad = j + 1;
-      const double rp = 1.0 / piv;
-      constexpr int kDummy = 0;
-      (void)kDummy;
+      const double rp = fast_rcp(piv);
+      if (tid == 0) rdiag[j] = rp;
       const int bj = ap >> 1;  // column block of column j (compile-time after unrolling)
-      double u[4];
-#pragma unroll
-      for (int b = 0; b < 4; b++) u[b] = (b >= bj) ? rowb[cur][tj + 32 * b] : 0.0;
       const bool own_col = tj == (j & 31);
+      double v[4], vs[4];
+#pragma unroll
+      for (int b = 0; b < 4; b++) {
+        v[b] = rowb[cur][tj + 32 * b];  // c > j: U[j][c];  c < j: inv(L)[j][c]
+        vs[b] = v[b] * rp;              // multipliers of the U^T elimination (c > j)
+      }
 #pragma unroll
       for (int a = 0; a < 8; a++) {
-        if (a < ap) continue;                 // rows above the pivot block: done (static)
         const int r = ti + 16 * a;
-        if (a > ap || r > j) {                // warp-uniform
-          const double l = colb[cur][r] * rp;
+        const double w = colb[cur][r];  // r > j: A[r][j];  r < j: Z[j][r]
+        if (a > ap || (a == ap && r > j)) {
+          // rows below the pivot: A update (c > j), inv(L) update (c < j), L output (c == j)
+          const double l = w * rp;
 #pragma unroll
           for (int b = 0; b < 4; b++) {
-            if (b < bj) continue;             // columns left of the pivot block: done (static)
-            if (b > bj || tj + 32 * b > j) x[a][b] = fma(-l, u[b], x[a][b]);
-            if (b == bj && own_col) x[a][b] = l;
+            if (b == bj && own_col) {
+              D[r * DLD + j] = l;
+              x[a][b] = -l;
+            } else {
+              x[a][b] = fma(-l, v[b], x[a][b]);
+            }
+          }
+        } else if (a < ap || (a == ap && r < j)) {
+          // rows above the pivot: Z update on the columns right of the pivot
+#pragma unroll
+          for (int b = 0; b < 4; b++) {
+            if (b < bj) continue;
+            if (b > bj || tj + 32 * b > j) x[a][b] = fma(-w, vs[b], x[a][b]);
+          }
+        } else {
+          // the pivot row itself: U output, then seed Z[c][j] = -U[j][c] / U[j][j]
+#pragma unroll
+          for (int b = 0; b < 4; b++) {
+            if (b < bj) continue;
+            const int c = tj + 32 * b;
+            if (b > bj || c >= j) D[j * DLD + c] = x[a][b];
+            if (b > bj || c > j) x[a][b] = -vs[b];
           }
         }
       }
@@ -362,13 +411,12 @@ diag_kernel(double* __restrict__ M, int64_t ld, int64_t o, double* __restrict__ 
           if (jj < 15) {
 #pragma unroll
             for (int b = 0; b < 4; b++) rowb[nxt][tj + 32 * b] = x[ap][b];
-          } else if (ap + 1 < 8) {
+          } else {
 #pragma unroll
             for (int b = 0; b < 4; b++) rowb[nxt][tj + 32 * b] = x[ap + 1 < 8 ? ap + 1 : 7][b];
           }
         }
         if (tj == (jn & 31)) {
-          // column block of jn: ap>>1, or (ap+1)>>1 when jj == 15
           if (jj < 15 || ((ap + 1) >> 1) == bj) {
 #pragma unroll
             for (int a = 0; a < 8; a++) colb[nxt][ti + 16 * a] = x[a][bj];
@@ -382,141 +430,55 @@ diag_kernel(double* __restrict__ M, int64_t ld, int64_t o, double* __restrict__ 
     }
   }
   if (tid == 0 && bad) atomicCAS(info, 0, block_index * NB + bad);
-  // factors -> global (in place) and shared
 #pragma unroll
   for (int a = 0; a < 8; a++)
 #pragma unroll
     for (int b = 0; b < 4; b++) {
       const int r = ti + 16 * a, c = tj + 32 * b;
-      blk[(int64_t)r * ld + c] = x[a][b];
-      D[r * DLD + c] = x[a][b];
-      x[a][b] = (r == c) ? 1.0 : 0.0;  // identity: strict lower -> inv(L), upper incl. diag -> inv(U)
-    }
-  __syncthreads();
-  // initial broadcasts: row 0 of inv(L) = e_0 ; row 127 of inv(U) = e_127 / u_127,127
-  {
-    const double rpu = 1.0 / D[(NB - 1) * DLD + NB - 1];
-    if (ti == 0) {
-#pragma unroll
-      for (int b = 0; b < 4; b++) rowb[0][tj + 32 * b] = (tj + 32 * b == 0) ? 1.0 : 0.0;
-    }
-    if (ti == ((NB - 1) & 15)) {
-#pragma unroll
-      for (int b = 0; b < 4; b++) {
-        const int c = tj + 32 * b;
-        if (c == NB - 1) x[7][b] = rpu;
-        colb[0][c] = (c == NB - 1) ? rpu : 0.0;
-      }
-    }
-  }
-  __syncthreads();
-  // step s = 16*sp + ss: jL = s (row block sp), jU = 127 - s (row block 7 - sp); outer index
-  // unrolled so that all register indices are compile-time constants
-#pragma unroll
-  for (int sp = 0; sp < 8; sp++) {
-#pragma unroll 1
-    for (int ss = 0; ss < 16; ss++) {
-      const int s = 16 * sp + ss;
-      if (s >= NB - 1) break;
-      const int cur = s & 1, nxt = cur ^ 1;
-      const int jL = s, jU = NB - 1 - s;
-      const int bL = sp >> 1;        // column block of jL
-      const int bU = (7 - sp) >> 1;  // column block of jU
-      double xl[4], xu[4];
-#pragma unroll
-      for (int b = 0; b < 4; b++) {
-        xl[b] = (b <= bL) ? rowb[cur][tj + 32 * b] : 0.0;
-        xu[b] = (b >= bU) ? colb[cur][tj + 32 * b] : 0.0;
-      }
-#pragma unroll
-      for (int a = 0; a < 8; a++) {
-        const int r = ti + 16 * a;
-        if (a >= sp && (a > sp || r > jL)) {  // inv(L):  X[r][c] -= L[r][jL] * X[jL][c],  c <= jL
-          const double l = D[r * DLD + jL];
-#pragma unroll
-          for (int b = 0; b < 4; b++) {
-            if (b > bL) continue;
-            if (b < bL || tj + 32 * b <= jL) x[a][b] = fma(-l, xl[b], x[a][b]);
-          }
-        }
-        if (a <= 7 - sp && (a < 7 - sp || r < jU)) {  // inv(U):  X[r][c] -= U[r][jU] * X[jU][c],  c >= jU
-          const double uu = D[r * DLD + jU];
-#pragma unroll
-          for (int b = 0; b < 4; b++) {
-            if (b < bU) continue;
-            if (b > bU || tj + 32 * b >= jU) x[a][b] = fma(-uu, xu[b], x[a][b]);
-          }
-        }
-      }
-      const int jLn = s + 1, jUn = NB - 2 - s;
-      if (ti == (jLn & 15)) {
-        // row block of jLn: sp, or sp + 1 when ss == 15
-        if (ss < 15) {
-#pragma unroll
-          for (int b = 0; b < 4; b++) {
-            const int c = tj + 32 * b;
-            rowb[nxt][c] = c < jLn ? x[sp][b] : (c == jLn ? 1.0 : 0.0);
-          }
-        } else {
-#pragma unroll
-          for (int b = 0; b < 4; b++) {
-            const int c = tj + 32 * b;
-            rowb[nxt][c] = c < jLn ? x[sp + 1 < 8 ? sp + 1 : 7][b] : (c == jLn ? 1.0 : 0.0);
-          }
-        }
-      }
-      if (ti == (jUn & 15)) {
-        const double rpu = 1.0 / D[jUn * DLD + jUn];
-        // row block of jUn: 7 - sp, or 6 - sp when ss == 15
-        if (ss < 15) {
-#pragma unroll
-          for (int b = 0; b < 4; b++) {
-            const int c = tj + 32 * b;
-            if (c >= jUn) x[7 - sp][b] *= rpu;
-            colb[nxt][c] = c >= jUn ? x[7 - sp][b] : 0.0;
-          }
-        } else {
-#pragma unroll
-          for (int b = 0; b < 4; b++) {
-            const int c = tj + 32 * b;
-            if (c >= jUn) x[6 - sp >= 0 ? 6 - sp : 0][b] *= rpu;
-            colb[nxt][c] = c >= jUn ? x[6 - sp >= 0 ? 6 - sp : 0][b] : 0.0;
-          }
-        }
-      }
-      __syncthreads();
-    }
-  }
-#pragma unroll
-  for (int a = 0; a < 8; a++)
-#pragma unroll
-    for (int b = 0; b < 4; b++) {
-      const int r = ti + 16 * a, c = tj + 32 * b;
+      blk[(int64_t)r * ld + c] = D[r * DLD + c];
       const double v = x[a][b];
       invL[r * NB + c] = c < r ? v : (c == r ? 1.0 : 0.0);
-      invU[r * NB + c] = c >= r ? v : 0.0;
+      invU[r * NB + c] = c > r ? v * rdiag[c] : (c == r ? rdiag[c] : 0.0);
     }
 }
 
 static bool g_attr_set = false;
+static int g_stagger_ns = 0;
 
 }  // namespace scb
 
 using namespace scb;
 
-extern "C" int64_t scb_getrf_dinv_bytes(int64_t n_pad) {
-  const int64_t nb = n_pad / NB;
-  // [nb][2][128][128] block inverses + Lpack [n_pad x 128] + Upack [128 x n_pad]
-  return (nb * 2 * NB * NB + 2 * n_pad * NB) * (int64_t)sizeof(double);
+static int lu_outer_blocks() {
+  static int q = -1;
+  if (q < 0) {
+    q = 8;
+    if (const char* e = getenv("SCB_LU_Q")) q = atoi(e);
+    if (q < 1) q = 1;
+    if (q > 8) q = 8;
+  }
+  return q;
 }
 
+extern "C" int64_t scb_getrf_dinv_bytes(int64_t n_pad) {
+  const int64_t nb = n_pad / NB;
+  // [nb][2][128][128] block inverses + Lpack [n_pad x KB] + Upack [KB x n_pad], KB = q * 128
+  return (nb * 2 * NB * NB + 2 * n_pad * NB * lu_outer_blocks()) * (int64_t)sizeof(double);
+}
+
+// Two-level right-looking LU: inner panels of NB = 128 columns are factored and applied only to
+// the L-shaped strip of the current outer panel (KB = q*128 columns); the big trailing block is
+// updated once per outer panel with K = KB, which amortises the C-tile traffic and the CTA
+// prologue/epilogue of the DMMA update kernel over q times more math.
 extern "C" int scb_getrf_nopiv(int64_t n_pad, double* M, double* dinv, int32_t* info,
                                scb_stream_t stream) {
   SCB_CHECK_ARG(n_pad > 0 && n_pad % NB == 0, "n_pad must be a positive multiple of 128");
   cudaStream_t s = (cudaStream_t)stream;
   const int64_t nb = n_pad / NB;
+  const int q = lu_outer_blocks();
+  const int tile_chunks = q * NCHUNK;
   double* Lpack = dinv + nb * 2 * NB * NB;
-  double* Upack = Lpack + n_pad * NB;
+  double* Upack = Lpack + n_pad * NB * q;
   const int diag_smem = NB * DLD * sizeof(double);
   const int trsm_smem = kTrsmSmemDoubles * sizeof(double);
   const int upd_smem = 2 * sizeof(UpdateStage);
@@ -525,22 +487,49 @@ extern "C" int scb_getrf_nopiv(int64_t n_pad, double* M, double* dinv, int32_t* 
     SCB_CUDA(cudaFuncSetAttribute(update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, upd_smem));
     SCB_CUDA(cudaFuncSetAttribute(trsm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, trsm_smem));
     SCB_CUDA(cudaFuncSetAttribute(update_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    if (const char* e = getenv("SCB_UPDATE_STAGGER_NS")) g_stagger_ns = atoi(e);
     g_attr_set = true;
   }
   SCB_CUDA(cudaMemsetAsync(info, 0, sizeof(int32_t), s));
-  for (int64_t k = 0; k < nb; k++) {
-    const int64_t o = k * NB;
-    double* invL = dinv + k * 2 * NB * NB;
-    double* invU = invL + NB * NB;
-    diag_kernel<<<1, 512, diag_smem, s>>>(M, n_pad, o, invL, invU, info, (int)k);
-    SCB_LAUNCH_CHECK();
-    const int ntiles = (int)(nb - k - 1);
-    if (ntiles == 0) break;
-    trsm_kernel<<<4 * ntiles, 256, trsm_smem, s>>>(M, n_pad, o, 2 * ntiles, invL, invU, Lpack, Upack);
-    SCB_LAUNCH_CHECK();
-    dim3 grid(2 * ntiles, ntiles);
-    update_kernel<<<grid, 256, upd_smem, s>>>(M, n_pad, o + NB, Lpack, Upack);
-    SCB_LAUNCH_CHECK();
+  for (int64_t kb = 0; kb < nb; kb += q) {
+    const int q_eff = (int)((nb - kb) < q ? (nb - kb) : q);
+    const int64_t panel_end = (kb + q_eff) * NB;  // first row/col after the outer panel
+    for (int i = 0; i < q_eff; i++) {
+      const int64_t k = kb + i;
+      const int64_t o = k * NB;
+      double* invL = dinv + k * 2 * NB * NB;
+      double* invU = invL + NB * NB;
+      diag_kernel<<<1, 512, diag_smem, s>>>(M, n_pad, o, invL, invU, info, (int)k);
+      SCB_LAUNCH_CHECK();
+      const int nt = (int)(nb - k - 1);  // 128-tiles after this block
+      if (nt == 0) break;
+      trsm_kernel<<<4 * nt, 256, trsm_smem, s>>>(M, n_pad, o, 2 * nt, invL, invU, Lpack, Upack, tile_chunks,
+                                                 i * NCHUNK);
+      SCB_LAUNCH_CHECK();
+      const int inner_rem = q_eff - 1 - i;  // inner blocks still to factor in this outer panel
+      if (inner_rem > 0) {
+        // (a) column strip: all rows below, the remaining columns of the outer panel
+        dim3 ga(2 * inner_rem, nt);
+        update_kernel<<<ga, 256, upd_smem, s>>>(M, n_pad, o + NB, o + NB, Lpack, Upack, tile_chunks, i * NCHUNK,
+                                                NCHUNK, 0u);
+        SCB_LAUNCH_CHECK();
+        // (b) row strip: the remaining rows of the outer panel, all columns right of the panel
+        const int nright = nt - inner_rem;
+        if (nright > 0) {
+          dim3 gb(2 * nright, inner_rem);
+          update_kernel<<<gb, 256, upd_smem, s>>>(M, n_pad, o + NB, panel_end, Lpack, Upack, tile_chunks,
+                                                  i * NCHUNK, NCHUNK, 0u);
+          SCB_LAUNCH_CHECK();
+        }
+      }
+    }
+    const int ntb = (int)(nb - kb - q_eff);  // 128-tiles after the outer panel
+    if (ntb > 0) {
+      dim3 grid(2 * ntb, ntb);
+      update_kernel<<<grid, 256, upd_smem, s>>>(M, n_pad, panel_end, panel_end, Lpack, Upack, tile_chunks, 0,
+                                                q_eff * NCHUNK, (unsigned)(ntb >= 24 ? g_stagger_ns : 0));
+      SCB_LAUNCH_CHECK();
+    }
   }
   return SCB_OK;
 }
