@@ -220,11 +220,13 @@ class Device:
         self.set_meshes(meshes)
 
     def mutual_inductance_matrix(self, hole_polygon_mapping: Dict[str, np.ndarray], units: str = "pH",
-                                 all_iterations: bool = False, **solve_kwargs):
+                                 all_iterations: bool = False, comm=None, **solve_kwargs):
         """reference device/device.py:538-648.  ``hole_polygon_mapping`` is required (the default
-        shapely-buffered polygons of fluxoid.py:12-52 are out of scope).  All columns share one
-        factorization."""
-        from .solver import factorize_model, solve
+        shapely-buffered polygons of fluxoid.py:12-52 are out of scope).  The reference solves once
+        per driven hole against one factorization; here all columns are one batched solve
+        (``solve_batch``).  As in the reference, ``iterations`` is forwarded to the solver only if
+        given explicitly."""
+        from .solver import factorize_model, solve_batch
 
         holes = self.holes
         hole_names = list(holes)
@@ -234,10 +236,7 @@ class Device:
             if not points_in_polygon(polygon, holes[hole_name].points).all():
                 raise ValueError(f"Hole '{hole_name}' is not completely contained within the given polygon.")
         n_holes = len(hole_polygon_mapping)
-        solve_kwargs = dict(solve_kwargs)
         iterations = solve_kwargs.get("iterations", 1)
-        solve_kwargs["current_units"] = None
-        solve_kwargs["progress_bar"] = False
         I_circ_A = _u.to_quantity("1 mA", "A").to("A").magnitude
         if all_iterations:
             n_iter = 1 if len(self.layers) == 1 else iterations + 1
@@ -247,20 +246,19 @@ class Device:
             sl = slice(-1, None)
         M = np.zeros((n_iter, n_holes, n_holes))
         films_by_hole = {h.name: film for film, hs in self.holes_by_film().items() for h in hs}
-        model = None
+        model = factorize_model(device=self, current_units="mA", comm=comm)
+        batch = solve_batch(
+            model=model, applied_fields=[solve_kwargs.get("applied_field")] * len(hole_names),
+            circulating_currents=[{name: 1.0} for name in hole_names],
+            field_units=solve_kwargs.get("field_units", "mT"), iterations=solve_kwargs.get("iterations", 0),
+            check_inversion=solve_kwargs.get("check_inversion", False))
+        to_units = _u.conversion_factor("H", units)
         for j, hole_name in enumerate(hole_names):
-            if model is None:
-                model = factorize_model(device=self, current_units="mA", circulating_currents={hole_name: "1 mA"})
-                I_val = model.circulating_currents[hole_name]
-            else:
-                model.set_circulating_currents({hole_name: I_val})
-            solutions = solve(model=model, **solve_kwargs)[sl]
-            for nn, solution in enumerate(solutions):
+            for nn, solution in enumerate(batch[j][sl]):
                 for i, name in enumerate(hole_names):
                     fluxoid = solution.polygon_fluxoid(hole_polygon_mapping[name], film=films_by_hole[name],
                                                        units="Phi_0", with_units=False)
-                    phi = sum(fluxoid) * _u.PHI_0  # Wb
-                    M[nn, i, j] = phi / I_circ_A * _u.conversion_factor("H", units)
+                    M[nn, i, j] = sum(fluxoid) * _u.PHI_0 / I_circ_A * to_units
         result = [m for m in M]
         if not all_iterations:
             result = result[0]

@@ -1,4 +1,4 @@
-from .solve import FactorizedModel, biot_savart_film_to_film, factorize_model, solve
+from .solve import FactorizedModel, biot_savart_film_to_film, factorize_model, solve, solve_batch
 from .solve_film import LinearSystem, factorize_linear_systems, solve_film
 from .utils import (
     FilmInfo,

@@ -46,14 +46,18 @@ def biot_savart_film_to_film(*, film1_sites, film1_z0: float, film1_areas, film1
 
 
 def film_to_film_device(src_sites, src_z0: float, src_areas, src_J, tgt_sites, tgt_z0: float):
+    """Field of the source film's sheet current at the target sites, solver units.  ``src_J`` is
+    ``(n, 2)`` -> ``(m,)`` or a batch ``(B, n, 2)`` -> ``(B, m)``."""
     torch = _torch()
     L = _lib.lib()
     m, n = int(tgt_sites.shape[0]), int(src_sites.shape[0])
+    nsets = int(src_J.shape[0]) if src_J.dim() == 3 else 1
     with torch.cuda.device(tgt_sites.device):
-        out = torch.empty(m, dtype=torch.float64, device=tgt_sites.device)
+        J = src_J.contiguous()
+        out = torch.empty((nsets, m) if src_J.dim() == 3 else (m,), dtype=torch.float64, device=tgt_sites.device)
         _lib.check(L.scb_biot_savart(0, m, _lib.ptr(tgt_sites), n, _lib.ptr(src_sites), _lib.ptr(src_areas),
-                                     _lib.ptr(src_J.contiguous()), float(tgt_z0) - float(src_z0),
-                                     1.0 / (4.0 * np.pi), 1, _lib.ptr(out), _lib.stream_ptr()))
+                                     _lib.ptr(J), float(tgt_z0) - float(src_z0),
+                                     1.0 / (4.0 * np.pi), nsets, _lib.ptr(out), _lib.stream_ptr()))
     return out
 
 
@@ -70,6 +74,7 @@ class FactorizedModel:
     circulating_currents: Dict[str, float]
     vortices: Union[Sequence[Vortex], Dict[str, Sequence[Vortex]]]
     current_units: str
+    comm: object = None  # parallel.Comm: film -> owner rank (None = single process)
 
     def set_circulating_currents(self, circulating_currents: Dict[str, float]) -> None:
         diff = set(circulating_currents) - set(self.device.holes)
@@ -99,8 +104,9 @@ class FactorizedModel:
 
 
 def factorize_model(*, device: Device, current_units: str, terminal_currents=None, circulating_currents=None,
-                    vortices: Optional[Sequence[Vortex]] = None) -> FactorizedModel:
-    """reference solver/solve.py:223-287"""
+                    vortices: Optional[Sequence[Vortex]] = None, comm=None) -> FactorizedModel:
+    """reference solver/solve.py:223-287.  With a multi-rank ``comm`` (``parallel.DistComm``) each
+    rank assembles and factorizes only the films it owns (one film factorization per GPU)."""
     ureg = device.ureg
     circulating_currents = currents_to_floats(circulating_currents or {}, ureg, current_units)
     terminal_currents = {
@@ -115,35 +121,102 @@ def factorize_model(*, device: Device, current_units: str, terminal_currents=Non
         raise ValueError("The device does not have a mesh. Call device.make_mesh() to generate it.")
     film_info = make_film_info(device=device, vortices=vortices, circulating_currents=circulating_currents,
                                terminal_currents=terminal_currents)
-    film_systems, hole_systems, terminal_systems = factorize_linear_systems(device, film_info)
+    from ..parallel import Comm, film_owners
+
+    comm = comm or Comm()
+    owners = film_owners(list(device.films), comm)
+    owned = {f for f, r in owners.items() if r == comm.rank}
+    film_systems, hole_systems, terminal_systems = factorize_linear_systems(device, film_info, owned=owned)
     return FactorizedModel(device, film_info, film_systems, hole_systems, terminal_systems, terminal_currents,
-                           circulating_currents, vortices, current_units)
+                           circulating_currents, vortices, current_units, comm)
 
 
-def _to_solution(device, film_info, results, applied_fields, others, field_conversion, solution_kwargs) -> Solution:
+def _to_solution(device, film_names, results, applied_fields, others, field_conversion, solution_kwargs,
+                 batch_index=None) -> Solution:
+    """Device tensors (solver units) -> host FilmSolutions (reference solve_film.py:566-573)."""
     film_solutions = {}
-    for name, (g, J, self_field) in results.items():
-        other = None if others is None else (others[name] / field_conversion).cpu().numpy()
+    for name in film_names:
+        g, J, self_field = results[name]
+        applied = applied_fields[name]
+        other = None if others is None else others[name]
+        if batch_index is not None:
+            g, J, self_field = g[:, batch_index], J[batch_index], self_field[:, batch_index]
+            applied = applied[:, batch_index]
+            other = None if other is None else other[:, batch_index]
         film_solutions[name] = FilmSolution(
             stream=g.cpu().numpy(),
             current_density=J.cpu().numpy(),
-            applied_field=(applied_fields[name] / field_conversion).cpu().numpy(),
+            applied_field=(applied / field_conversion).cpu().numpy(),
             self_field=(self_field / field_conversion).cpu().numpy(),
-            field_from_other_films=other,
+            field_from_other_films=None if other is None else (other / field_conversion).cpu().numpy(),
         )
     return Solution(device=device, film_solutions=film_solutions, **solution_kwargs)
 
 
-def solve(device: Optional[Device] = None, *, model: Optional[FactorizedModel] = None,
-          applied_field: Optional[Callable] = None, terminal_currents=None, circulating_currents=None,
-          vortices: Optional[Sequence[Vortex]] = None, field_units: str = "mT", current_units: str = "uA",
-          check_inversion: bool = False, iterations: int = 0, return_solutions: bool = True,
-          save_path: Optional[os.PathLike] = None, log_level: Optional[int] = None, progress_bar: bool = True,
-          _solver: str = "superscreen_b200.solve") -> List[Solution]:
-    """reference solver/solve.py:290-549"""
+def _evaluate_applied_field(applied_field, device, film_info, meshes, field_conversion):
+    """reference solver/solve.py:422-436 -> {film: host float64 (n,) in solver units}"""
+    out = {}
+    for film, mesh in meshes.items():
+        layer = device.layers[film_info[film].layer]
+        z0 = layer.z0 * np.ones(len(mesh.sites))
+        Hz_applied = np.squeeze(applied_field(mesh.sites[:, 0], mesh.sites[:, 1], z0) * field_conversion)
+        Hz_applied = np.asarray(Hz_applied, dtype=np.float64)
+        if Hz_applied.ndim != 1:
+            raise ValueError(
+                "Expected applied_field to return a 1D vector,"
+                f" got a {Hz_applied.shape[1]}D vector."
+            )
+        out[film] = np.ascontiguousarray(Hz_applied)
+    return out
+
+
+def _run(model: "FactorizedModel", applied_fields, circ_by_film, vortex_flux, iterations, check_inversion):
+    """Runs the solve + film-to-film iterations on the device for single or batched right-hand
+    sides; returns the per-iteration results replicated on every rank."""
     torch = _torch()
-    if log_level is not None:
-        logging.basicConfig(level=log_level)
+    from ..parallel import Comm, film_owners, gather_film_results, run_film_iterations
+
+    device = model.device
+    comm = model.comm or Comm()
+    film_names = list(device.films)
+    owners = film_owners(film_names, comm)
+    meshes = device.meshes
+    film_info = model.film_info
+    z0s = {name: float(device.layers[film_info[name].layer].z0) for name in film_names}
+    some = next(iter(applied_fields.values()))
+    batch = some.shape[1] if some.dim() == 2 else None
+
+    def solve_fn(name, other):
+        return solve_film_device(
+            film_info=film_info[name], film_system=model.film_systems[name],
+            hole_systems=model.hole_systems[name], applied_field=applied_fields[name], vortex_flux=vortex_flux,
+            field_from_other_films=other, check_inversion=check_inversion,
+            circulating_currents=None if circ_by_film is None else circ_by_film[name])
+
+    def coupling_fn(src_name, J_src, dst_name):
+        src, dst = meshes[src_name]._data, meshes[dst_name]._data
+        out = film_to_film_device(src.sites.to(dst.device), z0s[src_name], src.t["vertex_areas"].to(dst.device),
+                                  J_src.to(dst.device), dst.sites, z0s[dst_name])
+        return out.t().contiguous() if batch is not None else out
+
+    def zeros_fn(name):
+        return torch.zeros_like(applied_fields[name])
+
+    def j_shape(name):
+        n = len(meshes[name].sites)
+        return (batch, n, 2) if batch is not None else (n, 2)
+
+    def v_shape(name):
+        n = len(meshes[name].sites)
+        return (n, batch) if batch is not None else (n,)
+
+    per_iter = run_film_iterations(film_names, owners, comm, solve_fn, coupling_fn, zeros_fn, j_shape, iterations)
+    return gather_film_results(per_iter, film_names, owners, comm,
+                               {"g": v_shape, "J": j_shape, "self": v_shape, "other": v_shape}, some)
+
+
+def _check_model_args(device, model, terminal_currents, circulating_currents, vortices, current_units):
+    """Argument validation shared by solve / solve_batch (reference solver/solve.py:357-389)."""
     if model is None:
         if device is None:
             raise ValueError("Either a model or a device must be provided.")
@@ -159,78 +232,94 @@ def solve(device: Optional[Device] = None, *, model: Optional[FactorizedModel] =
             )
     if not isinstance(model, FactorizedModel):
         raise TypeError(f"model must be an instance of FactorizedModel (got {type(model)}).")
+    if not model.device.meshes:
+        raise ValueError("The device does not have a mesh. Call device.make_mesh() to generate it.")
+    return model
+
+
+def solve(device: Optional[Device] = None, *, model: Optional[FactorizedModel] = None,
+          applied_field: Optional[Callable] = None, terminal_currents=None, circulating_currents=None,
+          vortices: Optional[Sequence[Vortex]] = None, field_units: str = "mT", current_units: str = "uA",
+          check_inversion: bool = False, iterations: int = 0, return_solutions: bool = True,
+          save_path: Optional[os.PathLike] = None, log_level: Optional[int] = None, progress_bar: bool = True,
+          _solver: str = "superscreen_b200.solve") -> List[Solution]:
+    """reference solver/solve.py:290-549"""
+    torch = _torch()
+    if log_level is not None:
+        logging.basicConfig(level=log_level)
+    model = _check_model_args(device, model, terminal_currents, circulating_currents, vortices, current_units)
     if save_path is not None:
         raise NotImplementedError("HDF5 persistence is a 'next' row of the hot-path scope (SURVEY.md 8f.3).")
-
     device = model.device
-    film_info = model.film_info
-    film_systems = model.film_systems
-    hole_systems = model.hole_systems
-    circulating_currents = model.circulating_currents
-    terminal_currents = model.terminal_currents
-    vortices = model.vortices
     current_units = model.current_units
-    if not device.meshes:
-        raise ValueError("The device does not have a mesh. Call device.make_mesh() to generate it.")
-
     length_units = device.length_units
-    meshes = device.meshes
     applied_field = applied_field or ConstantField(0)
     field_conversion = field_conversion_factor(field_units, current_units, length_units=length_units).magnitude
-
-    applied_fields = {}
-    for film, mesh in meshes.items():
-        layer = device.layers[film_info[film].layer]
-        z0 = layer.z0 * np.ones(len(mesh.sites))
-        Hz_applied = np.squeeze(applied_field(mesh.sites[:, 0], mesh.sites[:, 1], z0) * field_conversion)
-        Hz_applied = np.asarray(Hz_applied, dtype=np.float64)
-        if Hz_applied.ndim != 1:
-            raise ValueError(
-                "Expected applied_field to return a 1D vector,"
-                f" got a {Hz_applied.shape[1]}D vector."
-            )
-        applied_fields[film] = torch.as_tensor(np.ascontiguousarray(Hz_applied)).to(mesh._data.device)
-
+    host_fields = _evaluate_applied_field(applied_field, device, model.film_info, device.meshes, field_conversion)
+    applied_fields = {f: torch.as_tensor(h).to(device.meshes[f]._data.device) for f, h in host_fields.items()}
     # Phi_0 / mu_0 in [current_units * length_units]  (reference solve.py:441)
     vortex_flux = _u.PHI_0 / _u.MU_0 * _u.conversion_factor("A * m", f"({current_units}) * ({length_units})")
-
     solution_kwargs = dict(applied_field_func=applied_field, field_units=field_units, current_units=current_units,
-                           circulating_currents=circulating_currents, terminal_currents=terminal_currents,
-                           vortices=vortices, solver=_solver)
+                           circulating_currents=model.circulating_currents,
+                           terminal_currents=model.terminal_currents, vortices=model.vortices, solver=_solver)
+    per_iter = _run(model, applied_fields, None, vortex_flux, iterations, check_inversion)
+    if not return_solutions:
+        return None
+    film_names = list(device.films)
+    return [_to_solution(device, film_names, results, applied_fields, others, field_conversion, solution_kwargs)
+            for results, others in per_iter]
 
-    def run(others):
-        return {
-            name: solve_film_device(
-                film_info=film_info[name], film_system=film_systems[name], hole_systems=hole_systems[name],
-                applied_field=applied_fields[name], vortex_flux=vortex_flux,
-                field_from_other_films=None if others is None else others[name], check_inversion=check_inversion)
-            for name in device.films
+
+def solve_batch(*, model: FactorizedModel, applied_fields: Sequence[Optional[Callable]],
+                circulating_currents: Optional[Sequence[Dict[str, float]]] = None, field_units: str = "mT",
+                iterations: int = 0, check_inversion: bool = False,
+                _solver: str = "superscreen_b200.solve_batch") -> List[List[Solution]]:
+    """Solves B models that share one factorization in a single batched pass (multi-RHS getrs,
+    multi-RHS matrix-free operator, one film-to-film exchange per iteration for the whole batch).
+
+    This is an extension with no counterpart in the reference, which would call ``solve`` B times
+    (e.g. once per driven hole in ``Device.mutual_inductance_matrix``, device/device.py:610-639, or
+    once per applied field in a sweep).  ``out[b]`` equals
+    ``solve(model=model_b, applied_field=applied_fields[b], iterations=iterations)`` where
+    ``model_b`` has ``circulating_currents[b]`` (floats in ``model.current_units``).
+    """
+    torch = _torch()
+    model = _check_model_args(None, model, None, None, None, None)
+    device = model.device
+    B = len(applied_fields)
+    if B == 0:
+        return []
+    if circulating_currents is None:
+        circulating_currents = [model.circulating_currents] * B
+    if len(circulating_currents) != B:
+        raise ValueError("applied_fields and circulating_currents must have the same length.")
+    for cc in circulating_currents:
+        diff = set(cc) - set(device.holes)
+        if diff:
+            raise KeyError(f"circulating_currents contains keys not in self.device.holes: {list(diff)!r}")
+    current_units = model.current_units
+    length_units = device.length_units
+    field_conversion = field_conversion_factor(field_units, current_units, length_units=length_units).magnitude
+    funcs = [f or ConstantField(0) for f in applied_fields]
+    per_b = [_evaluate_applied_field(f, device, model.film_info, device.meshes, field_conversion) for f in funcs]
+    film_names = list(device.films)
+    dev_fields = {}
+    circ_by_film = {}
+    for name in film_names:
+        dev = device.meshes[name]._data.device
+        dev_fields[name] = torch.as_tensor(np.ascontiguousarray(np.stack([h[name] for h in per_b], axis=1))).to(dev)
+        circ_by_film[name] = {
+            hole: torch.tensor([float(cc.get(hole, 0.0)) for cc in circulating_currents], dtype=torch.float64,
+                               device=dev)
+            for hole in model.film_info[name].hole_indices
         }
-
-    solutions: List[Solution] = []
-    results = run(None)
-    if return_solutions:
-        solutions.append(_to_solution(device, film_info, results, applied_fields, None, field_conversion,
-                                      solution_kwargs))
-    if len(device.films) < 2 or iterations < 1:
-        return solutions if return_solutions else None
-
-    z0s = {name: float(device.layers[film_info[name].layer].z0) for name in device.films}
-    for i in range(iterations):
-        # Jacobi step: all film-to-film fields from the previous iterate, then all re-solves
-        others = {name: torch.zeros_like(applied_fields[name]) for name in device.films}
-        for source_film, film in itertools.product(device.films, repeat=2):
-            if film == source_film:
-                continue
-            src, dst = meshes[source_film]._data, meshes[film]._data
-            J = results[source_film][1]
-            if J.device != dst.device:  # multi-GPU placement: bring the source film over NVLink
-                J = J.to(dst.device)
-            others[film] += film_to_film_device(
-                src.sites.to(dst.device), z0s[source_film], src.t["vertex_areas"].to(dst.device), J,
-                dst.sites, z0s[film])
-        results = run(others)
-        if return_solutions:
-            solutions.append(_to_solution(device, film_info, results, applied_fields, others, field_conversion,
-                                          solution_kwargs))
-    return solutions if return_solutions else None
+    vortex_flux = _u.PHI_0 / _u.MU_0 * _u.conversion_factor("A * m", f"({current_units}) * ({length_units})")
+    per_iter = _run(model, dev_fields, circ_by_film, vortex_flux, iterations, check_inversion)
+    out: List[List[Solution]] = []
+    for b in range(B):
+        kwargs = dict(applied_field_func=funcs[b], field_units=field_units, current_units=current_units,
+                      circulating_currents=dict(circulating_currents[b]),
+                      terminal_currents=model.terminal_currents, vortices=model.vortices, solver=_solver)
+        out.append([_to_solution(device, film_names, results, dev_fields, others, field_conversion, kwargs,
+                                 batch_index=b) for results, others in per_iter])
+    return out

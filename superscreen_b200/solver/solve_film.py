@@ -79,14 +79,18 @@ def assemble_negA(info: FilmInfo, ix_dev, n_int: int, n_pad: int, T=None, out=No
     return M, margin
 
 
-def factorize_linear_systems(device: Device, film_info_dict: Dict[str, FilmInfo]):
-    """reference solver/solve_film.py:151-282 (films without terminals)."""
+def factorize_linear_systems(device: Device, film_info_dict: Dict[str, FilmInfo], owned=None):
+    """reference solver/solve_film.py:151-282 (films without terminals).  ``owned`` restricts the
+    (expensive) assembly + LU to the films this rank owns (multi-GPU film sharding)."""
     torch = _torch()
     L = _lib.lib()
     film_systems: Dict[str, LinearSystem] = {}
     hole_systems: Dict[str, Dict[str, LinearSystem]] = {}
     terminal_systems: Dict[str, object] = {}
     for film_name, info in film_info_dict.items():
+        if owned is not None and film_name not in owned:
+            hole_systems[film_name] = {}
+            continue
         d = info.mesh._data
         with torch.cuda.device(d.device):
             T = None
@@ -121,6 +125,8 @@ def factorize_linear_systems(device: Device, film_info_dict: Dict[str, FilmInfo]
             film_systems[film_name] = system
     # one synchronising read per model: singularity flag + dominance margin of every film
     for film_name, info in film_info_dict.items():
+        if film_name not in film_systems:
+            continue
         flag = int(info.dev["lu_info"].item())
         mm = float(info.dev["margin_min"].item())
         if flag != 0:
@@ -193,22 +199,37 @@ def spmv(d, key: str, x, alpha: float = 1.0):
 
 def solve_film_device(*, film_info: FilmInfo, film_system: LinearSystem, hole_systems: Dict[str, LinearSystem],
                       applied_field, vortex_flux: float, field_from_other_films=None,
-                      check_inversion: bool = False):
+                      check_inversion: bool = False, circulating_currents=None):
     """Device-side body of ``solve_film`` (reference solve_film.py:483-565): all arguments and
-    results are device tensors in solver units.  Returns (g, J, self_field)."""
+    results are device tensors in solver units.
+
+    ``applied_field`` is ``(n,)`` or, for a batch of B right-hand sides sharing the factorization,
+    ``(n, B)``; ``circulating_currents`` (default: ``film_info.circulating_currents``) maps hole
+    names to a float or to a ``(B,)`` tensor.  Returns ``(g, J, self_field)`` with shapes
+    ``(n,), (n, 2), (n,)`` or ``(n, B), (B, n, 2), (n, B)``.
+    """
     torch = _torch()
     info = film_info
     d = info.mesh._data
+    circ = info.circulating_currents if circulating_currents is None else circulating_currents
+    batched = applied_field.dim() == 2
     with torch.cuda.device(d.device):
         Hz = applied_field if field_from_other_films is None else applied_field + field_from_other_films
         g = torch.zeros_like(Hz)
         Ha_eff = None
         # hole boundary conditions: g[hole] = I_circ; Ha_eff = -sum_k A[:, hole_k] @ g[hole_k]
         if hole_systems:
-            src = torch.cat([s.indices_dev for s in hole_systems.values()])
+            any_current = False
             for name, s in hole_systems.items():
-                g[s.indices_dev] += float(info.circulating_currents.get(name, 0))
-            if any(info.circulating_currents.get(name, 0) for name in hole_systems):
+                cur = circ.get(name, 0)
+                if torch.is_tensor(cur):
+                    g[s.indices_dev] += cur.to(g.dtype)[None, :] if batched else cur.to(g.dtype)
+                    any_current = True
+                elif cur:
+                    g[s.indices_dev] += float(cur)
+                    any_current = True
+            if any_current:
+                src = torch.cat([s.indices_dev for s in hole_systems.values()])
                 Ha_eff = -apply_operator(info, g, src_idx=src)
         ix = film_system.indices_dev
         h = Hz[ix] if Ha_eff is None else Hz[ix] - Ha_eff[ix]
@@ -232,9 +253,14 @@ def solve_film_device(*, film_info: FilmInfo, film_system: LinearSystem, hole_sy
             e = torch.zeros(len(film_system.indices), dtype=torch.float64, device=d.device)
             e[j_film] = 1.0
             Kj = -lu_solve(film_system, e)
-            g[ix] += vortex_flux * vortex.nPhi0 * Kj / d.t["vertex_areas"][j_device]
+            gv = vortex_flux * vortex.nPhi0 * Kj / d.t["vertex_areas"][j_device]
+            g[ix] += gv[:, None] if batched else gv
         # J = curl(g z) = [dg/dy, -dg/dx]
-        J = torch.stack([spmv(d, "gradient_y", g), spmv(d, "gradient_x", g, alpha=-1.0)], dim=1)
+        Jx, Jy = spmv(d, "gradient_y", g), spmv(d, "gradient_x", g, alpha=-1.0)
+        if batched:
+            J = torch.stack([Jx.t(), Jy.t()], dim=2).contiguous()  # (B, n, 2)
+        else:
+            J = torch.stack([Jx, Jy], dim=1)
         # Q @ (w * g), matrix-free
         self_field = apply_operator(info, g, src_idx=None, with_sparse=False)
     return g, J, self_field
