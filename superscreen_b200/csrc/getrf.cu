@@ -21,6 +21,8 @@
 // dgetrf).  Pivoting is unnecessary here; parity is on the solution (1e-8 rel-L2), see DESIGN.md.
 #include <stdlib.h>
 
+#include <vector>
+
 #include "scb_common.cuh"
 
 namespace scb {
@@ -102,7 +104,7 @@ struct __align__(128) UpdateStage {
 __global__ void __launch_bounds__(256, 2)
 update_kernel(double* __restrict__ M, int64_t ld, int64_t row0, int64_t col0,
               const double* __restrict__ Lpack, const double* __restrict__ Upack, int tile_chunks,
-              int chunk0, int nchunks, unsigned stagger_ns) {
+              int chunk0, int nchunks) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   UpdateStage* stage = reinterpret_cast<UpdateStage*>(smem_raw);
   __shared__ uint64_t bars[2];
@@ -121,14 +123,6 @@ update_kernel(double* __restrict__ M, int64_t ld, int64_t row0, int64_t col0,
     mbar_init(&bars[0], 1);
     mbar_init(&bars[1], 1);
     fence_barrier_init();
-  }
-  // The two CTAs resident on an SM would otherwise run in lock-step (same start, same length),
-  // so their C-tile load/store phases would coincide and leave the DMMA pipe idle.  Delay the
-  // second first-wave resident of every SM by about half a tile time once; later CTAs inherit
-  // the phase shift because each starts when its predecessor on that slot exits.
-  if (stagger_ns) {
-    const unsigned bid = blockIdx.y * gridDim.x + blockIdx.x;
-    if (bid >= 148u && bid < 296u) __nanosleep(stagger_ns);
   }
   __syncthreads();
   if (tid == 0) {
@@ -442,8 +436,301 @@ diag_kernel(double* __restrict__ M, int64_t ld, int64_t o, double* __restrict__ 
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// 1b. diagonal block, small-footprint version (256 threads, 3 x 34 KB shared): same outputs as
+//     diag_kernel, but organised as a 2x2 recursion over 64x64 quadrants so that one CTA fits in
+//     the slot of an update CTA (256 threads, <= 128 registers, < 113 KB shared).  This is what
+//     allows the panel factorization of the next outer panel to run on a high-priority stream
+//     CONCURRENTLY with the big trailing update (look-ahead): the hardware block scheduler only
+//     places a high-priority CTA into a slot it fits in.
+//       A11 -> sweep64 -> L11, U11, inv(L11), inv(U11)
+//       U12 = inv(L11) A12,  L21 = A21 inv(U11),  A22 -= L21 U12           (64^3 DMMA GEMMs)
+//       A22 -> sweep64 -> L22, U22, inv(L22), inv(U22)
+//       inv(L)21 = -inv(L22) L21 inv(L11),  inv(U)12 = -inv(U11) U12 inv(U22)
+// ---------------------------------------------------------------------------------------
+constexpr int QN = 64;        // quadrant size
+constexpr int QLD = QN + 4;   // 68: conflict-free DMMA fragment loads (ld % 16 == 4)
+
+// fused LU + inv(L) + inv(U)^T-elimination sweep on a 64x64 block held in registers:
+// thread (ti = warp 0..7, tj = lane) owns rows ti + 8a (a < 8) and columns tj + 32b (b < 2).
+// Dout[64][QLD] receives the finished L (strictly lower) and U (upper) entries.
+__device__ __forceinline__ int sweep64(double (&x)[8][2], double* __restrict__ Dout, double (*rowb)[QN],
+                                       double (*colb)[QN], double* __restrict__ rdiag) {
+  const int tid = threadIdx.x;
+  const int ti = tid >> 5, tj = tid & 31;
+  int bad = 0;
+  if (ti == 0) {
+#pragma unroll
+    for (int b = 0; b < 2; b++) rowb[0][tj + 32 * b] = x[0][b];
+    if (tj == 0) rdiag[0] = fast_rcp(x[0][0]);
+  }
+  if (tj == 0) {
+#pragma unroll
+    for (int a = 0; a < 8; a++) colb[0][ti + 8 * a] = x[a][0];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int ap = 0; ap < 8; ap++) {
+#pragma unroll 1
+    for (int jj = 0; jj < 8; jj++) {
+      const int j = 8 * ap + jj;
+      const int cur = j & 1, nxt = cur ^ 1;
+      const double piv = rowb[cur][j];
+      if (bad == 0 && !(fabs(piv) > 0.0 && isfinite(piv))) bad = j + 1;
+      const double rp = rdiag[j];
+      const int bj = ap >> 2;  // column block of column j (compile-time after unrolling)
+      const bool own_col = tj == (j & 31);
+      double v[2], vs[2];
+#pragma unroll
+      for (int b = 0; b < 2; b++) {
+        v[b] = rowb[cur][tj + 32 * b];
+        vs[b] = v[b] * rp;
+      }
+#pragma unroll
+      for (int a = 0; a < 8; a++) {
+        const int r = ti + 8 * a;
+        const double w = colb[cur][r];
+        if (a > ap || (a == ap && r > j)) {
+          const double l = w * rp;
+#pragma unroll
+          for (int b = 0; b < 2; b++) {
+            if (b == bj && own_col) {
+              Dout[r * QLD + j] = l;
+              x[a][b] = -l;
+            } else {
+              x[a][b] = fma(-l, v[b], x[a][b]);
+            }
+          }
+        } else if (a < ap || (a == ap && r < j)) {
+#pragma unroll
+          for (int b = 0; b < 2; b++) {
+            if (b < bj) continue;
+            if (b > bj || tj + 32 * b > j) x[a][b] = fma(-w, vs[b], x[a][b]);
+          }
+        } else {
+#pragma unroll
+          for (int b = 0; b < 2; b++) {
+            if (b < bj) continue;
+            const int c = tj + 32 * b;
+            if (b > bj || c >= j) Dout[j * QLD + c] = x[a][b];
+            if (b > bj || c > j) x[a][b] = -vs[b];
+          }
+        }
+      }
+      const int jn = j + 1;
+      if (jn < QN) {
+        if (ti == (jn & 7)) {
+          // publish register row jn (row block ap, or ap + 1 when jj == 7) and 1 / pivot
+          const int bn = jn >> 5;
+#pragma unroll
+          for (int b = 0; b < 2; b++) {
+            const double val = (jj < 7) ? x[ap][b] : x[ap + 1 < 8 ? ap + 1 : 7][b];
+            rowb[nxt][tj + 32 * b] = val;
+            if (b == bn && tj == (jn & 31)) rdiag[jn] = fast_rcp(val);
+          }
+        }
+        if (tj == (jn & 31)) {
+          const bool next_block = (jj == 7) && ((ap & 3) == 3);  // jn crosses into column block bj + 1
+#pragma unroll
+          for (int a = 0; a < 8; a++) colb[nxt][ti + 8 * a] = next_block ? x[a][bj + 1 < 2 ? bj + 1 : 1] : x[a][bj];
+        }
+      }
+      __syncthreads();
+    }
+  }
+  return bad;
+}
+
+// acc (warp tile 16 x 32, warps 4 x 2) = A[64][QLD] * B[64][QLD]
+__device__ __forceinline__ void gemm64(const double* __restrict__ As, const double* __restrict__ Bs,
+                                       double (&acc)[2][4][2]) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int wm = warp >> 1, wn = warp & 1;
+  const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int i = 0; i < 2; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+#pragma unroll 4
+  for (int s = 0; s < QN / 4; s++) {
+    double a[2], b[4];
+#pragma unroll
+    for (int i = 0; i < 2; i++) a[i] = As[(wm * 16 + i * 8 + g) * QLD + s * 4 + t];
+#pragma unroll
+    for (int j = 0; j < 4; j++) b[j] = Bs[(s * 4 + t) * QLD + wn * 32 + j * 8 + g];
+#pragma unroll
+    for (int i = 0; i < 2; i++)
+#pragma unroll
+      for (int j = 0; j < 4; j++) dmma(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+  }
+}
+
+// fragment (i, j) of this thread covers row frag_row(i), columns frag_col(j), frag_col(j) + 1
+__device__ __forceinline__ int frag_row(int i) { return ((threadIdx.x >> 5) >> 1) * 16 + i * 8 + ((threadIdx.x & 31) >> 2); }
+__device__ __forceinline__ int frag_col(int j) { return ((threadIdx.x >> 5) & 1) * 32 + j * 8 + 2 * (threadIdx.x & 3); }
+
+__device__ __forceinline__ void load_quadrant(double* __restrict__ S, const double* __restrict__ G, int64_t ldg) {
+#pragma unroll
+  for (int q = 0; q < 8; q++) {
+    const int idx = q * 256 + threadIdx.x;
+    const int r = idx >> 5, c = (idx & 31) * 2;
+    *reinterpret_cast<double2*>(&S[r * QLD + c]) = *reinterpret_cast<const double2*>(G + (int64_t)r * ldg + c);
+  }
+}
+__device__ __forceinline__ void store_quadrant(double* __restrict__ G, int64_t ldg, const double* __restrict__ S) {
+#pragma unroll
+  for (int q = 0; q < 8; q++) {
+    const int idx = q * 256 + threadIdx.x;
+    const int r = idx >> 5, c = (idx & 31) * 2;
+    *reinterpret_cast<double2*>(G + (int64_t)r * ldg + c) = *reinterpret_cast<const double2*>(&S[r * QLD + c]);
+  }
+}
+// sweep registers -> inv(L) and inv(U) of the quadrant, to shared buffers and to global
+__device__ __forceinline__ void emit_inverses(const double (&x)[8][2], const double* __restrict__ rdiag,
+                                              double* __restrict__ SL, double* __restrict__ SU,
+                                              double* __restrict__ GL, double* __restrict__ GU) {
+  const int ti = threadIdx.x >> 5, tj = threadIdx.x & 31;
+#pragma unroll
+  for (int a = 0; a < 8; a++)
+#pragma unroll
+    for (int b = 0; b < 2; b++) {
+      const int r = ti + 8 * a, c = tj + 32 * b;
+      const double v = x[a][b];
+      const double il = c < r ? v : (c == r ? 1.0 : 0.0);
+      const double iu = c > r ? v * rdiag[c] : (c == r ? rdiag[c] : 0.0);
+      if (SL) SL[r * QLD + c] = il;
+      if (SU) SU[r * QLD + c] = iu;
+      GL[r * NB + c] = il;
+      GU[r * NB + c] = iu;
+    }
+}
+
+__global__ void __launch_bounds__(256, 2)
+diag_kernel_small(double* __restrict__ M, int64_t ld, int64_t o, double* __restrict__ invL,
+                  double* __restrict__ invU, int32_t* __restrict__ info, int block_index) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* S0 = reinterpret_cast<double*>(smem_raw);
+  double* S1 = S0 + QN * QLD;
+  double* S2 = S1 + QN * QLD;
+  __shared__ double rowb[2][QN], colb[2][QN], rdiag[QN];
+  const int tid = threadIdx.x, ti = tid >> 5, tj = tid & 31;
+  double* A11 = M + o * ld + o;
+  double* A12 = A11 + QN;
+  double* A21 = A11 + (int64_t)QN * ld;
+  double* A22 = A21 + QN;
+  double x[8][2];
+  double acc[2][4][2];
+
+  // ---- phase 1: A11 ----
+#pragma unroll
+  for (int a = 0; a < 8; a++)
+#pragma unroll
+    for (int b = 0; b < 2; b++) x[a][b] = A11[(int64_t)(ti + 8 * a) * ld + tj + 32 * b];
+  int bad = sweep64(x, S0, rowb, colb, rdiag);
+  emit_inverses(x, rdiag, S1, S2, invL, invU);  // S1 = inv(L11), S2 = inv(U11)
+  store_quadrant(A11, ld, S0);                   // L11 \ U11 in place
+  __syncthreads();
+  // ---- phase 2a: U12 = inv(L11) A12 ----
+  load_quadrant(S0, A12, ld);
+  __syncthreads();
+  gemm64(S1, S0, acc);
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 2; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const int r = frag_row(i), c = frag_col(j);
+      const double2 v = make_double2(acc[i][j][0], acc[i][j][1]);
+      *reinterpret_cast<double2*>(&S0[r * QLD + c]) = v;            // S0 = U12
+      *reinterpret_cast<double2*>(A12 + (int64_t)r * ld + c) = v;
+    }
+  // ---- phase 2b: L21 = A21 inv(U11) ----
+  load_quadrant(S1, A21, ld);
+  __syncthreads();
+  gemm64(S1, S2, acc);
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 2; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const int r = frag_row(i), c = frag_col(j);
+      const double2 v = make_double2(acc[i][j][0], acc[i][j][1]);
+      *reinterpret_cast<double2*>(&S1[r * QLD + c]) = v;            // S1 = L21
+      *reinterpret_cast<double2*>(A21 + (int64_t)r * ld + c) = v;
+    }
+  __syncthreads();
+  // ---- phase 3: A22 -= L21 U12  -> S2 ----
+  gemm64(S1, S0, acc);
+#pragma unroll
+  for (int i = 0; i < 2; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const int r = frag_row(i), c = frag_col(j);
+      const double2 cin = *reinterpret_cast<const double2*>(A22 + (int64_t)r * ld + c);
+      *reinterpret_cast<double2*>(&S2[r * QLD + c]) = make_double2(cin.x - acc[i][j][0], cin.y - acc[i][j][1]);
+    }
+  __syncthreads();
+  // ---- phase 4: A22 ----
+#pragma unroll
+  for (int a = 0; a < 8; a++)
+#pragma unroll
+    for (int b = 0; b < 2; b++) x[a][b] = S2[(ti + 8 * a) * QLD + tj + 32 * b];
+  __syncthreads();
+  const int bad2 = sweep64(x, S2, rowb, colb, rdiag);
+  if (bad == 0 && bad2) bad = QN + bad2;
+  if (tid == 0 && bad) atomicCAS(info, 0, block_index * NB + bad);
+  store_quadrant(A22, ld, S2);                   // L22 \ U22 in place
+  __syncthreads();
+  double* iL22 = invL + QN * NB + QN;
+  double* iU22 = invU + QN * NB + QN;
+  emit_inverses(x, rdiag, S2, nullptr, iL22, iU22);  // S2 = inv(L22)
+  __syncthreads();
+  // ---- phase 5a: inv(L)21 = -(inv(L22) L21) inv(L11) ----
+  gemm64(S2, S1, acc);
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 2; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+      *reinterpret_cast<double2*>(&S1[frag_row(i) * QLD + frag_col(j)]) = make_double2(acc[i][j][0], acc[i][j][1]);
+  load_quadrant(S2, invL, NB);                   // inv(L11) (written in phase 1 by this CTA)
+  __syncthreads();
+  gemm64(S1, S2, acc);
+#pragma unroll
+  for (int i = 0; i < 2; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const int r = frag_row(i), c = frag_col(j);
+      *reinterpret_cast<double2*>(invL + (int64_t)(QN + r) * NB + c) = make_double2(-acc[i][j][0], -acc[i][j][1]);
+      *reinterpret_cast<double2*>(invL + (int64_t)r * NB + QN + c) = make_double2(0.0, 0.0);
+      *reinterpret_cast<double2*>(invU + (int64_t)(QN + r) * NB + c) = make_double2(0.0, 0.0);
+    }
+  __syncthreads();
+  // ---- phase 5b: inv(U)12 = -inv(U11) (U12 inv(U22)) ----
+  load_quadrant(S2, iU22, NB);
+  __syncthreads();
+  gemm64(S0, S2, acc);
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 2; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+      *reinterpret_cast<double2*>(&S0[frag_row(i) * QLD + frag_col(j)]) = make_double2(acc[i][j][0], acc[i][j][1]);
+  load_quadrant(S2, invU, NB);                   // inv(U11)
+  __syncthreads();
+  gemm64(S2, S0, acc);
+#pragma unroll
+  for (int i = 0; i < 2; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const int r = frag_row(i), c = frag_col(j);
+      *reinterpret_cast<double2*>(invU + (int64_t)r * NB + QN + c) = make_double2(-acc[i][j][0], -acc[i][j][1]);
+    }
+}
+
 static bool g_attr_set = false;
-static int g_stagger_ns = 0;
+static int g_diag_small = 1;
+static int g_lookahead = 1;
 
 }  // namespace scb
 
@@ -460,16 +747,38 @@ static int lu_outer_blocks() {
   return q;
 }
 
+// per-device helper stream (highest priority) and event pool for the look-ahead
+struct LuStreams {
+  cudaStream_t panel = nullptr;
+  std::vector<cudaEvent_t> events;
+  cudaEvent_t event(size_t i) {
+    while (events.size() <= i) {
+      cudaEvent_t e;
+      cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+      events.push_back(e);
+    }
+    return events[i];
+  }
+};
+static LuStreams g_lu_streams[64];
+
 extern "C" int64_t scb_getrf_dinv_bytes(int64_t n_pad) {
   const int64_t nb = n_pad / NB;
-  // [nb][2][128][128] block inverses + Lpack [n_pad x KB] + Upack [KB x n_pad], KB = q * 128
-  return (nb * 2 * NB * NB + 2 * n_pad * NB * lu_outer_blocks()) * (int64_t)sizeof(double);
+  // [nb][2][128][128] block inverses + 2 x (Lpack [n_pad x KB] + Upack [KB x n_pad]), KB = q * 128
+  // (two pack sets: the next outer panel is factored while the previous one is still being applied)
+  return (nb * 2 * NB * NB + 4 * n_pad * NB * lu_outer_blocks()) * (int64_t)sizeof(double);
 }
 
-// Two-level right-looking LU: inner panels of NB = 128 columns are factored and applied only to
-// the L-shaped strip of the current outer panel (KB = q*128 columns); the big trailing block is
-// updated once per outer panel with K = KB, which amortises the C-tile traffic and the CTA
-// prologue/epilogue of the DMMA update kernel over q times more math.
+// Two-level right-looking LU with look-ahead.
+//  * Inner panels of NB = 128 columns are factored and applied only to the L-shaped strip of the
+//    current outer panel (KB = q*128 columns); the big trailing block is updated once per outer
+//    panel with K = KB, which amortises the C-tile traffic and the CTA prologue/epilogue of the
+//    DMMA update kernel over q times more math.
+//  * Look-ahead: the trailing update of outer panel P is split into the L-shaped strip that the
+//    next panel needs (done first) and the rest; the factorization of panel P+1 (a latency-bound
+//    chain of small kernels) then runs on a high-priority stream concurrently with "the rest".
+//    Every kernel of that chain fits into the SM slot of an update CTA, so the hardware block
+//    scheduler interleaves them as slots free up.
 extern "C" int scb_getrf_nopiv(int64_t n_pad, double* M, double* dinv, int32_t* info,
                                scb_stream_t stream) {
   SCB_CHECK_ARG(n_pad > 0 && n_pad % NB == 0, "n_pad must be a positive multiple of 128");
@@ -477,59 +786,130 @@ extern "C" int scb_getrf_nopiv(int64_t n_pad, double* M, double* dinv, int32_t* 
   const int64_t nb = n_pad / NB;
   const int q = lu_outer_blocks();
   const int tile_chunks = q * NCHUNK;
-  double* Lpack = dinv + nb * 2 * NB * NB;
-  double* Upack = Lpack + n_pad * NB * q;
+  double* pack_base = dinv + nb * 2 * NB * NB;
+  const int64_t pack_set = 2 * n_pad * NB * q;  // doubles per (Lpack + Upack) set
   const int diag_smem = NB * DLD * sizeof(double);
+  const int diag_small_smem = 3 * QN * QLD * sizeof(double);
   const int trsm_smem = kTrsmSmemDoubles * sizeof(double);
   const int upd_smem = 2 * sizeof(UpdateStage);
   if (!g_attr_set) {
     SCB_CUDA(cudaFuncSetAttribute(diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, diag_smem));
+    SCB_CUDA(cudaFuncSetAttribute(diag_kernel_small, cudaFuncAttributeMaxDynamicSharedMemorySize, diag_small_smem));
     SCB_CUDA(cudaFuncSetAttribute(update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, upd_smem));
     SCB_CUDA(cudaFuncSetAttribute(trsm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, trsm_smem));
     SCB_CUDA(cudaFuncSetAttribute(update_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    if (const char* e = getenv("SCB_UPDATE_STAGGER_NS")) g_stagger_ns = atoi(e);
+    if (const char* e = getenv("SCB_DIAG_SMALL")) g_diag_small = atoi(e);
+    if (const char* e = getenv("SCB_LU_LOOKAHEAD")) g_lookahead = atoi(e);
     g_attr_set = true;
   }
+  int dev = 0;
+  SCB_CUDA(cudaGetDevice(&dev));
+  LuStreams& ls = g_lu_streams[dev & 63];
+  const bool lookahead = g_lookahead && g_diag_small;
+  cudaStream_t sp = s;
+  if (lookahead) {
+    if (!ls.panel) {
+      int lo = 0, hi = 0;
+      SCB_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+      SCB_CUDA(cudaStreamCreateWithPriority(&ls.panel, cudaStreamNonBlocking, hi));
+    }
+    sp = ls.panel;
+  }
   SCB_CUDA(cudaMemsetAsync(info, 0, sizeof(int32_t), s));
-  for (int64_t kb = 0; kb < nb; kb += q) {
+
+  // factorization of outer panel P (inner blocks kb .. kb+q_eff-1) on stream st, packs -> set (P & 1)
+  auto factor_panel = [&](int64_t P, cudaStream_t st) -> int {
+    const int64_t kb = P * q;
     const int q_eff = (int)((nb - kb) < q ? (nb - kb) : q);
-    const int64_t panel_end = (kb + q_eff) * NB;  // first row/col after the outer panel
+    const int64_t panel_end = (kb + q_eff) * NB;
+    double* Lpack = pack_base + (P & 1) * pack_set;
+    double* Upack = Lpack + n_pad * NB * q;
     for (int i = 0; i < q_eff; i++) {
       const int64_t k = kb + i;
       const int64_t o = k * NB;
       double* invL = dinv + k * 2 * NB * NB;
       double* invU = invL + NB * NB;
-      diag_kernel<<<1, 512, diag_smem, s>>>(M, n_pad, o, invL, invU, info, (int)k);
+      if (g_diag_small)
+        diag_kernel_small<<<1, 256, diag_small_smem, st>>>(M, n_pad, o, invL, invU, info, (int)k);
+      else
+        diag_kernel<<<1, 512, diag_smem, st>>>(M, n_pad, o, invL, invU, info, (int)k);
       SCB_LAUNCH_CHECK();
       const int nt = (int)(nb - k - 1);  // 128-tiles after this block
       if (nt == 0) break;
-      trsm_kernel<<<4 * nt, 256, trsm_smem, s>>>(M, n_pad, o, 2 * nt, invL, invU, Lpack, Upack, tile_chunks,
-                                                 i * NCHUNK);
+      trsm_kernel<<<4 * nt, 256, trsm_smem, st>>>(M, n_pad, o, 2 * nt, invL, invU, Lpack, Upack, tile_chunks,
+                                                  i * NCHUNK);
       SCB_LAUNCH_CHECK();
       const int inner_rem = q_eff - 1 - i;  // inner blocks still to factor in this outer panel
       if (inner_rem > 0) {
         // (a) column strip: all rows below, the remaining columns of the outer panel
         dim3 ga(2 * inner_rem, nt);
-        update_kernel<<<ga, 256, upd_smem, s>>>(M, n_pad, o + NB, o + NB, Lpack, Upack, tile_chunks, i * NCHUNK,
-                                                NCHUNK, 0u);
+        update_kernel<<<ga, 256, upd_smem, st>>>(M, n_pad, o + NB, o + NB, Lpack, Upack, tile_chunks, i * NCHUNK,
+                                                 NCHUNK);
         SCB_LAUNCH_CHECK();
         // (b) row strip: the remaining rows of the outer panel, all columns right of the panel
         const int nright = nt - inner_rem;
         if (nright > 0) {
           dim3 gb(2 * nright, inner_rem);
-          update_kernel<<<gb, 256, upd_smem, s>>>(M, n_pad, o + NB, panel_end, Lpack, Upack, tile_chunks,
-                                                  i * NCHUNK, NCHUNK, 0u);
+          update_kernel<<<gb, 256, upd_smem, st>>>(M, n_pad, o + NB, panel_end, Lpack, Upack, tile_chunks,
+                                                   i * NCHUNK, NCHUNK);
           SCB_LAUNCH_CHECK();
         }
       }
     }
-    const int ntb = (int)(nb - kb - q_eff);  // 128-tiles after the outer panel
-    if (ntb > 0) {
-      dim3 grid(2 * ntb, ntb);
-      update_kernel<<<grid, 256, upd_smem, s>>>(M, n_pad, panel_end, panel_end, Lpack, Upack, tile_chunks, 0,
-                                                q_eff * NCHUNK, (unsigned)(ntb >= 24 ? g_stagger_ns : 0));
+    return SCB_OK;
+  };
+
+  const int64_t np = (nb + q - 1) / q;
+  size_t ev = 0;
+  if (lookahead) {
+    cudaEvent_t e0 = ls.event(ev++);
+    SCB_CUDA(cudaEventRecord(e0, s));
+    SCB_CUDA(cudaStreamWaitEvent(sp, e0, 0));
+  }
+  if (int rc = factor_panel(0, sp)) return rc;
+  for (int64_t P = 0; P < np; P++) {
+    const int64_t kb = P * q;
+    const int q_eff = (int)((nb - kb) < q ? (nb - kb) : q);
+    const int64_t e0 = (kb + q_eff) * NB;  // first row/col after panel P
+    if (e0 >= n_pad) break;
+    const int64_t e1 = (e0 + (int64_t)q * NB) < n_pad ? (e0 + (int64_t)q * NB) : n_pad;  // end of panel P+1
+    const double* Lpack = pack_base + (P & 1) * pack_set;
+    const double* Upack = Lpack + n_pad * NB * q;
+    const int nchunks = q_eff * NCHUNK;
+    if (lookahead) {  // the main stream waits for the factorization of panel P
+      cudaEvent_t e = ls.event(ev++);
+      SCB_CUDA(cudaEventRecord(e, sp));
+      SCB_CUDA(cudaStreamWaitEvent(s, e, 0));
+    }
+    // A: the L-shaped strip that panel P+1 lives in (rows e0..e1 x all columns, rows below x cols e0..e1)
+    const int nt0 = (int)((n_pad - e0) / NB), ntp = (int)((e1 - e0) / NB), nt1 = (int)((n_pad - e1) / NB);
+    {
+      dim3 g1(2 * nt0, ntp);
+      update_kernel<<<g1, 256, upd_smem, s>>>(M, n_pad, e0, e0, Lpack, Upack, tile_chunks, 0, nchunks);
+      SCB_LAUNCH_CHECK();
+      if (nt1 > 0) {
+        dim3 g2(2 * ntp, nt1);
+        update_kernel<<<g2, 256, upd_smem, s>>>(M, n_pad, e1, e0, Lpack, Upack, tile_chunks, 0, nchunks);
+        SCB_LAUNCH_CHECK();
+      }
+    }
+    if (lookahead) {  // panel P+1 can be factored as soon as its strip is up to date
+      cudaEvent_t e = ls.event(ev++);
+      SCB_CUDA(cudaEventRecord(e, s));
+      SCB_CUDA(cudaStreamWaitEvent(sp, e, 0));
+    }
+    if (int rc = factor_panel(P + 1, sp)) return rc;
+    // B: the rest of the trailing block, concurrently with the factorization of panel P+1
+    if (nt1 > 0) {
+      dim3 g3(2 * nt1, nt1);
+      update_kernel<<<g3, 256, upd_smem, s>>>(M, n_pad, e1, e1, Lpack, Upack, tile_chunks, 0, nchunks);
       SCB_LAUNCH_CHECK();
     }
+  }
+  if (lookahead) {
+    cudaEvent_t e = ls.event(ev++);
+    SCB_CUDA(cudaEventRecord(e, sp));
+    SCB_CUDA(cudaStreamWaitEvent(s, e, 0));
   }
   return SCB_OK;
 }
