@@ -190,7 +190,9 @@ update_kernel(double* __restrict__ M, int64_t ld, int64_t row0, int64_t col0,
 // ---------------------------------------------------------------------------------------
 constexpr int TA_LD = KC + 4;  // 36: A chunk [TM][36]   (ld % 16 == 4 -> conflict-free fragments)
 
-template <int TM, int TN, int WMW, int WNW>
+// TRI = 1: B is upper triangular (B[k][n] = 0 for k > n): a warp skips chunk c when c > wn.
+// TRI = 2: A is lower triangular (A[m][k] = 0 for k > m): a warp skips chunk c when c > wm.
+template <int TM, int TN, int WMW, int WNW, int TRI>
 __device__ __forceinline__ void gemm_k128(const double* __restrict__ A, int64_t lda,
                                           const double* __restrict__ B, int64_t ldb, double* As,
                                           double* Bs, double (&acc)[4][4][2]) {
@@ -223,6 +225,7 @@ __device__ __forceinline__ void gemm_k128(const double* __restrict__ A, int64_t 
           *reinterpret_cast<const double2*>(B + (int64_t)(c * KC + kr) * ldb + cc);
     }
     __syncthreads();
+    if ((TRI == 1 && c > wn) || (TRI == 2 && c > wm)) continue;  // structurally zero block
 #pragma unroll
     for (int s = 0; s < 8; s++) {
       double a[4], b[4];
@@ -258,7 +261,7 @@ trsm_kernel(double* __restrict__ M, int64_t ld, int64_t o, int ncol, const doubl
     const int tile = blockIdx.x;
     double* Atile = M + (o2 + (int64_t)tile * 64) * ld + o;
     double* Bs = As + 64 * TA_LD;
-    gemm_k128<64, 128, 2, 4>(Atile, ld, invU, NB, As, Bs, acc);
+    gemm_k128<64, 128, 2, 4, 1>(Atile, ld, invU, NB, As, Bs, acc);
     const int wm = warp / 4, wn = warp % 4;
     double* P = Lpack + ((o2 >> 7) + (tile >> 1)) * ((int64_t)tile_chunks * A_CHUNK) + (int64_t)chunk0 * A_CHUNK;
     const int rbase = (tile & 1) * 64;
@@ -277,7 +280,7 @@ trsm_kernel(double* __restrict__ M, int64_t ld, int64_t o, int ncol, const doubl
     const int tile = blockIdx.x - ncol;
     double* Btile = M + o * ld + o2 + (int64_t)tile * 64;
     double* Bs = As + 128 * TA_LD;
-    gemm_k128<128, 64, 4, 2>(invL, NB, Btile, ld, As, Bs, acc);
+    gemm_k128<128, 64, 4, 2, 2>(invL, NB, Btile, ld, As, Bs, acc);
     const int wm = warp / 2, wn = warp % 2;
     double* P = Upack + ((o2 >> 6) + tile) * ((int64_t)tile_chunks * B_CHUNK) + (int64_t)chunk0 * B_CHUNK;
 #pragma unroll
