@@ -765,11 +765,20 @@ struct LuStreams {
 };
 static LuStreams g_lu_streams[64];
 
+// offset (in doubles) of the small integer scratch used by scb_getrs_nopiv (ready flags + work counter)
+namespace scb {
+int64_t lu_flags_offset(int64_t n_pad) {
+  const int64_t nb = n_pad / NB;
+  return nb * 2 * NB * NB + 4 * n_pad * NB * lu_outer_blocks();
+}
+}  // namespace scb
+
 extern "C" int64_t scb_getrf_dinv_bytes(int64_t n_pad) {
   const int64_t nb = n_pad / NB;
   // [nb][2][128][128] block inverses + 2 x (Lpack [n_pad x KB] + Upack [KB x n_pad]), KB = q * 128
   // (two pack sets: the next outer panel is factored while the previous one is still being applied)
-  return (nb * 2 * NB * NB + 4 * n_pad * NB * lu_outer_blocks()) * (int64_t)sizeof(double);
+  // + getrs scratch (nb ready flags + counters)
+  return (lu_flags_offset(n_pad) + nb + 16) * (int64_t)sizeof(double);
 }
 
 // Two-level right-looking LU with look-ahead.
@@ -819,6 +828,8 @@ extern "C" int scb_getrf_nopiv(int64_t n_pad, double* M, double* dinv, int32_t* 
     sp = ls.panel;
   }
   SCB_CUDA(cudaMemsetAsync(info, 0, sizeof(int32_t), s));
+  // ready flags / counters of scb_getrs_nopiv live behind the packed panels: start from zero
+  SCB_CUDA(cudaMemsetAsync(dinv + lu_flags_offset(n_pad), 0, (nb + 16) * sizeof(double), s));
 
   // factorization of outer panel P (inner blocks kb .. kb+q_eff-1) on stream st, packs -> set (P & 1)
   auto factor_panel = [&](int64_t P, cudaStream_t st) -> int {

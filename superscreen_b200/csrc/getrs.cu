@@ -1,16 +1,21 @@
 // Multi-RHS triangular solves with the no-pivot LU (K12): scipy.linalg.lu_solve at
 // solver/solve_film.py:367,388,530,545.
 //
-// Right-looking blocked substitution over the 128-row blocks of the factorization.  One kernel per
-// block step k:  every CTA applies the rank-128 update  B[i] -= F[i, block k] x_k  to its share of
-// the rows still to be solved (one warp per row, 1 KB coalesced reads of the factor row), and
-// CTA 0 -- which owns the 128 rows of the NEXT block -- finishes that block with the stored inverse
-// of its diagonal block (x_next = inv(F_next,next) b_next), so the next kernel starts from a
-// finished x.  The chain per step is therefore launch + one tall GEMV + one 128x128 GEMV by a
-// single CTA; nrhs = 1 is HBM-bound in the limit (8 n^2 bytes for both sweeps).
+// One PERSISTENT kernel per sweep (forward L y = b, backward U x = y).  The factor is processed in
+// 128-row blocks; CTAs grab blocks in sweep order from an atomic work counter (so a CTA only ever
+// waits for blocks that are already owned by running or finished CTAs: deadlock-free without
+// co-residency assumptions).  For its block i a CTA streams the block row of the factor,
+//     acc_i = b_i - sum_{j before i} F_ij x_j ,
+// waiting on a per-block ready flag before it touches x_j, then finishes the block with the stored
+// inverse of the diagonal block, x_i = inv(F_ii) acc_i, publishes x_i (threadfence + flag) and grabs
+// the next block.  The critical chain per block is flag -> one 128x128 GEMV whose factor rows are
+// already in registers -> one 128x128 GEMV from L2-prefetched data -> flag; all the HBM traffic
+// (8 n^2 bytes for both sweeps at nrhs <= 8) streams off the chain.
 #include "scb_common.cuh"
 
 namespace scb {
+
+int64_t lu_flags_offset(int64_t n_pad);  // getrf.cu
 
 constexpr int NB = SCB_LU_BLOCK;
 
@@ -32,123 +37,115 @@ __device__ __forceinline__ void row_dot(const double (&a)[4], const double (*xs)
   }
 }
 
-// step kernel.  x_k (final) is stored in rows [k*128, k*128+128) of B.
-//   do_update : apply B[i] -= F[i, block k] x_k for rows in [row_lo, row_hi) (minus the next block)
-//   next      : index of the block to finish (x_next = dnext * b_next), or -1
-template <int RT>  // rhs columns per pass (1 for the single right-hand side of solve_film, else 8)
+__device__ __forceinline__ void prefetch_tile_l2(const double* tile, int64_t ld_bytes, int warp, int lane) {
+  // 128 rows x 1 KB: warp w covers rows 16w..16w+15, lane -> (row, 128-byte line)
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    const int idx = q * 32 + lane;  // 0..127 -> 16 rows x 8 lines
+    const int r = warp * 16 + (idx >> 3), line = idx & 7;
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(tile) + r * ld_bytes + line * 128));
+  }
+}
+
+// RT: right-hand sides per pass.  lower = 1: forward sweep with L (unit diagonal handled through the
+// stored inverse), lower = 0: backward sweep with U.
+template <int RT>
 __global__ void __launch_bounds__(256)
-getrs_step_kernel(const double* __restrict__ F, int64_t ld, const double* __restrict__ dnext, int64_t k,
-                  int64_t next, int do_update, int64_t nrhs, double* __restrict__ B, int64_t row_lo,
-                  int64_t row_hi) {
+trsv_sweep_kernel(const double* __restrict__ F, int64_t ld, const double* __restrict__ dinv, int64_t nb,
+                  int lower, int64_t nrhs, int64_t r0, double* __restrict__ B, int* __restrict__ flags,
+                  int* __restrict__ counter, int epoch) {
   __shared__ double xs[NB][RT + 1];
   __shared__ double bs[NB][RT + 1];
+  __shared__ int s_p;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int64_t o = k * NB;
-  const int64_t on = next * NB;
-  for (int64_t r0 = 0; r0 < nrhs; r0 += RT) {
-    const int nr = (int)((nrhs - r0) < RT ? (nrhs - r0) : RT);
+  const int nr = (int)((nrhs - r0) < RT ? (nrhs - r0) : RT);
+  const int64_t ldb = ld * (int64_t)sizeof(double);
+  for (;;) {
     __syncthreads();
-    if (do_update) {
+    if (tid == 0) s_p = atomicAdd(counter, 1);
+    __syncthreads();
+    const int p = s_p;  // position in sweep order
+    if (p >= nb) break;
+    const int64_t i = lower ? p : nb - 1 - p;
+    const double* dblk = dinv + i * 2 * NB * NB + (lower ? 0 : NB * NB);
+    prefetch_tile_l2(dblk, NB * sizeof(double), warp, lane);
+    // right-hand side entries of my 16 rows (lane c < nr holds column c)
+    double bval[16];
+#pragma unroll
+    for (int rr = 0; rr < 16; rr++) bval[rr] = lane < nr ? B[(i * NB + warp + 8 * rr) * nrhs + r0 + lane] : 0.0;
+    if (p > 0) {
+      const int64_t j0 = lower ? 0 : nb - 1;
+      prefetch_tile_l2(F + i * NB * ld + j0 * NB, ldb, warp, lane);
+    }
+    for (int q = 0; q < p; q++) {
+      const int64_t j = lower ? q : nb - 1 - q;
+      // factor rows first (independent of x_j), next tile into L2, then wait for x_j
+      double fa[16][4];
+#pragma unroll
+      for (int rr = 0; rr < 16; rr++) {
+        const double* Frow = F + (i * NB + warp + 8 * rr) * ld + j * NB;
+#pragma unroll
+        for (int k = 0; k < 4; k++) fa[rr][k] = Frow[lane + 32 * k];
+      }
+      if (q + 1 < p) {
+        const int64_t jn = lower ? q + 1 : nb - 2 - q;
+        prefetch_tile_l2(F + i * NB * ld + jn * NB, ldb, warp, lane);
+      }
+      if (tid == 0) {
+        while (*reinterpret_cast<volatile int*>(flags + j) != epoch) {
+        }
+        __threadfence();
+      }
+      __syncthreads();
       for (int idx = tid; idx < NB * RT; idx += 256) {
         const int r = idx / RT, c = idx % RT;
-        xs[r][c] = c < nr ? B[(o + r) * nrhs + r0 + c] : 0.0;
+        xs[r][c] = c < nr ? __ldcg(&B[(j * NB + r) * nrhs + r0 + c]) : 0.0;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int rr = 0; rr < 16; rr++) {
+        double accv[RT];
+        row_dot<RT>(fa[rr], xs, lane, accv);
+        double v = 0.0;
+#pragma unroll
+        for (int c = 0; c < RT; c++) v = (lane == c) ? accv[c] : v;
+        bval[rr] -= v;
       }
     }
+    // finish: x_i = inv(F_ii) acc_i
+#pragma unroll
+    for (int rr = 0; rr < 16; rr++)
+      if (lane < RT) bs[warp + 8 * rr][lane] = bval[rr];
+    double da[16][4];
+#pragma unroll
+    for (int rr = 0; rr < 16; rr++) {
+      const double* Drow = dblk + (int64_t)(warp + 8 * rr) * NB;
+#pragma unroll
+      for (int k = 0; k < 4; k++) da[rr][k] = Drow[lane + 32 * k];
+    }
     __syncthreads();
-    if (blockIdx.x == 0) {
-      if (next >= 0) {
-        // The 128 rows of the next block; each warp owns 16 rows.  The rows of the stored inverse
-        // are prefetched into L2 first, and the 64 loads of each phase are issued up front, so a
-        // step costs two short memory round trips instead of 32 dependent ones.
-        {
-          const char* base = reinterpret_cast<const char*>(dnext);
 #pragma unroll
-          for (int q = 0; q < 4; q++) {
-            const int line = (warp * 4 + q) * 32 + lane;  // 1024 lines of 128 B = 128 KB
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (int64_t)line * 128));
-          }
-        }
-        double bval[16];
+    for (int rr = 0; rr < 16; rr++) {
+      double accv[RT];
+      row_dot<RT>(da[rr], bs, lane, accv);
+      if (lane < nr) {
+        double v = 0.0;
 #pragma unroll
-        for (int rr = 0; rr < 16; rr++) {
-          const int r = warp + 8 * rr;
-          bval[rr] = lane < nr ? B[(on + r) * nrhs + r0 + lane] : 0.0;
-        }
-        if (do_update) {
-          double fa[16][4];
-#pragma unroll
-          for (int rr = 0; rr < 16; rr++) {
-            const double* Frow = F + (on + warp + 8 * rr) * ld + o;
-#pragma unroll
-            for (int q = 0; q < 4; q++) fa[rr][q] = Frow[lane + 32 * q];
-          }
-#pragma unroll
-          for (int rr = 0; rr < 16; rr++) {
-            double accv[RT];
-            row_dot<RT>(fa[rr], xs, lane, accv);
-            double v = 0.0;
-#pragma unroll
-            for (int c = 0; c < RT; c++) v = (lane == c) ? accv[c] : v;
-            bval[rr] -= v;
-          }
-        }
-#pragma unroll
-        for (int rr = 0; rr < 16; rr++)
-          if (lane < RT) bs[warp + 8 * rr][lane] = bval[rr];
-        __syncthreads();
-        {
-          double da[16][4];
-#pragma unroll
-          for (int rr = 0; rr < 16; rr++) {
-            const double* Drow = dnext + (int64_t)(warp + 8 * rr) * NB;
-#pragma unroll
-            for (int q = 0; q < 4; q++) da[rr][q] = Drow[lane + 32 * q];
-          }
-#pragma unroll
-          for (int rr = 0; rr < 16; rr++) {
-            double accv[RT];
-            row_dot<RT>(da[rr], bs, lane, accv);
-            if (lane < nr) {
-              double v = 0.0;
-#pragma unroll
-              for (int c = 0; c < RT; c++) v = (lane == c) ? accv[c] : v;
-              B[(on + warp + 8 * rr) * nrhs + r0 + lane] = v;
-            }
-          }
-        }
+        for (int c = 0; c < RT; c++) v = (lane == c) ? accv[c] : v;
+        B[(i * NB + warp + 8 * rr) * nrhs + r0 + lane] = v;
       }
-    } else if (do_update) {
-      // rank-128 update of the remaining rows (next block excluded): 2 rows per warp, all loads
-      // (factor rows and the right-hand-side entries) issued before the first use
-      const int64_t i0 = row_lo + ((int64_t)(blockIdx.x - 1) * 8 + warp) * 2;
-      double a[2][4], bv[2];
-      bool ok[2];
-#pragma unroll
-      for (int u = 0; u < 2; u++) {
-        const int64_t i = i0 + u;
-        ok[u] = i < row_hi && !(next >= 0 && i >= on && i < on + NB);
-        if (ok[u]) {
-          const double* Frow = F + i * ld + o;
-#pragma unroll
-          for (int q = 0; q < 4; q++) a[u][q] = Frow[lane + 32 * q];
-          bv[u] = lane < nr ? B[i * nrhs + r0 + lane] : 0.0;
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < 2; u++) {
-        if (!ok[u]) continue;
-        double accv[RT];
-        row_dot<RT>(a[u], xs, lane, accv);
-        if (lane < nr) {
-          double v = 0.0;
-#pragma unroll
-          for (int c = 0; c < RT; c++) v = (lane == c) ? accv[c] : v;
-          B[(i0 + u) * nrhs + r0 + lane] = bv[u] - v;
-        }
-      }
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+      __threadfence();
+      *reinterpret_cast<volatile int*>(flags + i) = epoch;
     }
   }
 }
+
+static int g_epoch = 0;
+static int g_capacity[64][2] = {};  // resident CTAs per device for RT = 1 / 8
 
 }  // namespace scb
 
@@ -160,31 +157,35 @@ extern "C" int scb_getrs_nopiv(int64_t n_pad, const double* LU, const double* di
   SCB_CHECK_ARG(nrhs > 0, "nrhs must be positive");
   cudaStream_t s = (cudaStream_t)stream;
   const int64_t nb = n_pad / NB;
-  auto grid_for = [](int64_t rows) { return (int)((rows + 15) / 16) + 1; };  // CTA 0 + 16 rows per CTA
-  auto launch = [&](int grid, const double* dnext, int64_t k, int64_t next, int upd, int64_t lo, int64_t hi) {
-    if (nrhs == 1)
-      getrs_step_kernel<1><<<grid, 256, 0, s>>>(LU, n_pad, dnext, k, next, upd, nrhs, B, lo, hi);
+  int dev = 0;
+  SCB_CUDA(cudaGetDevice(&dev));
+  const int which = nrhs == 1 ? 0 : 1;
+  int& cap = g_capacity[dev & 63][which];
+  if (cap == 0) {
+    int per_sm = 0, sms = 0;
+    if (which == 0)
+      SCB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trsv_sweep_kernel<1>, 256, 0));
     else
-      getrs_step_kernel<8><<<grid, 256, 0, s>>>(LU, n_pad, dnext, k, next, upd, nrhs, B, lo, hi);
-  };
-  const double* invL = dinv;            // block k: dinv + k*2*128*128
-  const double* invU = dinv + NB * NB;  // block k: dinv + k*2*128*128 + 128*128
-  const int64_t bs = 2 * NB * NB;
-  // forward: L y = b.  prologue finishes block 0, step k updates rows below and finishes block k+1
-  launch(1, invL, 0, 0, 0, 0, 0);
-  SCB_LAUNCH_CHECK();
-  for (int64_t k = 0; k + 1 < nb; k++) {
-    const int64_t lo = (k + 1) * NB, hi = n_pad;
-    launch(grid_for(hi - lo), invL + (k + 1) * bs, k, k + 1, 1, lo, hi);
-    SCB_LAUNCH_CHECK();
+      SCB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trsv_sweep_kernel<8>, 256, 0));
+    SCB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    cap = per_sm * sms;
+    if (cap < 1) cap = 1;
   }
-  // backward: U x = y
-  launch(1, invU + (nb - 1) * bs, 0, nb - 1, 0, 0, 0);
-  SCB_LAUNCH_CHECK();
-  for (int64_t k = nb - 1; k >= 1; k--) {
-    const int64_t lo = 0, hi = k * NB;
-    launch(grid_for(hi - lo), invU + (k - 1) * bs, k, k - 1, 1, lo, hi);
-    SCB_LAUNCH_CHECK();
+  // integer scratch behind the packed panels of the factorization workspace
+  int* flags = reinterpret_cast<int*>(const_cast<double*>(dinv) + lu_flags_offset(n_pad));
+  int* counters = flags + nb;  // [0]: work counter
+  const int grid = (int)(nb < cap ? nb : cap);
+  const int RTv = which == 0 ? 1 : 8;
+  for (int lower = 1; lower >= 0; lower--) {
+    for (int64_t r0 = 0; r0 < nrhs; r0 += RTv) {
+      const int epoch = ++g_epoch;
+      SCB_CUDA(cudaMemsetAsync(counters, 0, sizeof(int), s));
+      if (which == 0)
+        trsv_sweep_kernel<1><<<grid, 256, 0, s>>>(LU, n_pad, dinv, nb, lower, nrhs, r0, B, flags, counters, epoch);
+      else
+        trsv_sweep_kernel<8><<<grid, 256, 0, s>>>(LU, n_pad, dinv, nb, lower, nrhs, r0, B, flags, counters, epoch);
+      SCB_LAUNCH_CHECK();
+    }
   }
   return SCB_OK;
 }
