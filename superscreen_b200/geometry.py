@@ -68,9 +68,9 @@ def orient_ccw(points: np.ndarray) -> np.ndarray:
 def path_vectors(path: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
     """Edge lengths and unit normals of a path (reference geometry.py:160-182)."""
     dr = np.diff(np.asarray(path, dtype=float), axis=0)
-    normals = np.cross(dr, [0, 0, 1])
+    normals = np.stack([dr[:, 1], -dr[:, 0]], axis=1)  # == np.cross(dr, [0, 0, 1])[:, :2]
     edge_lengths = np.linalg.norm(dr, axis=1)
-    unit_normals = normals[:, :2] / edge_lengths[:, np.newaxis]
+    unit_normals = normals / edge_lengths[:, np.newaxis]
     return edge_lengths, unit_normals
 
 

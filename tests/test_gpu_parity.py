@@ -274,3 +274,43 @@ def test_full_size_c2_properties(sc):
     # screening: |total field| in the centre is far below the applied 1 mT for Lambda << size
     centre = np.linalg.norm(sites, axis=1) < 2.0
     assert np.abs(s1.total_field[centre]).mean() < 0.2
+
+
+def test_non_delaunay_mesh_uses_refinement(sc, caplog):
+    """Vertex-perturbed (non-Delaunay) mesh: cotangent weights of interior edges can be negative, so
+    the row-dominance bound fails (SURVEY.md Q11 caveat).  The unpivoted LU + iterative refinement
+    must still reproduce the oracle's pivoted LAPACK solution."""
+    from oracle import port
+    from superscreen_b200.geometry import box
+    from superscreen_b200.synthetic import square_mesh
+
+    sites, elements = square_mesh(10.0, 2500, seed=21)
+    rng = np.random.default_rng(5)
+    om0 = port.build_mesh(sites, elements, with_Q=False)
+    interior = np.setdiff1d(np.arange(len(sites)), om0.boundary_indices)
+    h = np.sqrt(100.0 / len(sites))
+    moved = sites.copy()
+    moved[interior] += 0.42 * h * (rng.random((len(interior), 2)) * 2 - 1)
+    # keep only perturbations that leave every triangle counter-clockwise
+    p = moved[elements]
+    cross = (p[:, 1, 0] - p[:, 0, 0]) * (p[:, 2, 1] - p[:, 0, 1]) - (p[:, 1, 1] - p[:, 0, 1]) * (p[:, 2, 0] - p[:, 0, 0])
+    bad_vertices = np.unique(elements[cross <= 0.05 * h * h])
+    moved[bad_vertices] = sites[bad_vertices]
+    p = moved[elements]
+    cross = (p[:, 1, 0] - p[:, 0, 0]) * (p[:, 2, 1] - p[:, 0, 1]) - (p[:, 1, 1] - p[:, 0, 1]) * (p[:, 2, 0] - p[:, 0, 0])
+    assert (cross > 0).all()
+    device = sc.Device("sq", layers=[sc.Layer("layer", Lambda=2.0, z0=0.0)],
+                       films=[sc.Polygon("film", layer="layer", points=box(10.0, points=4))])
+    device.set_meshes({"film": (moved, elements)})
+    model = sc.factorize_model(device=device, current_units="uA")
+    system = model.film_systems["film"]
+    sol = sc.solve(model=model, applied_field=sc.ConstantField(1.0), check_inversion=True)[0]
+    fs = sol.film_solutions["film"]
+    om = port.build_mesh(moved, elements)
+    film = port.factorize_film(port.OracleFilm(name="film", mesh=om, z0=0.0, Lambda=np.full(len(sites), 2.0),
+                                               interior_indices=interior, hole_indices={}))
+    conv = port.field_conversion_mT_to_uA_per_um()
+    ref = port.solve_film(film, np.full(len(sites), conv), {}, conv)
+    assert rel_l2(fs.stream, ref.stream) <= TOL_SOLUTION, (rel_l2(fs.stream, ref.stream), system.refine)
+    assert rel_l2(fs.current_density, ref.current_density) <= TOL_SOLUTION
+    assert rel_l2(fs.total_field, ref.total_field) <= TOL_SOLUTION
