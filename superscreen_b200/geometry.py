@@ -86,17 +86,18 @@ def points_in_polygon(poly_points: np.ndarray, query_points: np.ndarray) -> np.n
     if len(poly) > 1 and np.array_equal(poly[0], poly[-1]):
         poly = poly[:-1]
     q = np.atleast_2d(np.asarray(query_points, dtype=float))
-    x, y = q[:, 0], q[:, 1]
-    inside = np.zeros(len(q), dtype=bool)
     x1, y1 = poly[:, 0], poly[:, 1]
     x2, y2 = np.roll(x1, -1), np.roll(y1, -1)
-    # loop over edges (polygons have O(100) vertices; queries are O(1e4-1e6))
-    for k in range(len(poly)):
-        cond = (y1[k] > y) != (y2[k] > y)
-        if not cond.any():
-            continue
-        denom = y2[k] - y1[k]
-        with np.errstate(divide="ignore", invalid="ignore"):
-            xint = (x2[k] - x1[k]) * (y - y1[k]) / denom + x1[k]
-        inside ^= cond & (x < xint)
+    dy = y2 - y1
+    with np.errstate(divide="ignore", invalid="ignore"):
+        slope = (x2 - x1) / dy
+    inside = np.zeros(len(q), dtype=bool)
+    chunk = max(1, (1 << 22) // max(1, len(poly)))  # bound the (points x edges) temporaries
+    for s in range(0, len(q), chunk):
+        x, y = q[s:s + chunk, 0][:, None], q[s:s + chunk, 1][:, None]
+        cond = (y1[None, :] > y) != (y2[None, :] > y)
+        with np.errstate(invalid="ignore"):
+            xint = slope[None, :] * (y - y1[None, :]) + x1[None, :]
+            crossing = cond & (x < xint)
+        inside[s:s + chunk] = np.count_nonzero(crossing, axis=1) & 1
     return inside

@@ -66,32 +66,65 @@ class FilmSolution:
         return self._total_field
 
 
+_LOCATORS: Dict[int, Any] = {}
+
+
+def _triangle_locator(sites: np.ndarray, elements: np.ndarray):
+    """KD-tree over triangle centroids, cached per elements array."""
+    from scipy.spatial import cKDTree
+
+    key = (id(elements), id(sites))
+    hit = _LOCATORS.get(key)
+    if hit is None or hit[0] is not elements or hit[1] is not sites:
+        hit = (elements, sites, cKDTree(sites[elements].mean(axis=1)))
+        if len(_LOCATORS) > 64:
+            _LOCATORS.clear()
+        _LOCATORS[key] = hit
+    return hit[2]
+
+
+def _barycentric(p: np.ndarray, xy: np.ndarray):
+    """Barycentric coordinates of points xy (q, 2) in triangles p (q, k, 3, 2) -> (q, k, 3)."""
+    a, b, c = p[..., 0, :], p[..., 1, :], p[..., 2, :]
+    det = (b[..., 1] - c[..., 1]) * (a[..., 0] - c[..., 0]) + (c[..., 0] - b[..., 0]) * (a[..., 1] - c[..., 1])
+    dx = xy[:, None, 0] - c[..., 0]
+    dy = xy[:, None, 1] - c[..., 1]
+    l1 = ((b[..., 1] - c[..., 1]) * dx + (c[..., 0] - b[..., 0]) * dy) / det
+    l2 = ((c[..., 1] - a[..., 1]) * dx + (a[..., 0] - c[..., 0]) * dy) / det
+    return np.stack([l1, l2, 1.0 - l1 - l2], axis=-1)
+
+
 def linear_tri_interpolate(sites: np.ndarray, elements: np.ndarray, values: np.ndarray, xy: np.ndarray,
-                           chunk: int = 256) -> np.ndarray:
+                           candidates: int = 16) -> np.ndarray:
     """Piecewise-linear interpolation on a triangulation; NaN outside the mesh.  Stands in for
-    ``matplotlib.tri.LinearTriInterpolator`` (reference solution.py:272-276,310-312)."""
+    ``matplotlib.tri.LinearTriInterpolator`` (reference solution.py:272-276,310-312).  The containing
+    triangle is searched among the triangles with the nearest centroids (all triangles as a
+    fallback for points that are not resolved that way)."""
     xy = np.atleast_2d(np.asarray(xy, dtype=float))
     values = np.asarray(values, dtype=float)
-    p = sites[elements]
-    a, b, c = p[:, 0], p[:, 1], p[:, 2]
-    det = (b[:, 1] - c[:, 1]) * (a[:, 0] - c[:, 0]) + (c[:, 0] - b[:, 0]) * (a[:, 1] - c[:, 1])
     out = np.full((len(xy),) + values.shape[1:], np.nan)
-    for s in range(0, len(xy), chunk):
-        q = xy[s:s + chunk]
-        dx = q[:, 0][:, None] - c[None, :, 0]
-        dy = q[:, 1][:, None] - c[None, :, 1]
-        l1 = ((b[:, 1] - c[:, 1])[None] * dx + (c[:, 0] - b[:, 0])[None] * dy) / det[None]
-        l2 = ((c[:, 1] - a[:, 1])[None] * dx + (a[:, 0] - c[:, 0])[None] * dy) / det[None]
-        l3 = 1.0 - l1 - l2
-        mn = np.minimum(np.minimum(l1, l2), l3)
-        t = np.argmax(mn, axis=1)
-        r = np.arange(len(q))
-        ok = mn[r, t] >= -1e-12
-        v = values[elements[t]]  # (q, 3, ...)
-        w = np.stack([l1[r, t], l2[r, t], l3[r, t]], axis=1)
-        res = np.einsum("qk,qk...->q...", w, v)
-        res[~ok] = np.nan
-        out[s:s + chunk] = res
+    if len(xy) == 0:
+        return out
+    k = min(candidates, len(elements))
+    _, cand = _triangle_locator(sites, elements).query(xy, k=k)
+    cand = cand.reshape(len(xy), k)
+    lam = _barycentric(sites[elements[cand]], xy)          # (q, k, 3)
+    mn = lam.min(axis=2)
+    best = np.argmax(mn, axis=1)
+    r = np.arange(len(xy))
+    ok = mn[r, best] >= -1e-12
+    tri = cand[r, best]
+    w = lam[r, best]
+    # unresolved points: exhaustive search (outside the mesh, or very anisotropic neighbourhoods)
+    for q in np.where(~ok)[0]:
+        lam_all = _barycentric(sites[elements][None, :, :, :], xy[q:q + 1])[0]
+        mn_all = lam_all.min(axis=1)
+        t = int(np.argmax(mn_all))
+        if mn_all[t] >= -1e-12:
+            ok[q], tri[q], w[q] = True, t, lam_all[t]
+    v = values[elements[tri]]                                # (q, 3, ...)
+    res = np.einsum("qk,qk...->q...", w, v)
+    out[ok] = res[ok]
     return out
 
 

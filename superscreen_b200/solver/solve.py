@@ -131,26 +131,34 @@ def factorize_model(*, device: Device, current_units: str, terminal_currents=Non
                            circulating_currents, vortices, current_units, comm)
 
 
-def _to_solution(device, film_names, results, applied_fields, others, field_conversion, solution_kwargs,
-                 batch_index=None) -> Solution:
-    """Device tensors (solver units) -> host FilmSolutions (reference solve_film.py:566-573)."""
-    film_solutions = {}
+def _to_solutions(device, film_names, results, applied_fields, others, field_conversion, kwargs_list):
+    """Device tensors (solver units) -> host FilmSolutions (reference solve_film.py:566-573).  One
+    device->host copy per array per film, shared by all batch entries; ``kwargs_list`` holds the
+    Solution keyword arguments of every batch entry (length 1 when not batched)."""
+    host = {}
     for name in film_names:
         g, J, self_field = results[name]
-        applied = applied_fields[name]
-        other = None if others is None else others[name]
-        if batch_index is not None:
-            g, J, self_field = g[:, batch_index], J[batch_index], self_field[:, batch_index]
-            applied = applied[:, batch_index]
-            other = None if other is None else other[:, batch_index]
-        film_solutions[name] = FilmSolution(
-            stream=g.cpu().numpy(),
-            current_density=J.cpu().numpy(),
-            applied_field=(applied / field_conversion).cpu().numpy(),
-            self_field=(self_field / field_conversion).cpu().numpy(),
-            field_from_other_films=None if other is None else (other / field_conversion).cpu().numpy(),
+        host[name] = (
+            g.cpu().numpy(), J.cpu().numpy(),
+            (applied_fields[name] / field_conversion).cpu().numpy(),
+            (self_field / field_conversion).cpu().numpy(),
+            None if others is None else (others[name] / field_conversion).cpu().numpy(),
         )
-    return Solution(device=device, film_solutions=film_solutions, **solution_kwargs)
+    batched = next(iter(results.values()))[0].dim() == 2
+    out = []
+    for b, kwargs in enumerate(kwargs_list):
+        film_solutions = {}
+        for name in film_names:
+            g, J, applied, self_field, other = host[name]
+            if batched:
+                g, J, applied, self_field = g[:, b], J[b], applied[:, b], self_field[:, b]
+                other = None if other is None else other[:, b]
+            film_solutions[name] = FilmSolution(
+                stream=np.ascontiguousarray(g), current_density=np.ascontiguousarray(J),
+                applied_field=np.ascontiguousarray(applied), self_field=np.ascontiguousarray(self_field),
+                field_from_other_films=None if other is None else np.ascontiguousarray(other))
+        out.append(Solution(device=device, film_solutions=film_solutions, **kwargs))
+    return out
 
 
 def _evaluate_applied_field(applied_field, device, film_info, meshes, field_conversion):
@@ -266,8 +274,8 @@ def solve(device: Optional[Device] = None, *, model: Optional[FactorizedModel] =
     if not return_solutions:
         return None
     film_names = list(device.films)
-    return [_to_solution(device, film_names, results, applied_fields, others, field_conversion, solution_kwargs)
-            for results, others in per_iter]
+    return [_to_solutions(device, film_names, results, applied_fields, others, field_conversion,
+                          [solution_kwargs])[0] for results, others in per_iter]
 
 
 def solve_batch(*, model: FactorizedModel, applied_fields: Sequence[Optional[Callable]],
@@ -315,11 +323,10 @@ def solve_batch(*, model: FactorizedModel, applied_fields: Sequence[Optional[Cal
         }
     vortex_flux = _u.PHI_0 / _u.MU_0 * _u.conversion_factor("A * m", f"({current_units}) * ({length_units})")
     per_iter = _run(model, dev_fields, circ_by_film, vortex_flux, iterations, check_inversion)
-    out: List[List[Solution]] = []
-    for b in range(B):
-        kwargs = dict(applied_field_func=funcs[b], field_units=field_units, current_units=current_units,
-                      circulating_currents=dict(circulating_currents[b]),
-                      terminal_currents=model.terminal_currents, vortices=model.vortices, solver=_solver)
-        out.append([_to_solution(device, film_names, results, dev_fields, others, field_conversion, kwargs,
-                                 batch_index=b) for results, others in per_iter])
-    return out
+    kwargs_list = [dict(applied_field_func=funcs[b], field_units=field_units, current_units=current_units,
+                        circulating_currents=dict(circulating_currents[b]),
+                        terminal_currents=model.terminal_currents, vortices=model.vortices, solver=_solver)
+                   for b in range(B)]
+    per_iter_solutions = [_to_solutions(device, film_names, results, dev_fields, others, field_conversion,
+                                        kwargs_list) for results, others in per_iter]
+    return [[it[b] for it in per_iter_solutions] for b in range(B)]
