@@ -88,16 +88,16 @@ def points_in_polygon(poly_points: np.ndarray, query_points: np.ndarray) -> np.n
     q = np.atleast_2d(np.asarray(query_points, dtype=float))
     x1, y1 = poly[:, 0], poly[:, 1]
     x2, y2 = np.roll(x1, -1), np.roll(y1, -1)
-    dy = y2 - y1
-    with np.errstate(divide="ignore", invalid="ignore"):
-        slope = (x2 - x1) / dy
+    dx, dy = x2 - x1, y2 - y1
     inside = np.zeros(len(q), dtype=bool)
     chunk = max(1, (1 << 22) // max(1, len(poly)))  # bound the (points x edges) temporaries
     for s in range(0, len(q), chunk):
         x, y = q[s:s + chunk, 0][:, None], q[s:s + chunk, 1][:, None]
         cond = (y1[None, :] > y) != (y2[None, :] > y)
-        with np.errstate(invalid="ignore"):
-            xint = slope[None, :] * (y - y1[None, :]) + x1[None, :]
+        # same operation order as the scalar formula (x2-x1)*(y-y1)/(y2-y1)+x1: mesh vertices that
+        # lie exactly ON a polygon vertex/edge must classify reproducibly (golden index sets)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            xint = dx[None, :] * (y - y1[None, :]) / dy[None, :] + x1[None, :]
             crossing = cond & (x < xint)
         inside[s:s + chunk] = np.count_nonzero(crossing, axis=1) & 1
     return inside

@@ -85,3 +85,32 @@ def test_device_model_and_error_paths():
         sc.Device("bad", layers=[layer], films=[sc.Polygon("f", layer="nope", points=circle(1, 16))])
     with pytest.raises(ValueError):
         sc.Layer("x")
+
+
+def test_index_sets_reproduce_golden(golden):
+    """Mesh vertices lie exactly ON the film / hole polygons, so the point-in-polygon arithmetic must
+    be reproducible bit for bit: the golden index sets are inputs of both the oracle and the CUDA path."""
+    g = golden("ring")
+    hole = np.where(points_in_polygon(g["in_hole_polygon"], g["in_sites"]))[0]
+    assert np.array_equal(hole, g["in_hole_indices"])
+    g = golden("two_rings")
+    for k in ("lower", "upper"):
+        hole = np.where(points_in_polygon(g[f"in_{k}_hole_polygon"], g[f"in_{k}_sites"]))[0]
+        assert np.array_equal(hole, g[f"in_{k}_hole_indices"])
+        film = np.where(points_in_polygon(g[f"in_{k}_film_polygon"], g[f"in_{k}_sites"]))[0]
+        assert set(g[f"in_{k}_interior_indices"]).issubset(set(film))
+
+
+def test_linear_tri_interpolate_matches_bruteforce():
+    from oracle import port
+    from superscreen_b200.solution import linear_tri_interpolate
+
+    rng = np.random.default_rng(0)
+    sites, el = disk_mesh(4.4, 1500, embedded=[circle(4, 64), circle(2, 40)])
+    vals = np.column_stack([np.sin(sites[:, 0]), sites[:, 1] ** 2])
+    pts = np.concatenate([circle(3.0, 201), rng.uniform(-5, 5, (200, 2))])
+    a = linear_tri_interpolate(sites, el, vals, pts)
+    b = port.linear_tri_interp(sites, el, vals, pts)
+    m = np.isfinite(b).all(axis=1)
+    assert np.array_equal(np.isfinite(a).all(axis=1), m)
+    assert np.abs(a[m] - b[m]).max() <= 1e-13
