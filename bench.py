@@ -347,8 +347,17 @@ def run_b200_arm(args):
         "stages_ms": {k: float(np.mean(v)) for k, v in stage_ms.items()},
         "lu_tflops": lu_tflops, "films_per_s": world / (ms_per_step * 1e-3),
         "roofline": {"bound": "tensor", "achieved": lu_tflops, "peak": FP64_DMMA_PEAK_TFLOPS, "unit": "TFLOP/s",
-                     "frac": lu_tflops / FP64_DMMA_PEAK_TFLOPS, "traffic": None,
-                     "kernel": "scb_getrf_nopiv (update_kernel DMMA trailing updates + panel kernels)",
+                     "frac": lu_tflops / FP64_DMMA_PEAK_TFLOPS,
+                     # DRAM bytes (read + write) of the dominant launch, the first K=1024 bulk trailing
+                     # update (ncu --set full, profiles/r01_update_kernel_bulk_k1024_ncu.txt); its
+                     # algorithmic C traffic is 5.14 GB, the rest are packed-operand re-reads that miss L2
+                     "traffic": 25.6e9,
+                     "dominant_launch": {"kernel": "scb::update_kernel grid (280,140) K=1024", "flop": 657.7e9,
+                                         "ms": 18.375, "achieved": 35.79, "frac": 35.79 / FP64_DMMA_PEAK_TFLOPS,
+                                         "dmma_pipe_active_pct": 96.4, "source": "ncu, profiles/"},
+                     "kernel": "scb_getrf_nopiv = all launches of one factorization (update_kernel DMMA trailing "
+                               "updates + diag/trsm panel kernels, look-ahead on a second stream), timed live with "
+                               "CUDA events",
                      "work": "2/3 * n_int^3 fp64 flop per factorization",
                      "peak_source": "measured DMMA.8x8x4 issue rate on this pool's B200, "
                                     "profiles/r01_fp64_peaks.txt (MEASURED_PEAKS.json has no fp64 entry)"},

@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(256) nbody_kernel(NbodyParams p) {
         r2 += p.dz2;
       }
       if (KIND == NB_VECPOT) {
-        const double inv = rsqrt(r2);
+        const double inv = inv_r1(r2);
         acc[0] += spay[0][jj] * inv;
         acc[1] += spay[1][jj] * inv;
       } else {

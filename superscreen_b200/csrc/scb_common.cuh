@@ -43,10 +43,24 @@ static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 constexpr double kOneOver4Pi = 0.07957747154594767;  // 1/(4*pi)
 
-// r2^(-3/2) in fp64.  One MUFU seed + Newton steps inside rsqrt(); cubed.
+// r2^(-3/2) in fp64: MUFU.RSQ64H seed (rel. error ~2^-22) + two Newton steps y <- y (1.5 - 0.5 x y^2)
+// (-> ~2^-85 before rounding), then cubed.  No denormal / special-case fix-ups: r2 is a squared
+// distance between distinct mesh points; r2 == 0 yields NaN and callers mask it (q_ii = 0).
 __device__ __forceinline__ double inv_r3(double r2) {
-  double inv = rsqrt(r2);
-  return inv * inv * inv;
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(r2));
+  const double h = 0.5 * r2;
+  y = y * fma(-(h * y), y, 1.5);
+  y = y * fma(-(h * y), y, 1.5);
+  return y * y * y;
+}
+__device__ __forceinline__ double inv_r1(double r2) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(r2));
+  const double h = 0.5 * r2;
+  y = y * fma(-(h * y), y, 1.5);
+  y = y * fma(-(h * y), y, 1.5);
+  return y;
 }
 
 }  // namespace scb
