@@ -21,6 +21,13 @@ import tempfile
 import threading
 import time
 
+if "reference" in sys.argv:
+    # The CPU arm must use every host core.  torchrun exports OMP_NUM_THREADS=1 to its workers; the
+    # BLAS / numba thread pools read these variables when they are first imported, so set them
+    # before numpy / scipy / numba are loaded.
+    for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS", "NUMBA_NUM_THREADS"):
+        os.environ[_v] = str(os.cpu_count() or 1)
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -140,12 +147,21 @@ STAGE_EXPONENT = {"mesh_operators": 1.0, "Q_matrix": 2.0, "laplacian_toarray": 2
 
 
 def cpu_threads():
+    """Threads actually used by the CPU arm: min(numba threads, BLAS threads)."""
     try:
         import numba
 
         nt = numba.get_num_threads()
     except Exception:
         nt = os.cpu_count()
+    try:
+        from threadpoolctl import threadpool_info
+
+        blas = [p["num_threads"] for p in threadpool_info() if p.get("user_api") == "blas"]
+        if blas:
+            nt = min(int(nt), max(blas))
+    except Exception:
+        pass
     return int(nt)
 
 
