@@ -194,6 +194,13 @@ int scb_biot_savart(int kind, int64_t m, const double* tgt, int64_t n, const dou
                     const double* area, const double* J, double dz, double prefactor,
                     int64_t nsets, double* out, scb_stream_t stream);
 
+/* ------------------------------------------------------------------------------------
+ * Pairwise distances (K20): distance.py:5-84 cdist / (sq)euclidean_distance_2d/3d
+ *   out[m, n] = |XA_i - XB_j|  (squared != 0: squared distance), dim = 2 or 3.  HBM-write bound.
+ * ------------------------------------------------------------------------------------ */
+int scb_cdist(int dim, int squared, int64_t m, const double* XA, int64_t n, const double* XB,
+              double* out, scb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -245,10 +245,58 @@ def golden_square_inhomogeneous(sc):
     return out
 
 
+def golden_transport(sc):
+    """Transport-terminal branch (reference solve_film.py:308-437,505-524,557-562): a 8 x 3 bar with a
+    hole, current fed through terminals on the two short edges, plus a uniform field and a
+    circulating current.  ``Device.boundary_vertices`` (matplotlib + shapely) is replaced by the
+    package's own counter-clockwise boundary ordering, which is an input."""
+    from superscreen.solver.solve_film import factorize_linear_systems, solve_film
+    from superscreen_b200.mesh import boundary_vertices_ccw
+
+    hole_poly = circle(0.6, 24, center=(0.5, 0.2))
+    film_poly = box(8.0, 3.0, points=4)
+    sites, elements = make_mesh(film_poly, target_vertices=700, embedded=[hole_poly], seed=4)
+    out = dict(in_sites=sites, in_elements=elements, in_film_polygon=film_poly, in_hole_polygon=hole_poly)
+    mesh = _ref_mesh_outputs(sc, sites, elements, out)
+    n = len(sites)
+    Lambda = np.full(n, 0.4)
+    boundary = boundary_vertices_ccw(elements)
+    in_film = np.where(points_in_polygon(film_poly, sites))[0]
+    interior = np.setdiff1d(in_film, boundary)
+    hole_ix = np.where(points_in_polygon(hole_poly, sites))[0]
+    term_polys = {"source": box(0.2, 2.0, points=4, center=(-4.0, 0.0)),
+                  "drain": box(0.2, 2.0, points=4, center=(4.0, 0.0))}
+    terminals = [SimpleNamespace(name=k, contains_points=(lambda pts, index=True, poly=v:
+                                                         np.where(points_in_polygon(poly, pts))[0]))
+                 for k, v in term_polys.items()]
+    out.update(in_Lambda=Lambda, in_boundary_ordered=boundary, in_interior_indices=interior, in_hole_indices=hole_ix,
+               in_source_polygon=term_polys["source"], in_drain_polygon=term_polys["drain"])
+    device = SimpleNamespace(meshes={"bar": mesh}, terminals={"bar": terminals})
+    cases = {
+        "current": dict(term={"source": 10.0, "drain": -10.0}, circ={}, H=np.zeros(n)),
+        "mixed": dict(term={"source": 25.0, "drain": -25.0}, circ={"hole": 3.0}, H=np.full(n, 0.1) * CONV),
+        "nocurrent": dict(term={"source": 0.0, "drain": 0.0}, circ={}, H=np.full(n, 0.1) * CONV),
+    }
+    for key, c in cases.items():
+        info = _film_info(sc, "bar", mesh, Lambda, interior, {"hole": hole_ix}, c["circ"])
+        info.boundary_indices = boundary
+        info.terminal_currents = dict(c["term"])
+        fsys, hsys, tsys = factorize_linear_systems(device, {"bar": info})
+        if key == "current":
+            out["out_system_indices"] = fsys["bar"].indices
+            out["out_with_holes_indices"] = tsys["bar"].film_without_boundary.indices
+        fs = solve_film(device=device, applied_field=c["H"], film_info=info, film_system=fsys["bar"],
+                        hole_systems=hsys["bar"], field_conversion=CONV, vortex_flux=VORTEX_FLUX,
+                        terminal_systems=tsys["bar"])
+        _store_solution(out, key, fs)
+    np.savez_compressed(os.path.join(OUT, "transport.npz"), **out)
+    return out
+
+
 def main():
     sc = load_reference()
     os.makedirs(OUT, exist_ok=True)
-    for fn in (golden_ring, golden_two_rings, golden_square_inhomogeneous):
+    for fn in (golden_ring, golden_two_rings, golden_square_inhomogeneous, golden_transport):
         o = fn(sc)
         print(fn.__name__, {k: v.shape for k, v in o.items() if hasattr(v, "shape") and k.startswith("in_") and v.ndim > 0})
     with open(os.path.join(OUT, "README.md"), "w") as f:

@@ -492,6 +492,13 @@ class OracleFilm:
     hole_A: Dict[str, np.ndarray] = field(default_factory=dict)
     inhomogeneous: bool = False
     film_polygon: Optional[np.ndarray] = None
+    # transport terminals (reference solve_film.py:220-263): CCW-ordered boundary vertex ids, per
+    # terminal the ascending positions (into boundary_ordered) of the boundary vertices it contains
+    boundary_ordered: Optional[np.ndarray] = None
+    terminals: Optional[Dict[str, np.ndarray]] = None
+    boundary_A: Optional[np.ndarray] = None
+    indices_with_holes: Optional[np.ndarray] = None
+    lu_piv_with_holes: tuple = None
 
 
 def factorize_film(film: OracleFilm, keep_A: bool = True) -> OracleFilm:
@@ -510,13 +517,96 @@ def factorize_film(film: OracleFilm, keep_A: bool = True) -> OracleFilm:
         for name, ix in film.hole_indices.items()
     }
     ix = film.interior_indices
+    if film.terminals is not None:
+        # reference solve_film.py:220-263: boundary slab + LU of the interior INCLUDING holes
+        film.boundary_A = build_system_1d(Q, w, film.Lambda, lap, glt, film.boundary_ordered)
+        film.indices_with_holes = ix
+        film.lu_piv_with_holes = la.lu_factor(-build_system_2d(Q, w, film.Lambda, lap, glt, ix))
     if film.hole_indices:
         ix = np.setdiff1d(ix, np.concatenate(list(film.hole_indices.values())))
+    if film.terminals is not None:
+        ix = np.setdiff1d(ix, film.boundary_ordered)
     film.indices = ix
     A = build_system_2d(Q, w, film.Lambda, lap, glt, ix)
     film.lu_piv = la.lu_factor(-A)
     film.A = A if keep_A else None
     return film
+
+
+def path_vectors(path: np.ndarray):
+    """reference geometry.py:160-182 (edge lengths and unit normals)"""
+    dr = np.diff(path, axis=0)
+    normals = np.stack([dr[:, 1], -dr[:, 0]], axis=1)  # cross(dr, z)
+    edge_lengths = la.norm(dr, axis=1)
+    return edge_lengths, normals / edge_lengths[:, np.newaxis]
+
+
+def stream_from_terminal_current(points: np.ndarray, current: float) -> np.ndarray:
+    """reference solver/utils.py:440-488"""
+    from scipy import integrate
+
+    edge_lengths, unit_normals = path_vectors(points)
+    J = current * unit_normals / np.sum(edge_lengths)
+    zhat_cross_J = J[:, [1, 0]]
+    zhat_cross_J[:, 0] *= -1
+    dl = np.diff(points, axis=0)
+    integrand = np.sum(zhat_cross_J * dl, axis=1)
+    g = integrate.cumulative_trapezoid(integrand, initial=0)
+    return g * current / g[-1]
+
+
+def solve_for_terminal_current_stream(film: "OracleFilm", terminal_currents: Dict[str, float]) -> np.ndarray:
+    """reference solve_film.py:308-390"""
+    mesh = film.mesh
+    points, weights = mesh.sites, mesh.vertex_areas
+    npoints = len(points)
+    if not any(terminal_currents.values()):
+        return np.zeros(npoints)
+    boundary_indices = film.boundary_ordered
+    g = np.zeros(npoints)
+    for name, ix_boundary in film.terminals.items():
+        current = terminal_currents[name]
+        ix_boundary = np.sort(ix_boundary)
+        remaining_boundary = boundary_indices[ix_boundary[-1]:]
+        ix_terminal = boundary_indices[ix_boundary]
+        stream = stream_from_terminal_current(points[ix_terminal], -current)
+        g[ix_terminal[:-1]] += stream
+        g[remaining_boundary] += stream[-1]
+    g = g - np.max(g) + np.ptp(g) / 2
+    Ha_eff = -(film.boundary_A @ g[boundary_indices])
+    ixa = film.indices_with_holes
+    g[ixa] = la.lu_solve(film.lu_piv_with_holes, -Ha_eff[ixa])
+    if len(film.hole_indices) == 0:
+        return g
+    Ha_eff = np.zeros(npoints)
+    for name, ix in film.hole_indices.items():
+        g[ix] = np.average(g[ix], weights=weights[ix])
+        Ha_eff += -(film.hole_A[name] @ g[ix])
+    Ha_eff += -(film.boundary_A @ g[boundary_indices])
+    ix = film.indices
+    g[ix] = la.lu_solve(film.lu_piv, -Ha_eff[ix])
+    return g
+
+
+def boundary_effective_field(sites, centers, lengths, normals, stream) -> np.ndarray:
+    """reference solve_film.py:393-412 (vectorised)"""
+    out = np.zeros(len(sites))
+    for s in range(0, len(sites), 2048):
+        dr = sites[s:s + 2048, None, :] - centers[None, :, :]
+        r3 = np.sum(dr * dr, axis=2) ** 1.5
+        out[s:s + 2048] = np.sum(stream / r3 * np.sum(dr * -normals[None, :, :], axis=2) * lengths, axis=1)
+    return out / (4 * np.pi)
+
+
+def biot_savart_within_film(sites, centroids, areas, J_tri) -> np.ndarray:
+    """reference solve_film.py:415-437 (vectorised)"""
+    out = np.zeros(len(sites))
+    for s in range(0, len(sites), 1024):
+        dx = sites[s:s + 1024, None, 0] - centroids[None, :, 0]
+        dy = sites[s:s + 1024, None, 1] - centroids[None, :, 1]
+        pref = areas * (dx * dx + dy * dy) ** (-1.5)
+        out[s:s + 1024] = np.sum(pref * J_tri[:, 0] * dy, axis=1) - np.sum(pref * J_tri[:, 1] * dx, axis=1)
+    return out / (4 * np.pi)
 
 
 # ----------------------------------------------------------------------------------------
@@ -546,8 +636,9 @@ def solve_film(
     vortices: Sequence[Tuple[float, float, float]] = (),
     vortex_flux: float = PHI_0 / MU_0 * 1e12,
     field_from_other_films: Optional[np.ndarray] = None,
+    terminal_currents: Optional[Dict[str, float]] = None,
 ) -> OracleFilmSolution:
-    """reference solve_film.py:440-574 (no-terminal branch)."""
+    """reference solve_film.py:440-574 (transport-terminal branch when film.terminals is set)."""
     mesh = film.mesh
     w = mesh.vertex_areas
     Q = mesh.Q
@@ -560,6 +651,18 @@ def solve_film(
         current = circulating_currents.get(name, 0)
         g[ix] += current
         Ha_eff += -(film.hole_A[name] @ g[ix])
+    if film.terminals is not None:
+        # reference solve_film.py:505-524
+        g_transport = solve_for_terminal_current_stream(film, terminal_currents or {})
+        g += g_transport
+        b = film.boundary_ordered
+        boundary_sites = mesh.sites[b]
+        boundary_stream = g_transport[b]
+        centers = 0.5 * (boundary_sites + np.roll(boundary_sites, -1, axis=0))
+        boundary_stream = 0.5 * (boundary_stream + np.roll(boundary_stream, -1, axis=0))
+        closed = np.concatenate([boundary_sites, boundary_sites[:1]], axis=0)
+        lengths, normals = path_vectors(closed)
+        Ha_eff += boundary_effective_field(mesh.sites, centers, lengths, normals, boundary_stream)
     ix = film.indices
     h = Hz[ix] - Ha_eff[ix]
     gf = la.lu_solve(film.lu_piv, h)
@@ -572,7 +675,12 @@ def solve_film(
         j_dev = np.argmin(la.norm(mesh.sites - (vx, vy), axis=1))
         g[ix] += vortex_flux * nphi0 * K[:, j_film] / w[j_dev]
     J = np.array([mesh.gradient_y @ g, -(mesh.gradient_x @ g)]).T
-    screening = Q @ (w * g)
+    if film.terminals is not None:
+        # reference solve_film.py:557-562
+        J_tri = np.array([mesh.gradient_tri_y @ g, -(mesh.gradient_tri_x @ g)]).T
+        screening = biot_savart_within_film(mesh.sites, mesh.triangle_centroids, mesh.triangle_areas, J_tri)
+    else:
+        screening = Q @ (w * g)
     other = None
     if field_from_other_films is not None:
         other = field_from_other_films / field_conversion

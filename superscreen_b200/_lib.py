@@ -54,6 +54,7 @@ EXPORTS = {
     "scb_getrs_nopiv": (c_int, [c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
     "scb_spmv": (c_int, [c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_double, c_double, c_void_p, c_void_p]),
     "scb_biot_savart": (c_int, [c_int, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_double, c_double, c_int64, c_void_p, c_void_p]),
+    "scb_cdist": (c_int, [c_int, c_int, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
 }
 
 

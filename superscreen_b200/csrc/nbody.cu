@@ -195,6 +195,39 @@ int nbody_kernel_sum(int64_t m, const double* tgt, int64_t n, const double* src,
   return SCB_OK;
 }
 
+// out[i, j] = |XA_i - XB_j| (or its square): one thread per 2 adjacent columns, 128-bit stores
+template <int DIM>
+__global__ void cdist_kernel(int squared, int64_t m, const double* __restrict__ XA, int64_t n,
+                             const double* __restrict__ XB, double* __restrict__ out) {
+  const int64_t j = 2 * (blockIdx.x * (int64_t)blockDim.x + threadIdx.x);
+  const int64_t i0 = blockIdx.y * 16ll;
+  if (j >= n) return;
+  double b[2][3];
+#pragma unroll
+  for (int k = 0; k < 2; k++)
+#pragma unroll
+    for (int d = 0; d < DIM; d++) b[k][d] = (j + k < n) ? XB[(j + k) * DIM + d] : 0.0;
+  for (int64_t i = i0; i < i0 + 16 && i < m; i++) {
+    double v[2];
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+      double r2 = 0.0;
+#pragma unroll
+      for (int d = 0; d < DIM; d++) {
+        const double t = XA[i * DIM + d] - b[k][d];
+        r2 = fma(t, t, r2);
+      }
+      v[k] = squared ? r2 : sqrt(r2);
+    }
+    if (j + 1 < n && (n % 2 == 0)) {
+      *reinterpret_cast<double2*>(out + i * n + j) = make_double2(v[0], v[1]);
+    } else {
+      out[i * n + j] = v[0];
+      if (j + 1 < n) out[i * n + j + 1] = v[1];
+    }
+  }
+}
+
 __global__ void qdw_finish_kernel(int64_t n, const double* __restrict__ C, double* qdw) {
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i < n) qdw[i] = C[i] + qdw[i];
@@ -236,5 +269,19 @@ extern "C" int scb_biot_savart(int kind, int64_t m, const double* tgt, int64_t n
     }
     if (rc) return rc;
   }
+  return SCB_OK;
+}
+
+extern "C" int scb_cdist(int dim, int squared, int64_t m, const double* XA, int64_t n, const double* XB,
+                         double* out, scb_stream_t stream) {
+  SCB_CHECK_ARG(dim == 2 || dim == 3, "dim must be 2 or 3");
+  SCB_CHECK_ARG(m >= 0 && n >= 0, "bad sizes");
+  if (m == 0 || n == 0) return SCB_OK;
+  dim3 grid((unsigned)ceil_div(ceil_div(n, 2), 128), (unsigned)ceil_div(m, 16));
+  if (dim == 2)
+    cdist_kernel<2><<<grid, 128, 0, (cudaStream_t)stream>>>(squared, m, XA, n, XB, out);
+  else
+    cdist_kernel<3><<<grid, 128, 0, (cudaStream_t)stream>>>(squared, m, XA, n, XB, out);
+  SCB_LAUNCH_CHECK();
   return SCB_OK;
 }

@@ -114,6 +114,9 @@ class Device:
         self.terminals: Dict[str, List[Polygon]] = terminals or {}
         if not set(self.terminals).issubset(self.films):
             raise ValueError(f"terminals.keys() must be a subset of films.keys() ({list(self.films)!r}).")
+        for film_name, film_terminals in self.terminals.items():
+            for terminal in film_terminals:
+                terminal.layer = self.films[film_name].layer
         self.abstract_regions: Dict[str, Polygon] = _as_dict(abstract_regions)
         for polygons, label in [(self.films.values(), "film"), (self.holes.values(), "hole")]:
             for polygon in polygons:
@@ -218,6 +221,15 @@ class Device:
                 outline = pts
             meshes[name] = make_mesh(outline, target_vertices=nv, embedded=embedded, seed=seed + k)
         self.set_meshes(meshes)
+
+    def boundary_vertices(self, film: str) -> np.ndarray:
+        """Boundary vertex indices of a film's mesh ordered counter-clockwise (reference
+        device/device.py:473-485 -> device/utils.py:205-227)."""
+        from .mesh import boundary_vertices_ccw
+
+        if not self.meshes:
+            raise ValueError("The device does not have a mesh.")
+        return boundary_vertices_ccw(self.meshes[film].elements)
 
     def mutual_inductance_matrix(self, hole_polygon_mapping: Dict[str, np.ndarray], units: str = "pH",
                                  all_iterations: bool = False, comm=None, **solve_kwargs):

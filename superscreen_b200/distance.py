@@ -30,3 +30,28 @@ def q_matrix(points: np.ndarray) -> np.ndarray:
                                          _lib.ptr(indptr), _lib.ptr(indptr), _lib.ptr(zeros), None, n, _lib.ptr(ix),
                                          _lib.ptr(pos), n_pad, _lib.ptr(M), None, _lib.stream_ptr()))
         return M[:n, :n].cpu().numpy()
+
+
+def cdist(XA: np.ndarray, XB: np.ndarray, metric: str = "euclidean") -> np.ndarray:
+    """Pointwise distance between observations in 2D or 3D (reference distance.py:57-84)."""
+    import torch
+
+    from . import _lib
+
+    metrics = ("euclidean", "sqeuclidean")
+    if metric not in metrics:
+        raise ValueError(f"Metric must be one of {metrics!r}, got {metric!r}.")
+    XA = np.ascontiguousarray(XA, dtype=np.float64)
+    XB = np.ascontiguousarray(XB, dtype=np.float64)
+    if XA.shape[1] != XB.shape[1]:
+        raise ValueError(f"XA.shape[1] ({XA.shape[1]}) must be equal to XB.shape[1] ({XB.shape[1]}).")
+    if XA.shape[1] not in (2, 3):
+        raise ValueError(f"Excpected shape (n, 2) arrays, got {XA.shape} and {XB.shape}.")
+    L = _lib.lib()
+    dev = torch.device(f"cuda:{torch.cuda.current_device()}")
+    with torch.cuda.device(dev):
+        a, b = torch.as_tensor(XA).to(dev), torch.as_tensor(XB).to(dev)
+        out = torch.empty(len(XA), len(XB), dtype=torch.float64, device=dev)
+        _lib.check(L.scb_cdist(XA.shape[1], 1 if metric == "sqeuclidean" else 0, len(XA), _lib.ptr(a), len(XB),
+                               _lib.ptr(b), _lib.ptr(out), _lib.stream_ptr()))
+        return out.cpu().numpy()

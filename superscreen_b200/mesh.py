@@ -25,6 +25,36 @@ def _torch():
     return torch
 
 
+def boundary_vertices_ccw(elements: np.ndarray) -> np.ndarray:
+    """Boundary vertex indices of a consistently CCW-oriented triangulation, ordered counter-
+    clockwise along the (single) outer boundary, starting at the smallest boundary vertex index.
+    Stands in for ``device.utils.boundary_vertices`` (reference device/utils.py:205-227, which
+    needs matplotlib + shapely and starts at a shapely-defined vertex): the ordering is an INPUT of
+    the transport-terminal branch, handed identically to the oracle / the reference."""
+    el = np.asarray(elements, dtype=np.int64)
+    a = el.ravel()
+    b = el[:, [1, 2, 0]].ravel()
+    n = int(el.max()) + 1
+    key = a * n + b
+    rev = b * n + a
+    is_boundary = ~np.isin(key, rev)           # directed edges whose reverse is in no triangle
+    ea, eb = a[is_boundary], b[is_boundary]
+    nxt = dict(zip(ea.tolist(), eb.tolist()))
+    if len(nxt) != len(ea):
+        raise ValueError("mesh boundary is not a simple loop (a boundary vertex has two outgoing edges)")
+    start = int(ea.min())
+    loop = [start]
+    v = nxt[start]
+    while v != start:
+        loop.append(v)
+        v = nxt[v]
+        if len(loop) > len(ea):
+            raise ValueError("mesh boundary is not a single closed loop")
+    if len(loop) != len(ea):
+        raise ValueError("mesh has more than one boundary loop")
+    return np.asarray(loop, dtype=np.int64)
+
+
 class DeviceMeshData:
     """Device-resident arrays of one mesh (owned by torch, filled through the C ABI)."""
 

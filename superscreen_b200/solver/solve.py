@@ -199,7 +199,8 @@ def _run(model: "FactorizedModel", applied_fields, circ_by_film, vortex_flux, it
             film_info=film_info[name], film_system=model.film_systems[name],
             hole_systems=model.hole_systems[name], applied_field=applied_fields[name], vortex_flux=vortex_flux,
             field_from_other_films=other, check_inversion=check_inversion,
-            circulating_currents=None if circ_by_film is None else circ_by_film[name])
+            circulating_currents=None if circ_by_film is None else circ_by_film[name],
+            terminal_systems=model.terminal_systems.get(name), device=device)
 
     def coupling_fn(src_name, J_src, dst_name):
         src, dst = meshes[src_name]._data, meshes[dst_name]._data

@@ -63,6 +63,20 @@ class LinearSystem:
         return self.lu[:n, :n].cpu().numpy(), np.arange(n, dtype=np.int32)
 
 
+@dataclass
+class TerminalSystems:
+    """reference solver/solve_film.py:80-100: the systems needed for the transport-current stream
+    function.  ``boundary`` / ``holes`` carry indices only (their slabs are applied matrix-free);
+    ``film_without_boundary`` is the LU of the film interior INCLUDING holes;
+    ``film_without_boundary_or_holes`` is the film's main system (interior minus holes)."""
+
+    film: str
+    boundary: LinearSystem
+    holes: Dict[str, LinearSystem]
+    film_without_boundary: LinearSystem
+    film_without_boundary_or_holes: Optional[LinearSystem] = None
+
+
 def assemble_negA(info: FilmInfo, ix_dev, n_int: int, n_pad: int, T=None, out=None, want_margin=False):
     """-A restricted to ``ix`` in a padded workspace (reference solve_film.py:296-305)."""
     torch = _torch()
@@ -88,6 +102,7 @@ def factorize_linear_systems(device: Device, film_info_dict: Dict[str, FilmInfo]
     film_systems: Dict[str, LinearSystem] = {}
     hole_systems: Dict[str, Dict[str, LinearSystem]] = {}
     terminal_systems: Dict[str, object] = {}
+    pending = []  # (film, system, info flag tensor, margin-min tensor): read back once at the end
     for film_name, info in film_info_dict.items():
         if owned is not None and film_name not in owned:
             hole_systems[film_name] = {}
@@ -106,30 +121,48 @@ def factorize_linear_systems(device: Device, film_info_dict: Dict[str, FilmInfo]
                 hole_systems[film_name][hole_name] = LinearSystem(
                     indices=indices, film_info=info, grad_Lambda_term=T if T is not None else 0.0,
                     indices_dev=torch.as_tensor(indices).to(d.device))
+            def factor(indices):
+                indices = np.ascontiguousarray(indices, dtype=np.int64)
+                n_int = len(indices)
+                if n_int == 0:
+                    raise ValueError(f"Film {film_name!r} has no interior mesh vertices.")
+                n_pad = -(-n_int // LU_BLOCK) * LU_BLOCK
+                ix_dev = torch.as_tensor(indices).to(d.device)
+                M, margin = assemble_negA(info, ix_dev, n_int, n_pad, T, want_margin=True)
+                dinv = torch.empty(int(L.scb_getrf_dinv_bytes(n_pad)) // 8, dtype=torch.float64, device=d.device)
+                lu_info = torch.zeros(1, dtype=torch.int32, device=d.device)
+                _lib.check(L.scb_getrf_nopiv(n_pad, _lib.ptr(M), _lib.ptr(dinv), _lib.ptr(lu_info),
+                                             _lib.stream_ptr()))
+                system = LinearSystem(indices=indices, film_info=info, grad_Lambda_term=T if T is not None else 0.0,
+                                      n_pad=n_pad, lu=M, dinv=dinv, indices_dev=ix_dev, margin=margin)
+                pending.append((film_name, system, lu_info, margin.min()))
+                return system
+
             interior = info.interior_indices
+            interior_no_holes = interior
             if info.hole_indices:
-                interior = np.setdiff1d(interior, np.concatenate(list(info.hole_indices.values())))
-            interior = np.ascontiguousarray(interior, dtype=np.int64)
-            n_int = len(interior)
-            if n_int == 0:
-                raise ValueError(f"Film {film_name!r} has no interior mesh vertices.")
-            n_pad = -(-n_int // LU_BLOCK) * LU_BLOCK
-            ix_dev = torch.as_tensor(interior).to(d.device)
-            M, margin = assemble_negA(info, ix_dev, n_int, n_pad, T, want_margin=True)
-            dinv = torch.empty(int(L.scb_getrf_dinv_bytes(n_pad)) // 8, dtype=torch.float64, device=d.device)
-            lu_info = torch.zeros(1, dtype=torch.int32, device=d.device)
-            _lib.check(L.scb_getrf_nopiv(n_pad, _lib.ptr(M), _lib.ptr(dinv), _lib.ptr(lu_info), _lib.stream_ptr()))
-            system = LinearSystem(indices=interior, film_info=info, grad_Lambda_term=T if T is not None else 0.0,
-                                  n_pad=n_pad, lu=M, dinv=dinv, indices_dev=ix_dev, margin=margin)
-            info.dev["lu_info"] = lu_info
-            info.dev["margin_min"] = margin.min()
-            film_systems[film_name] = system
-    # one synchronising read per model: singularity flag + dominance margin of every film
-    for film_name, info in film_info_dict.items():
-        if film_name not in film_systems:
-            continue
-        flag = int(info.dev["lu_info"].item())
-        mm = float(info.dev["margin_min"].item())
+                interior_no_holes = np.setdiff1d(interior, np.concatenate(list(info.hole_indices.values())))
+            # (for terminal films the boundary vertices are already excluded from `interior`,
+            #  reference solve_film.py:273-274)
+            film_systems[film_name] = factor(interior_no_holes)
+            if film_name in device.terminals:
+                # reference solve_film.py:220-263.  The reference factors the system without holes
+                # twice (as the film system and as film_without_boundary_or_holes); once here.
+                boundary = np.ascontiguousarray(info.boundary_indices, dtype=np.int64)
+                with_holes = factor(interior) if info.hole_indices else film_systems[film_name]
+                terminal_systems[film_name] = TerminalSystems(
+                    film=film_name,
+                    boundary=LinearSystem(indices=boundary, film_info=info,
+                                          grad_Lambda_term=T if T is not None else 0.0,
+                                          indices_dev=torch.as_tensor(boundary).to(d.device)),
+                    holes=hole_systems[film_name],
+                    film_without_boundary=with_holes,
+                    film_without_boundary_or_holes=film_systems[film_name] if info.hole_indices else None,
+                )
+    # one synchronising read per model: singularity flag + dominance margin of every system
+    for film_name, system, lu_info, margin_min in pending:
+        flag = int(lu_info.item())
+        mm = float(margin_min.item())
         if flag != 0:
             raise np.linalg.LinAlgError(
                 f"Film {film_name!r}: zero or non-finite pivot at row {flag - 1} in the unpivoted LU."
@@ -139,7 +172,7 @@ def factorize_linear_systems(device: Device, film_info_dict: Dict[str, FilmInfo]
             # inhomogeneous Lambda.  The unpivoted factors are then used as a preconditioner:
             # every solve is iteratively refined against the matrix-free operator and the
             # final residual is checked (see solve_film_device).
-            film_systems[film_name].refine = True
+            system.refine = True
             logger.info(
                 f"Film {film_name!r}: system matrix is not provably row-diagonally dominant "
                 f"(margin lower bound {mm:.3e}); solves will use iterative refinement."
@@ -204,7 +237,8 @@ def spmv(d, key: str, x, alpha: float = 1.0):
 
 def solve_film_device(*, film_info: FilmInfo, film_system: LinearSystem, hole_systems: Dict[str, LinearSystem],
                       applied_field, vortex_flux: float, field_from_other_films=None,
-                      check_inversion: bool = False, circulating_currents=None):
+                      check_inversion: bool = False, circulating_currents=None, terminal_systems=None,
+                      device: Optional[Device] = None):
     """Device-side body of ``solve_film`` (reference solve_film.py:483-565): all arguments and
     results are device tensors in solver units.
 
@@ -236,6 +270,29 @@ def solve_film_device(*, film_info: FilmInfo, film_system: LinearSystem, hole_sy
             if any_current:
                 src = torch.cat([s.indices_dev for s in hole_systems.values()])
                 Ha_eff = -apply_operator(info, g, src_idx=src)
+        transport = terminal_systems is not None
+        if transport:
+            # reference solve_film.py:505-524
+            if batched:
+                raise NotImplementedError("Batched right-hand sides are not supported for terminal films.")
+            g_transport = solve_for_terminal_current_stream(device, info, terminal_systems,
+                                                            info.terminal_currents or {})
+            g = g + g_transport
+            b = terminal_systems.boundary.indices_dev
+            boundary_sites = d.sites[b]
+            boundary_stream = g_transport[b]
+            centers = (0.5 * (boundary_sites + torch.roll(boundary_sites, -1, dims=0))).contiguous()
+            boundary_stream = 0.5 * (boundary_stream + torch.roll(boundary_stream, -1, dims=0))
+            dr = torch.roll(boundary_sites, -1, dims=0) - boundary_sites  # edges of the closed curve
+            lengths = torch.linalg.norm(dr, dim=1)
+            normals = (torch.stack([dr[:, 1], -dr[:, 0]], dim=1) / lengths[:, None]).contiguous()
+            Ha_transport = torch.empty(d.n, dtype=torch.float64, device=d.device)
+            # _get_boundary_effective_field (solve_film.py:393-412): kind 4, area = stream * length
+            _lib.check(_lib.lib().scb_biot_savart(
+                4, d.n, _lib.ptr(d.sites), int(b.numel()), _lib.ptr(centers),
+                _lib.ptr((boundary_stream * lengths).contiguous()), _lib.ptr(normals), 0.0, 1.0 / (4.0 * np.pi), 1,
+                _lib.ptr(Ha_transport), _lib.stream_ptr()))
+            Ha_eff = Ha_transport if Ha_eff is None else Ha_eff + Ha_transport
         ix = film_system.indices_dev
         h = Hz[ix] if Ha_eff is None else Hz[ix] - Ha_eff[ix]
         gf = lu_solve(film_system, h)
@@ -279,9 +336,68 @@ def solve_film_device(*, film_info: FilmInfo, film_system: LinearSystem, hole_sy
             J = torch.stack([Jx.t(), Jy.t()], dim=2).contiguous()  # (B, n, 2)
         else:
             J = torch.stack([Jx, Jy], dim=1)
-        # Q @ (w * g), matrix-free
-        self_field = apply_operator(info, g, src_idx=None, with_sparse=False)
+        if transport:
+            # _biot_savart_within_film on per-triangle current densities (solve_film.py:557-562)
+            J_tri = torch.stack([spmv(d, "gtri_y", g), spmv(d, "gtri_x", g, alpha=-1.0)], dim=1).contiguous()
+            self_field = torch.empty(d.n, dtype=torch.float64, device=d.device)
+            _lib.check(_lib.lib().scb_biot_savart(
+                0, d.n, _lib.ptr(d.sites), d.m, _lib.ptr(d.t["centroids"]), _lib.ptr(d.t["triangle_areas"]),
+                _lib.ptr(J_tri), 0.0, 1.0 / (4.0 * np.pi), 1, _lib.ptr(self_field), _lib.stream_ptr()))
+        else:
+            # Q @ (w * g), matrix-free
+            self_field = apply_operator(info, g, src_idx=None, with_sparse=False)
     return g, J, self_field
+
+
+def solve_for_terminal_current_stream(device: Device, film_info: FilmInfo, terminal_systems: TerminalSystems,
+                                      terminal_currents: Dict[str, float]):
+    """reference solver/solve_film.py:308-390.  The boundary values are a few hundred numbers and
+    are set on the host exactly as the reference does; the slab products ``A_boundary @ g`` and
+    ``A_hole @ g`` are matrix-free device operations and the two solves use the device LUs."""
+    torch = _torch()
+    from .utils import stream_from_terminal_current
+
+    d = film_info.mesh._data
+    points = film_info.mesh.sites
+    npoints = len(points)
+    if not any(terminal_currents.values()):
+        return torch.zeros(npoints, dtype=torch.float64, device=d.device)
+    terminals = list(device.terminals[film_info.name])
+    boundary_indices = terminal_systems.boundary.indices
+    boundary_points = points[boundary_indices]
+    # 1. stream function on the boundary
+    g = np.zeros(npoints)
+    for terminal in terminals:
+        current = terminal_currents[terminal.name]
+        ix_boundary = np.sort(terminal.contains_points(boundary_points, index=True))
+        remaining_boundary = boundary_indices[ix_boundary[-1]:]
+        ix_terminal = boundary_indices[ix_boundary]
+        stream = stream_from_terminal_current(points[ix_terminal], -current)
+        g[ix_terminal[:-1]] += stream
+        g[remaining_boundary] += stream[-1]
+    g = g - np.max(g) + np.ptp(g) / 2
+    with torch.cuda.device(d.device):
+        b_dev = terminal_systems.boundary.indices_dev
+        g_dev = torch.as_tensor(g).to(d.device)
+        Ha_eff = -apply_operator(film_info, g_dev, src_idx=b_dev)
+        # 2. interior ignoring the holes
+        sys_all = terminal_systems.film_without_boundary
+        g_dev[sys_all.indices_dev] = lu_solve(sys_all, -Ha_eff[sys_all.indices_dev])
+        if len(terminal_systems.holes) == 0:
+            return g_dev
+        # 3. holes at the weighted average of step 2, then the interior without holes
+        w = d.t["vertex_areas"]
+        v = torch.zeros_like(g_dev)
+        v[b_dev] = g_dev[b_dev]
+        for system in terminal_systems.holes.values():
+            ixh = system.indices_dev
+            g_dev[ixh] = (g_dev[ixh] * w[ixh]).sum() / w[ixh].sum()
+            v[ixh] = g_dev[ixh]
+        src = torch.cat([b_dev] + [s.indices_dev for s in terminal_systems.holes.values()])
+        Ha_eff = -apply_operator(film_info, v, src_idx=src)
+        sys_nh = terminal_systems.film_without_boundary_or_holes
+        g_dev[sys_nh.indices_dev] = lu_solve(sys_nh, -Ha_eff[sys_nh.indices_dev])
+    return g_dev
 
 
 def solve_film(*, device: Device, applied_field: np.ndarray, film_info: FilmInfo, film_system: LinearSystem,
@@ -297,7 +413,8 @@ def solve_film(*, device: Device, applied_field: np.ndarray, film_info: FilmInfo
         other = torch.as_tensor(np.ascontiguousarray(field_from_other_films, dtype=np.float64)).to(dev)
     g, J, self_field = solve_film_device(
         film_info=film_info, film_system=film_system, hole_systems=hole_systems, applied_field=H,
-        vortex_flux=vortex_flux, field_from_other_films=other, check_inversion=check_inversion)
+        vortex_flux=vortex_flux, field_from_other_films=other, check_inversion=check_inversion,
+        terminal_systems=terminal_systems, device=device)
     if field_from_other_films is not None:
         field_from_other_films = np.asarray(field_from_other_films) / field_conversion
     return FilmSolution(

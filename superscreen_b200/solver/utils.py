@@ -120,10 +120,6 @@ def make_film_info(*, device: Device, vortices: Sequence, circulating_currents: 
     holes_by_film, vortices_by_film = get_holes_and_vortices_by_film(device, vortices)
     film_info = {}
     for name, film in device.films.items():
-        if name in device.terminals and device.terminals[name]:
-            raise NotImplementedError(
-                "Transport terminals are a 'next' row of the hot-path scope (SURVEY.md 8f.1)."
-            )
         mesh = device.meshes[name]
         layer = device.layers[film.layer]
         london_lambda = layer.london_lambda
@@ -146,7 +142,10 @@ def make_film_info(*, device: Device, vortices: Sequence, circulating_currents: 
             in_hole[np.concatenate(list(hole_indices.values()))] = True
         circ = {h: c for h, c in circulating_currents.items() if h in hole_indices}
         lambda_info = LambdaInfo(film=name, Lambda=Lambda, london_lambda=london_lambda, thickness=layer.thickness)
-        boundary_indices = mesh.boundary_indices
+        if name in device.terminals:
+            boundary_indices = device.boundary_vertices(name)  # ordered counter-clockwise
+        else:
+            boundary_indices = mesh.boundary_indices
         interior_indices = np.setdiff1d(film.contains_points(mesh.sites, index=True), boundary_indices).astype(np.int64)
         info = FilmInfo(
             name=name, layer=layer.name, lambda_info=lambda_info, vortices=tuple(vortices_by_film[name]),
@@ -213,3 +212,24 @@ def field_conversion_factor(field_units: str, current_units: str, length_units: 
             raise _u.DimensionalityError(f"Cannot convert {field_units!r} to {target!r}")
         mag = s / s_mu / st
     return _u.Quantity(mag, f"({target}) / ({field_units})")
+
+
+def stream_from_current_density(points: np.ndarray, J: np.ndarray) -> np.ndarray:
+    """reference solver/utils.py:440-463"""
+    from scipy import integrate
+
+    zhat_cross_J = J[:, [1, 0]]
+    zhat_cross_J[:, 0] *= -1
+    dl = np.diff(points, axis=0)
+    integrand = np.sum(zhat_cross_J * dl, axis=1)
+    return integrate.cumulative_trapezoid(integrand, initial=0)
+
+
+def stream_from_terminal_current(points: np.ndarray, current: float) -> np.ndarray:
+    """reference solver/utils.py:466-488: the current is spread uniformly along the terminal."""
+    from ..geometry import path_vectors
+
+    edge_lengths, unit_normals = path_vectors(points)
+    J = current * unit_normals / np.sum(edge_lengths)
+    g = stream_from_current_density(points, J)
+    return g * current / g[-1]

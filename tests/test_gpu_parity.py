@@ -208,6 +208,21 @@ def test_square_inhomogeneous_lambda(sc, golden):
     _check_solution(g, "inhom", sol.film_solutions["sq"])
 
 
+@pytest.mark.parametrize("dim", [2, 3])
+@pytest.mark.parametrize("metric", ["euclidean", "sqeuclidean"])
+def test_cdist_matches_scipy(sc, dim, metric):
+    """The reference's only pinned hot-path kernel test (test_distance.py:27-37)."""
+    from scipy.spatial import distance
+
+    rng = np.random.default_rng(1)
+    XA, XB = rng.random((123, dim)), rng.random((77, dim))
+    out = sc.distance.cdist(XA, XB, metric=metric)
+    assert out.shape == (123, 77)
+    assert np.allclose(out, distance.cdist(XA, XB, metric=metric), rtol=1e-14, atol=1e-15)
+    with pytest.raises(ValueError):
+        sc.distance.cdist(XA, XB, metric="invalid")
+
+
 def test_q_matrix_function(sc):
     from oracle import port
 
@@ -314,3 +329,38 @@ def test_non_delaunay_mesh_uses_refinement(sc, caplog):
     assert rel_l2(fs.stream, ref.stream) <= TOL_SOLUTION, (rel_l2(fs.stream, ref.stream), system.refine)
     assert rel_l2(fs.current_density, ref.current_density) <= TOL_SOLUTION
     assert rel_l2(fs.total_field, ref.total_field) <= TOL_SOLUTION
+
+
+def test_transport_terminals_against_reference_golden(sc, golden):
+    """Transport-terminal branch against the live-reference golden."""
+    from superscreen_b200.mesh import boundary_vertices_ccw
+
+    g = golden("transport")
+    sites, elements = g["in_sites"], g["in_elements"]
+    terminals = {"bar": [sc.Polygon("source", points=g["in_source_polygon"]),
+                         sc.Polygon("drain", points=g["in_drain_polygon"])]}
+    device = sc.Device("bar", layers=[sc.Layer("layer", Lambda=float(g["in_Lambda"][0]), z0=0.0)],
+                       films=[sc.Polygon("bar", layer="layer", points=g["in_film_polygon"])],
+                       holes=[sc.Polygon("hole", layer="layer", points=g["in_hole_polygon"])], terminals=terminals)
+    device.set_meshes({"bar": (sites, elements)})
+    assert np.array_equal(device.boundary_vertices("bar"), g["in_boundary_ordered"])
+    assert np.array_equal(boundary_vertices_ccw(elements), g["in_boundary_ordered"])
+    cases = {
+        "current": dict(term={"bar": {"source": "10 uA", "drain": "-10 uA"}}, circ=None, field=None),
+        "mixed": dict(term={"bar": {"source": 25.0, "drain": -25.0}}, circ={"hole": 3.0}, field=sc.ConstantField(0.1)),
+        "nocurrent": dict(term={"bar": {"source": 0.0, "drain": 0.0}}, circ=None, field=sc.ConstantField(0.1)),
+    }
+    for key, c in cases.items():
+        model = sc.factorize_model(device=device, current_units="uA", terminal_currents=c["term"],
+                                   circulating_currents=c["circ"])
+        info = model.film_info["bar"]
+        assert np.array_equal(info.interior_indices, g["in_interior_indices"])
+        assert np.array_equal(model.film_systems["bar"].indices, g["out_system_indices"])
+        ts = model.terminal_systems["bar"]
+        assert np.array_equal(ts.film_without_boundary.indices, g["out_with_holes_indices"])
+        assert ts.film_without_boundary_or_holes is model.film_systems["bar"]
+        sol = sc.solve(model=model, applied_field=c["field"], check_inversion=True)[0]
+        _check_solution(g, key, sol.film_solutions["bar"])
+    # current conservation is enforced like the reference (solve.py:260-264)
+    with pytest.raises(ValueError):
+        sc.factorize_model(device=device, current_units="uA", terminal_currents={"bar": {"source": 1.0, "drain": 0.0}})
