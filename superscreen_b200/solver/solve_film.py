@@ -379,7 +379,11 @@ def solve_for_terminal_current_stream(device: Device, film_info: FilmInfo, termi
     with torch.cuda.device(d.device):
         b_dev = terminal_systems.boundary.indices_dev
         g_dev = torch.as_tensor(g).to(d.device)
-        Ha_eff = -apply_operator(film_info, g_dev, src_idx=b_dev)
+        # only the boundary entries enter A_boundary @ g[boundary] (the constant shift above also
+        # moved the interior entries, which the solve below overwrites)
+        v = torch.zeros_like(g_dev)
+        v[b_dev] = g_dev[b_dev]
+        Ha_eff = -apply_operator(film_info, v, src_idx=b_dev)
         # 2. interior ignoring the holes
         sys_all = terminal_systems.film_without_boundary
         g_dev[sys_all.indices_dev] = lu_solve(sys_all, -Ha_eff[sys_all.indices_dev])

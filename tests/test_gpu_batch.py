@@ -136,3 +136,20 @@ def test_field_at_position_sharded_single_rank(sc, golden):
         ref += np.einsum("ijk,j->ik", J[None, :, :] / rho[:, :, None], mesh.vertex_areas)
     ref *= port.MU_0 / (4 * np.pi) * 1e-6 * 1e3 * 1e6  # uA -> A, T*m -> mT*um
     assert rel_l2(A[:, :2], ref) <= 1e-8
+
+
+def test_find_fluxoid_solution(sc):
+    """reference fluxoid.py:55-119 / test_solve.py:300-328: the circulating currents that realise a
+    target fluxoid state; checked by recomputing the fluxoids of the returned solution."""
+    from superscreen_b200 import configs
+
+    device, polygons = configs.c1_ring(1200)
+    model = sc.factorize_model(device=device, current_units="uA")
+    for target in (0.0, 1.0):
+        sol = sc.find_fluxoid_solution(model, fluxoids={"ring_hole": target}, hole_polygon_mapping=polygons,
+                                       applied_field=sc.ConstantField(0.05))
+        fl = sol.hole_fluxoid("ring_hole", points=polygons["ring_hole"], with_units=False)
+        assert abs(sum(fl) - target) <= 1e-6, (target, sum(fl))
+        assert "ring_hole" in sol.circulating_currents
+    # the model's own circulating currents are restored afterwards
+    assert model.circulating_currents == {}
