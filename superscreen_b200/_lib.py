@@ -64,6 +64,19 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
     if _lib is not None and path is None:
         return _lib
     p = path or LIB_PATH
+    if not os.path.exists(p) and path is None:
+        # the library is built in-tree (python -m superscreen_b200._build); build it on first use
+        # when the sources are present but the artefact is not (fresh checkout with nvcc available)
+        try:
+            from . import _build
+
+            _build.build()
+        except Exception as exc:  # noqa: BLE001
+            raise SCBError(
+                f"{p} not found and building it failed ({exc}). Run "
+                "`python -c 'import __graft_entry__ as g; g.build()'` (needs nvcc). "
+                "superscreen_b200 has no CPU fallback."
+            ) from exc
     if not os.path.exists(p):
         raise SCBError(
             f"{p} not found: the CUDA library has not been built. Run "
