@@ -734,6 +734,7 @@ diag_kernel_small(double* __restrict__ M, int64_t ld, int64_t o, double* __restr
 static bool g_attr_set = false;
 static int g_diag_small = 1;
 static int g_lookahead = 1;
+static int g_lazy_strips = 0;  // left-looking inner strips: same flops, measured no faster (narrow grids)
 
 }  // namespace scb
 
@@ -812,6 +813,7 @@ extern "C" int scb_getrf_nopiv(int64_t n_pad, double* M, double* dinv, int32_t* 
     SCB_CUDA(cudaFuncSetAttribute(update_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     if (const char* e = getenv("SCB_DIAG_SMALL")) g_diag_small = atoi(e);
     if (const char* e = getenv("SCB_LU_LOOKAHEAD")) g_lookahead = atoi(e);
+    if (const char* e = getenv("SCB_LU_LAZY")) g_lazy_strips = atoi(e);
     g_attr_set = true;
   }
   int dev = 0;
@@ -843,24 +845,35 @@ extern "C" int scb_getrf_nopiv(int64_t n_pad, double* M, double* dinv, int32_t* 
       const int64_t o = k * NB;
       double* invL = dinv + k * 2 * NB * NB;
       double* invU = invL + NB * NB;
+      const int nt = (int)(nb - k - 1);  // 128-tiles after this block
+      if (i > 0 && g_lazy_strips) {
+        // left-looking inside the outer panel: bring block column i and block row i up to date
+        // with ALL previous inner panels at once (K = 128 i) right before they are factored
+        dim3 gc(2, nt + 1);  // rows [o, n) x cols [o, o+128)
+        update_kernel<<<gc, 256, upd_smem, st>>>(M, n_pad, o, o, Lpack, Upack, tile_chunks, 0, i * NCHUNK);
+        SCB_LAUNCH_CHECK();
+        if (nt > 0) {
+          dim3 gr(2 * nt, 1);  // rows [o, o+128) x cols [o+128, n)
+          update_kernel<<<gr, 256, upd_smem, st>>>(M, n_pad, o, o + NB, Lpack, Upack, tile_chunks, 0, i * NCHUNK);
+          SCB_LAUNCH_CHECK();
+        }
+      }
       if (g_diag_small)
         diag_kernel_small<<<1, 256, diag_small_smem, st>>>(M, n_pad, o, invL, invU, info, (int)k);
       else
         diag_kernel<<<1, 512, diag_smem, st>>>(M, n_pad, o, invL, invU, info, (int)k);
       SCB_LAUNCH_CHECK();
-      const int nt = (int)(nb - k - 1);  // 128-tiles after this block
       if (nt == 0) break;
       trsm_kernel<<<4 * nt, 256, trsm_smem, st>>>(M, n_pad, o, 2 * nt, invL, invU, Lpack, Upack, tile_chunks,
                                                   i * NCHUNK);
       SCB_LAUNCH_CHECK();
       const int inner_rem = q_eff - 1 - i;  // inner blocks still to factor in this outer panel
-      if (inner_rem > 0) {
-        // (a) column strip: all rows below, the remaining columns of the outer panel
+      if (inner_rem > 0 && !g_lazy_strips) {
+        // right-looking variant: apply inner panel i to the rest of the outer panel's L-shaped strip
         dim3 ga(2 * inner_rem, nt);
         update_kernel<<<ga, 256, upd_smem, st>>>(M, n_pad, o + NB, o + NB, Lpack, Upack, tile_chunks, i * NCHUNK,
                                                  NCHUNK);
         SCB_LAUNCH_CHECK();
-        // (b) row strip: the remaining rows of the outer panel, all columns right of the panel
         const int nright = nt - inner_rem;
         if (nright > 0) {
           dim3 gb(2 * nright, inner_rem);
