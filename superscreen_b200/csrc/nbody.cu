@@ -55,8 +55,9 @@ struct Traits {
 template <int KIND, int SL, int NR>
 __global__ void __launch_bounds__(256) nbody_kernel(NbodyParams p) {
   constexpr int TD = Traits<KIND>::tdim;
-  constexpr int NACC = KIND == NB_KERNEL ? NR : Traits<KIND>::nacc;
-  constexpr int NPAY = KIND == NB_KERNEL ? NR : 2;
+  // NR = right-hand sides (NB_KERNEL) or current-density sets sharing the geometry (NB_FILM_TO_FILM)
+  constexpr int NACC = (KIND == NB_KERNEL || KIND == NB_FILM_TO_FILM) ? NR : Traits<KIND>::nacc;
+  constexpr int NPAY = KIND == NB_KERNEL ? NR : (KIND == NB_FILM_TO_FILM ? 2 * NR : 2);
   __shared__ double sx[kTile], sy[kTile], sz[TD == 3 ? kTile : 1];
   __shared__ double spay[NPAY][kTile];
 
@@ -86,6 +87,12 @@ __global__ void __launch_bounds__(256) nbody_kernel(NbodyParams p) {
       if (KIND == NB_KERNEL) {
 #pragma unroll
         for (int r = 0; r < NR; r++) spay[r][tid] = p.J ? w * p.J[js * p.ldv + p.rhs0 + r] : w;
+      } else if (KIND == NB_FILM_TO_FILM) {
+#pragma unroll
+        for (int r = 0; r < NR; r++) {
+          spay[2 * r][tid] = w * p.J[(r * p.n + js) * 2];
+          spay[2 * r + 1][tid] = w * p.J[(r * p.n + js) * 2 + 1];
+        }
       } else {
         spay[0][tid] = w * p.J[2 * js];
         spay[1][tid] = w * p.J[2 * js + 1];
@@ -116,7 +123,8 @@ __global__ void __launch_bounds__(256) nbody_kernel(NbodyParams p) {
 #pragma unroll
           for (int r = 0; r < NR; r++) acc[r] += spay[r][jj] * k3;
         } else if (KIND == NB_FILM_TO_FILM) {
-          acc[0] += (spay[0][jj] * dy - spay[1][jj] * dx) * k3;
+#pragma unroll
+          for (int r = 0; r < NR; r++) acc[r] += (spay[2 * r][jj] * dy - spay[2 * r + 1][jj] * dx) * k3;
         } else if (KIND == NB_BOUNDARY) {
           acc[0] -= (spay[0][jj] * dx + spay[1][jj] * dy) * k3;
         } else if (KIND == NB_Z) {
@@ -155,6 +163,9 @@ __global__ void __launch_bounds__(256) nbody_kernel(NbodyParams p) {
   } else if (KIND == NB_VECPOT) {
     p.out[2 * i] = pf * acc[0];
     p.out[2 * i + 1] = pf * acc[1];
+  } else if (KIND == NB_FILM_TO_FILM) {
+#pragma unroll
+    for (int r = 0; r < NR; r++) p.out[r * p.m + i] = pf * acc[r];
   } else {
     p.out[i] = pf * acc[0];
   }
@@ -187,7 +198,8 @@ int nbody_kernel_sum(int64_t m, const double* tgt, int64_t n, const double* src,
   while (r < nrhs) {
     p.rhs0 = r;
     int rc;
-    if (nrhs - r >= 4) { rc = launch_nbody<NB_KERNEL, 4>(p, s); r += 4; }
+    if (nrhs - r >= 8) { rc = launch_nbody<NB_KERNEL, 8>(p, s); r += 8; }
+    else if (nrhs - r >= 4) { rc = launch_nbody<NB_KERNEL, 4>(p, s); r += 4; }
     else if (nrhs - r >= 2) { rc = launch_nbody<NB_KERNEL, 2>(p, s); r += 2; }
     else { rc = launch_nbody<NB_KERNEL, 1>(p, s); r += 1; }
     if (rc) return rc;
@@ -254,13 +266,21 @@ extern "C" int scb_biot_savart(int kind, int64_t m, const double* tgt, int64_t n
   SCB_CHECK_ARG(m >= 0 && n >= 0 && nsets >= 1, "bad sizes");
   cudaStream_t s = (cudaStream_t)stream;
   const int64_t ocomp = kind == SCB_BS_VECTOR ? 3 : (kind == SCB_BS_VECTOR_POTENTIAL ? 2 : 1);
-  for (int64_t k = 0; k < nsets; k++) {
+  int64_t k = 0;
+  while (k < nsets) {
     NbodyParams p{};
     p.m = m; p.tgt = tgt; p.n = n; p.src = src; p.area = area; p.J = J + k * n * 2;
     p.dz2 = dz * dz; p.prefactor = prefactor; p.out = out + k * m * ocomp;
     int rc;
+    int64_t step = 1;
     switch (kind) {
-      case SCB_BS_FILM_TO_FILM: rc = launch_nbody<NB_FILM_TO_FILM, 1>(p, s); break;
+      case SCB_BS_FILM_TO_FILM:
+        // current-density sets that share the geometry are evaluated together (one r^-3 per pair)
+        if (nsets - k >= 8) { rc = launch_nbody<NB_FILM_TO_FILM, 8>(p, s); step = 8; }
+        else if (nsets - k >= 4) { rc = launch_nbody<NB_FILM_TO_FILM, 4>(p, s); step = 4; }
+        else if (nsets - k >= 2) { rc = launch_nbody<NB_FILM_TO_FILM, 2>(p, s); step = 2; }
+        else rc = launch_nbody<NB_FILM_TO_FILM, 1>(p, s);
+        break;
       case SCB_BS_Z: rc = launch_nbody<NB_Z, 1>(p, s); break;
       case SCB_BS_VECTOR: rc = launch_nbody<NB_VECTOR, 1>(p, s); break;
       case SCB_BS_VECTOR_POTENTIAL: rc = launch_nbody<NB_VECPOT, 1>(p, s); break;
@@ -268,6 +288,7 @@ extern "C" int scb_biot_savart(int kind, int64_t m, const double* tgt, int64_t n
       default: set_error("scb_biot_savart: unknown kind %d", kind); return SCB_ERR_INVALID;
     }
     if (rc) return rc;
+    k += step;
   }
   return SCB_OK;
 }

@@ -81,8 +81,23 @@ class Polygon:
     def extents(self) -> Tuple[float, float]:
         return tuple(np.ptp(self._points, axis=0))
 
+    _mask_cache: Dict[tuple, np.ndarray] = {}
+
     def contains_points(self, points, index: bool = False, radius: float = 0):
-        mask = points_in_polygon(self._points, np.atleast_2d(points))
+        pts = np.atleast_2d(points)
+        if len(pts) >= 1024:
+            # the same (polygon, mesh sites) query is repeated for every fluxoid / film-info
+            # evaluation; memoise on a content key (bytes of the polygon, checksum of the points)
+            key = (self._points.tobytes(), pts.shape, float(pts[0, 0]), float(pts[-1, 1]), float(pts.sum()))
+            mask = Polygon._mask_cache.get(key)
+            if mask is None:
+                if len(Polygon._mask_cache) > 256:
+                    Polygon._mask_cache.clear()
+                mask = points_in_polygon(self._points, pts)
+                mask.setflags(write=False)
+                Polygon._mask_cache[key] = mask
+        else:
+            mask = points_in_polygon(self._points, pts)
         if index:
             return np.where(mask)[0]
         return mask
