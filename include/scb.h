@@ -105,6 +105,10 @@ int scb_mesh_build(int64_t n, int64_t m, const double* sites, const int64_t* ele
  *   solver/solve_film.py:181-185 grad_Lambda_term, :285-305 _build_system_1d/_2d
  * ------------------------------------------------------------------------------------ */
 
+/* Edge-correction vector C for arbitrary points (MeshOperators.C_vector, device/mesh.py:400-432).
+ * scratch: device double[8]. */
+int scb_c_vector(int64_t n, const double* points, double* scratch, double* C, scb_stream_t stream);
+
 /* qdw[i] = C[i] + sum_{j != i} q_ij w_j  ( == Q_ii * w_i, device/mesh.py:456 ) */
 int scb_kernel_diagonal(int64_t n, const double* sites, const double* weights, const double* C,
                         double* qdw, scb_stream_t stream);
@@ -148,17 +152,23 @@ int scb_apply_operator(int64_t n, const double* sites, const double* weights, co
  *   solver/solve_film.py:232,253,279 and :367,388,530,545
  * ------------------------------------------------------------------------------------ */
 
-/* bytes of the block-inverse store `dinv` for an n_pad x n_pad system */
+/* bytes of the factorization side buffer `dinv` for an n_pad x n_pad system: inverses of the
+ * 128x128 diagonal blocks (kept, used by scb_getrs_nopiv), two sets of fragment-major packed
+ * panels (scratch of the look-ahead LU) and the ready flags / work counter of scb_getrs_nopiv */
 int64_t scb_getrf_dinv_bytes(int64_t n_pad);
 
-/* In-place blocked right-looking LU of the row-major matrix M[n_pad, n_pad] WITHOUT pivoting
- * (valid for the row-diagonally-dominant systems of this path; the caller
- * checks `margin` from scb_system_assemble).  On return M holds L (unit lower) and U; dinv
- * holds inv(L_kk), inv(U_kk) of every 128x128 diagonal block (used by scb_getrs).
- * info (device int32[1]) <- 0, or 1 + index of the first zero/non-finite pivot. */
+/* In-place two-level blocked right-looking LU of the row-major matrix M[n_pad, n_pad] WITHOUT
+ * pivoting (valid for the row-diagonally-dominant systems of this path; the caller
+ * checks `margin` from scb_system_assemble).  Inner panels of 128 columns, outer panels of 1024
+ * columns whose trailing update runs on DMMA tensor cores with TMA-staged packed panels; the
+ * factorization of the next outer panel runs on an internal high-priority stream concurrently
+ * with the trailing update (look-ahead) and is joined back into `stream` before returning.
+ * On return M holds L (unit lower) and U; dinv holds inv(L_kk), inv(U_kk) of every 128x128
+ * diagonal block.  info (device int32[1]) <- 0, or 1 + index of the first zero/non-finite pivot. */
 int scb_getrf_nopiv(int64_t n_pad, double* M, double* dinv, int32_t* info, scb_stream_t stream);
 
-/* Solves M X = B in place for nrhs right-hand sides, B[n_pad, nrhs] row-major. */
+/* Solves M X = B in place for nrhs right-hand sides, B[n_pad, nrhs] row-major, with the factors
+ * and the `dinv` buffer produced by scb_getrf_nopiv (two persistent sweep kernels per 8 rhs). */
 int scb_getrs_nopiv(int64_t n_pad, const double* LU, const double* dinv, int64_t nrhs, double* B,
                     scb_stream_t stream);
 

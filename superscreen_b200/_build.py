@@ -13,7 +13,7 @@ LIB = os.path.join(HERE, "libsc_b200.so")
 SOURCES = ["api.cu", "mesh_ops.cu", "nbody.cu", "assemble.cu", "getrf.cu", "getrs.cu", "spmv.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-    "-Xcompiler", "-fPIC", "--use_fast_math=false" if False else "-Xptxas=-v",
+    "-Xcompiler", "-fPIC", "-Xptxas=-v",
 ]
 
 

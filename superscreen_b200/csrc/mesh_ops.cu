@@ -488,3 +488,13 @@ extern "C" int scb_mesh_build(int64_t n, int64_t m, const double* sites, const i
   SCB_LAUNCH_CHECK();
   return SCB_OK;
 }
+
+extern "C" int scb_c_vector(int64_t n, const double* points, double* scratch, double* C, scb_stream_t stream) {
+  SCB_CHECK_ARG(n > 0, "n must be positive");
+  cudaStream_t s = (cudaStream_t)stream;
+  c_vector_stats_kernel<<<1, 1024, 0, s>>>(n, points, scratch);
+  SCB_LAUNCH_CHECK();
+  c_vector_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, s>>>(n, points, scratch, C);
+  SCB_LAUNCH_CHECK();
+  return SCB_OK;
+}

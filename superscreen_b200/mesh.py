@@ -234,9 +234,31 @@ class MeshOperators:
 
     @staticmethod
     def C_vector(points: np.ndarray) -> np.ndarray:
-        """Edge vector C for arbitrary points (device/mesh.py:400-432), evaluated on the device
-        through a throw-away two-triangle-free path is not possible; use a Mesh."""
-        raise NotImplementedError("Use Mesh(...).operators.C")
+        """Edge vector C for arbitrary points (reference device/mesh.py:400-432)."""
+        torch = _torch()
+        L = _lib.lib()
+        pts = np.ascontiguousarray(points, dtype=np.float64)
+        dev = torch.device(f"cuda:{torch.cuda.current_device()}")
+        with torch.cuda.device(dev):
+            p = torch.as_tensor(pts).to(dev)
+            scratch = torch.empty(8, dtype=torch.float64, device=dev)
+            C = torch.empty(len(pts), dtype=torch.float64, device=dev)
+            _lib.check(L.scb_c_vector(len(pts), _lib.ptr(p), _lib.ptr(scratch), _lib.ptr(C), _lib.stream_ptr()))
+            return C.cpu().numpy()
+
+    @staticmethod
+    def Q_matrix(points: np.ndarray, weights: np.ndarray) -> np.ndarray:
+        """Dense kernel matrix Q for arbitrary points / weights (reference device/mesh.py:434-458):
+        Q = -q off the diagonal, Q_ii = (C_i + sum_j q_ij w_j) / w_i."""
+        from .distance import q_matrix
+
+        q = q_matrix(points)
+        C = MeshOperators.C_vector(points)
+        w = np.asarray(weights, dtype=np.float64)
+        diag = (C + q @ w) / w
+        Q = -q
+        np.fill_diagonal(Q, diag)
+        return Q
 
     def copy(self) -> "MeshOperators":
         return self

@@ -364,3 +364,22 @@ def test_transport_terminals_against_reference_golden(sc, golden):
     # current conservation is enforced like the reference (solve.py:260-264)
     with pytest.raises(ValueError):
         sc.factorize_model(device=device, current_units="uA", terminal_currents={"bar": {"source": 1.0, "drain": 0.0}})
+
+
+def test_static_c_vector_and_q_matrix(sc):
+    """MeshOperators.C_vector / Q_matrix as static functions of (points, weights) (device/mesh.py:400-458)."""
+    from oracle import port
+
+    rng = np.random.default_rng(7)
+    pts = rng.random((400, 2)) * np.array([3.0, 2.0])
+    w = 0.01 + rng.random(400)
+    C = sc.MeshOperators.C_vector(pts)
+    Cref = port.C_vector(pts)
+    inner = (np.abs(pts[:, 0] - pts[:, 0].mean()) < 0.45 * np.ptp(pts[:, 0])) & \
+            (np.abs(pts[:, 1] - pts[:, 1].mean()) < 0.45 * np.ptp(pts[:, 1]))
+    assert rel_l2(C[inner], Cref[inner]) <= 1e-12
+    Q = sc.MeshOperators.Q_matrix(pts, w)
+    Qref = port.Q_matrix(pts, w)
+    off = ~np.eye(400, dtype=bool)
+    assert rel_l2(Q[off], Qref[off]) <= TOL_LOCAL
+    assert rel_l2(np.diag(Q)[inner], np.diag(Qref)[inner]) <= 1e-11

@@ -19,6 +19,27 @@ device = sc.Device("c2", layers=[sc.Layer("layer", Lambda=0.1, z0=0.0)],
                    films=[sc.Polygon("film", layer="layer", points=box(10.0, points=4))])
 device.set_meshes({"film": (sites, elements)})
 torch.cuda.synchronize()
+if args.stage == "nbody":
+    # kernel-only rates of the N-body family (CUDA events, inputs resident)
+    rng = np.random.default_rng(0)
+    n = args.n
+    src3 = torch.as_tensor(np.column_stack([sites, np.zeros(len(sites))])).cuda().contiguous()
+    src2 = torch.as_tensor(sites).cuda()
+    area = torch.rand(len(sites), dtype=torch.float64, device="cuda")
+    J = torch.randn(len(sites), 2, dtype=torch.float64, device="cuda")
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for m in (len(sites), 1_000_000):
+        tgt3 = torch.as_tensor(np.column_stack([rng.uniform(-7, 7, m), rng.uniform(-7, 7, m), np.full(m, 1.0)])).cuda()
+        tgt2 = tgt3[:, :2].contiguous()
+        for kind, name, tgt, src, oc, flop in ((0, "film_to_film", tgt2, src2, 1, 20), (1, "Bz", tgt3, src3, 1, 22), (2, "Bvec", tgt3, src3, 3, 28)):
+            out = torch.empty(m * oc, dtype=torch.float64, device="cuda")
+            for rep in range(3):
+                e0.record()
+                _lib.check(L.scb_biot_savart(kind, m, _lib.ptr(tgt), len(sites), _lib.ptr(src), _lib.ptr(area), _lib.ptr(J), 0.5, 1.0, 1, _lib.ptr(out), _lib.stream_ptr()))
+                e1.record(); torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1); pairs = m * len(sites)
+            print(f"nbody {name}: targets={m} sources={len(sites)} {ms:.3f} ms  {pairs/ms*1e-6:.1f} Gpair/s  ~{pairs*flop/ms*1e-9:.2f} TFLOP/s (at {flop} flop/pair)")
+    sys.exit(0)
 if args.stage == "mesh":
     for _ in range(args.reps):
         sc.Mesh.from_triangulation(sites, elements)
