@@ -731,7 +731,7 @@ diag_kernel_small(double* __restrict__ M, int64_t ld, int64_t o, double* __restr
     }
 }
 
-static bool g_attr_set = false;
+static bool g_attr_set[64] = {};  // kernel attributes are per device
 static int g_diag_small = 1;
 static int g_lookahead = 1;
 static int g_lazy_strips = 0;  // left-looking inner strips: same flops, measured no faster (narrow grids)
@@ -805,7 +805,9 @@ extern "C" int scb_getrf_nopiv(int64_t n_pad, double* M, double* dinv, int32_t* 
   const int diag_small_smem = 3 * QN * QLD * sizeof(double);
   const int trsm_smem = kTrsmSmemDoubles * sizeof(double);
   const int upd_smem = 2 * sizeof(UpdateStage);
-  if (!g_attr_set) {
+  int dev = 0;
+  SCB_CUDA(cudaGetDevice(&dev));
+  if (!g_attr_set[dev & 63]) {
     SCB_CUDA(cudaFuncSetAttribute(diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, diag_smem));
     SCB_CUDA(cudaFuncSetAttribute(diag_kernel_small, cudaFuncAttributeMaxDynamicSharedMemorySize, diag_small_smem));
     SCB_CUDA(cudaFuncSetAttribute(update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, upd_smem));
@@ -814,10 +816,8 @@ extern "C" int scb_getrf_nopiv(int64_t n_pad, double* M, double* dinv, int32_t* 
     if (const char* e = getenv("SCB_DIAG_SMALL")) g_diag_small = atoi(e);
     if (const char* e = getenv("SCB_LU_LOOKAHEAD")) g_lookahead = atoi(e);
     if (const char* e = getenv("SCB_LU_LAZY")) g_lazy_strips = atoi(e);
-    g_attr_set = true;
+    g_attr_set[dev & 63] = true;
   }
-  int dev = 0;
-  SCB_CUDA(cudaGetDevice(&dev));
   LuStreams& ls = g_lu_streams[dev & 63];
   const bool lookahead = g_lookahead && g_diag_small;
   cudaStream_t sp = s;
