@@ -217,7 +217,7 @@ def run_b200_arm(args):
     from superscreen_b200 import _lib
     from superscreen_b200.geometry import box
     from superscreen_b200.mesh import DeviceMeshData
-    from superscreen_b200.solver.solve_film import LinearSystem, assemble_negA, solve_film_device
+    from superscreen_b200.solver.solve_film import LinearSystem, assemble_negA, solve_film_device, use_symmetric
     from superscreen_b200.solver.utils import FilmInfo, LambdaInfo
 
     rank = int(os.environ.get("RANK", "0"))
@@ -259,6 +259,8 @@ def run_b200_arm(args):
             self._data = data
             self.sites = None
 
+    symmetric = use_symmetric()
+
     def resident_step(record: bool):
         stream = torch.cuda.current_stream()
         if record: ev["mesh"][0].record(stream)
@@ -270,12 +272,17 @@ def run_b200_arm(args):
         info.dev["Lambda"] = Lambda_d
         info.dev["T"] = None
         if record: ev["assemble"][0].record(stream)
-        assemble_negA(info, ix_d, n_int, n_pad, None, out=lu_ws)
+        # constant Lambda: same choice as factorize_linear_systems -- the diagonally similar symmetric
+        # form S = D (-A) D^-1, D = sqrt(w), factored by the symmetric LU (half the flops)
+        sym_full = torch.sqrt(data.t["vertex_areas"]) if symmetric else None
+        assemble_negA(info, ix_d, n_int, n_pad, None, out=lu_ws, sym_scale_full=sym_full)
         if record: ev["assemble"][1].record(stream)
         if record: ev["getrf"][0].record(stream)
-        _lib.check(L.scb_getrf_nopiv(n_pad, _lib.ptr(lu_ws), _lib.ptr(dinv), _lib.ptr(lu_info), _lib.stream_ptr()))
+        getrf = L.scb_getrf_sym_nopiv if symmetric else L.scb_getrf_nopiv
+        _lib.check(getrf(n_pad, _lib.ptr(lu_ws), _lib.ptr(dinv), _lib.ptr(lu_info), _lib.stream_ptr()))
         if record: ev["getrf"][1].record(stream)
-        system = LinearSystem(indices=interior, film_info=info, n_pad=n_pad, lu=lu_ws, dinv=dinv, indices_dev=ix_d)
+        system = LinearSystem(indices=interior, film_info=info, n_pad=n_pad, lu=lu_ws, dinv=dinv, indices_dev=ix_d,
+                              sym_scale=None if sym_full is None else sym_full[ix_d].contiguous())
         if record: ev["solve"][0].record(stream)
         out = solve_film_device(film_info=info, film_system=system, hole_systems={}, applied_field=H_d,
                                 vortex_flux=0.0)
@@ -350,8 +357,10 @@ def run_b200_arm(args):
         dist.all_reduce(vals, op=dist.ReduceOp.MAX)
     ms_per_step, e2e_s, getrf_ms = (float(v) for v in vals.cpu())
 
-    lu_flops = (2.0 / 3.0) * float(n_int) ** 3
+    # flops actually executed: n^3/3 for the symmetric factorization, 2 n^3/3 for the general one
+    lu_flops = ((1.0 if symmetric else 2.0) / 3.0) * float(n_int) ** 3
     lu_tflops = lu_flops / (getrf_ms * 1e-3) * 1e-12
+    getrf_equiv_tflops = (2.0 / 3.0) * float(n_int) ** 3 / (getrf_ms * 1e-3) * 1e-12
     line = {
         "metric": METRIC, "value": ms_per_step * 1e-3, "unit": "s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": False, "scaling": "weak",
@@ -361,7 +370,8 @@ def run_b200_arm(args):
                    "n_vertices": int(n), "n_triangles": int(m), "n_interior": int(n_int), "n_pad": int(n_pad),
                    "l2": "256 MiB buffer written between timed iterations (flushes the 126 MB L2)"},
         "stages_ms": {k: float(np.mean(v)) for k, v in stage_ms.items()},
-        "lu_tflops": lu_tflops, "films_per_s": world / (ms_per_step * 1e-3),
+        "lu_tflops": lu_tflops, "lu_mode": "symmetric" if symmetric else "general",
+        "lu_getrf_equivalent_tflops": getrf_equiv_tflops, "films_per_s": world / (ms_per_step * 1e-3),
         "roofline": {"bound": "tensor", "achieved": lu_tflops, "peak": FP64_DMMA_PEAK_TFLOPS, "unit": "TFLOP/s",
                      "frac": lu_tflops / FP64_DMMA_PEAK_TFLOPS,
                      # DRAM bytes (read + write) of the dominant launch, the first K=1024 bulk trailing
@@ -371,10 +381,12 @@ def run_b200_arm(args):
                      "dominant_launch": {"kernel": "scb::update_kernel grid (280,140) K=1024", "flop": 657.7e9,
                                          "ms": 18.375, "achieved": 35.79, "frac": 35.79 / FP64_DMMA_PEAK_TFLOPS,
                                          "dmma_pipe_active_pct": 96.4, "source": "ncu, profiles/"},
-                     "kernel": "scb_getrf_nopiv = all launches of one factorization (update_kernel DMMA trailing "
+                     "kernel": ("scb_getrf_sym_nopiv" if symmetric else "scb_getrf_nopiv") + " = all launches of one factorization (update_kernel DMMA trailing "
                                "updates + diag/trsm panel kernels, look-ahead on a second stream), timed live with "
                                "CUDA events",
-                     "work": "2/3 * n_int^3 fp64 flop per factorization",
+                     "work": ("1/3 * n_int^3 fp64 flop executed per symmetric factorization (a general getrf "
+                              "of the same matrix is 2/3 n^3: lu_getrf_equivalent_tflops)") if symmetric
+                     else "2/3 * n_int^3 fp64 flop per factorization",
                      "peak_source": "measured DMMA.8x8x4 issue rate on this pool's B200, "
                                     "profiles/r01_fp64_peaks.txt (MEASURED_PEAKS.json has no fp64 entry)"},
         "e2e": {"value": e2e_s, "unit": "s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},

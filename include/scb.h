@@ -126,13 +126,17 @@ int scb_grad_lambda_term(int64_t n, const int32_t* op_indptr, const int32_t* op_
  *   M[r,r] = -qdw[ix_r]           + Lambda[ix_r] lap[ix_r, ix_r] + T[ix_r, ix_r]
  * T may be NULL (homogeneous Lambda).  margin (may be NULL; needs C) receives a lower bound
  * of the row-dominance margin |M_rr| - sum_{c != r} |M_rc| (exact when ix covers every vertex)
- * used to validate the unpivoted LU. */
+ * used to validate the unpivoted LU.
+ * sym_scale (NULL, or sqrt(w) per mesh vertex; needs T == NULL and a constant Lambda): writes the
+ * diagonally similar SYMMETRIC matrix S = D M D^-1, D = diag(sqrt(w[ix])), instead of M, for
+ * scb_getrf_sym_nopiv:  S[r,c] = q sqrt(w_r w_c) + Lambda lap[r,c] sqrt(w_r / w_c),  S[r,r] = M[r,r];
+ * M x = h  <=>  S (D x) = D h. */
 int scb_system_assemble(int64_t n, const double* sites, const double* weights, const double* qdw,
                         const double* C, const double* Lambda, const int32_t* op_indptr,
                         const int32_t* op_indices,
                         const double* laplacian, const double* T, int64_t n_int, const int64_t* ix,
                         int32_t* pos_scratch, int64_t n_pad, double* negA, double* margin,
-                        scb_stream_t stream);
+                        const double* sym_scale, scb_stream_t stream);
 
 /* Matrix-free action of the FULL (n x n) operator A on nrhs vectors, sources restricted
  * to `src_idx` (NULL = all vertices):
@@ -166,6 +170,13 @@ int64_t scb_getrf_dinv_bytes(int64_t n_pad);
  * On return M holds L (unit lower) and U; dinv holds inv(L_kk), inv(U_kk) of every 128x128
  * diagonal block.  info (device int32[1]) <- 0, or 1 + index of the first zero/non-finite pivot. */
 int scb_getrf_nopiv(int64_t n_pad, double* M, double* dinv, int32_t* info, scb_stream_t stream);
+
+/* Same for a SYMMETRIC matrix (the symmetrised system of scb_system_assemble): only the lower
+ * triangle is read and updated, the row panels are obtained from the column panels
+ * (U12 = diag(U11) L21^T), and the trailing update touches only tiles on or below the diagonal --
+ * 1/3 n^3 flop instead of 2/3 n^3.  On return M holds L (unit lower) and U (upper) of the LU
+ * factorization of the symmetric matrix, exactly as scb_getrf_nopiv would produce. */
+int scb_getrf_sym_nopiv(int64_t n_pad, double* M, double* dinv, int32_t* info, scb_stream_t stream);
 
 /* Solves M X = B in place for nrhs right-hand sides, B[n_pad, nrhs] row-major, with the factors
  * and the `dinv` buffer produced by scb_getrf_nopiv (two persistent sweep kernels per 8 rhs). */

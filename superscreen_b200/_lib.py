@@ -12,7 +12,7 @@ from ctypes import POINTER, Structure, c_char_p, c_double, c_int, c_int32, c_int
 from typing import Optional
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsc_b200.so")
+LIB_PATH = os.environ.get("SCB_LIB_PATH") or os.path.join(_HERE, "libsc_b200.so")
 
 _lib = None
 
@@ -48,10 +48,11 @@ EXPORTS = {
     "scb_c_vector": (c_int, [c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "scb_kernel_diagonal": (c_int, [c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "scb_grad_lambda_term": (c_int, [c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
-    "scb_system_assemble": (c_int, [c_int64] + [c_void_p] * 9 + [c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
+    "scb_system_assemble": (c_int, [c_int64] + [c_void_p] * 9 + [c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "scb_apply_operator": (c_int, [c_int64] + [c_void_p] * 8 + [c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int, c_void_p]),
     "scb_getrf_dinv_bytes": (c_int64, [c_int64]),
     "scb_getrf_nopiv": (c_int, [c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "scb_getrf_sym_nopiv": (c_int, [c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "scb_getrs_nopiv": (c_int, [c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
     "scb_spmv": (c_int, [c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_double, c_double, c_void_p, c_void_p]),
     "scb_biot_savart": (c_int, [c_int, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_double, c_double, c_int64, c_void_p, c_void_p]),

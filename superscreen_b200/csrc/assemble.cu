@@ -28,9 +28,9 @@ constexpr int TC = 128;
 
 __global__ void __launch_bounds__(256) assemble_dense_kernel(
     const double* __restrict__ sites, const double* __restrict__ weights,
-    const double* __restrict__ qdw, int64_t n_int, const int64_t* __restrict__ ix, int64_t n_pad,
-    double* __restrict__ M) {
-  __shared__ double rx[TR], ry[TR], rd[TR];
+    const double* __restrict__ qdw, const double* __restrict__ sym_scale, int64_t n_int,
+    const int64_t* __restrict__ ix, int64_t n_pad, double* __restrict__ M) {
+  __shared__ double rx[TR], ry[TR], rd[TR], rs[TR];
   const int tid = threadIdx.x;
   const int64_t row0 = blockIdx.y * (int64_t)TR;
   const int64_t col0 = blockIdx.x * (int64_t)TC;
@@ -41,8 +41,10 @@ __global__ void __launch_bounds__(256) assemble_dense_kernel(
       rx[tid] = sites[2 * i];
       ry[tid] = sites[2 * i + 1];
       rd[tid] = -qdw[i];
+      rs[tid] = sym_scale ? sym_scale[i] : 1.0;
     } else {
       rx[tid] = 0.0; ry[tid] = 0.0; rd[tid] = 1.0;  // identity padding
+      rs[tid] = 1.0;
     }
   }
   const int cp = tid & 63;   // column pair
@@ -57,7 +59,8 @@ __global__ void __launch_bounds__(256) assemble_dense_kernel(
       const int64_t j = ix[c + k];
       cx[k] = sites[2 * j];
       cy[k] = sites[2 * j + 1];
-      cw[k] = weights[j] * kOneOver4Pi;
+      // general: q w_c.  symmetrised (S = W^1/2 (-A) W^-1/2): q sqrt(w_r) sqrt(w_c)
+      cw[k] = (sym_scale ? sym_scale[j] : weights[j]) * kOneOver4Pi;
     } else {
       cx[k] = 0.0; cy[k] = 0.0; cw[k] = 0.0;
     }
@@ -67,14 +70,14 @@ __global__ void __launch_bounds__(256) assemble_dense_kernel(
   for (int rr = 0; rr < TR / 4; rr++) {
     const int lr = rg * (TR / 4) + rr;
     const int64_t r = row0 + lr;
-    const double x = rx[lr], y = ry[lr];
+    const double x = rx[lr], y = ry[lr], sr = rs[lr];
     double2 v;
     double* vv = &v.x;
 #pragma unroll
     for (int k = 0; k < 2; k++) {
       const double dx = x - cx[k], dy = y - cy[k];
       const double r2 = dx * dx + dy * dy;
-      double val = inv_r3(r2) * cw[k];
+      double val = inv_r3(r2) * (cw[k] * sr);
       // padding rows/cols and the (overwritten) diagonal never see inf: mask them
       val = (r2 > 0.0 && cvalid[k] && r < n_int) ? val : 0.0;
       if (r == c + k) val = rd[lr];
@@ -96,7 +99,7 @@ __global__ void assemble_sparse_kernel(const double* __restrict__ sites,
                                        int64_t n_int, const int64_t* __restrict__ ix,
                                        const int32_t* __restrict__ pos, int64_t n_pad,
                                        double* __restrict__ M, double* __restrict__ margin,
-                                       const double* __restrict__ C) {
+                                       const double* __restrict__ C, const double* __restrict__ sym_scale) {
   int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (r >= n_int) return;
   const int64_t i = ix[r];
@@ -114,7 +117,8 @@ __global__ void assemble_sparse_kernel(const double* __restrict__ sites,
       const double dx = xi - sites[2 * j], dy = yi - sites[2 * j + 1];
       const double qw = inv_r3(dx * dx + dy * dy) * (weights[j] * kOneOver4Pi);
       const double val = qw + s;
-      M[r * n_pad + c] = val;
+      // symmetrised storage: entry scaled by sqrt(w_r) / sqrt(w_c)
+      M[r * n_pad + c] = sym_scale ? val * (sym_scale[i] / sym_scale[j]) : val;
       extra += fabs(val) - qw;
     }
   }
@@ -181,8 +185,10 @@ extern "C" int scb_system_assemble(int64_t n, const double* sites, const double*
                                    const int32_t* op_indptr, const int32_t* op_indices,
                                    const double* laplacian, const double* T, int64_t n_int,
                                    const int64_t* ix, int32_t* pos_scratch, int64_t n_pad,
-                                   double* negA, double* margin, scb_stream_t stream) {
+                                   double* negA, double* margin, const double* sym_scale,
+                                   scb_stream_t stream) {
   SCB_CHECK_ARG(n > 0 && n_int > 0 && n_int <= n, "bad sizes");
+  SCB_CHECK_ARG(sym_scale == nullptr || T == nullptr, "the symmetrised form needs homogeneous Lambda (T == NULL)");
   SCB_CHECK_ARG(n_pad >= n_int && n_pad % SCB_LU_BLOCK == 0, "n_pad must be a multiple of 128 >= n_int");
   SCB_CHECK_ARG(margin == nullptr || C != nullptr, "margin needs C");
   cudaStream_t s = (cudaStream_t)stream;
@@ -191,11 +197,11 @@ extern "C" int scb_system_assemble(int64_t n, const double* sites, const double*
   pos_kernel<<<(unsigned)ceil_div(n_int, 256), 256, 0, s>>>(n_int, ix, pos_scratch);
   SCB_LAUNCH_CHECK();
   dim3 grid((unsigned)(n_pad / TC), (unsigned)(n_pad / TR));
-  assemble_dense_kernel<<<grid, 256, 0, s>>>(sites, weights, qdw, n_int, ix, n_pad, negA);
+  assemble_dense_kernel<<<grid, 256, 0, s>>>(sites, weights, qdw, sym_scale, n_int, ix, n_pad, negA);
   SCB_LAUNCH_CHECK();
   assemble_sparse_kernel<<<(unsigned)ceil_div(n_int, 128), 128, 0, s>>>(
       sites, weights, qdw, Lambda, op_indptr, op_indices, laplacian, T, n_int, ix, pos_scratch,
-      n_pad, negA, margin, C);
+      n_pad, negA, margin, C, sym_scale);
   SCB_LAUNCH_CHECK();
   return SCB_OK;
 }

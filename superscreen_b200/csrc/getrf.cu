@@ -17,6 +17,13 @@
 // CTAs per SM overlap one CTA's C traffic with the other's DMMA work; K = KB amortises the C
 // traffic and CTA prologue/epilogue over q times more math than a plain rank-128 update.
 //
+// Symmetric variant (scb_getrf_sym_nopiv): for a constant Lambda the system is diagonally similar
+// (D = W^1/2) to a symmetric matrix S.  Every Schur complement of S is symmetric, so only the tiles
+// that intersect the lower triangle are updated (update_kernel_t<true>: CTAs of upper tiles exit
+// at once), only the column panel is solved (trsm_sym_kernel), and the row panel follows from
+// U12 = diag(U11) L21^T -- half the flops of step 3 / the bulk update.  The output is still an
+// ordinary (L, U) pair in M, so scb_getrs_nopiv and lu_piv are unchanged.
+//
 // Reference semantics: scipy.linalg.lu_factor(-A) at solver/solve_film.py:232,253,279 (LAPACK
 // dgetrf).  Pivoting is unnecessary here; parity is on the solution (1e-8 rel-L2), see DESIGN.md.
 #include <stdlib.h>
@@ -101,10 +108,11 @@ struct __align__(128) UpdateStage {
   double b[B_CHUNK];
 };
 
+template <bool TRI>
 __global__ void __launch_bounds__(256, 2)
-update_kernel(double* __restrict__ M, int64_t ld, int64_t row0, int64_t col0,
-              const double* __restrict__ Lpack, const double* __restrict__ Upack, int tile_chunks,
-              int chunk0, int nchunks) {
+update_kernel_t(double* __restrict__ M, int64_t ld, int64_t row0, int64_t col0,
+                const double* __restrict__ Lpack, const double* __restrict__ Upack, int tile_chunks,
+                int chunk0, int nchunks) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   UpdateStage* stage = reinterpret_cast<UpdateStage*>(smem_raw);
   __shared__ uint64_t bars[2];
@@ -114,9 +122,13 @@ update_kernel(double* __restrict__ M, int64_t ld, int64_t row0, int64_t col0,
   const int wm = warp >> 1, wn = warp & 1;  // 4 x 2 warps, 32x32 warp tiles
   const int g = lane >> 2, t = lane & 3;
 
+  // tile coordinates.  TRI: the region is square and only the tiles that intersect its lower
+  // triangle are updated (row tile by owns column tiles 0 .. 2 by + 1); the others exit at once.
+  const int by = blockIdx.y, bx = blockIdx.x;
+  if (TRI && bx > 2 * by + 1) return;
   // packed operands are indexed by ABSOLUTE 128-row / 64-column tile and by chunk slot
-  const double* Ltile = Lpack + ((row0 >> 7) + blockIdx.y) * ((int64_t)tile_chunks * A_CHUNK) + (int64_t)chunk0 * A_CHUNK;
-  const double* Utile = Upack + ((col0 >> 6) + blockIdx.x) * ((int64_t)tile_chunks * B_CHUNK) + (int64_t)chunk0 * B_CHUNK;
+  const double* Ltile = Lpack + ((row0 >> 7) + by) * ((int64_t)tile_chunks * A_CHUNK) + (int64_t)chunk0 * A_CHUNK;
+  const double* Utile = Upack + ((col0 >> 6) + bx) * ((int64_t)tile_chunks * B_CHUNK) + (int64_t)chunk0 * B_CHUNK;
   constexpr uint32_t kStageBytes = (A_CHUNK + B_CHUNK) * sizeof(double);
 
   if (tid == 0) {
@@ -136,8 +148,7 @@ update_kernel(double* __restrict__ M, int64_t ld, int64_t row0, int64_t col0,
 
   // accumulators start as the C tile
   double acc[4][4][2];
-  double* Cbase = M + (row0 + (int64_t)blockIdx.y * BM + wm * 32 + g) * ld + col0 + (int64_t)blockIdx.x * BN +
-                  wn * 32 + 2 * t;
+  double* Cbase = M + (row0 + (int64_t)by * BM + wm * 32 + g) * ld + col0 + (int64_t)bx * BN + wn * 32 + 2 * t;
 #pragma unroll
   for (int i = 0; i < 4; i++)
 #pragma unroll
@@ -294,6 +305,48 @@ trsm_kernel(double* __restrict__ M, int64_t ld, int64_t o, int ncol, const doubl
         P[upack_index(r, cc + 1)] = acc[i][j][1];
       }
   }
+}
+
+// Symmetric variant: only the column panel is solved (64 rows per CTA); the row panel follows from
+// symmetry, U12 = diag(U11) L21^T, and is emitted here as the packed B operand of the update kernel
+// and, transposed, into the upper triangle of M (so getrs and lu_piv see an ordinary LU).
+__global__ void __launch_bounds__(256)
+trsm_sym_kernel(double* __restrict__ M, int64_t ld, int64_t o, const double* __restrict__ invU,
+                double* __restrict__ Lpack, double* __restrict__ Upack, int tile_chunks, int chunk0) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* As = reinterpret_cast<double*>(smem_raw);
+  __shared__ double dU[NB];  // diagonal of U11
+  const int tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int64_t o2 = o + NB;
+  if (tid < NB) dU[tid] = M[(o + tid) * ld + o + tid];
+  double acc[4][4][2];
+  const int tile = blockIdx.x;
+  double* Atile = M + (o2 + (int64_t)tile * 64) * ld + o;
+  double* Bs = As + 64 * TA_LD;
+  gemm_k128<64, 128, 2, 4, 1>(Atile, ld, invU, NB, As, Bs, acc);  // ends after a __syncthreads: dU visible
+  const int wm = warp / 4, wn = warp % 4;
+  double* PL = Lpack + ((o2 >> 7) + (tile >> 1)) * ((int64_t)tile_chunks * A_CHUNK) + (int64_t)chunk0 * A_CHUNK;
+  double* PU = Upack + ((o2 >> 6) + tile) * ((int64_t)tile_chunks * B_CHUNK) + (int64_t)chunk0 * B_CHUNK;
+  const int rbase = (tile & 1) * 64;
+  double* Urow0 = M + o * ld + o2 + (int64_t)tile * 64;  // U12[k][c]: row o + k, column o2 + 64 tile + c
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const int r = wm * 32 + i * 8 + g;       // row inside this 64-row tile
+      const int cc = wn * 32 + j * 8 + 2 * t;  // k index 0..127
+      const double v0 = acc[i][j][0], v1 = acc[i][j][1];
+      *reinterpret_cast<double2*>(Atile + (int64_t)r * ld + cc) = make_double2(v0, v1);
+      PL[lpack_index(rbase + r, cc)] = -v0;
+      PL[lpack_index(rbase + r, cc + 1)] = -v1;
+      const double u0 = dU[cc] * v0, u1 = dU[cc + 1] * v1;
+      PU[upack_index(cc, r)] = u0;
+      PU[upack_index(cc + 1, r)] = u1;
+      Urow0[(int64_t)cc * ld + r] = u0;
+      Urow0[(int64_t)(cc + 1) * ld + r] = u1;
+    }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -792,8 +845,7 @@ extern "C" int64_t scb_getrf_dinv_bytes(int64_t n_pad) {
 //    chain of small kernels) then runs on a high-priority stream concurrently with "the rest".
 //    Every kernel of that chain fits into the SM slot of an update CTA, so the hardware block
 //    scheduler interleaves them as slots free up.
-extern "C" int scb_getrf_nopiv(int64_t n_pad, double* M, double* dinv, int32_t* info,
-                               scb_stream_t stream) {
+static int getrf_impl(int64_t n_pad, double* M, double* dinv, int32_t* info, scb_stream_t stream, bool sym) {
   SCB_CHECK_ARG(n_pad > 0 && n_pad % NB == 0, "n_pad must be a positive multiple of 128");
   cudaStream_t s = (cudaStream_t)stream;
   const int64_t nb = n_pad / NB;
@@ -810,9 +862,12 @@ extern "C" int scb_getrf_nopiv(int64_t n_pad, double* M, double* dinv, int32_t* 
   if (!g_attr_set[dev & 63]) {
     SCB_CUDA(cudaFuncSetAttribute(diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, diag_smem));
     SCB_CUDA(cudaFuncSetAttribute(diag_kernel_small, cudaFuncAttributeMaxDynamicSharedMemorySize, diag_small_smem));
-    SCB_CUDA(cudaFuncSetAttribute(update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, upd_smem));
+    SCB_CUDA(cudaFuncSetAttribute(update_kernel_t<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, upd_smem));
+    SCB_CUDA(cudaFuncSetAttribute(update_kernel_t<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, upd_smem));
     SCB_CUDA(cudaFuncSetAttribute(trsm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, trsm_smem));
-    SCB_CUDA(cudaFuncSetAttribute(update_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    SCB_CUDA(cudaFuncSetAttribute(trsm_sym_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, trsm_smem));
+    SCB_CUDA(cudaFuncSetAttribute(update_kernel_t<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    SCB_CUDA(cudaFuncSetAttribute(update_kernel_t<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     if (const char* e = getenv("SCB_DIAG_SMALL")) g_diag_small = atoi(e);
     if (const char* e = getenv("SCB_LU_LOOKAHEAD")) g_lookahead = atoi(e);
     if (const char* e = getenv("SCB_LU_LAZY")) g_lazy_strips = atoi(e);
@@ -850,11 +905,11 @@ extern "C" int scb_getrf_nopiv(int64_t n_pad, double* M, double* dinv, int32_t* 
         // left-looking inside the outer panel: bring block column i and block row i up to date
         // with ALL previous inner panels at once (K = 128 i) right before they are factored
         dim3 gc(2, nt + 1);  // rows [o, n) x cols [o, o+128)
-        update_kernel<<<gc, 256, upd_smem, st>>>(M, n_pad, o, o, Lpack, Upack, tile_chunks, 0, i * NCHUNK);
+        update_kernel_t<false><<<gc, 256, upd_smem, st>>>(M, n_pad, o, o, Lpack, Upack, tile_chunks, 0, i * NCHUNK);
         SCB_LAUNCH_CHECK();
         if (nt > 0) {
           dim3 gr(2 * nt, 1);  // rows [o, o+128) x cols [o+128, n)
-          update_kernel<<<gr, 256, upd_smem, st>>>(M, n_pad, o, o + NB, Lpack, Upack, tile_chunks, 0, i * NCHUNK);
+          update_kernel_t<false><<<gr, 256, upd_smem, st>>>(M, n_pad, o, o + NB, Lpack, Upack, tile_chunks, 0, i * NCHUNK);
           SCB_LAUNCH_CHECK();
         }
       }
@@ -864,20 +919,23 @@ extern "C" int scb_getrf_nopiv(int64_t n_pad, double* M, double* dinv, int32_t* 
         diag_kernel<<<1, 512, diag_smem, st>>>(M, n_pad, o, invL, invU, info, (int)k);
       SCB_LAUNCH_CHECK();
       if (nt == 0) break;
-      trsm_kernel<<<4 * nt, 256, trsm_smem, st>>>(M, n_pad, o, 2 * nt, invL, invU, Lpack, Upack, tile_chunks,
-                                                  i * NCHUNK);
+      if (sym)
+        trsm_sym_kernel<<<2 * nt, 256, trsm_smem, st>>>(M, n_pad, o, invU, Lpack, Upack, tile_chunks, i * NCHUNK);
+      else
+        trsm_kernel<<<4 * nt, 256, trsm_smem, st>>>(M, n_pad, o, 2 * nt, invL, invU, Lpack, Upack, tile_chunks,
+                                                    i * NCHUNK);
       SCB_LAUNCH_CHECK();
       const int inner_rem = q_eff - 1 - i;  // inner blocks still to factor in this outer panel
       if (inner_rem > 0 && !g_lazy_strips) {
         // right-looking variant: apply inner panel i to the rest of the outer panel's L-shaped strip
         dim3 ga(2 * inner_rem, nt);
-        update_kernel<<<ga, 256, upd_smem, st>>>(M, n_pad, o + NB, o + NB, Lpack, Upack, tile_chunks, i * NCHUNK,
+        update_kernel_t<false><<<ga, 256, upd_smem, st>>>(M, n_pad, o + NB, o + NB, Lpack, Upack, tile_chunks, i * NCHUNK,
                                                  NCHUNK);
         SCB_LAUNCH_CHECK();
         const int nright = nt - inner_rem;
-        if (nright > 0) {
+        if (nright > 0 && !sym) {  // (symmetric: the row strip is never read)
           dim3 gb(2 * nright, inner_rem);
-          update_kernel<<<gb, 256, upd_smem, st>>>(M, n_pad, o + NB, panel_end, Lpack, Upack, tile_chunks,
+          update_kernel_t<false><<<gb, 256, upd_smem, st>>>(M, n_pad, o + NB, panel_end, Lpack, Upack, tile_chunks,
                                                    i * NCHUNK, NCHUNK);
           SCB_LAUNCH_CHECK();
         }
@@ -911,12 +969,13 @@ extern "C" int scb_getrf_nopiv(int64_t n_pad, double* M, double* dinv, int32_t* 
     // A: the L-shaped strip that panel P+1 lives in (rows e0..e1 x all columns, rows below x cols e0..e1)
     const int nt0 = (int)((n_pad - e0) / NB), ntp = (int)((e1 - e0) / NB), nt1 = (int)((n_pad - e1) / NB);
     {
-      dim3 g1(2 * nt0, ntp);
-      update_kernel<<<g1, 256, upd_smem, s>>>(M, n_pad, e0, e0, Lpack, Upack, tile_chunks, 0, nchunks);
+      // rows of panel P+1: all columns to the right (symmetric: only the panel's own square)
+      dim3 g1(sym ? 2 * ntp : 2 * nt0, ntp);
+      update_kernel_t<false><<<g1, 256, upd_smem, s>>>(M, n_pad, e0, e0, Lpack, Upack, tile_chunks, 0, nchunks);
       SCB_LAUNCH_CHECK();
       if (nt1 > 0) {
         dim3 g2(2 * ntp, nt1);
-        update_kernel<<<g2, 256, upd_smem, s>>>(M, n_pad, e1, e0, Lpack, Upack, tile_chunks, 0, nchunks);
+        update_kernel_t<false><<<g2, 256, upd_smem, s>>>(M, n_pad, e1, e0, Lpack, Upack, tile_chunks, 0, nchunks);
         SCB_LAUNCH_CHECK();
       }
     }
@@ -928,8 +987,13 @@ extern "C" int scb_getrf_nopiv(int64_t n_pad, double* M, double* dinv, int32_t* 
     if (int rc = factor_panel(P + 1, sp)) return rc;
     // B: the rest of the trailing block, concurrently with the factorization of panel P+1
     if (nt1 > 0) {
-      dim3 g3(2 * nt1, nt1);
-      update_kernel<<<g3, 256, upd_smem, s>>>(M, n_pad, e1, e1, Lpack, Upack, tile_chunks, 0, nchunks);
+      if (sym) {  // tiles on / below the diagonal only
+        update_kernel_t<true><<<dim3(2 * nt1, nt1), 256, upd_smem, s>>>(M, n_pad, e1, e1, Lpack, Upack, tile_chunks, 0,
+                                                                         nchunks);
+      } else {
+        dim3 g3(2 * nt1, nt1);
+        update_kernel_t<false><<<g3, 256, upd_smem, s>>>(M, n_pad, e1, e1, Lpack, Upack, tile_chunks, 0, nchunks);
+      }
       SCB_LAUNCH_CHECK();
     }
   }
@@ -939,4 +1003,13 @@ extern "C" int scb_getrf_nopiv(int64_t n_pad, double* M, double* dinv, int32_t* 
     SCB_CUDA(cudaStreamWaitEvent(s, e, 0));
   }
   return SCB_OK;
+}
+
+extern "C" int scb_getrf_nopiv(int64_t n_pad, double* M, double* dinv, int32_t* info, scb_stream_t stream) {
+  return getrf_impl(n_pad, M, dinv, info, stream, false);
+}
+
+extern "C" int scb_getrf_sym_nopiv(int64_t n_pad, double* M, double* dinv, int32_t* info,
+                                   scb_stream_t stream) {
+  return getrf_impl(n_pad, M, dinv, info, stream, true);
 }

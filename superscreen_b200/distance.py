@@ -28,7 +28,7 @@ def q_matrix(points: np.ndarray) -> np.ndarray:
         # weights = 1, qdw = 0, empty sparse pattern: M[r, c] = q_rc (r != c), M[r, r] = 0
         _lib.check(L.scb_system_assemble(n, _lib.ptr(sites), _lib.ptr(ones), _lib.ptr(zeros), None, _lib.ptr(zeros),
                                          _lib.ptr(indptr), _lib.ptr(indptr), _lib.ptr(zeros), None, n, _lib.ptr(ix),
-                                         _lib.ptr(pos), n_pad, _lib.ptr(M), None, _lib.stream_ptr()))
+                                         _lib.ptr(pos), n_pad, _lib.ptr(M), None, None, _lib.stream_ptr()))
         return M[:n, :n].cpu().numpy()
 
 

@@ -218,7 +218,7 @@ class MeshOperators:
             _lib.check(L.scb_system_assemble(
                 n, _lib.ptr(d.sites), _lib.ptr(d.t["vertex_areas"]), _lib.ptr(d.qdw), None, _lib.ptr(zeros),
                 _lib.ptr(d.t["op_indptr"]), _lib.ptr(d.t["op_indices"]), _lib.ptr(d.t["laplacian"]), None,
-                n, _lib.ptr(ix), _lib.ptr(pos), n_pad, _lib.ptr(M), None, _lib.stream_ptr()))
+                n, _lib.ptr(ix), _lib.ptr(pos), n_pad, _lib.ptr(M), None, None, _lib.stream_ptr()))
             # M = -(Q * w[None, :])
             return -(M[:n, :n] / d.t["vertex_areas"][None, :])
 

@@ -46,6 +46,8 @@ class LinearSystem:
     indices_dev: object = field(repr=False, default=None)
     margin: object = field(repr=False, default=None)  # torch (n_int,) row-dominance lower bound
     refine: bool = False  # not provably dominant -> iterative refinement in every solve
+    # symmetric mode: the factors are those of S = D (-A) D^-1, D = diag(sym_scale) = sqrt(w[indices])
+    sym_scale: object = field(repr=False, default=None)
 
     @property
     def A(self) -> np.ndarray:
@@ -53,14 +55,21 @@ class LinearSystem:
         torch = _torch()
         M = assemble_negA(self.film_info, self.indices_dev, len(self.indices), self.n_pad,
                           self.grad_Lambda_term if not isinstance(self.grad_Lambda_term, float) else None)[0]
+        # (always the plain, unsymmetrised -A)
         n = len(self.indices)
         return (-M[:n, :n]).cpu().numpy()
 
     @property
     def lu_piv(self) -> Tuple[np.ndarray, np.ndarray]:
-        """(lu, piv) in scipy.linalg.lu_factor layout; piv is the identity (no pivoting)."""
+        """(lu, piv) of ``-A`` in scipy.linalg.lu_factor layout; piv is the identity (no pivoting).
+        In symmetric mode the stored factors belong to S = D (-A) D^-1; since
+        -A = (D^-1 L D)(D^-1 U D) with D^-1 L D still unit lower triangular, they are rescaled
+        element-wise on the way out."""
         n = len(self.indices)
-        return self.lu[:n, :n].cpu().numpy(), np.arange(n, dtype=np.int32)
+        lu = self.lu[:n, :n]
+        if self.sym_scale is not None:
+            lu = lu * (self.sym_scale[None, :] / self.sym_scale[:, None])
+        return lu.cpu().numpy(), np.arange(n, dtype=np.int32)
 
 
 @dataclass
@@ -77,8 +86,10 @@ class TerminalSystems:
     film_without_boundary_or_holes: Optional[LinearSystem] = None
 
 
-def assemble_negA(info: FilmInfo, ix_dev, n_int: int, n_pad: int, T=None, out=None, want_margin=False):
-    """-A restricted to ``ix`` in a padded workspace (reference solve_film.py:296-305)."""
+def assemble_negA(info: FilmInfo, ix_dev, n_int: int, n_pad: int, T=None, out=None, want_margin=False,
+                  sym_scale_full=None):
+    """-A restricted to ``ix`` in a padded workspace (reference solve_film.py:296-305), or, with
+    ``sym_scale_full`` = sqrt(w) per mesh vertex, its diagonally similar symmetric form."""
     torch = _torch()
     L = _lib.lib()
     d = info.mesh._data
@@ -90,7 +101,7 @@ def assemble_negA(info: FilmInfo, ix_dev, n_int: int, n_pad: int, T=None, out=No
             d.n, _lib.ptr(d.sites), _lib.ptr(d.t["vertex_areas"]), _lib.ptr(d.qdw), _lib.ptr(d.t["C"]),
             _lib.ptr(info.dev["Lambda"]), _lib.ptr(d.t["op_indptr"]), _lib.ptr(d.t["op_indices"]),
             _lib.ptr(d.t["laplacian"]), _lib.ptr(T), n_int, _lib.ptr(ix_dev), _lib.ptr(pos), n_pad,
-            _lib.ptr(M), _lib.ptr(margin), _lib.stream_ptr()))
+            _lib.ptr(M), _lib.ptr(margin), _lib.ptr(sym_scale_full), _lib.stream_ptr()))
     return M, margin
 
 
@@ -116,6 +127,12 @@ def factorize_linear_systems(device: Device, film_info_dict: Dict[str, FilmInfo]
                     d.n, _lib.ptr(d.t["op_indptr"]), _lib.ptr(d.t["op_indices"]), _lib.ptr(d.t["gradient_x"]),
                     _lib.ptr(d.t["gradient_y"]), _lib.ptr(info.dev["Lambda"]), _lib.ptr(T), _lib.stream_ptr()))
             info.dev["T"] = T
+            # For a constant Lambda, -A is diagonally similar (D = W^1/2) to a symmetric matrix:
+            # factor that one with the symmetric LU at half the flops.
+            Lam = info.lambda_info.Lambda
+            sym_full = None
+            if use_symmetric() and T is None and float(Lam.max()) == float(Lam.min()):
+                sym_full = torch.sqrt(d.t["vertex_areas"])
             hole_systems[film_name] = {}
             for hole_name, indices in info.hole_indices.items():
                 hole_systems[film_name][hole_name] = LinearSystem(
@@ -128,13 +145,14 @@ def factorize_linear_systems(device: Device, film_info_dict: Dict[str, FilmInfo]
                     raise ValueError(f"Film {film_name!r} has no interior mesh vertices.")
                 n_pad = -(-n_int // LU_BLOCK) * LU_BLOCK
                 ix_dev = torch.as_tensor(indices).to(d.device)
-                M, margin = assemble_negA(info, ix_dev, n_int, n_pad, T, want_margin=True)
+                M, margin = assemble_negA(info, ix_dev, n_int, n_pad, T, want_margin=True, sym_scale_full=sym_full)
                 dinv = torch.empty(int(L.scb_getrf_dinv_bytes(n_pad)) // 8, dtype=torch.float64, device=d.device)
                 lu_info = torch.zeros(1, dtype=torch.int32, device=d.device)
-                _lib.check(L.scb_getrf_nopiv(n_pad, _lib.ptr(M), _lib.ptr(dinv), _lib.ptr(lu_info),
-                                             _lib.stream_ptr()))
+                getrf = L.scb_getrf_sym_nopiv if sym_full is not None else L.scb_getrf_nopiv
+                _lib.check(getrf(n_pad, _lib.ptr(M), _lib.ptr(dinv), _lib.ptr(lu_info), _lib.stream_ptr()))
                 system = LinearSystem(indices=indices, film_info=info, grad_Lambda_term=T if T is not None else 0.0,
-                                      n_pad=n_pad, lu=M, dinv=dinv, indices_dev=ix_dev, margin=margin)
+                                      n_pad=n_pad, lu=M, dinv=dinv, indices_dev=ix_dev, margin=margin,
+                                      sym_scale=None if sym_full is None else sym_full[ix_dev].contiguous())
                 pending.append((film_name, system, lu_info, margin.min()))
                 return system
 
@@ -180,6 +198,13 @@ def factorize_linear_systems(device: Device, film_info_dict: Dict[str, FilmInfo]
     return film_systems, hole_systems, terminal_systems
 
 
+def use_symmetric() -> bool:
+    """Symmetric factorization for constant-Lambda films (default on; SCB_SYMMETRIC=0 disables)."""
+    import os
+
+    return os.environ.get("SCB_SYMMETRIC", "1") != "0"
+
+
 def apply_operator(info: FilmInfo, v, src_idx=None, with_sparse: bool = True, out=None, accumulate: bool = False):
     """out[n, nrhs] (+)= A_full[:, src] @ v[src]  (matrix-free; v must vanish outside src)."""
     torch = _torch()
@@ -211,10 +236,13 @@ def lu_solve(system: LinearSystem, h):
     nrhs = h2.shape[1]
     with torch.cuda.device(system.lu.device):
         B = torch.zeros(system.n_pad, nrhs, dtype=torch.float64, device=system.lu.device)
-        B[:n_int] = h2
+        # symmetric mode: (-A) x = h  <=>  S (D x) = D h
+        B[:n_int] = h2 if system.sym_scale is None else h2 * system.sym_scale[:, None]
         _lib.check(L.scb_getrs_nopiv(system.n_pad, _lib.ptr(system.lu), _lib.ptr(system.dinv), nrhs, _lib.ptr(B),
                                      _lib.stream_ptr()))
     x = B[:n_int]
+    if system.sym_scale is not None:
+        x = x / system.sym_scale[:, None]
     return x if h.dim() == 2 else x[:, 0]
 
 

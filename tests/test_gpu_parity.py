@@ -199,6 +199,7 @@ def test_square_inhomogeneous_lambda(sc, golden):
     device.set_meshes({"sq": mesh})
     model = sc.factorize_model(device=device, current_units="uA")
     assert model.film_info["sq"].lambda_info.inhomogeneous
+    assert model.film_systems["sq"].sym_scale is None  # grad-Lambda term: general (unsymmetric) LU
     assert np.array_equal(model.film_systems["sq"].indices, g["in_interior_indices"])
     assert rel_l2(model.film_systems["sq"].A, g["out_A"]) <= TOL_LOCAL
     conv = sc.field_conversion_factor("mT", "uA", "um").magnitude
@@ -383,3 +384,39 @@ def test_static_c_vector_and_q_matrix(sc):
     off = ~np.eye(400, dtype=bool)
     assert rel_l2(Q[off], Qref[off]) <= TOL_LOCAL
     assert rel_l2(np.diag(Q)[inner], np.diag(Qref)[inner]) <= 1e-11
+
+
+def test_symmetric_factorization_matches_general(sc, monkeypatch):
+    """Constant-Lambda films are factored through the diagonally similar symmetric form
+    S = D (-A) D^-1 (half the flops).  It must agree with the general factorization far inside
+    the solution tolerance, be bit-reproducible run to run, and still expose (lu, piv) of -A."""
+    import torch
+
+    from superscreen_b200.geometry import box
+    from superscreen_b200.synthetic import square_mesh
+
+    sites, elements = square_mesh(10.0, 6000, seed=5)
+
+    def run(mode):
+        monkeypatch.setenv("SCB_SYMMETRIC", mode)
+        device = sc.Device("sq", layers=[sc.Layer("layer", Lambda=0.1, z0=0.0)],
+                           films=[sc.Polygon("film", layer="layer", points=box(10.0, points=4))])
+        device.set_meshes({"film": (sites, elements)})
+        model = sc.factorize_model(device=device, current_units="uA")
+        sol = sc.solve(model=model, applied_field=sc.ConstantField(1.0))[0].film_solutions["film"]
+        return model.film_systems["film"], sol
+
+    sys_g, sol_g = run("0")
+    sys_s, sol_s = run("1")
+    sys_s2, sol_s2 = run("1")
+    assert sys_g.sym_scale is None and sys_s.sym_scale is not None
+    assert rel_l2(sol_s.stream, sol_g.stream) <= 1e-11
+    assert rel_l2(sol_s.current_density, sol_g.current_density) <= 1e-10
+    assert torch.equal(sys_s.lu, sys_s2.lu), "symmetric LU must be bit-reproducible"
+    assert np.array_equal(sol_s.stream, sol_s2.stream)
+    # host view: unit-lower L and U of the plain -A (no row exchanges)
+    lu, piv = sys_s.lu_piv
+    assert np.array_equal(piv, np.arange(len(piv), dtype=np.int32))
+    Lf = np.tril(lu, -1) + np.eye(len(lu))
+    assert rel_l2(Lf @ np.triu(lu), -sys_s.A) <= 1e-12
+

@@ -12,6 +12,7 @@ ap.add_argument("--stage", default="getrf")
 ap.add_argument("--n", type=int, default=20164)
 ap.add_argument("--reps", type=int, default=1)
 ap.add_argument("--nrhs", type=int, default=1)
+ap.add_argument("--sym", type=int, default=1)
 args = ap.parse_args()
 L = _lib.lib()
 sites, elements = square_mesh(10.0, args.n, seed=0)
@@ -53,16 +54,20 @@ M = torch.empty(n_pad, n_pad, dtype=torch.float64, device="cuda")
 dinv = torch.empty(int(L.scb_getrf_dinv_bytes(n_pad)) // 8, dtype=torch.float64, device="cuda")
 flag = torch.zeros(1, dtype=torch.int32, device="cuda")
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+sym_full = torch.sqrt(info.mesh._data.t["vertex_areas"]) if args.sym else None
 for rep in range(args.reps):
-    assemble_negA(info, ix, n_int, n_pad, None, out=M)
+    assemble_negA(info, ix, n_int, n_pad, None, out=M, sym_scale_full=sym_full)
     torch.cuda.synchronize()
     e0.record()
-    _lib.check(L.scb_getrf_nopiv(n_pad, _lib.ptr(M), _lib.ptr(dinv), _lib.ptr(flag), _lib.stream_ptr()))
+    fn = L.scb_getrf_sym_nopiv if args.sym else L.scb_getrf_nopiv
+    _lib.check(fn(n_pad, _lib.ptr(M), _lib.ptr(dinv), _lib.ptr(flag), _lib.stream_ptr()))
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
-    print(f"getrf n_int={n_int} n_pad={n_pad}: {ms:.2f} ms  {(2/3)*n_int**3/ms*1e-9:.2f} TFLOP/s  info={int(flag.item())}")
+    fl = (1/3 if args.sym else 2/3) * n_int**3
+    print(f"getrf sym={args.sym} n_int={n_int} n_pad={n_pad}: {ms:.2f} ms  {fl/ms*1e-9:.2f} TFLOP/s executed  ({(2/3)*n_int**3/ms*1e-9:.2f} getrf-equivalent)  info={int(flag.item())}")
 if args.stage == "getrs":
-    system = LinearSystem(indices=info.interior_indices, film_info=info, n_pad=n_pad, lu=M, dinv=dinv, indices_dev=ix)
+    system = LinearSystem(indices=info.interior_indices, film_info=info, n_pad=n_pad, lu=M, dinv=dinv, indices_dev=ix,
+                          sym_scale=None if sym_full is None else sym_full[ix].contiguous())
     h = torch.randn(n_int, args.nrhs, dtype=torch.float64, device="cuda")
     for rep in range(args.reps + 1):
         e0.record(); x = lu_solve(system, h); e1.record(); torch.cuda.synchronize()
