@@ -374,13 +374,18 @@ def run_b200_arm(args):
         "lu_getrf_equivalent_tflops": getrf_equiv_tflops, "films_per_s": world / (ms_per_step * 1e-3),
         "roofline": {"bound": "tensor", "achieved": lu_tflops, "peak": FP64_DMMA_PEAK_TFLOPS, "unit": "TFLOP/s",
                      "frac": lu_tflops / FP64_DMMA_PEAK_TFLOPS,
-                     # DRAM bytes (read + write) of the dominant launch, the first K=1024 bulk trailing
-                     # update (ncu --set full, profiles/r01_update_kernel_bulk_k1024_ncu.txt); its
-                     # algorithmic C traffic is 5.14 GB, the rest are packed-operand re-reads that miss L2
-                     "traffic": 25.6e9,
-                     "dominant_launch": {"kernel": "scb::update_kernel grid (280,140) K=1024", "flop": 657.7e9,
-                                         "ms": 18.375, "achieved": 35.79, "frac": 35.79 / FP64_DMMA_PEAK_TFLOPS,
-                                         "dmma_pipe_active_pct": 96.4, "source": "ncu, profiles/"},
+                     # DRAM bytes (read + write) of the dominant launch = the first K=1024 bulk trailing
+                     # update (ncu --set full, profiles/r01_update_kernel*_bulk_k1024_ncu.txt); most of it
+                     # are packed-operand re-reads that miss L2 (algorithmic C traffic: 2.59 / 5.14 GB)
+                     "traffic": 10.26e9 if symmetric else 25.6e9,
+                     "dominant_launch": (
+                         {"kernel": "scb::update_kernel_t<true> grid (280,140), 19740 lower-triangle tiles, K=1024",
+                          "flop": 331.2e9, "ms": 9.326, "achieved": 35.51, "frac": 35.51 / FP64_DMMA_PEAK_TFLOPS,
+                          "dmma_pipe_active_pct": 96.2, "source": "ncu, profiles/r01_update_kernel_tri_bulk_k1024_ncu.txt"}
+                         if symmetric else
+                         {"kernel": "scb::update_kernel_t<false> grid (280,140) K=1024", "flop": 657.7e9,
+                          "ms": 18.375, "achieved": 35.79, "frac": 35.79 / FP64_DMMA_PEAK_TFLOPS,
+                          "dmma_pipe_active_pct": 96.4, "source": "ncu, profiles/r01_update_kernel_bulk_k1024_ncu.txt"}),
                      "kernel": ("scb_getrf_sym_nopiv" if symmetric else "scb_getrf_nopiv") + " = all launches of one factorization (update_kernel DMMA trailing "
                                "updates + diag/trsm panel kernels, look-ahead on a second stream), timed live with "
                                "CUDA events",

@@ -98,6 +98,14 @@ int scb_mesh_build(int64_t n, int64_t m, const double* sites, const int64_t* ele
                    const int32_t* workspace, int weight_method, const scb_mesh_out* out,
                    scb_stream_t stream);
 
+/* One Laplacian-smoothing sweep (Mesh.smooth, device/mesh.py:172-211): out_sites[i] = mean of the
+ * neighbours of i (summed in the reference's order: neighbours > i ascending, then neighbours < i
+ * ascending), boundary vertices copied unchanged.  adj_* and boundary_indices are the arrays
+ * produced by scb_mesh_build for the same triangulation.  Not in place. */
+int scb_mesh_smooth(int64_t n, const double* sites, const int32_t* adj_indptr, const int32_t* adj_indices,
+                    int64_t n_boundary, const int64_t* boundary_indices, double* out_sites,
+                    scb_stream_t stream);
+
 /* ------------------------------------------------------------------------------------
  * Kernel matrix pieces and system assembly  (K1-K3, K8-K10, K19, rows a1-a3, a9-a11)
  *   distance.py:87-115 q_matrix, device/mesh.py:434-458 Q_matrix,

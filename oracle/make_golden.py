@@ -293,10 +293,26 @@ def golden_transport(sc):
     return out
 
 
+def golden_smooth(sc):
+    """Mesh.smooth (device/mesh.py:172-211) on the jittered ring mesh: sites after 1 and after 4 sweeps."""
+    from superscreen.device.mesh import Mesh
+
+    ring = np.load(os.path.join(OUT, "ring.npz"))
+    sites, elements = ring["in_sites"], ring["in_elements"]
+    out = {"in_sites": sites, "in_elements": elements}
+    mesh = Mesh.from_triangulation(sites, elements, build_operators=False)
+    out["out_sites_1"] = mesh.smooth(1, build_operators=False).sites
+    m4 = mesh.smooth(4, build_operators=True)
+    out["out_sites_4"] = m4.sites
+    out["out_vertex_areas_4"] = m4.vertex_areas
+    np.savez_compressed(os.path.join(OUT, "smooth.npz"), **out)
+    return out
+
+
 def main():
     sc = load_reference()
     os.makedirs(OUT, exist_ok=True)
-    for fn in (golden_ring, golden_two_rings, golden_square_inhomogeneous, golden_transport):
+    for fn in (golden_ring, golden_two_rings, golden_square_inhomogeneous, golden_transport, golden_smooth):
         o = fn(sc)
         print(fn.__name__, {k: v.shape for k, v in o.items() if hasattr(v, "shape") and k.startswith("in_") and v.ndim > 0})
     with open(os.path.join(OUT, "README.md"), "w") as f:

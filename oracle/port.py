@@ -100,6 +100,25 @@ def directed_star(triangles: np.ndarray, num_sites: int):
 # ----------------------------------------------------------------------------------------
 # mesh float structures (a4, a6-a8)
 # ----------------------------------------------------------------------------------------
+def smooth_sites(sites: np.ndarray, elements: np.ndarray, iterations: int) -> np.ndarray:
+    """Laplacian smoothing of the vertex positions (reference device/mesh.py:172-211): each sweep
+    moves every vertex to the mean of its neighbours (two bincount passes over the sorted edge
+    list, then a division by the neighbour count) and restores the boundary vertices."""
+    edges, _ = get_edges(elements)
+    n = len(sites)
+    boundary = find_boundary_indices(elements)
+    num_neighbors = np.bincount(edges.ravel(), minlength=n)
+    sites = np.asarray(sites, dtype=np.float64)
+    for _ in range(iterations):
+        new = np.zeros((n, 2))
+        new += np.array([np.bincount(edges[:, 0], v, minlength=n) for v in sites[edges[:, 1]].T]).T
+        new += np.array([np.bincount(edges[:, 1], v, minlength=n) for v in sites[edges[:, 0]].T]).T
+        new /= num_neighbors[:, np.newaxis]
+        new[boundary] = sites[boundary]
+        sites = new
+    return sites
+
+
 def triangle_areas(points: np.ndarray, triangles: np.ndarray) -> np.ndarray:
     """Signed triangle areas (reference device/utils.py:230-248)."""
     xy = points[triangles]

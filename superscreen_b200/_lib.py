@@ -45,6 +45,7 @@ EXPORTS = {
     "scb_mesh_workspace_elems": (c_int64, [c_int64, c_int64]),
     "scb_mesh_analyze": (c_int, [c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "scb_mesh_build": (c_int, [c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_int, POINTER(MeshOut), c_void_p]),
+    "scb_mesh_smooth": (c_int, [c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     "scb_c_vector": (c_int, [c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "scb_kernel_diagonal": (c_int, [c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "scb_grad_lambda_term": (c_int, [c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),

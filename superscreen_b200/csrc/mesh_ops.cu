@@ -498,3 +498,58 @@ extern "C" int scb_c_vector(int64_t n, const double* points, double* scratch, do
   SCB_LAUNCH_CHECK();
   return SCB_OK;
 }
+
+// ---------------------------------------------------------------------------------------
+// Laplacian smoothing sweep (reference device/mesh.py:172-211): every vertex moves to the mean of
+// its neighbours; boundary vertices are restored afterwards.  The reference accumulates, per
+// coordinate, first the neighbours j > i and then the neighbours j < i, each in ascending order
+// (two np.bincount passes over the lexicographically sorted edge list), and divides by the
+// neighbour count: the same order is used here so the result is bit-identical.
+// ---------------------------------------------------------------------------------------
+namespace scb {
+__global__ void smooth_kernel(int64_t n, const double* __restrict__ sites, const int32_t* __restrict__ indptr,
+                              const int32_t* __restrict__ indices, double* __restrict__ out) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int b = indptr[i], e = indptr[i + 1];
+  double lox = 0.0, loy = 0.0, hix = 0.0, hiy = 0.0;
+  for (int p = b; p < e; p++) {  // rows are sorted: j < i first, then j > i
+    const int j = indices[p];
+    const double2 sj = *reinterpret_cast<const double2*>(sites + 2 * (int64_t)j);
+    if (j < i) {
+      lox += sj.x;
+      loy += sj.y;
+    } else {
+      hix += sj.x;
+      hiy += sj.y;
+    }
+  }
+  const double cnt = (double)(e - b);
+  out[2 * i] = (hix + lox) / cnt;
+  out[2 * i + 1] = (hiy + loy) / cnt;
+}
+__global__ void restore_boundary_kernel(int64_t nb, const int64_t* __restrict__ boundary,
+                                        const double* __restrict__ sites, double* __restrict__ out) {
+  const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (k >= nb) return;
+  const int64_t i = boundary[k];
+  out[2 * i] = sites[2 * i];
+  out[2 * i + 1] = sites[2 * i + 1];
+}
+}  // namespace scb
+
+extern "C" int scb_mesh_smooth(int64_t n, const double* sites, const int32_t* adj_indptr,
+                               const int32_t* adj_indices, int64_t n_boundary, const int64_t* boundary_indices,
+                               double* out_sites, scb_stream_t stream) {
+  SCB_CHECK_ARG(n > 0, "empty mesh");
+  SCB_CHECK_ARG(sites != out_sites, "smoothing cannot run in place");
+  cudaStream_t s = (cudaStream_t)stream;
+  scb::smooth_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(n, sites, adj_indptr, adj_indices, out_sites);
+  SCB_LAUNCH_CHECK();
+  if (n_boundary > 0) {
+    scb::restore_boundary_kernel<<<(unsigned)((n_boundary + 127) / 128), 128, 0, s>>>(n_boundary, boundary_indices,
+                                                                                     sites, out_sites);
+    SCB_LAUNCH_CHECK();
+  }
+  return SCB_OK;
+}

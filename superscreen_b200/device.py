@@ -217,9 +217,11 @@ class Device:
         self.meshes = out
 
     def make_mesh(self, target_vertices: Union[int, Dict[str, int]] = 2000, buffer_factor: float = 0.05,
-                  seed: int = 0) -> None:
+                  seed: int = 0, smooth: int = 0) -> None:
         """Synthetic stand-in for ``Device.make_mesh`` (reference device/device.py:383-471): meshes
-        the bounding disk/box of each film (convex outlines only) with ``synthetic.make_mesh``."""
+        the bounding disk/box of each film (convex outlines only) with ``synthetic.make_mesh``;
+        ``smooth`` Laplacian-smoothing sweeps are applied on the device like the reference's
+        ``smooth`` argument (device/device.py:463-467 -> Mesh.smooth)."""
         from .synthetic import make_mesh
 
         holes_by_film = self.holes_by_film()
@@ -236,6 +238,8 @@ class Device:
                 outline = pts
             meshes[name] = make_mesh(outline, target_vertices=nv, embedded=embedded, seed=seed + k)
         self.set_meshes(meshes)
+        if smooth:
+            self.meshes = {name: mesh.smooth(smooth) for name, mesh in self.meshes.items()}
 
     def boundary_vertices(self, film: str) -> np.ndarray:
         """Boundary vertex indices of a film's mesh ordered counter-clockwise (reference

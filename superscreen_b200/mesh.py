@@ -314,6 +314,29 @@ class Mesh:
         d = self._data
         return d.host("star_indptr"), d.host("star_heads"), d.host("star_tris")
 
+    def smooth(self, iterations: int, build_operators: bool = True) -> "Mesh":
+        """Laplacian smoothing: every interior vertex moves to the arithmetic mean of its
+        neighbours, ``iterations`` times (reference device/mesh.py:172-211).  The sweeps run on the
+        device (``scb_mesh_smooth``) with the reference's summation order; the topology is
+        unchanged, so only the final mesh is rebuilt."""
+        if iterations <= 0:
+            return self
+        torch = _torch()
+        L = _lib.lib()
+        d = self._data
+        with torch.cuda.device(d.device):
+            cur = d.sites
+            nb = int(d.t["boundary_indices"].numel())
+            for _ in range(int(iterations)):
+                new = torch.empty_like(cur)
+                _lib.check(L.scb_mesh_smooth(d.n, _lib.ptr(cur), _lib.ptr(d.t["adj_indptr"]),
+                                             _lib.ptr(d.t["adj_indices"]), nb, _lib.ptr(d.t["boundary_indices"]),
+                                             _lib.ptr(new), _lib.stream_ptr()))
+                cur = new
+            new_sites = cur.cpu().numpy()
+        return Mesh.from_triangulation(new_sites, self.elements, build_operators=build_operators,
+                                       weight_method=d.weight_method, device=str(d.device))
+
     def stats(self) -> Dict[str, Union[int, float]]:
         el = self.edge_mesh.edge_lengths
         va = self.vertex_areas

@@ -420,3 +420,17 @@ def test_symmetric_factorization_matches_general(sc, monkeypatch):
     Lf = np.tril(lu, -1) + np.eye(len(lu))
     assert rel_l2(Lf @ np.triu(lu), -sys_s.A) <= 1e-12
 
+
+
+def test_mesh_smooth_against_reference_golden(sc, golden):
+    """Mesh.smooth on the device (scb_mesh_smooth) against the reference's Mesh.smooth: the
+    summation order is reproduced, so the smoothed coordinates are bit-identical."""
+    g = golden("smooth")
+    mesh = sc.Mesh.from_triangulation(g["in_sites"], g["in_elements"], build_operators=False)
+    assert mesh.smooth(0) is mesh
+    assert np.array_equal(mesh.smooth(1, build_operators=False).sites, g["out_sites_1"])
+    m4 = mesh.smooth(4)
+    assert np.array_equal(m4.sites, g["out_sites_4"])
+    assert np.array_equal(m4.boundary_indices, mesh.boundary_indices)
+    assert rel_l2(m4.vertex_areas, g["out_vertex_areas_4"]) <= TOL_LOCAL
+    assert m4.operators is not None
