@@ -375,6 +375,16 @@ __device__ __forceinline__ double fast_rcp(double a) {
   return fma(r, e, r);
 }
 
+// two Newton steps (what the compiler's own fp64 division uses on the MUFU.RCP64H seed)
+__device__ __forceinline__ double fast_rcp2(double a) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(a));
+  double e = fma(-a, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-a, r, 1.0);
+  return fma(r, e, r);
+}
+
 __global__ void __launch_bounds__(512, 1)
 diag_kernel(double* __restrict__ M, int64_t ld, int64_t o, double* __restrict__ invL,
             double* __restrict__ invU, int32_t* __restrict__ info, int block_index) {
@@ -504,12 +514,18 @@ diag_kernel(double* __restrict__ M, int64_t ld, int64_t o, double* __restrict__ 
 //       A22 -> sweep64 -> L22, U22, inv(L22), inv(U22)
 //       inv(L)21 = -inv(L22) L21 inv(L11),  inv(U)12 = -inv(U11) U12 inv(U22)
 // ---------------------------------------------------------------------------------------
+#ifndef SCB_STAMP
+#define SCB_STAMP(i)  // phase time stamps, only defined by tools/diag_phases.cu
+#endif
 constexpr int QN = 64;        // quadrant size
 constexpr int QLD = QN + 4;   // 68: conflict-free DMMA fragment loads (ld % 16 == 4)
 
 // fused LU + inv(L) + inv(U)^T-elimination sweep on a 64x64 block held in registers:
 // thread (ti = warp 0..7, tj = lane) owns rows ti + 8a (a < 8) and columns tj + 32b (b < 2).
 // Dout[64][QLD] receives the finished L (strictly lower) and U (upper) entries.
+// SYM: the block is symmetric, so inv(U) = inv(L)^T D^-1 is derived afterwards and the U^T
+// elimination (rows above the pivot) is skipped; slots above the diagonal then keep U.
+template <bool SYM>
 __device__ __forceinline__ int sweep64(double (&x)[8][2], double* __restrict__ Dout, double (*rowb)[QN],
                                        double (*colb)[QN], double* __restrict__ rdiag) {
   const int tid = threadIdx.x;
@@ -558,10 +574,12 @@ __device__ __forceinline__ int sweep64(double (&x)[8][2], double* __restrict__ D
             }
           }
         } else if (a < ap || (a == ap && r < j)) {
+          if (!SYM) {
 #pragma unroll
-          for (int b = 0; b < 2; b++) {
-            if (b < bj) continue;
-            if (b > bj || tj + 32 * b > j) x[a][b] = fma(-w, vs[b], x[a][b]);
+            for (int b = 0; b < 2; b++) {
+              if (b < bj) continue;
+              if (b > bj || tj + 32 * b > j) x[a][b] = fma(-w, vs[b], x[a][b]);
+            }
           }
         } else {
 #pragma unroll
@@ -569,7 +587,7 @@ __device__ __forceinline__ int sweep64(double (&x)[8][2], double* __restrict__ D
             if (b < bj) continue;
             const int c = tj + 32 * b;
             if (b > bj || c >= j) Dout[j * QLD + c] = x[a][b];
-            if (b > bj || c > j) x[a][b] = -vs[b];
+            if (!SYM && (b > bj || c > j)) x[a][b] = -vs[b];
           }
         }
       }
@@ -661,6 +679,33 @@ __device__ __forceinline__ void emit_inverses(const double (&x)[8][2], const dou
     }
 }
 
+// symmetric block: inv(L) from the sweep registers, inv(U) = inv(L)^T D^-1 through the shared copy
+__device__ __forceinline__ void emit_inverses_sym(const double (&x)[8][2], const double* __restrict__ rdiag,
+                                                  double* __restrict__ SL, double* __restrict__ SU,
+                                                  double* __restrict__ GL, double* __restrict__ GU) {
+  const int ti = threadIdx.x >> 5, tj = threadIdx.x & 31;
+#pragma unroll
+  for (int a = 0; a < 8; a++)
+#pragma unroll
+    for (int b = 0; b < 2; b++) {
+      const int r = ti + 8 * a, c = tj + 32 * b;
+      const double il = c < r ? x[a][b] : (c == r ? 1.0 : 0.0);
+      SL[r * QLD + c] = il;
+      GL[r * NB + c] = il;
+    }
+  __syncthreads();
+#pragma unroll
+  for (int a = 0; a < 8; a++)
+#pragma unroll
+    for (int b = 0; b < 2; b++) {
+      const int r = ti + 8 * a, c = tj + 32 * b;
+      const double iu = c > r ? SL[c * QLD + r] * rdiag[c] : (c == r ? rdiag[c] : 0.0);
+      if (SU) SU[r * QLD + c] = iu;
+      GU[r * NB + c] = iu;
+    }
+}
+
+template <bool SYM>
 __global__ void __launch_bounds__(256, 2)
 diag_kernel_small(double* __restrict__ M, int64_t ld, int64_t o, double* __restrict__ invL,
                   double* __restrict__ invU, int32_t* __restrict__ info, int block_index) {
@@ -668,7 +713,7 @@ diag_kernel_small(double* __restrict__ M, int64_t ld, int64_t o, double* __restr
   double* S0 = reinterpret_cast<double*>(smem_raw);
   double* S1 = S0 + QN * QLD;
   double* S2 = S1 + QN * QLD;
-  __shared__ double rowb[2][QN], colb[2][QN], rdiag[QN];
+  __shared__ double rowb[2][QN], colb[2][QN], rdiag[QN], dvec[QN];
   const int tid = threadIdx.x, ti = tid >> 5, tj = tid & 31;
   double* A11 = M + o * ld + o;
   double* A12 = A11 + QN;
@@ -682,25 +727,35 @@ diag_kernel_small(double* __restrict__ M, int64_t ld, int64_t o, double* __restr
   for (int a = 0; a < 8; a++)
 #pragma unroll
     for (int b = 0; b < 2; b++) x[a][b] = A11[(int64_t)(ti + 8 * a) * ld + tj + 32 * b];
-  int bad = sweep64(x, S0, rowb, colb, rdiag);
-  emit_inverses(x, rdiag, S1, S2, invL, invU);  // S1 = inv(L11), S2 = inv(U11)
+  SCB_STAMP(0);
+  int bad = sweep64<SYM>(x, S0, rowb, colb, rdiag);
+  SCB_STAMP(1);
+  if (SYM) {
+    emit_inverses_sym(x, rdiag, S1, S2, invL, invU);  // S1 = inv(L11), S2 = inv(U11)
+    if (tid < QN) dvec[tid] = S0[tid * QLD + tid];    // diagonal of U11
+  } else {
+    emit_inverses(x, rdiag, S1, S2, invL, invU);
+  }
   store_quadrant(A11, ld, S0);                   // L11 \ U11 in place
   __syncthreads();
-  // ---- phase 2a: U12 = inv(L11) A12 ----
-  load_quadrant(S0, A12, ld);
-  __syncthreads();
-  gemm64(S1, S0, acc);
-  __syncthreads();
+  SCB_STAMP(2);
+  if (!SYM) {
+    // ---- phase 2a: U12 = inv(L11) A12 ----
+    load_quadrant(S0, A12, ld);
+    __syncthreads();
+    gemm64(S1, S0, acc);
+    __syncthreads();
 #pragma unroll
-  for (int i = 0; i < 2; i++)
+    for (int i = 0; i < 2; i++)
 #pragma unroll
-    for (int j = 0; j < 4; j++) {
-      const int r = frag_row(i), c = frag_col(j);
-      const double2 v = make_double2(acc[i][j][0], acc[i][j][1]);
-      *reinterpret_cast<double2*>(&S0[r * QLD + c]) = v;            // S0 = U12
-      *reinterpret_cast<double2*>(A12 + (int64_t)r * ld + c) = v;
-    }
-  // ---- phase 2b: L21 = A21 inv(U11) ----
+      for (int j = 0; j < 4; j++) {
+        const int r = frag_row(i), c = frag_col(j);
+        const double2 v = make_double2(acc[i][j][0], acc[i][j][1]);
+        *reinterpret_cast<double2*>(&S0[r * QLD + c]) = v;            // S0 = U12
+        *reinterpret_cast<double2*>(A12 + (int64_t)r * ld + c) = v;
+      }
+  }
+  // ---- phase 2b: L21 = A21 inv(U11)   (symmetric: U12 = diag(U11) L21^T) ----
   load_quadrant(S1, A21, ld);
   __syncthreads();
   gemm64(S1, S2, acc);
@@ -713,8 +768,16 @@ diag_kernel_small(double* __restrict__ M, int64_t ld, int64_t o, double* __restr
       const double2 v = make_double2(acc[i][j][0], acc[i][j][1]);
       *reinterpret_cast<double2*>(&S1[r * QLD + c]) = v;            // S1 = L21
       *reinterpret_cast<double2*>(A21 + (int64_t)r * ld + c) = v;
+      if (SYM) {
+        const double u0 = dvec[c] * v.x, u1 = dvec[c + 1] * v.y;
+        S0[c * QLD + r] = u0;                                       // S0 = U12
+        S0[(c + 1) * QLD + r] = u1;
+        A12[(int64_t)c * ld + r] = u0;
+        A12[(int64_t)(c + 1) * ld + r] = u1;
+      }
     }
   __syncthreads();
+  SCB_STAMP(3);
   // ---- phase 3: A22 -= L21 U12  -> S2 ----
   gemm64(S1, S0, acc);
 #pragma unroll
@@ -732,15 +795,21 @@ diag_kernel_small(double* __restrict__ M, int64_t ld, int64_t o, double* __restr
 #pragma unroll
     for (int b = 0; b < 2; b++) x[a][b] = S2[(ti + 8 * a) * QLD + tj + 32 * b];
   __syncthreads();
-  const int bad2 = sweep64(x, S2, rowb, colb, rdiag);
+  SCB_STAMP(4);
+  const int bad2 = sweep64<SYM>(x, S2, rowb, colb, rdiag);
+  SCB_STAMP(5);
   if (bad == 0 && bad2) bad = QN + bad2;
   if (tid == 0 && bad) atomicCAS(info, 0, block_index * NB + bad);
   store_quadrant(A22, ld, S2);                   // L22 \ U22 in place
   __syncthreads();
   double* iL22 = invL + QN * NB + QN;
   double* iU22 = invU + QN * NB + QN;
-  emit_inverses(x, rdiag, S2, nullptr, iL22, iU22);  // S2 = inv(L22)
+  if (SYM)
+    emit_inverses_sym(x, rdiag, S2, nullptr, iL22, iU22);  // S2 = inv(L22)
+  else
+    emit_inverses(x, rdiag, S2, nullptr, iL22, iU22);
   __syncthreads();
+  SCB_STAMP(6);
   // ---- phase 5a: inv(L)21 = -(inv(L22) L21) inv(L11) ----
   gemm64(S2, S1, acc);
   __syncthreads();
@@ -760,32 +829,320 @@ diag_kernel_small(double* __restrict__ M, int64_t ld, int64_t o, double* __restr
       *reinterpret_cast<double2*>(invL + (int64_t)(QN + r) * NB + c) = make_double2(-acc[i][j][0], -acc[i][j][1]);
       *reinterpret_cast<double2*>(invL + (int64_t)r * NB + QN + c) = make_double2(0.0, 0.0);
       *reinterpret_cast<double2*>(invU + (int64_t)(QN + r) * NB + c) = make_double2(0.0, 0.0);
+      if (SYM) {  // inv(U)12 = (inv(L)21)^T D2^-1   (rdiag now holds 1 / diag(U22))
+        invU[(int64_t)c * NB + QN + r] = -acc[i][j][0] * rdiag[r];
+        invU[(int64_t)(c + 1) * NB + QN + r] = -acc[i][j][1] * rdiag[r];
+      }
     }
-  __syncthreads();
-  // ---- phase 5b: inv(U)12 = -inv(U11) (U12 inv(U22)) ----
-  load_quadrant(S2, iU22, NB);
-  __syncthreads();
-  gemm64(S0, S2, acc);
-  __syncthreads();
+  if (!SYM) {
+    __syncthreads();
+    // ---- phase 5b: inv(U)12 = -inv(U11) (U12 inv(U22)) ----
+    load_quadrant(S2, iU22, NB);
+    __syncthreads();
+    gemm64(S0, S2, acc);
+    __syncthreads();
 #pragma unroll
-  for (int i = 0; i < 2; i++)
+    for (int i = 0; i < 2; i++)
 #pragma unroll
-    for (int j = 0; j < 4; j++)
-      *reinterpret_cast<double2*>(&S0[frag_row(i) * QLD + frag_col(j)]) = make_double2(acc[i][j][0], acc[i][j][1]);
-  load_quadrant(S2, invU, NB);                   // inv(U11)
+      for (int j = 0; j < 4; j++)
+        *reinterpret_cast<double2*>(&S0[frag_row(i) * QLD + frag_col(j)]) = make_double2(acc[i][j][0], acc[i][j][1]);
+    load_quadrant(S2, invU, NB);                 // inv(U11)
+    __syncthreads();
+    gemm64(S2, S0, acc);
+#pragma unroll
+    for (int i = 0; i < 2; i++)
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const int r = frag_row(i), c = frag_col(j);
+        *reinterpret_cast<double2*>(invU + (int64_t)r * NB + QN + c) = make_double2(-acc[i][j][0], -acc[i][j][1]);
+      }
+  }
+  SCB_STAMP(7);
+}
+
+// ---------------------------------------------------------------------------------------
+// 1c. diagonal block of the SYMMETRIC factorization, blocked (the default in symmetric mode).
+//     Same outputs as diag_kernel_small<true> (L \ U in place with U = D L^T, inv(L), inv(U) =
+//     inv(L)^T D^-1), same 2x2 quadrant organisation and footprint, but each 64x64 quadrant is
+//     factored by a right-looking LDL^T with 8-wide panels instead of 64 rank-1 sweeps:
+//       (A) warp 0: LDL^T of the 8x8 diagonal tile in registers (one row per lane, shuffles);
+//       (B) 64 threads: panel rows below by forward substitution, written as L and, scaled by
+//           D, mirrored into the upper triangle as U; one more warp: inverse of the 8x8 tile;
+//       (C) all warps: trailing lower-triangle 8x8 tiles, C -= L U, one DMMA pair per tile;
+//     and inv(L) is assembled from the 8x8 tile inverses by three doubling levels of small DMMA
+//     products (X21 = -X22 L21 X11).  Only 128 pivots remain sequential.
+// ---------------------------------------------------------------------------------------
+constexpr int TLD = 36;  // row stride of the 32 x 32 scratch used by the doubling products
+
+// (i, j), j <= i, of the e-th tile of a lower-triangular tile grid (row-major enumeration)
+__device__ __forceinline__ void tri_tile(int e, int& i, int& j) {
+  i = 0;
+  while ((i + 1) * (i + 2) / 2 <= e) i++;
+  j = e - i * (i + 1) / 2;
+}
+
+// S: 64x64 symmetric block (lower triangle + diagonal are read).  On return S = L \ U,
+// SL = inv(L) (dense 64x64, unit lower), dd = diag(U), rd = 1 / dd.  tmp: 32 x TLD scratch.
+__device__ __forceinline__ int ldl64_blocked(double* __restrict__ S, double* __restrict__ SL,
+                                             double* __restrict__ tmp, double* __restrict__ dd,
+                                             double* __restrict__ rd, int* __restrict__ bad_s) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  for (int idx = tid; idx < QN * QLD; idx += 256) SL[idx] = 0.0;
+  if (tid == 0) *bad_s = 0x7fffffff;
+  int bad = 0;  // first bad pivot seen by this lane (warp 0 only)
   __syncthreads();
-  gemm64(S2, S0, acc);
+#pragma unroll 1
+  for (int kb = 0; kb < 8; kb++) {
+    const int k0 = 8 * kb;
+    if (kb == 0) SCB_STAMP(8);
+    // ---- (A) 8x8 diagonal tile: lane r < 8 owns row r ----
+    if (warp == 0) {
+      double a[8];
+#pragma unroll
+      for (int c = 0; c < 8; c++) a[c] = (lane < 8 && c <= lane) ? S[(k0 + lane) * QLD + k0 + c] : 0.0;
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        const double w = a[j];
+        const double dj = __shfl_sync(0xffffffffu, w, j);
+        // the products w_r w_c do not depend on the reciprocal: only one FMA follows it in the chain
+        double pw[8];
+#pragma unroll
+        for (int c = j + 1; c < 8; c++) pw[c] = w * __shfl_sync(0xffffffffu, w, c);
+        const double rdj = fast_rcp2(dj);
+#pragma unroll
+        for (int c = j + 1; c < 8; c++)
+          if (lane >= c) a[c] = fma(-pw[c], rdj, a[c]);
+        const double l = w * rdj;
+        if (lane > j) a[j] = l;
+        if (lane == j) {
+          dd[k0 + j] = dj;
+          rd[k0 + j] = rdj;
+          if (bad == 0 && !(fabs(dj) > 0.0 && isfinite(dj))) bad = k0 + j + 1;
+        }
+      }
+      // write back L (lower), U = D L^T (upper) of the tile
+      double dl = 0.0;
+#pragma unroll
+      for (int c = 0; c < 8; c++)
+        if (lane == c) dl = a[c];
+#pragma unroll
+      if (lane < 8) S[(k0 + lane) * QLD + k0 + lane] = dl;
+#pragma unroll
+      for (int c = 0; c < 8; c++) {
+        const double dc = __shfl_sync(0xffffffffu, dl, c);
+        if (lane < 8 && c < lane) {
+          S[(k0 + lane) * QLD + k0 + c] = a[c];
+          S[(k0 + c) * QLD + k0 + lane] = dc * a[c];
+        }
+      }
+    }
+    if (kb == 0) SCB_STAMP(9);
+    __syncthreads();
+    if (kb == 0) SCB_STAMP(10);
+    // ---- (B) panel rows below the tile (threads 0..63) and the tile inverse (warp 7) ----
+    {
+      const int r = k0 + 8 + tid;
+      if (r < QN) {
+        double u[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) u[j] = S[r * QLD + k0 + j];
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+#pragma unroll
+          for (int pp = 0; pp < j; pp++) u[j] = fma(-u[pp], S[(k0 + j) * QLD + k0 + pp], u[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          S[r * QLD + k0 + j] = u[j] * rd[k0 + j];  // L[r][k0 + j]
+          S[(k0 + j) * QLD + r] = u[j];             // U[k0 + j][r] = d_j L[r][k0 + j]
+        }
+      }
+      if (warp == 7 && lane < 8) {
+        // column `lane` of the inverse of the unit lower 8x8 tile
+        double xv[8];
+#pragma unroll
+        for (int rr = 0; rr < 8; rr++) {
+          double acc = (rr == lane) ? 1.0 : 0.0;
+#pragma unroll
+          for (int pp = 0; pp < rr; pp++)
+            if (pp >= lane) acc = fma(-S[(k0 + rr) * QLD + k0 + pp], xv[pp], acc);
+          xv[rr] = (rr >= lane) ? acc : 0.0;
+          SL[(k0 + rr) * QLD + k0 + lane] = xv[rr];
+        }
+      }
+    }
+    if (kb == 0) SCB_STAMP(11);
+    __syncthreads();
+    if (kb == 0) SCB_STAMP(12);
+    // ---- (C) trailing lower-triangle tiles: C -= L_panel U_panel ----
+    const int nt = 7 - kb;
+    const int ntiles = nt * (nt + 1) / 2;
+    for (int e = warp; e < ntiles; e += 8) {
+      int ti, tj;
+      tri_tile(e, ti, tj);
+      const int R0 = k0 + 8 + 8 * ti, C0 = k0 + 8 + 8 * tj;
+      double2 c = *reinterpret_cast<const double2*>(&S[(R0 + g) * QLD + C0 + 2 * t]);
+#pragma unroll
+      for (int ks = 0; ks < 2; ks++) {
+        const double av = -S[(R0 + g) * QLD + k0 + ks * 4 + t];
+        const double bv = S[(k0 + ks * 4 + t) * QLD + C0 + g];
+        dmma(c.x, c.y, av, bv);
+      }
+      *reinterpret_cast<double2*>(&S[(R0 + g) * QLD + C0 + 2 * t]) = c;
+    }
+    if (kb == 0) SCB_STAMP(13);
+    __syncthreads();
+    if (kb == 0) SCB_STAMP(14);
+  }
+  SCB_STAMP(15);
+  if (bad) atomicMin(bad_s, bad);  // (rare) the smallest bad index wins
+  // ---- inv(L) by doubling: X21 = -X22 (L21 X11) for block sizes 8, 16, 32 ----
+#pragma unroll 1
+  for (int sz = 8; sz < QN; sz *= 2) {
+    const int tps = sz / 8;               // tiles per side of one off-diagonal block
+    const int tpp = tps * tps;            // tiles per pair
+    const int total = (QN / (2 * sz)) * tpp;
+    for (int e = warp; e < total; e += 8) {  // T = L21 X11
+      const int pair = e / tpp, q = e % tpp, i = q / tps, j = q % tps;
+      const int a0 = pair * 2 * sz, b0 = a0 + sz;
+      double c0 = 0.0, c1 = 0.0;
+      for (int k = 0; k < sz; k += 4) {
+        const double av = S[(b0 + 8 * i + g) * QLD + a0 + k + t];
+        const double bv = SL[(a0 + k + t) * QLD + a0 + 8 * j + g];
+        dmma(c0, c1, av, bv);
+      }
+      *reinterpret_cast<double2*>(&tmp[(pair * sz + 8 * i + g) * TLD + 8 * j + 2 * t]) = make_double2(c0, c1);
+    }
+    __syncthreads();
+    for (int e = warp; e < total; e += 8) {  // X21 = -X22 T
+      const int pair = e / tpp, q = e % tpp, i = q / tps, j = q % tps;
+      const int a0 = pair * 2 * sz, b0 = a0 + sz;
+      double c0 = 0.0, c1 = 0.0;
+      for (int k = 0; k < sz; k += 4) {
+        const double av = -SL[(b0 + 8 * i + g) * QLD + b0 + k + t];
+        const double bv = tmp[(pair * sz + k + t) * TLD + 8 * j + g];
+        dmma(c0, c1, av, bv);
+      }
+      *reinterpret_cast<double2*>(&SL[(b0 + 8 * i + g) * QLD + a0 + 8 * j + 2 * t]) = make_double2(c0, c1);
+    }
+    __syncthreads();
+  }
+  return *bad_s == 0x7fffffff ? 0 : *bad_s;
+}
+
+// inv(L) (shared, dense) -> global inv(L) and inv(U) = inv(L)^T D^-1 (global, optionally shared)
+__device__ __forceinline__ void emit_inverses_symb(const double* __restrict__ SL, const double* __restrict__ rd,
+                                                   double* __restrict__ SU, double* __restrict__ GL,
+                                                   double* __restrict__ GU) {
+#pragma unroll
+  for (int q = 0; q < 16; q++) {
+    const int idx = q * 256 + threadIdx.x;
+    const int r = idx >> 6, c = idx & 63;
+    GL[r * NB + c] = SL[r * QLD + c];
+    const double iu = c > r ? SL[c * QLD + r] * rd[c] : (c == r ? rd[c] : 0.0);
+    if (SU) SU[r * QLD + c] = iu;
+    GU[r * NB + c] = iu;
+  }
+}
+
+__global__ void __launch_bounds__(256, 2)
+diag_kernel_symb(double* __restrict__ M, int64_t ld, int64_t o, double* __restrict__ invL,
+                 double* __restrict__ invU, int32_t* __restrict__ info, int block_index) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* S0 = reinterpret_cast<double*>(smem_raw);
+  double* S1 = S0 + QN * QLD;
+  double* S2 = S1 + QN * QLD;
+  double* tmp = S2 + QN * QLD;  // 32 x TLD
+  __shared__ double dd[QN], rd[QN];
+  __shared__ int bad_s;
+  const int tid = threadIdx.x;
+  double* A11 = M + o * ld + o;
+  double* A12 = A11 + QN;
+  double* A21 = A11 + (int64_t)QN * ld;
+  double* A22 = A21 + QN;
+  double acc[2][4][2];
+
+  // ---- phase 1: A11 = L11 D1 L11^T ----
+  load_quadrant(S0, A11, ld);
+  __syncthreads();
+  SCB_STAMP(0);
+  int bad = ldl64_blocked(S0, S1, tmp, dd, rd, &bad_s);  // S0 = L11 \ U11, S1 = inv(L11)
+  SCB_STAMP(1);
+  emit_inverses_symb(S1, rd, S2, invL, invU);            // S2 = inv(U11)
+  store_quadrant(A11, ld, S0);
+  __syncthreads();
+  SCB_STAMP(2);
+  // ---- phase 2: L21 = A21 inv(U11), U12 = D1 L21^T ----
+  load_quadrant(S1, A21, ld);
+  __syncthreads();
+  gemm64(S1, S2, acc);
+  __syncthreads();
 #pragma unroll
   for (int i = 0; i < 2; i++)
 #pragma unroll
     for (int j = 0; j < 4; j++) {
       const int r = frag_row(i), c = frag_col(j);
-      *reinterpret_cast<double2*>(invU + (int64_t)r * NB + QN + c) = make_double2(-acc[i][j][0], -acc[i][j][1]);
+      const double2 v = make_double2(acc[i][j][0], acc[i][j][1]);
+      *reinterpret_cast<double2*>(&S1[r * QLD + c]) = v;  // S1 = L21
+      *reinterpret_cast<double2*>(A21 + (int64_t)r * ld + c) = v;
+      const double u0 = dd[c] * v.x, u1 = dd[c + 1] * v.y;
+      S0[c * QLD + r] = u0;  // S0 = U12
+      S0[(c + 1) * QLD + r] = u1;
+      A12[(int64_t)c * ld + r] = u0;
+      A12[(int64_t)(c + 1) * ld + r] = u1;
     }
+  __syncthreads();
+  SCB_STAMP(3);
+  // ---- phase 3: A22 -= L21 U12 -> S2 ----
+  gemm64(S1, S0, acc);
+#pragma unroll
+  for (int i = 0; i < 2; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const int r = frag_row(i), c = frag_col(j);
+      const double2 cin = *reinterpret_cast<const double2*>(A22 + (int64_t)r * ld + c);
+      *reinterpret_cast<double2*>(&S2[r * QLD + c]) = make_double2(cin.x - acc[i][j][0], cin.y - acc[i][j][1]);
+    }
+  __syncthreads();
+  SCB_STAMP(4);
+  // ---- phase 4: A22 = L22 D2 L22^T ----
+  const int bad2 = ldl64_blocked(S2, S0, tmp, dd, rd, &bad_s);  // S2 = L22 \ U22, S0 = inv(L22); dd, rd: block 2
+  SCB_STAMP(5);
+  if (bad == 0 && bad2) bad = QN + bad2;
+  if (tid == 0 && bad) atomicCAS(info, 0, block_index * NB + bad);
+  store_quadrant(A22, ld, S2);
+  emit_inverses_symb(S0, rd, nullptr, invL + QN * NB + QN, invU + QN * NB + QN);
+  __syncthreads();
+  SCB_STAMP(6);
+  // ---- phase 5: inv(L)21 = -(inv(L22) L21) inv(L11), inv(U)12 = (inv(L)21)^T D2^-1 ----
+  gemm64(S0, S1, acc);
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 2; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+      *reinterpret_cast<double2*>(&S1[frag_row(i) * QLD + frag_col(j)]) = make_double2(acc[i][j][0], acc[i][j][1]);
+  load_quadrant(S2, invL, NB);  // inv(L11) (written in phase 1 by this CTA)
+  __syncthreads();
+  gemm64(S1, S2, acc);
+#pragma unroll
+  for (int i = 0; i < 2; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const int r = frag_row(i), c = frag_col(j);
+      *reinterpret_cast<double2*>(invL + (int64_t)(QN + r) * NB + c) = make_double2(-acc[i][j][0], -acc[i][j][1]);
+      *reinterpret_cast<double2*>(invL + (int64_t)r * NB + QN + c) = make_double2(0.0, 0.0);
+      *reinterpret_cast<double2*>(invU + (int64_t)(QN + r) * NB + c) = make_double2(0.0, 0.0);
+      invU[(int64_t)c * NB + QN + r] = -acc[i][j][0] * rd[r];
+      invU[(int64_t)(c + 1) * NB + QN + r] = -acc[i][j][1] * rd[r];
+    }
+  SCB_STAMP(7);
 }
 
 static bool g_attr_set[64] = {};  // kernel attributes are per device
 static int g_diag_small = 1;
+static int g_diag_symb = 1;  // blocked LDL^T diagonal kernel in symmetric mode (SCB_DIAG_SYMB=0: sweep version)
 static int g_lookahead = 1;
 static int g_lazy_strips = 0;  // left-looking inner strips: same flops, measured no faster (narrow grids)
 
@@ -855,13 +1212,16 @@ static int getrf_impl(int64_t n_pad, double* M, double* dinv, int32_t* info, scb
   const int64_t pack_set = 2 * n_pad * NB * q;  // doubles per (Lpack + Upack) set
   const int diag_smem = NB * DLD * sizeof(double);
   const int diag_small_smem = 3 * QN * QLD * sizeof(double);
+  const int diag_symb_smem = (3 * QN * QLD + 32 * TLD) * sizeof(double);
   const int trsm_smem = kTrsmSmemDoubles * sizeof(double);
   const int upd_smem = 2 * sizeof(UpdateStage);
   int dev = 0;
   SCB_CUDA(cudaGetDevice(&dev));
   if (!g_attr_set[dev & 63]) {
     SCB_CUDA(cudaFuncSetAttribute(diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, diag_smem));
-    SCB_CUDA(cudaFuncSetAttribute(diag_kernel_small, cudaFuncAttributeMaxDynamicSharedMemorySize, diag_small_smem));
+    SCB_CUDA(cudaFuncSetAttribute(diag_kernel_small<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, diag_small_smem));
+    SCB_CUDA(cudaFuncSetAttribute(diag_kernel_small<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, diag_small_smem));
+    SCB_CUDA(cudaFuncSetAttribute(diag_kernel_symb, cudaFuncAttributeMaxDynamicSharedMemorySize, diag_symb_smem));
     SCB_CUDA(cudaFuncSetAttribute(update_kernel_t<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, upd_smem));
     SCB_CUDA(cudaFuncSetAttribute(update_kernel_t<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, upd_smem));
     SCB_CUDA(cudaFuncSetAttribute(trsm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, trsm_smem));
@@ -869,6 +1229,7 @@ static int getrf_impl(int64_t n_pad, double* M, double* dinv, int32_t* info, scb
     SCB_CUDA(cudaFuncSetAttribute(update_kernel_t<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     SCB_CUDA(cudaFuncSetAttribute(update_kernel_t<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     if (const char* e = getenv("SCB_DIAG_SMALL")) g_diag_small = atoi(e);
+    if (const char* e = getenv("SCB_DIAG_SYMB")) g_diag_symb = atoi(e);
     if (const char* e = getenv("SCB_LU_LOOKAHEAD")) g_lookahead = atoi(e);
     if (const char* e = getenv("SCB_LU_LAZY")) g_lazy_strips = atoi(e);
     g_attr_set[dev & 63] = true;
@@ -913,8 +1274,12 @@ static int getrf_impl(int64_t n_pad, double* M, double* dinv, int32_t* info, scb
           SCB_LAUNCH_CHECK();
         }
       }
-      if (g_diag_small)
-        diag_kernel_small<<<1, 256, diag_small_smem, st>>>(M, n_pad, o, invL, invU, info, (int)k);
+      if (g_diag_small && sym && g_diag_symb)
+        diag_kernel_symb<<<1, 256, diag_symb_smem, st>>>(M, n_pad, o, invL, invU, info, (int)k);
+      else if (g_diag_small && sym)
+        diag_kernel_small<true><<<1, 256, diag_small_smem, st>>>(M, n_pad, o, invL, invU, info, (int)k);
+      else if (g_diag_small)
+        diag_kernel_small<false><<<1, 256, diag_small_smem, st>>>(M, n_pad, o, invL, invU, info, (int)k);
       else
         diag_kernel<<<1, 512, diag_smem, st>>>(M, n_pad, o, invL, invU, info, (int)k);
       SCB_LAUNCH_CHECK();
@@ -929,8 +1294,12 @@ static int getrf_impl(int64_t n_pad, double* M, double* dinv, int32_t* info, scb
       if (inner_rem > 0 && !g_lazy_strips) {
         // right-looking variant: apply inner panel i to the rest of the outer panel's L-shaped strip
         dim3 ga(2 * inner_rem, nt);
-        update_kernel_t<false><<<ga, 256, upd_smem, st>>>(M, n_pad, o + NB, o + NB, Lpack, Upack, tile_chunks, i * NCHUNK,
-                                                 NCHUNK);
+        if (sym)  // (tiles above the block diagonal of the panel's own square are never read)
+          update_kernel_t<true><<<ga, 256, upd_smem, st>>>(M, n_pad, o + NB, o + NB, Lpack, Upack, tile_chunks,
+                                                           i * NCHUNK, NCHUNK);
+        else
+          update_kernel_t<false><<<ga, 256, upd_smem, st>>>(M, n_pad, o + NB, o + NB, Lpack, Upack, tile_chunks,
+                                                            i * NCHUNK, NCHUNK);
         SCB_LAUNCH_CHECK();
         const int nright = nt - inner_rem;
         if (nright > 0 && !sym) {  // (symmetric: the row strip is never read)
@@ -968,9 +1337,14 @@ static int getrf_impl(int64_t n_pad, double* M, double* dinv, int32_t* info, scb
     }
     // A: the L-shaped strip that panel P+1 lives in (rows e0..e1 x all columns, rows below x cols e0..e1)
     const int nt0 = (int)((n_pad - e0) / NB), ntp = (int)((e1 - e0) / NB), nt1 = (int)((n_pad - e1) / NB);
-    {
-      // rows of panel P+1: all columns to the right (symmetric: only the panel's own square)
-      dim3 g1(sym ? 2 * ntp : 2 * nt0, ntp);
+    if (sym) {
+      // symmetric: one launch for the whole column strip of panel P+1 (its own square and everything below)
+      dim3 g12(2 * ntp, nt0);
+      update_kernel_t<true><<<g12, 256, upd_smem, s>>>(M, n_pad, e0, e0, Lpack, Upack, tile_chunks, 0, nchunks);
+      SCB_LAUNCH_CHECK();
+    } else {
+      // rows of panel P+1: all columns to the right
+      dim3 g1(2 * nt0, ntp);
       update_kernel_t<false><<<g1, 256, upd_smem, s>>>(M, n_pad, e0, e0, Lpack, Upack, tile_chunks, 0, nchunks);
       SCB_LAUNCH_CHECK();
       if (nt1 > 0) {
