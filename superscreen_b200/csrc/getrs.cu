@@ -144,6 +144,118 @@ trsv_sweep_kernel(const double* __restrict__ F, int64_t ld, const double* __rest
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// Many right-hand sides (nrhs > 8): blocked right-looking substitution on the fp64 tensor cores.
+// One launch per 128-row block step k; CTA (column chunk of 16 right-hand sides, row tile i):
+//     B_i -= F_ik X_k                                  (128x128 times 128x16, DMMA)
+// and the CTA of the NEXT block of the sweep goes on to solve it with the stored inverse of its
+// diagonal block, X_i = inv(F_ii) B_i, so the next launch finds X_{k+1} in place.  Step k = -1
+// only solves the first block.  The flops (4 n^2 nrhs) run at tensor rate and every factor tile
+// is read once per column chunk; the chain per block is one launch + two 128x128x16 products.
+// ---------------------------------------------------------------------------------------
+constexpr int RC = 16;        // right-hand sides per CTA
+constexpr int XLD = RC + 4;   // row stride of the shared X / Y tiles (conflict-free B fragments)
+
+__device__ __forceinline__ void dmma_rhs(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(d0), "+d"(d1)
+               : "d"(a), "d"(b));
+}
+
+// acc[rt][ct] (rows warp*16 + rt*8 + g, columns ct*8 + 2t, +1) += sign * A[128 x 128] * Xs[128 x RC]
+__device__ __forceinline__ void tile_product(const double* __restrict__ A, int64_t lda, const double* __restrict__ Xs,
+                                             double sign, double (&acc)[2][2][2]) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const double* A0 = A + (int64_t)(warp * 16 + g) * lda + t;
+  const double* A1 = A0 + 8 * lda;
+  // all A fragments of half the K range are requested before the first DMMA (latency-bound loads)
+#pragma unroll 1
+  for (int kh = 0; kh < NB / 4; kh += 16) {
+    double a0[16], a1[16];
+#pragma unroll
+    for (int u = 0; u < 16; u++) {
+      a0[u] = __ldg(A0 + (kh + u) * 4);
+      a1[u] = __ldg(A1 + (kh + u) * 4);
+    }
+#pragma unroll
+    for (int u = 0; u < 16; u++) {
+      const int ks = kh + u;
+      const double b0 = Xs[(ks * 4 + t) * XLD + g];
+      const double b1 = Xs[(ks * 4 + t) * XLD + 8 + g];
+      const double x0 = sign * a0[u], x1 = sign * a1[u];
+      dmma_rhs(acc[0][0][0], acc[0][0][1], x0, b0);
+      dmma_rhs(acc[0][1][0], acc[0][1][1], x0, b1);
+      dmma_rhs(acc[1][0][0], acc[1][0][1], x1, b0);
+      dmma_rhs(acc[1][1][0], acc[1][1][1], x1, b1);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+trsm_rhs_step_kernel(const double* __restrict__ F, int64_t ld, const double* __restrict__ dinv, int64_t nb,
+                     int lower, int64_t k, int64_t nrhs, double* __restrict__ B) {
+  __shared__ double Xs[NB * XLD];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int64_t c0 = (int64_t)blockIdx.x * RC;
+  // row tile of this CTA: the blocks after k in sweep order (k < 0: only the first block is solved)
+  const int64_t first = lower ? 0 : nb - 1;
+  const int64_t i = k < 0 ? first : (lower ? k + 1 + blockIdx.y : k - 1 - (int64_t)blockIdx.y);
+  const bool solve_here = blockIdx.y == 0;
+  double acc[2][2][2];
+  double* Bi = B + i * NB * nrhs;
+  if (solve_here) {
+    // the two tiles on the critical path of this and of the next step: into L2 ahead of use
+    prefetch_tile_l2(dinv + i * 2 * NB * NB + (lower ? 0 : NB * NB), NB * sizeof(double), warp, lane);
+    const int64_t inext = lower ? i + 1 : i - 1;
+    if (inext >= 0 && inext < nb)
+      prefetch_tile_l2(F + inext * NB * ld + i * NB, ld * (int64_t)sizeof(double), warp, lane);
+  }
+  // C fragments = B_i chunk (columns beyond nrhs read as zero and are never stored)
+#pragma unroll
+  for (int rt = 0; rt < 2; rt++)
+#pragma unroll
+    for (int ct = 0; ct < 2; ct++)
+#pragma unroll
+      for (int e = 0; e < 2; e++) {
+        const int64_t c = c0 + ct * 8 + 2 * t + e;
+        acc[rt][ct][e] = c < nrhs ? Bi[(int64_t)(warp * 16 + rt * 8 + g) * nrhs + c] : 0.0;
+      }
+  if (k >= 0) {
+    const double* Bk = B + k * NB * nrhs;
+    for (int idx = tid; idx < NB * RC; idx += 256) {
+      const int r = idx / RC, c = idx % RC;
+      Xs[r * XLD + c] = (c0 + c) < nrhs ? Bk[(int64_t)r * nrhs + c0 + c] : 0.0;
+    }
+    __syncthreads();
+    tile_product(F + i * NB * ld + k * NB, ld, Xs, -1.0, acc);
+  }
+  if (solve_here) {
+    __syncthreads();  // everyone is done reading Xs
+#pragma unroll
+    for (int rt = 0; rt < 2; rt++)
+#pragma unroll
+      for (int ct = 0; ct < 2; ct++)
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+          Xs[(warp * 16 + rt * 8 + g) * XLD + ct * 8 + 2 * t + e] = acc[rt][ct][e];
+          acc[rt][ct][e] = 0.0;
+        }
+    __syncthreads();
+    tile_product(dinv + i * 2 * NB * NB + (lower ? 0 : NB * NB), NB, Xs, 1.0, acc);
+  }
+#pragma unroll
+  for (int rt = 0; rt < 2; rt++)
+#pragma unroll
+    for (int ct = 0; ct < 2; ct++)
+#pragma unroll
+      for (int e = 0; e < 2; e++) {
+        const int64_t c = c0 + ct * 8 + 2 * t + e;
+        if (c < nrhs) Bi[(int64_t)(warp * 16 + rt * 8 + g) * nrhs + c] = acc[rt][ct][e];
+      }
+}
+
 static int g_epoch = 0;
 static int g_capacity[64][2] = {};  // resident CTAs per device for RT = 1 / 8
 
@@ -170,6 +282,20 @@ extern "C" int scb_getrs_nopiv(int64_t n_pad, const double* LU, const double* di
     SCB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     cap = per_sm * sms;
     if (cap < 1) cap = 1;
+  }
+  if (nrhs > 8) {
+    // tensor-core path: one launch per block step and sweep direction
+    const unsigned ncc = (unsigned)((nrhs + RC - 1) / RC);
+    for (int lower = 1; lower >= 0; lower--) {
+      trsm_rhs_step_kernel<<<dim3(ncc, 1), 256, 0, s>>>(LU, n_pad, dinv, nb, lower, -1, nrhs, B);
+      SCB_LAUNCH_CHECK();
+      for (int64_t q = 0; q + 1 < nb; q++) {
+        const int64_t k = lower ? q : nb - 1 - q;
+        trsm_rhs_step_kernel<<<dim3(ncc, (unsigned)(nb - 1 - q)), 256, 0, s>>>(LU, n_pad, dinv, nb, lower, k, nrhs, B);
+        SCB_LAUNCH_CHECK();
+      }
+    }
+    return SCB_OK;
   }
   // integer scratch behind the packed panels of the factorization workspace
   int* flags = reinterpret_cast<int*>(const_cast<double*>(dinv) + lu_flags_offset(n_pad));

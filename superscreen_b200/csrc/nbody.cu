@@ -187,6 +187,110 @@ static int launch_nbody(const NbodyParams& p, cudaStream_t s) {
   return SCB_OK;
 }
 
+// ---------------------------------------------------------------------------------------
+// Many right-hand sides: the same sum as NB_KERNEL, as a GEMM on the fp64 tensor cores whose A
+// operand (the kernel matrix) is never stored -- every lane evaluates the r^-3 entry that the
+// mma.sync m8n8k4 A fragment assigns to it (row = target g, k = source t) and feeds it straight
+// to DMMA against a shared-memory tile of the payload matrix  P[j][r] = w_j v[j][r].
+// CTA: 64 targets (8 warps x one 8-row tile) x NC = 8 CT right-hand sides; sources in tiles of 32,
+// double-buffered through registers.  One r^-3 evaluation now serves NC columns.
+// ---------------------------------------------------------------------------------------
+constexpr int kGemmSrc = 32;
+
+__device__ __forceinline__ void dmma_nb(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(d0), "+d"(d1)
+               : "d"(a), "d"(b));
+}
+
+template <int CT>
+__global__ void __launch_bounds__(256) kernel_gemm_kernel(NbodyParams p) {
+  constexpr int NC = 8 * CT;
+  constexpr int PLD = NC + 4;                    // conflict-free B fragments (ld % 16 == 4)
+  constexpr int PER = kGemmSrc * NC / 256;       // payload entries staged per thread
+  __shared__ double sx[2][kGemmSrc], sy[2][kGemmSrc];
+  __shared__ double sp[2][kGemmSrc * PLD];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int64_t i = blockIdx.x * 64ll + warp * 8 + g;
+  const bool active = i < p.m;
+  const double tx = active ? p.tgt[2 * i] : 0.0, ty = active ? p.tgt[2 * i + 1] : 0.0;
+  double acc[CT][2];
+#pragma unroll
+  for (int c = 0; c < CT; c++) acc[c][0] = acc[c][1] = 0.0;
+
+  double rpay[PER], rx = 0.0, ry = 0.0;
+  auto fetch = [&](int64_t base) {
+    // sources past the end: far away and weightless
+    if (tid < kGemmSrc) {
+      const int64_t j = base + tid;
+      const int64_t js = j < p.n ? (p.src_idx ? p.src_idx[j] : j) : -1;
+      rx = js >= 0 ? p.src[2 * js] : 1e100;
+      ry = js >= 0 ? p.src[2 * js + 1] : 1e100;
+    }
+#pragma unroll
+    for (int q = 0; q < PER; q++) {
+      const int e = tid + 256 * q;
+      const int r = e / NC, c = e % NC;
+      const int64_t j = base + r;
+      double v = 0.0;
+      if (j < p.n) {
+        const int64_t js = p.src_idx ? p.src_idx[j] : j;
+        v = p.area[js] * p.J[js * p.ldv + p.rhs0 + c];
+      }
+      rpay[q] = v;
+    }
+  };
+  auto stash = [&](int buf) {
+    if (tid < kGemmSrc) {
+      sx[buf][tid] = rx;
+      sy[buf][tid] = ry;
+    }
+#pragma unroll
+    for (int q = 0; q < PER; q++) {
+      const int e = tid + 256 * q;
+      sp[buf][(e / NC) * PLD + e % NC] = rpay[q];
+    }
+  };
+  fetch(0);
+  stash(0);
+  __syncthreads();
+  int buf = 0;
+  for (int64_t base = 0; base < p.n; base += kGemmSrc) {
+    const bool more = base + kGemmSrc < p.n;
+    if (more) fetch(base + kGemmSrc);
+#pragma unroll
+    for (int ks = 0; ks < kGemmSrc / 4; ks++) {
+      const int j = ks * 4 + t;
+      const double dx = tx - sx[buf][j], dy = ty - sy[buf][j];
+      const double r2 = dx * dx + dy * dy;
+      double k3 = inv_r3(r2);
+      k3 = r2 > 0.0 ? k3 : 0.0;  // q_ii = 0 (distance.py:104-105)
+#pragma unroll
+      for (int c = 0; c < CT; c++) dmma_nb(acc[c][0], acc[c][1], k3, sp[buf][j * PLD + c * 8 + g]);
+    }
+    if (more) stash(buf ^ 1);
+    __syncthreads();
+    buf ^= 1;
+  }
+  if (!active) return;
+  const double pf = p.prefactor;
+#pragma unroll
+  for (int c = 0; c < CT; c++)
+#pragma unroll
+    for (int e = 0; e < 2; e++) {
+      double* o = p.out + i * p.ldv + p.rhs0 + c * 8 + 2 * t + e;
+      *o = p.accumulate ? *o + pf * acc[c][e] : pf * acc[c][e];
+    }
+}
+
+template <int CT>
+static int launch_kernel_gemm(const NbodyParams& p, cudaStream_t s) {
+  kernel_gemm_kernel<CT><<<(unsigned)ceil_div(p.m, 64), 256, 0, s>>>(p);
+  SCB_LAUNCH_CHECK();
+  return SCB_OK;
+}
+
 // out[i, rhs0..] (+)= prefactor * sum_{j in src, r_ij > 0} q_ij w_j v[j, rhs0..]
 int nbody_kernel_sum(int64_t m, const double* tgt, int64_t n, const double* src,
                      const int64_t* src_idx, const double* w, const double* v, int64_t ldv,
@@ -195,6 +299,15 @@ int nbody_kernel_sum(int64_t m, const double* tgt, int64_t n, const double* src,
   p.m = m; p.tgt = tgt; p.n = n; p.src = src; p.src_idx = src_idx; p.area = w; p.J = v;
   p.ldv = ldv; p.prefactor = prefactor; p.out = out; p.accumulate = accumulate;
   int64_t r = 0;
+  // 16 or more right-hand sides: tensor-core GEMM against the on-the-fly kernel matrix
+  while (v != nullptr && nrhs - r >= 16) {
+    p.rhs0 = r;
+    int rc;
+    if (nrhs - r >= 64) { rc = launch_kernel_gemm<8>(p, s); r += 64; }
+    else if (nrhs - r >= 32) { rc = launch_kernel_gemm<4>(p, s); r += 32; }
+    else { rc = launch_kernel_gemm<2>(p, s); r += 16; }
+    if (rc) return rc;
+  }
   while (r < nrhs) {
     p.rhs0 = r;
     int rc;

@@ -131,28 +131,53 @@ def factorize_model(*, device: Device, current_units: str, terminal_currents=Non
                            circulating_currents, vortices, current_units, comm)
 
 
+_PINNED = {}  # device index -> pinned staging buffer (float64), grown on demand
+
+
+def _to_host(t) -> np.ndarray:
+    """Device tensor -> host numpy array.  Large arrays go through a cached pinned staging buffer
+    (a pageable cudaMemcpy runs at a fraction of the PCIe/C2C rate)."""
+    import torch
+
+    t = t.contiguous()
+    if t.dtype != torch.float64 or t.numel() < (1 << 17):
+        return t.cpu().numpy()
+    key = t.device.index
+    buf = _PINNED.get(key)
+    if buf is None or buf.numel() < t.numel():
+        buf = torch.empty(max(t.numel(), 1 << 22), dtype=torch.float64, pin_memory=True)
+        _PINNED[key] = buf
+    stage = buf[: t.numel()].view(t.shape)
+    stage.copy_(t, non_blocking=True)
+    torch.cuda.current_stream(t.device).synchronize()
+    return stage.numpy().copy()
+
+
 def _to_solutions(device, film_names, results, applied_fields, others, field_conversion, kwargs_list):
     """Device tensors (solver units) -> host FilmSolutions (reference solve_film.py:566-573).  One
     device->host copy per array per film, shared by all batch entries; ``kwargs_list`` holds the
     Solution keyword arguments of every batch entry (length 1 when not batched)."""
+    batched = next(iter(results.values()))[0].dim() == 2
     host = {}
     for name in film_names:
         g, J, self_field = results[name]
-        host[name] = (
-            g.cpu().numpy(), J.cpu().numpy(),
-            (applied_fields[name] / field_conversion).cpu().numpy(),
-            (self_field / field_conversion).cpu().numpy(),
-            None if others is None else (others[name] / field_conversion).cpu().numpy(),
-        )
-    batched = next(iter(results.values()))[0].dim() == 2
+        applied = applied_fields[name] / field_conversion
+        self_field = self_field / field_conversion
+        other = None if others is None else others[name] / field_conversion
+        if batched:
+            # batch-major on the device, so that every batch entry is a contiguous host row (no per-entry copies)
+            g, applied, self_field = g.t(), applied.t(), self_field.t()
+            other = None if other is None else other.t()
+        host[name] = (_to_host(g), _to_host(J), _to_host(applied), _to_host(self_field),
+                      None if other is None else _to_host(other))
     out = []
     for b, kwargs in enumerate(kwargs_list):
         film_solutions = {}
         for name in film_names:
             g, J, applied, self_field, other = host[name]
             if batched:
-                g, J, applied, self_field = g[:, b], J[b], applied[:, b], self_field[:, b]
-                other = None if other is None else other[:, b]
+                g, J, applied, self_field = g[b], J[b], applied[b], self_field[b]
+                other = None if other is None else other[b]
             film_solutions[name] = FilmSolution(
                 stream=np.ascontiguousarray(g), current_density=np.ascontiguousarray(J),
                 applied_field=np.ascontiguousarray(applied), self_field=np.ascontiguousarray(self_field),
@@ -316,7 +341,8 @@ def solve_batch(*, model: FactorizedModel, applied_fields: Sequence[Optional[Cal
     circ_by_film = {}
     for name in film_names:
         dev = device.meshes[name]._data.device
-        dev_fields[name] = torch.as_tensor(np.ascontiguousarray(np.stack([h[name] for h in per_b], axis=1))).to(dev)
+        # rows are contiguous on the host (fast stack + one H2D copy); the (n, nrhs) layout is made on the device
+        dev_fields[name] = torch.as_tensor(np.stack([h[name] for h in per_b], axis=0)).to(dev).t().contiguous()
         circ_by_film[name] = {
             hole: torch.tensor([float(cc.get(hole, 0.0)) for cc in circulating_currents], dtype=torch.float64,
                                device=dev)

@@ -153,3 +153,43 @@ def test_find_fluxoid_solution(sc):
         assert "ring_hole" in sol.circulating_currents
     # the model's own circulating currents are restored afterwards
     assert model.circulating_currents == {}
+
+
+@pytest.mark.parametrize("nrhs", [9, 16, 21, 70])
+def test_many_rhs_tensor_core_substitution(sc, nrhs):
+    """nrhs > 8 takes the blocked DMMA substitution (getrs.cu: trsm_rhs_step_kernel); it must agree
+    with column-by-column solves through the flag-driven sweeps, in both LU modes, including a
+    column count that is not a multiple of the 16-column chunk and a padded last block."""
+    import torch
+
+    from superscreen_b200.geometry import box
+    from superscreen_b200.solver.solve_film import apply_operator, lu_solve
+    from superscreen_b200.synthetic import square_mesh
+
+    sites, elements = square_mesh(10.0, 1500, seed=3)
+    device = sc.Device("sq", layers=[sc.Layer("layer", Lambda=0.1, z0=0.0)],
+                       films=[sc.Polygon("film", layer="layer", points=box(10.0, points=4))])
+    device.set_meshes({"film": (sites, elements)})
+    model = sc.factorize_model(device=device, current_units="uA")
+    system, info = model.film_systems["film"], model.film_info["film"]
+    assert system.n_pad > len(system.indices)  # identity-padded last block
+    gen = torch.Generator(device="cuda").manual_seed(1)
+    h = torch.randn(len(system.indices), nrhs, dtype=torch.float64, device="cuda", generator=gen)
+    x = lu_solve(system, h)
+    ref = torch.stack([lu_solve(system, h[:, c].contiguous()) for c in range(nrhs)], dim=1)
+    assert float((x - ref).norm() / ref.norm()) <= 1e-13
+    # and it solves the system: (-A) x = h through the matrix-free operator
+    ix = system.indices_dev
+    g = torch.zeros(info.mesh._data.n, dtype=torch.float64, device="cuda")
+    g[ix] = x[:, nrhs - 1]
+    res = -apply_operator(info, g, src_idx=ix)[ix] - h[:, nrhs - 1]
+    assert float(res.abs().max() / h[:, nrhs - 1].abs().max()) <= 1e-10
+    # the matrix-free operator itself: nrhs >= 16 columns go through the tensor-core kernel GEMM
+    # (nbody.cu: kernel_gemm_kernel), fewer through the CUDA-core N-body kernel
+    V = torch.zeros(info.mesh._data.n, nrhs, dtype=torch.float64, device="cuda")
+    V[ix] = x
+    out = apply_operator(info, V, src_idx=ix)
+    cols = torch.stack([apply_operator(info, V[:, c].contiguous(), src_idx=ix) for c in range(nrhs)], dim=1)
+    assert float((out - cols).norm() / cols.norm()) <= 1e-13
+    full = apply_operator(info, V)  # no gather list: every vertex is a source (V vanishes outside ix)
+    assert float((full - cols).norm() / cols.norm()) <= 1e-13

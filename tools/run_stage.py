@@ -72,3 +72,8 @@ if args.stage == "getrs":
     for rep in range(args.reps + 1):
         e0.record(); x = lu_solve(system, h); e1.record(); torch.cuda.synchronize()
         print(f"getrs nrhs={args.nrhs}: {e0.elapsed_time(e1):.3f} ms")
+    # consistency with the single-RHS flag-driven sweeps on a few columns
+    cols = sorted(set([0, args.nrhs // 2, args.nrhs - 1]))
+    ref = torch.stack([lu_solve(system, h[:, c].contiguous()) for c in cols], dim=1)
+    err = float((x[:, cols] - ref).norm() / ref.norm())
+    print(f"getrs nrhs={args.nrhs}: rel-L2 vs single-RHS solves on columns {cols}: {err:.3e}")
