@@ -85,6 +85,18 @@ def c5_large(n_vertices: int = 60000, seed: int = 0, Lambda: float = 0.1):
     return device, fields
 
 
+C5_LAMBDA_SWEEP = (0.05, 0.1, 0.2, 0.4)
+
+
+def with_lambda(device, Lambda: float):
+    """A copy of a single-layer device with another Lambda that shares the (device-resident) meshes:
+    only the system assembly and the LU are redone by ``factorize_model`` (C5 Lambda sweep)."""
+    layers = [Layer(layer.name, Lambda=Lambda, z0=layer.z0) for layer in device.layers.values()]
+    new = Device(device.name, layers=layers, films=list(device.films.values()), holes=list(device.holes.values()))
+    new.meshes = dict(device.meshes)
+    return new
+
+
 def evaluation_grid(n: int = 1000, half_width: float = 7.5, z: float = 1.0) -> np.ndarray:
     xs = np.linspace(-half_width, half_width, n)
     X, Y = np.meshgrid(xs, xs)

@@ -53,7 +53,17 @@ if "c5" in which:
         Bz, t_field = timed(lambda: parallel.field_at_position_sharded(batch[9][0], grid, comm=comm, units="mT"))
     lin = float(np.linalg.norm(batch[63][0].film_solutions["film"].stream - fields[63] * one[0].film_solutions["film"].stream)
                 / np.linalg.norm(fields[63] * one[0].film_solutions["film"].stream))
-    out["c5"] = {"vertices": n, "n_interior": n_int, "host_mesh_s": t_mesh_host, "factorize_s": t_fact,
+    # Lambda sweep: 4 refactorizations x 16 fields each; under torchrun one Lambda per rank (round-robin)
+    mine = [lam for k, lam in enumerate(configs.C5_LAMBDA_SWEEP) if k % world == rank]
+    def sweep():
+        res = {}
+        for lam in mine:
+            m = sc.factorize_model(device=configs.with_lambda(device, lam), current_units="uA")
+            sols = sc.solve_batch(model=m, applied_fields=[sc.ConstantField(float(f)) for f in fields[:16]])
+            res[lam] = float(np.abs(sols[15][0].film_solutions["film"].stream).max())
+        return res
+    sweep_res, t_sweep = timed(sweep)
+    out["c5"] = {"lambda_sweep_4x16_s": t_sweep, "lambda_sweep_max_stream_uA": sweep_res, "vertices": n, "n_interior": n_int, "host_mesh_s": t_mesh_host, "factorize_s": t_fact,
                  "lu_tflops_incl_assembly": (2 / 3) * n_int**3 / t_fact * 1e-12, "solve_64rhs_s": t_batch, "solve_1rhs_s": t_one,
                  "field_at_position_1M_s": t_field, "gpairs_per_s": 1e6 * n / t_field * 1e-9, "linearity_rel": lin,
                  "Bz_center_mT": float(Bz[len(Bz) // 2 + 500])}
