@@ -85,13 +85,16 @@ class Polygon:
 
     def contains_points(self, points, index: bool = False, radius: float = 0):
         pts = np.atleast_2d(points)
-        if len(pts) >= 1024:
-            # the same (polygon, mesh sites) query is repeated for every fluxoid / film-info
-            # evaluation; memoise on a content key (bytes of the polygon, checksum of the points)
-            key = (self._points.tobytes(), pts.shape, float(pts[0, 0]), float(pts[-1, 1]), float(pts.sum()))
+        if len(pts) >= 16:
+            # the same (polygon, points) query is repeated for every fluxoid / film-info evaluation;
+            # memoise on a content key (large point sets: shape, corner values and checksum)
+            if len(pts) >= 1024:
+                key = (self._points.tobytes(), pts.shape, float(pts[0, 0]), float(pts[-1, 1]), float(pts.sum()))
+            else:
+                key = (self._points.tobytes(), pts.shape, np.ascontiguousarray(pts, dtype=float).tobytes())
             mask = Polygon._mask_cache.get(key)
             if mask is None:
-                if len(Polygon._mask_cache) > 256:
+                if len(Polygon._mask_cache) > 1024:
                     Polygon._mask_cache.clear()
                 mask = points_in_polygon(self._points, pts)
                 mask.setflags(write=False)
@@ -103,7 +106,10 @@ class Polygon:
         return mask
 
     def copy(self) -> "Polygon":
-        return Polygon(self.name, layer=self.layer, points=self._points.copy())
+        # the stored points are already closed and counter-clockwise: skip the constructor's normalisation
+        new = object.__new__(Polygon)
+        new.name, new.layer, new._points = self.name, self.layer, self._points.copy()
+        return new
 
     def __repr__(self):
         return f"Polygon(name={self.name!r}, layer={self.layer!r}, points=<{len(self._points)} x 2>)"
@@ -282,7 +288,7 @@ class Device:
             model=model, applied_fields=[solve_kwargs.get("applied_field")] * len(hole_names),
             circulating_currents=[{name: 1.0} for name in hole_names],
             field_units=solve_kwargs.get("field_units", "mT"), iterations=solve_kwargs.get("iterations", 0),
-            check_inversion=solve_kwargs.get("check_inversion", False))
+            check_inversion=solve_kwargs.get("check_inversion", False), last_only=not all_iterations)
         to_units = _u.conversion_factor("H", units)
         for j, hole_name in enumerate(hole_names):
             for nn, solution in enumerate(batch[j][sl]):

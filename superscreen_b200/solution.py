@@ -94,17 +94,17 @@ def _barycentric(p: np.ndarray, xy: np.ndarray):
     return np.stack([l1, l2, 1.0 - l1 - l2], axis=-1)
 
 
-def linear_tri_interpolate(sites: np.ndarray, elements: np.ndarray, values: np.ndarray, xy: np.ndarray,
-                           candidates: int = 16) -> np.ndarray:
-    """Piecewise-linear interpolation on a triangulation; NaN outside the mesh.  Stands in for
-    ``matplotlib.tri.LinearTriInterpolator`` (reference solution.py:272-276,310-312).  The containing
-    triangle is searched among the triangles with the nearest centroids (all triangles as a
-    fallback for points that are not resolved that way)."""
-    xy = np.atleast_2d(np.asarray(xy, dtype=float))
-    values = np.asarray(values, dtype=float)
-    out = np.full((len(xy),) + values.shape[1:], np.nan)
-    if len(xy) == 0:
-        return out
+_LOCATIONS: Dict[tuple, Any] = {}
+
+
+def _locate(sites: np.ndarray, elements: np.ndarray, xy: np.ndarray, candidates: int):
+    """(inside mask, containing triangle, barycentric weights) of the query points; memoised per
+    (mesh, query points): fluxoid polygons are evaluated for many solutions on the same mesh."""
+    key = (id(elements), id(sites), xy.shape, xy.tobytes() if xy.size <= 4096 else None)
+    if key[3] is not None:
+        hit = _LOCATIONS.get(key)
+        if hit is not None and hit[0] is elements and hit[1] is sites:
+            return hit[2]
     k = min(candidates, len(elements))
     _, cand = _triangle_locator(sites, elements).query(xy, k=k)
     cand = cand.reshape(len(xy), k)
@@ -122,6 +122,25 @@ def linear_tri_interpolate(sites: np.ndarray, elements: np.ndarray, values: np.n
         t = int(np.argmax(mn_all))
         if mn_all[t] >= -1e-12:
             ok[q], tri[q], w[q] = True, t, lam_all[t]
+    if key[3] is not None:
+        if len(_LOCATIONS) > 256:
+            _LOCATIONS.clear()
+        _LOCATIONS[key] = (elements, sites, (ok, tri, w))
+    return ok, tri, w
+
+
+def linear_tri_interpolate(sites: np.ndarray, elements: np.ndarray, values: np.ndarray, xy: np.ndarray,
+                           candidates: int = 16) -> np.ndarray:
+    """Piecewise-linear interpolation on a triangulation; NaN outside the mesh.  Stands in for
+    ``matplotlib.tri.LinearTriInterpolator`` (reference solution.py:272-276,310-312).  The containing
+    triangle is searched among the triangles with the nearest centroids (all triangles as a
+    fallback for points that are not resolved that way)."""
+    xy = np.atleast_2d(np.asarray(xy, dtype=float))
+    values = np.asarray(values, dtype=float)
+    out = np.full((len(xy),) + values.shape[1:], np.nan)
+    if len(xy) == 0:
+        return out
+    ok, tri, w = _locate(sites, elements, xy, candidates)
     v = values[elements[tri]]                                # (q, 3, ...)
     res = np.einsum("qk,qk...->q...", w, v)
     out[ok] = res[ok]

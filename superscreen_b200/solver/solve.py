@@ -306,7 +306,7 @@ def solve(device: Optional[Device] = None, *, model: Optional[FactorizedModel] =
 
 def solve_batch(*, model: FactorizedModel, applied_fields: Sequence[Optional[Callable]],
                 circulating_currents: Optional[Sequence[Dict[str, float]]] = None, field_units: str = "mT",
-                iterations: int = 0, check_inversion: bool = False,
+                iterations: int = 0, check_inversion: bool = False, last_only: bool = False,
                 _solver: str = "superscreen_b200.solve_batch") -> List[List[Solution]]:
     """Solves B models that share one factorization in a single batched pass (multi-RHS getrs,
     multi-RHS matrix-free operator, one film-to-film exchange per iteration for the whole batch).
@@ -315,7 +315,8 @@ def solve_batch(*, model: FactorizedModel, applied_fields: Sequence[Optional[Cal
     (e.g. once per driven hole in ``Device.mutual_inductance_matrix``, device/device.py:610-639, or
     once per applied field in a sweep).  ``out[b]`` equals
     ``solve(model=model_b, applied_field=applied_fields[b], iterations=iterations)`` where
-    ``model_b`` has ``circulating_currents[b]`` (floats in ``model.current_units``).
+    ``model_b`` has ``circulating_currents[b]`` (floats in ``model.current_units``).  With
+    ``last_only`` only the final iterate is brought to the host (``out[b]`` has one element).
     """
     torch = _torch()
     model = _check_model_args(None, model, None, None, None, None)
@@ -354,6 +355,8 @@ def solve_batch(*, model: FactorizedModel, applied_fields: Sequence[Optional[Cal
                         circulating_currents=dict(circulating_currents[b]),
                         terminal_currents=model.terminal_currents, vortices=model.vortices, solver=_solver)
                    for b in range(B)]
+    if last_only:
+        per_iter = per_iter[-1:]
     per_iter_solutions = [_to_solutions(device, film_names, results, dev_fields, others, field_conversion,
                                         kwargs_list) for results, others in per_iter]
     return [[it[b] for it in per_iter_solutions] for b in range(B)]
