@@ -28,6 +28,9 @@
 // dgetrf).  Pivoting is unnecessary here; parity is on the solution (1e-8 rel-L2), see DESIGN.md.
 #include <stdlib.h>
 
+#include <map>
+#include <mutex>
+#include <utility>
 #include <vector>
 
 #include "scb_common.cuh"
@@ -1161,7 +1164,8 @@ static int lu_outer_blocks() {
   return q;
 }
 
-// per-device helper stream (highest priority) and event pool for the look-ahead
+// helper stream (highest priority) and event pool for the look-ahead, one set per (device, caller
+// stream): factorizations issued on different streams (independent films) overlap on the GPU
 struct LuStreams {
   cudaStream_t panel = nullptr;
   std::vector<cudaEvent_t> events;
@@ -1174,7 +1178,8 @@ struct LuStreams {
     return events[i];
   }
 };
-static LuStreams g_lu_streams[64];
+static std::map<std::pair<int, cudaStream_t>, LuStreams> g_lu_streams;
+static std::mutex g_lu_streams_mutex;
 
 // offset (in doubles) of the small integer scratch used by scb_getrs_nopiv (ready flags + work counter)
 namespace scb {
@@ -1234,7 +1239,12 @@ static int getrf_impl(int64_t n_pad, double* M, double* dinv, int32_t* info, scb
     if (const char* e = getenv("SCB_LU_LAZY")) g_lazy_strips = atoi(e);
     g_attr_set[dev & 63] = true;
   }
-  LuStreams& ls = g_lu_streams[dev & 63];
+  LuStreams* lsp;
+  {
+    std::lock_guard<std::mutex> lock(g_lu_streams_mutex);
+    lsp = &g_lu_streams[std::make_pair(dev, s)];  // (std::map nodes are address-stable)
+  }
+  LuStreams& ls = *lsp;
   const bool lookahead = g_lookahead && g_diag_small;
   cudaStream_t sp = s;
   if (lookahead) {

@@ -9,6 +9,9 @@ self-field ``Q @ (w*g)`` on the device and downloads only O(n) vectors.
 """
 from __future__ import annotations
 
+import contextlib
+import os
+
 import logging
 from dataclasses import dataclass, field
 from typing import Dict, Optional, Tuple, Union
@@ -87,7 +90,7 @@ class TerminalSystems:
 
 
 def assemble_negA(info: FilmInfo, ix_dev, n_int: int, n_pad: int, T=None, out=None, want_margin=False,
-                  sym_scale_full=None):
+                  sym_scale_full=None, pos=None, margin=None):
     """-A restricted to ``ix`` in a padded workspace (reference solve_film.py:296-305), or, with
     ``sym_scale_full`` = sqrt(w) per mesh vertex, its diagonally similar symmetric form."""
     torch = _torch()
@@ -95,8 +98,10 @@ def assemble_negA(info: FilmInfo, ix_dev, n_int: int, n_pad: int, T=None, out=No
     d = info.mesh._data
     with torch.cuda.device(d.device):
         M = out if out is not None else torch.empty(n_pad, n_pad, dtype=torch.float64, device=d.device)
-        pos = torch.empty(d.n, dtype=torch.int32, device=d.device)
-        margin = torch.empty(n_int, dtype=torch.float64, device=d.device) if want_margin else None
+        if pos is None:
+            pos = torch.empty(d.n, dtype=torch.int32, device=d.device)
+        if margin is None and want_margin:
+            margin = torch.empty(n_int, dtype=torch.float64, device=d.device)
         _lib.check(L.scb_system_assemble(
             d.n, _lib.ptr(d.sites), _lib.ptr(d.t["vertex_areas"]), _lib.ptr(d.qdw), _lib.ptr(d.t["C"]),
             _lib.ptr(info.dev["Lambda"]), _lib.ptr(d.t["op_indptr"]), _lib.ptr(d.t["op_indices"]),
@@ -113,7 +118,13 @@ def factorize_linear_systems(device: Device, film_info_dict: Dict[str, FilmInfo]
     film_systems: Dict[str, LinearSystem] = {}
     hole_systems: Dict[str, Dict[str, LinearSystem]] = {}
     terminal_systems: Dict[str, object] = {}
-    pending = []  # (film, system, info flag tensor, margin-min tensor): read back once at the end
+    pending = []  # (film, system, info flag tensor, side stream): read back once at the end
+    n_owned = sum(1 for f in film_info_dict if owned is None or f in owned)
+    n_side = int(os.environ.get("SCB_FILM_STREAMS", "8"))
+    side_streams = []  # several systems: factor them concurrently (small LUs are latency-bound)
+    if n_side > 0 and (n_owned > 1 or any(f in device.terminals for f in film_info_dict)):
+        dev0 = next(iter(film_info_dict.values())).mesh._data.device
+        side_streams = [torch.cuda.Stream(device=dev0) for _ in range(min(n_side, max(n_owned, 2)))]
     for film_name, info in film_info_dict.items():
         if owned is not None and film_name not in owned:
             hole_systems[film_name] = {}
@@ -144,16 +155,26 @@ def factorize_linear_systems(device: Device, film_info_dict: Dict[str, FilmInfo]
                 if n_int == 0:
                     raise ValueError(f"Film {film_name!r} has no interior mesh vertices.")
                 n_pad = -(-n_int // LU_BLOCK) * LU_BLOCK
+                # every buffer is allocated on the caller's stream; the kernels may run on a side stream
                 ix_dev = torch.as_tensor(indices).to(d.device)
-                M, margin = assemble_negA(info, ix_dev, n_int, n_pad, T, want_margin=True, sym_scale_full=sym_full)
+                M = torch.empty(n_pad, n_pad, dtype=torch.float64, device=d.device)
+                pos = torch.empty(d.n, dtype=torch.int32, device=d.device)
+                margin = torch.empty(n_int, dtype=torch.float64, device=d.device)
                 dinv = torch.empty(int(L.scb_getrf_dinv_bytes(n_pad)) // 8, dtype=torch.float64, device=d.device)
                 lu_info = torch.zeros(1, dtype=torch.int32, device=d.device)
+                sym_scale = None if sym_full is None else sym_full[ix_dev].contiguous()
                 getrf = L.scb_getrf_sym_nopiv if sym_full is not None else L.scb_getrf_nopiv
-                _lib.check(getrf(n_pad, _lib.ptr(M), _lib.ptr(dinv), _lib.ptr(lu_info), _lib.stream_ptr()))
+                side = side_streams[len(pending) % len(side_streams)] if side_streams else None
+                if side is not None:
+                    side.wait_stream(torch.cuda.current_stream(d.device))
+                with torch.cuda.stream(side) if side is not None else contextlib.nullcontext():
+                    assemble_negA(info, ix_dev, n_int, n_pad, T, out=M, want_margin=True, sym_scale_full=sym_full,
+                                  pos=pos, margin=margin)
+                    _lib.check(getrf(n_pad, _lib.ptr(M), _lib.ptr(dinv), _lib.ptr(lu_info), _lib.stream_ptr()))
                 system = LinearSystem(indices=indices, film_info=info, grad_Lambda_term=T if T is not None else 0.0,
                                       n_pad=n_pad, lu=M, dinv=dinv, indices_dev=ix_dev, margin=margin,
-                                      sym_scale=None if sym_full is None else sym_full[ix_dev].contiguous())
-                pending.append((film_name, system, lu_info, margin.min()))
+                                      sym_scale=sym_scale)
+                pending.append((film_name, system, lu_info, side))
                 return system
 
             interior = info.interior_indices
@@ -177,10 +198,14 @@ def factorize_linear_systems(device: Device, film_info_dict: Dict[str, FilmInfo]
                     film_without_boundary=with_holes,
                     film_without_boundary_or_holes=film_systems[film_name] if info.hole_indices else None,
                 )
-    # one synchronising read per model: singularity flag + dominance margin of every system
-    for film_name, system, lu_info, margin_min in pending:
+    # independent systems were factored on side streams: join them, then one synchronising read per
+    # system (singularity flag + dominance margin)
+    for side in {id(p[3]): p[3] for p in pending if p[3] is not None}.values():
+        with torch.cuda.device(side.device):
+            torch.cuda.current_stream(side.device).wait_stream(side)
+    for film_name, system, lu_info, _ in pending:
         flag = int(lu_info.item())
-        mm = float(margin_min.item())
+        mm = float(system.margin.min().item())
         if flag != 0:
             raise np.linalg.LinAlgError(
                 f"Film {film_name!r}: zero or non-finite pivot at row {flag - 1} in the unpivoted LU."
