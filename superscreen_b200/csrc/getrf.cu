@@ -26,6 +26,7 @@
 //
 // Reference semantics: scipy.linalg.lu_factor(-A) at solver/solve_film.py:232,253,279 (LAPACK
 // dgetrf).  Pivoting is unnecessary here; parity is on the solution (1e-8 rel-L2), see DESIGN.md.
+#include <stdio.h>
 #include <stdlib.h>
 
 #include <map>
@@ -1278,7 +1279,7 @@ static int getrf_impl(int64_t n_pad, double* M, double* dinv, int32_t* info, scb
         dim3 gc(2, nt + 1);  // rows [o, n) x cols [o, o+128)
         update_kernel_t<false><<<gc, 256, upd_smem, st>>>(M, n_pad, o, o, Lpack, Upack, tile_chunks, 0, i * NCHUNK);
         SCB_LAUNCH_CHECK();
-        if (nt > 0) {
+        if (nt > 0 && !sym) {  // (symmetric: the row panel is mirrored from the column panel)
           dim3 gr(2 * nt, 1);  // rows [o, o+128) x cols [o+128, n)
           update_kernel_t<false><<<gr, 256, upd_smem, st>>>(M, n_pad, o, o + NB, Lpack, Upack, tile_chunks, 0, i * NCHUNK);
           SCB_LAUNCH_CHECK();
@@ -1323,14 +1324,27 @@ static int getrf_impl(int64_t n_pad, double* M, double* dinv, int32_t* info, scb
     return SCB_OK;
   };
 
+  // SCB_LU_TRACE=1: time stamps (CUDA events) of the panel chain / strip / bulk phases, printed per call
+  static const bool trace = getenv("SCB_LU_TRACE") != nullptr;
+  struct Stamp { const char* what; int64_t panel; cudaEvent_t e; };
+  std::vector<Stamp> stamps;
+  auto stamp = [&](const char* what, int64_t panel, cudaStream_t st) {
+    if (!trace) return;
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, st);
+    stamps.push_back({what, panel, e});
+  };
   const int64_t np = (nb + q - 1) / q;
   size_t ev = 0;
+  stamp("start", -1, s);
   if (lookahead) {
     cudaEvent_t e0 = ls.event(ev++);
     SCB_CUDA(cudaEventRecord(e0, s));
     SCB_CUDA(cudaStreamWaitEvent(sp, e0, 0));
   }
   if (int rc = factor_panel(0, sp)) return rc;
+  stamp("chain_end", 0, sp);
   for (int64_t P = 0; P < np; P++) {
     const int64_t kb = P * q;
     const int q_eff = (int)((nb - kb) < q ? (nb - kb) : q);
@@ -1363,12 +1377,14 @@ static int getrf_impl(int64_t n_pad, double* M, double* dinv, int32_t* info, scb
         SCB_LAUNCH_CHECK();
       }
     }
+    stamp("strip_end", P + 1, s);
     if (lookahead) {  // panel P+1 can be factored as soon as its strip is up to date
       cudaEvent_t e = ls.event(ev++);
       SCB_CUDA(cudaEventRecord(e, s));
       SCB_CUDA(cudaStreamWaitEvent(sp, e, 0));
     }
     if (int rc = factor_panel(P + 1, sp)) return rc;
+    stamp("chain_end", P + 1, sp);
     // B: the rest of the trailing block, concurrently with the factorization of panel P+1
     if (nt1 > 0) {
       if (sym) {  // tiles on / below the diagonal only
@@ -1379,12 +1395,23 @@ static int getrf_impl(int64_t n_pad, double* M, double* dinv, int32_t* info, scb
         update_kernel_t<false><<<g3, 256, upd_smem, s>>>(M, n_pad, e1, e1, Lpack, Upack, tile_chunks, 0, nchunks);
       }
       SCB_LAUNCH_CHECK();
+      stamp("bulk_end", P, s);
     }
   }
   if (lookahead) {
     cudaEvent_t e = ls.event(ev++);
     SCB_CUDA(cudaEventRecord(e, sp));
     SCB_CUDA(cudaStreamWaitEvent(s, e, 0));
+  }
+  if (trace) {
+    stamp("end", -1, s);
+    cudaStreamSynchronize(s);
+    for (size_t k = 1; k < stamps.size(); k++) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, stamps[0].e, stamps[k].e);
+      fprintf(stderr, "[scb lu trace] %-10s panel %3lld  t = %8.3f ms\n", stamps[k].what, (long long)stamps[k].panel, ms);
+    }
+    for (auto& st : stamps) cudaEventDestroy(st.e);
   }
   return SCB_OK;
 }
