@@ -322,6 +322,28 @@ def run_b200_arm(args):
     assert int(lu_info.item()) == 0, "LU reported a bad pivot"
     getrf_ms = float(np.mean(stage_ms["getrf"]))
 
+    # the two kernels inside the "solve" stage, timed on their own against the last factorization
+    # (untimed with respect to `value`): triangular solves and the matrix-free screening mat-vec
+    from superscreen_b200.solver.solve_film import apply_operator, lu_solve
+
+    data = DeviceMeshData(sites_d, elements_d)
+    info = FilmInfo(name="film", layer="layer", lambda_info=None, vortices=(), interior_indices=interior,
+                    boundary_indices=None, hole_indices={}, in_hole=None, circulating_currents={}, mesh=_Mesh(data))
+    info.dev["Lambda"], info.dev["T"] = Lambda_d, None
+    sym_full = torch.sqrt(data.t["vertex_areas"]) if symmetric else None
+    system = LinearSystem(indices=interior, film_info=info, n_pad=n_pad, lu=lu_ws, dinv=dinv, indices_dev=ix_d,
+                          sym_scale=None if sym_full is None else sym_full[ix_d].contiguous())
+    detail = {}
+    ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for name, fn in (("getrs_1rhs", lambda: lu_solve(system, H_d[ix_d])),
+                     ("screening_matvec_1rhs", lambda: apply_operator(info, g, with_sparse=False))):
+        ts = []
+        for _ in range(3):
+            l2_flush.zero_()
+            ea.record(); fn(); eb.record(); torch.cuda.synchronize()
+            ts.append(ea.elapsed_time(eb))
+        detail[name] = float(np.median(ts))
+
     # ---- end-to-end leg: public API, host buffers in, host arrays out ----
     pinned_sites = torch.as_tensor(sites).pin_memory()
     pinned_elems = torch.as_tensor(elements).pin_memory()
@@ -370,6 +392,7 @@ def run_b200_arm(args):
                    "n_vertices": int(n), "n_triangles": int(m), "n_interior": int(n_int), "n_pad": int(n_pad),
                    "l2": "256 MiB buffer written between timed iterations (flushes the 126 MB L2)"},
         "stages_ms": {k: float(np.mean(v)) for k, v in stage_ms.items()},
+        "solve_stage_kernels_ms": detail,
         "lu_tflops": lu_tflops, "lu_mode": "symmetric" if symmetric else "general",
         "lu_getrf_equivalent_tflops": getrf_equiv_tflops, "films_per_s": world / (ms_per_step * 1e-3),
         "roofline": {"bound": "tensor", "achieved": lu_tflops, "peak": FP64_DMMA_PEAK_TFLOPS, "unit": "TFLOP/s",
