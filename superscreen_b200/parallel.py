@@ -130,6 +130,8 @@ def run_film_iterations(
     zeros_fn: Callable[[str], object],
     j_shape_fn: Callable[[str], Tuple[int, ...]],
     iterations: int,
+    film_scope: Optional[Callable[[str], object]] = None,
+    join: Optional[Callable[[], None]] = None,
 ) -> List[Tuple[Dict[str, Tuple[object, object, object]], Optional[Dict[str, object]]]]:
     """The driver loop of reference solver/solve.py:454-547 for the films owned by this rank.
 
@@ -139,13 +141,24 @@ def run_film_iterations(
             the target film's sites (reference biot_savart_film_to_film).
         zeros_fn(film) -> zero field tensor for that film.
         j_shape_fn(film) -> shape of that film's J tensor.
+        film_scope(film) -> context manager inside which all the work of one film and one Jacobi
+            step is issued; ``join()`` is called after every step.  The films of a step are
+            independent, so the CUDA backend runs them on one stream per film.
 
     Returns one ``(results, others)`` pair per solution (``iterations + 1`` of them when there are
     at least two films): ``results[film] = (g, J, self_field)`` and ``others[film]`` = field from the
     other films used for that solve, for the films this rank owns.
     """
+    import contextlib
+
+    scope = film_scope or (lambda f: contextlib.nullcontext())
+    join = join or (lambda: None)
     mine = [f for f in film_names if owners[f] == comm.rank]
-    results = {f: solve_fn(f, None) for f in mine}
+    results = {}
+    for f in mine:
+        with scope(f):
+            results[f] = solve_fn(f, None)
+    join()
     out = [(results, None)]
     if len(film_names) < 2 or iterations < 1:
         return out
@@ -159,13 +172,17 @@ def run_film_iterations(
     for _ in range(iterations):
         # Jacobi step: all film-to-film fields from the previous iterate, then all re-solves
         J_all = exchange_films({f: results[f][1] for f in mine}, owners, shapes, comm, like)
-        others = {f: zeros_fn(f) for f in mine}
-        for src in film_names:
-            for dst in mine:
-                if src == dst:
-                    continue
-                others[dst] = others[dst] + coupling_fn(src, J_all[src], dst)
-        results = {f: solve_fn(f, others[f]) for f in mine}
+        others, new = {}, {}
+        for dst in mine:
+            with scope(dst):
+                acc = zeros_fn(dst)
+                for src in film_names:  # (fixed summation order: results do not depend on the scopes)
+                    if src != dst:
+                        acc = acc + coupling_fn(src, J_all[src], dst)
+                others[dst] = acc
+                new[dst] = solve_fn(dst, acc)
+        join()
+        results = new
         out.append((results, others))
     return out
 

@@ -244,7 +244,34 @@ def _run(model: "FactorizedModel", applied_fields, circ_by_film, vortex_flux, it
         n = len(meshes[name].sites)
         return (n, batch) if batch is not None else (n,)
 
-    per_iter = run_film_iterations(film_names, owners, comm, solve_fn, coupling_fn, zeros_fn, j_shape, iterations)
+    # the films of one Jacobi step are independent and each is latency-bound (getrs sweeps, small
+    # N-body launches): one side stream per owned film, joined after every step
+    import contextlib
+    import os
+
+    mine = [f for f in film_names if owners[f] == comm.rank]
+    side = {}
+    if len(mine) > 1 and int(os.environ.get("SCB_FILM_STREAMS", "8")) > 0:
+        pool = [torch.cuda.Stream(device=some.device) for _ in range(min(len(mine), int(os.environ.get("SCB_FILM_STREAMS", "8"))))]
+        side = {f: pool[k % len(pool)] for k, f in enumerate(mine)}
+
+    @contextlib.contextmanager
+    def film_scope(name):
+        st = side.get(name)
+        if st is None:
+            yield
+            return
+        st.wait_stream(torch.cuda.current_stream(some.device))
+        with torch.cuda.stream(st):
+            yield
+
+    def join():
+        main = torch.cuda.current_stream(some.device)
+        for st in set(side.values()):
+            main.wait_stream(st)
+
+    per_iter = run_film_iterations(film_names, owners, comm, solve_fn, coupling_fn, zeros_fn, j_shape, iterations,
+                                   film_scope=film_scope, join=join)
     return gather_film_results(per_iter, film_names, owners, comm,
                                {"g": v_shape, "J": j_shape, "self": v_shape, "other": v_shape}, some)
 

@@ -27,18 +27,22 @@ def sync():
 def timed(fn):
     sync(); t0 = time.perf_counter(); r = fn(); sync(); return r, time.perf_counter() - t0
 
+def median_timed(fn, reps=7):
+    ts = []
+    for _ in range(reps):
+        r, t = timed(fn); ts.append(t)
+    return r, float(np.median(ts[1:]))
+
 if "c3" in which:
     device, polys = configs.c3_susceptometer(4000)
     n = {k: len(m.sites) for k, m in device.meshes.items()}
-    for rep in range(2):
-        model, t_fact = timed(lambda: sc.factorize_model(device=device, current_units="uA", circulating_currents={"fc_center": "1 mA"}, comm=comm))
-        sols, t_solve = timed(lambda: sc.solve(model=model, iterations=5))
+    model, t_fact = median_timed(lambda: sc.factorize_model(device=device, current_units="uA", circulating_currents={"fc_center": "1 mA"}, comm=comm))
+    sols, t_solve = median_timed(lambda: sc.solve(model=model, iterations=5))
     fl = sols[-1].hole_fluxoid("pl_center", points=polys["pl_center"], with_units=False)
     out["c3"] = {"vertices": n, "factorize_s": t_fact, "solve_iter5_s": t_solve, "M_Phi0_per_A": sum(fl) / 1e-3}
 if "c4" in which:
     device, polys = configs.c4_ring_array(8, 5000)
-    for rep in range(2):
-        M, t_M = timed(lambda: np.array(device.mutual_inductance_matrix(polys, units="pH", iterations=5, comm=comm)))
+    M, t_M = median_timed(lambda: np.array(device.mutual_inductance_matrix(polys, units="pH", iterations=5, comm=comm)), reps=5)
     out["c4"] = {"vertices_per_ring": len(device.meshes["ring0"].sites), "mutual_inductance_matrix_iter5_s": t_M,
                  "M00_pH": float(M[0, 0]), "M01_pH": float(M[0, 1]), "asym": float(np.abs(M - M.T).max() / abs(M[0, 1]))}
 if "c5" in which:
