@@ -35,6 +35,8 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 METRIC = "sc.solve wall time at 20k vertices (Q assembly + LU + solve)"
+WORKLOAD = ("C2: single square film box(10 um), ~20k-vertex jittered-hex Delaunay mesh, Lambda=0.1 um, "
+            "uniform 1 mT; one independent film per GPU")
 FP64_DMMA_PEAK_TFLOPS = 37.0  # measured on this pool's B200 (profiles/r01_fp64_peaks.txt)
 N_VERTICES = 20164
 SIDE = 10.0
@@ -196,9 +198,9 @@ def run_reference_arm(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": value * 1e3, "higher_is_better": False,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "C2: single square film, ~20k-vertex mesh, uniform 1 mT, Lambda=0.1 (oracle port of "
-                               "the reference CPU path; reference is pure Python and does not travel)",
-                   "n_vertices": int(len(full_sites))},
+        "config": {"workload": WORKLOAD, "n_vertices": int(len(full_sites)),
+                   "implementation": "oracle port of the reference CPU path (the reference is pure Python with "
+                                     "dependencies that are absent on the GPU box and does not travel)"},
         "cpu_baseline": {"value": value, "unit": "s", "cores": cpu_threads(), "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -387,8 +389,7 @@ def run_b200_arm(args):
         "metric": METRIC, "value": ms_per_step * 1e-3, "unit": "s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": False, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "C2: single square film box(10 um), ~20k-vertex jittered-hex Delaunay mesh, "
-                               "Lambda=0.1 um, uniform 1 mT; one independent film per GPU",
+        "config": {"workload": WORKLOAD,
                    "n_vertices": int(n), "n_triangles": int(m), "n_interior": int(n_int), "n_pad": int(n_pad),
                    "l2": "256 MiB buffer written between timed iterations (flushes the 126 MB L2)"},
         "stages_ms": {k: float(np.mean(v)) for k, v in stage_ms.items()},
