@@ -177,10 +177,11 @@ def biot_savart_2d(x, y, z, *, positions, current_densities, z0: float = 0, area
     to_meter = _u.conversion_factor(length_units, "m")
     to_amp_per_meter = _u.conversion_factor(f"({current_units}) / ({length_units})", "A / m")
     x, y, z = np.atleast_1d(x, y, z)
-    if z.shape[0] == 1:
-        z = z * np.ones_like(x)
     dev = torch.device(f"cuda:{torch.cuda.current_device()}")
-    ev = np.ascontiguousarray(np.array([x, y, z], dtype=np.float64).T * to_meter)
+    ev = np.empty((len(x), 3), dtype=np.float64)  # filled column by column: no (3, m) temporary + transpose
+    np.multiply(x, to_meter, out=ev[:, 0])
+    np.multiply(y, to_meter, out=ev[:, 1])
+    np.multiply(z, to_meter, out=ev[:, 2])  # (a length-1 z broadcasts)
     positions, current_densities = np.atleast_2d(positions, current_densities)
     J = np.ascontiguousarray(current_densities * to_amp_per_meter, dtype=np.float64)
     pos = positions * to_meter
@@ -195,7 +196,9 @@ def biot_savart_2d(x, y, z, *, positions, current_densities, z0: float = 0, area
         _lib.check(L.scb_biot_savart(2 if vector else 1, m, _lib.ptr(ev_d), n, _lib.ptr(pos_d), _lib.ptr(ar_d),
                                      _lib.ptr(J_d), 0.0, _MU0_BIOT_SAVART / (4 * np.pi), 1, _lib.ptr(out),
                                      _lib.stream_ptr()))
-        return out.cpu().numpy()
+        from .solver.solve import _to_host
+
+        return _to_host(out)
 
 
 class Solution:
@@ -352,7 +355,12 @@ class Solution:
                     fin = np.array([zeros, zeros, fin]).T
                 field_from_film[in_film] = fin
             out = ~in_film
-            if out.any():
+            if out.all():  # (the usual case of an evaluation plane above the device: no masked copies)
+                field_from_film = biot_savart_2d(
+                    positions[:, 0], positions[:, 1], zs, positions=mesh.sites, areas=mesh.vertex_areas,
+                    current_densities=self.film_solutions[name].current_density, z0=layer.z0,
+                    length_units=device.length_units, current_units=self.current_units, vector=vector)
+            elif out.any():
                 field_from_film[out] = biot_savart_2d(
                     positions[out, 0], positions[out, 1], zs[out], positions=mesh.sites, areas=mesh.vertex_areas,
                     current_densities=self.film_solutions[name].current_density, z0=layer.z0,
@@ -388,7 +396,11 @@ class Solution:
                                                         units=self.field_units)
                 break
         mask = ~in_film
-        if mask.any():
+        if mask.all():
+            Hz_applied = np.asarray(np.squeeze(
+                self.applied_field_func(positions[:, 0], positions[:, 1], zs[:, np.newaxis])), dtype=dtype)
+            Hz_applied = np.broadcast_to(Hz_applied, (len(positions),)) if Hz_applied.ndim == 0 else Hz_applied
+        elif mask.any():
             Hz_applied[mask] = np.squeeze(
                 self.applied_field_func(positions[mask, 0], positions[mask, 1], zs[mask, np.newaxis]))
         fields["applied_field"] = np.atleast_1d(Hz_applied).squeeze()
