@@ -114,3 +114,47 @@ def test_linear_tri_interpolate_matches_bruteforce():
     m = np.isfinite(b).all(axis=1)
     assert np.array_equal(np.isfinite(a).all(axis=1), m)
     assert np.abs(a[m] - b[m]).max() <= 1e-13
+
+
+def test_memoised_host_queries_and_cheap_copies():
+    """The memoised point location / point-in-polygon queries and the constructor-free Polygon.copy
+    used by the batched post-processing return exactly what the direct computation returns."""
+    from superscreen_b200.solution import linear_tri_interpolate
+
+    poly = sc.Polygon("p", layer="l", points=circle(2.0, 40))
+    cp = poly.copy()
+    assert cp is not poly and cp.name == "p" and cp.layer == "l"
+    assert np.array_equal(cp.points, poly.points) and cp.points is not poly.points
+    rng = np.random.default_rng(0)
+    for m in (5, 300, 2000):  # below, inside and above the memoisation thresholds
+        pts = rng.uniform(-3, 3, (m, 2))
+        direct = points_in_polygon(poly.points, pts)
+        assert np.array_equal(poly.contains_points(pts), direct)
+        assert np.array_equal(cp.contains_points(pts), direct)          # served from the memo
+        assert np.array_equal(poly.contains_points(pts, index=True), np.where(direct)[0])
+    sites, elements = disk_mesh(3.0, 400, seed=2)
+    xy = rng.uniform(-2, 2, (50, 2))
+    v1, v2 = rng.standard_normal(len(sites)), rng.standard_normal((len(sites), 2))
+    a = linear_tri_interpolate(sites, elements, v1, xy)
+    b = linear_tri_interpolate(sites, elements, v1, xy)                  # second call: memoised location
+    c = linear_tri_interpolate(sites, elements, v2, xy)
+    assert np.array_equal(a, b) and c.shape == (50, 2)
+    # linear functions are reproduced exactly (up to rounding) by piecewise-linear interpolation
+    lin = 0.3 * sites[:, 0] - 1.7 * sites[:, 1] + 0.5
+    assert np.allclose(linear_tri_interpolate(sites, elements, lin, xy), 0.3 * xy[:, 0] - 1.7 * xy[:, 1] + 0.5,
+                       atol=1e-12)
+
+
+def test_with_lambda_shares_meshes():
+    """configs.with_lambda: a new Device with another Lambda around the same mesh objects (no GPU needed
+    to build it when the meshes dict is given)."""
+    from superscreen_b200 import configs
+
+    device = sc.Device("square", layers=[sc.Layer("layer", Lambda=0.1, z0=0.25)],
+                       films=[sc.Polygon("film", layer="layer", points=box(10.0, points=4))])
+    sentinel = object()
+    device.meshes = {"film": sentinel}
+    other = configs.with_lambda(device, 0.4)
+    assert other.layers["layer"].Lambda == 0.4 and other.layers["layer"].z0 == 0.25
+    assert device.layers["layer"].Lambda == 0.1
+    assert other.meshes["film"] is sentinel and list(other.films) == ["film"]
