@@ -900,44 +900,35 @@ __device__ __forceinline__ int ldl64_blocked(double* __restrict__ S, double* __r
   for (int kb = 0; kb < 8; kb++) {
     const int k0 = 8 * kb;
     if (kb == 0) SCB_STAMP(8);
-    // ---- (A) 8x8 diagonal tile: lane r < 8 owns row r ----
+    // ---- (A) 8x8 diagonal tile: every lane of warp 0 holds the whole lower triangle in registers
+    //      and runs the same straight-line LDL^T (no shuffles, no divergence); lanes share the stores
     if (warp == 0) {
-      double a[8];
+      double a[8][8];  // a[r][c], c <= r
 #pragma unroll
-      for (int c = 0; c < 8; c++) a[c] = (lane < 8 && c <= lane) ? S[(k0 + lane) * QLD + k0 + c] : 0.0;
+      for (int r = 0; r < 8; r++)
+#pragma unroll
+        for (int c = 0; c <= r; c++) a[r][c] = S[(k0 + r) * QLD + k0 + c];
 #pragma unroll
       for (int j = 0; j < 8; j++) {
-        const double w = a[j];
-        const double dj = __shfl_sync(0xffffffffu, w, j);
-        // the products w_r w_c do not depend on the reciprocal: only one FMA follows it in the chain
-        double pw[8];
+        const double djj = a[j][j];
+        const double rjj = fast_rcp2(djj);
+        // trailing lower triangle: a[r][c] -= (a[r][j] / d_j) * a[c][j]
 #pragma unroll
-        for (int c = j + 1; c < 8; c++) pw[c] = w * __shfl_sync(0xffffffffu, w, c);
-        const double rdj = fast_rcp2(dj);
+        for (int r = j + 1; r < 8; r++) {
+          const double l = a[r][j] * rjj;
 #pragma unroll
-        for (int c = j + 1; c < 8; c++)
-          if (lane >= c) a[c] = fma(-pw[c], rdj, a[c]);
-        const double l = w * rdj;
-        if (lane > j) a[j] = l;
-        if (lane == j) {
-          dd[k0 + j] = dj;
-          rd[k0 + j] = rdj;
-          if (bad == 0 && !(fabs(dj) > 0.0 && isfinite(dj))) bad = k0 + j + 1;
+          for (int c = j + 1; c <= r; c++) a[r][c] = fma(-l, a[c][j], a[r][c]);
+          // column j of row r is final: store it now (off the dependency chain)
+          if (lane == 8 + r) {
+            S[(k0 + r) * QLD + k0 + j] = l;            // L[r][j]
+            S[(k0 + j) * QLD + k0 + r] = a[r][j];      // U[j][r] = d_j L[r][j]
+          }
         }
-      }
-      // write back L (lower), U = D L^T (upper) of the tile
-      double dl = 0.0;
-#pragma unroll
-      for (int c = 0; c < 8; c++)
-        if (lane == c) dl = a[c];
-#pragma unroll
-      if (lane < 8) S[(k0 + lane) * QLD + k0 + lane] = dl;
-#pragma unroll
-      for (int c = 0; c < 8; c++) {
-        const double dc = __shfl_sync(0xffffffffu, dl, c);
-        if (lane < 8 && c < lane) {
-          S[(k0 + lane) * QLD + k0 + c] = a[c];
-          S[(k0 + c) * QLD + k0 + lane] = dc * a[c];
+        if (lane == j) {
+          dd[k0 + j] = djj;
+          rd[k0 + j] = rjj;
+          S[(k0 + j) * QLD + k0 + j] = djj;
+          if (bad == 0 && !(fabs(djj) > 0.0 && isfinite(djj))) bad = k0 + j + 1;
         }
       }
     }
