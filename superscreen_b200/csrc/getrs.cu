@@ -19,6 +19,12 @@ int64_t lu_flags_offset(int64_t n_pad);  // getrf.cu
 
 constexpr int NB = SCB_LU_BLOCK;
 
+__device__ __forceinline__ void dmma_rhs(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(d0), "+d"(d1)
+               : "d"(a), "d"(b));
+}
+
 // one warp: acc[c] = sum_q a[q] * xs[lane + 32 q][c], reduced over the warp
 template <int RT>
 __device__ __forceinline__ void row_dot(const double (&a)[4], const double (*xs)[RT + 1], int lane,
@@ -135,7 +141,8 @@ trsv_sweep_kernel(const double* __restrict__ F, int64_t ld, const double* __rest
         B[(i * NB + warp + 8 * rr) * nrhs + r0 + lane] = v;
       }
     }
-    __threadfence();
+    // publish: the barrier orders every thread's x_i stores before thread 0's fence (cumulative at
+    // gpu scope), which orders them before the flag store -- one fence per block instead of 257
     __syncthreads();
     if (tid == 0) {
       __threadfence();
@@ -145,7 +152,7 @@ trsv_sweep_kernel(const double* __restrict__ F, int64_t ld, const double* __rest
 }
 
 // ---------------------------------------------------------------------------------------
-// Many right-hand sides (nrhs > 8): blocked right-looking substitution on the fp64 tensor cores.
+// Many right-hand sides (nrhs > 16): blocked right-looking substitution on the fp64 tensor cores.
 // One launch per 128-row block step k; CTA (column chunk of 16 right-hand sides, row tile i):
 //     B_i -= F_ik X_k                                  (128x128 times 128x16, DMMA)
 // and the CTA of the NEXT block of the sweep goes on to solve it with the stored inverse of its
@@ -156,11 +163,6 @@ trsv_sweep_kernel(const double* __restrict__ F, int64_t ld, const double* __rest
 constexpr int RC = 16;        // right-hand sides per CTA
 constexpr int XLD = RC + 4;   // row stride of the shared X / Y tiles (conflict-free B fragments)
 
-__device__ __forceinline__ void dmma_rhs(double& d0, double& d1, double a, double b) {
-  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
-               : "+d"(d0), "+d"(d1)
-               : "d"(a), "d"(b));
-}
 
 // acc[rt][ct] (rows warp*16 + rt*8 + g, columns ct*8 + 2t, +1) += sign * A[128 x 128] * Xs[128 x RC]
 __device__ __forceinline__ void tile_product(const double* __restrict__ A, int64_t lda, const double* __restrict__ Xs,
@@ -256,6 +258,111 @@ trsm_rhs_step_kernel(const double* __restrict__ F, int64_t ld, const double* __r
       }
 }
 
+// ---------------------------------------------------------------------------------------
+// 2..8 right-hand sides: the same persistent flag-driven sweep, but the two 128x128 products per
+// block run on the fp64 tensor cores (mma.sync m8n8k4: the 8 right-hand sides are exactly one n
+// tile), so there is no warp-shuffle reduction on the critical chain.  Warp w owns rows
+// 16 w .. 16 w + 15 of the block; the A fragments of the factor tile are loaded straight from
+// global memory before the ready flag of x_j is awaited.
+// ---------------------------------------------------------------------------------------
+constexpr int XP = 12;  // row stride of the shared x tile: conflict-free B fragments
+
+__global__ void __launch_bounds__(256)
+trsv_sweep_dmma_kernel(const double* __restrict__ F, int64_t ld, const double* __restrict__ dinv, int64_t nb,
+                       int lower, int64_t nrhs, int64_t r0, double* __restrict__ B, int* __restrict__ flags,
+                       int* __restrict__ counter, int epoch) {
+  __shared__ double xs[NB * XP];
+  __shared__ int s_p;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int nr = (int)((nrhs - r0) < 8 ? (nrhs - r0) : 8);
+  const int64_t ldb = ld * (int64_t)sizeof(double);
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) s_p = atomicAdd(counter, 1);
+    __syncthreads();
+    const int p = s_p;  // position in sweep order
+    if (p >= nb) break;
+    const int64_t i = lower ? p : nb - 1 - p;
+    const double* dblk = dinv + i * 2 * NB * NB + (lower ? 0 : NB * NB);
+    prefetch_tile_l2(dblk, NB * sizeof(double), warp, lane);
+    // C fragments: rows 16 warp + 8 rt + g, columns 2t, 2t + 1 of the right-hand side block
+    double acc[2][2];
+#pragma unroll
+    for (int rt = 0; rt < 2; rt++)
+#pragma unroll
+      for (int e = 0; e < 2; e++)
+        acc[rt][e] = (2 * t + e) < nr ? B[(i * NB + warp * 16 + rt * 8 + g) * nrhs + r0 + 2 * t + e] : 0.0;
+    if (p > 0) {
+      const int64_t j0 = lower ? 0 : nb - 1;
+      prefetch_tile_l2(F + i * NB * ld + j0 * NB, ldb, warp, lane);
+    }
+    for (int q = 0; q < p; q++) {
+      const int64_t j = lower ? q : nb - 1 - q;
+      // A fragments of the factor tile first (independent of x_j), next tile into L2, then wait
+      double a[2][NB / 4];
+#pragma unroll
+      for (int rt = 0; rt < 2; rt++) {
+        const double* Frow = F + (i * NB + warp * 16 + rt * 8 + g) * ld + j * NB + t;
+#pragma unroll
+        for (int ks = 0; ks < NB / 4; ks++) a[rt][ks] = Frow[ks * 4];
+      }
+      if (q + 1 < p) {
+        const int64_t jn = lower ? q + 1 : nb - 2 - q;
+        prefetch_tile_l2(F + i * NB * ld + jn * NB, ldb, warp, lane);
+      }
+      if (tid == 0) {
+        while (*reinterpret_cast<volatile int*>(flags + j) != epoch) {
+        }
+        __threadfence();
+      }
+      __syncthreads();
+      for (int idx = tid; idx < NB * 8; idx += 256) {
+        const int r = idx >> 3, c = idx & 7;
+        xs[r * XP + c] = c < nr ? __ldcg(&B[(j * NB + r) * nrhs + r0 + c]) : 0.0;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int ks = 0; ks < NB / 4; ks++) {
+        const double b = xs[(ks * 4 + t) * XP + g];
+        dmma_rhs(acc[0][0], acc[0][1], -a[0][ks], b);
+        dmma_rhs(acc[1][0], acc[1][1], -a[1][ks], b);
+      }
+    }
+    // finish: x_i = inv(F_ii) acc_i
+    double da[2][NB / 4];
+#pragma unroll
+    for (int rt = 0; rt < 2; rt++) {
+      const double* Drow = dblk + (int64_t)(warp * 16 + rt * 8 + g) * NB + t;
+#pragma unroll
+      for (int ks = 0; ks < NB / 4; ks++) da[rt][ks] = Drow[ks * 4];
+    }
+    __syncthreads();  // everyone is done with the x tile of the last product
+#pragma unroll
+    for (int rt = 0; rt < 2; rt++)
+#pragma unroll
+      for (int e = 0; e < 2; e++) xs[(warp * 16 + rt * 8 + g) * XP + 2 * t + e] = acc[rt][e];
+    __syncthreads();
+    double out[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+#pragma unroll
+    for (int ks = 0; ks < NB / 4; ks++) {
+      const double b = xs[(ks * 4 + t) * XP + g];
+      dmma_rhs(out[0][0], out[0][1], da[0][ks], b);
+      dmma_rhs(out[1][0], out[1][1], da[1][ks], b);
+    }
+#pragma unroll
+    for (int rt = 0; rt < 2; rt++)
+#pragma unroll
+      for (int e = 0; e < 2; e++)
+        if ((2 * t + e) < nr) B[(i * NB + warp * 16 + rt * 8 + g) * nrhs + r0 + 2 * t + e] = out[rt][e];
+    __syncthreads();
+    if (tid == 0) {
+      __threadfence();
+      *reinterpret_cast<volatile int*>(flags + i) = epoch;
+    }
+  }
+}
+
 static int g_epoch = 0;
 static int g_capacity[64][2] = {};  // resident CTAs per device for RT = 1 / 8
 
@@ -278,12 +385,13 @@ extern "C" int scb_getrs_nopiv(int64_t n_pad, const double* LU, const double* di
     if (which == 0)
       SCB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trsv_sweep_kernel<1>, 256, 0));
     else
-      SCB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trsv_sweep_kernel<8>, 256, 0));
+      SCB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trsv_sweep_dmma_kernel, 256, 0));
     SCB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     cap = per_sm * sms;
     if (cap < 1) cap = 1;
   }
-  if (nrhs > 8) {
+  if (nrhs > 16) {
+    // (up to 16 right-hand sides two passes of the flag-driven DMMA sweep are faster)
     // tensor-core path: one launch per block step and sweep direction
     const unsigned ncc = (unsigned)((nrhs + RC - 1) / RC);
     for (int lower = 1; lower >= 0; lower--) {
@@ -309,7 +417,7 @@ extern "C" int scb_getrs_nopiv(int64_t n_pad, const double* LU, const double* di
       if (which == 0)
         trsv_sweep_kernel<1><<<grid, 256, 0, s>>>(LU, n_pad, dinv, nb, lower, nrhs, r0, B, flags, counters, epoch);
       else
-        trsv_sweep_kernel<8><<<grid, 256, 0, s>>>(LU, n_pad, dinv, nb, lower, nrhs, r0, B, flags, counters, epoch);
+        trsv_sweep_dmma_kernel<<<grid, 256, 0, s>>>(LU, n_pad, dinv, nb, lower, nrhs, r0, B, flags, counters, epoch);
       SCB_LAUNCH_CHECK();
     }
   }

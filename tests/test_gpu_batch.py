@@ -155,11 +155,12 @@ def test_find_fluxoid_solution(sc):
     assert model.circulating_currents == {}
 
 
-@pytest.mark.parametrize("nrhs", [9, 16, 21, 70])
+@pytest.mark.parametrize("nrhs", [3, 9, 16, 21, 70])
 def test_many_rhs_tensor_core_substitution(sc, nrhs):
-    """nrhs > 8 takes the blocked DMMA substitution (getrs.cu: trsm_rhs_step_kernel); it must agree
-    with column-by-column solves through the flag-driven sweeps, in both LU modes, including a
-    column count that is not a multiple of the 16-column chunk and a padded last block."""
+    """2..16 right-hand sides take the flag-driven DMMA sweeps (getrs.cu: trsv_sweep_dmma_kernel, 8
+    columns per pass), more the blocked DMMA substitution (trsm_rhs_step_kernel); both must agree with
+    column-by-column solves, including column counts that are not a multiple of the 8- / 16-column
+    chunks and a padded last block."""
     import torch
 
     from superscreen_b200.geometry import box
