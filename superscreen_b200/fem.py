@@ -52,6 +52,44 @@ def adj_directed_tri_indices(triangles, num_sites: int):
     return sp.csr_array((tris + 1, heads, indptr), shape=(num_sites, num_sites)).tocsc()
 
 
+def _weights_from_laplacian(points, triangles, method: str, sparse: bool):
+    """Off-diagonal weights W recovered from the device Laplacian L = M^-1 (W - diag(sum W)):
+    W_ij = m_i L_ij for i != j (one rounding away from the reference's direct evaluation)."""
+    import scipy.sparse as sp
+
+    mesh = _mesh(points, triangles, method)
+    lap = sp.csr_array(mesh.operators.laplacian)
+    w = sp.csr_array(sp.diags(mesh.vertex_areas) @ lap)
+    w.setdiag(0.0)
+    w.eliminate_zeros()
+    return w if sparse else w.toarray()
+
+
+def weights_inv_euclidean(points, triangles, sparse: bool = True):
+    """reference fem.py:124-162"""
+    return _weights_from_laplacian(points, triangles, "inv_euclidean", sparse)
+
+
+def weights_half_cotangent(points, triangles, sparse: bool = True):
+    """reference fem.py:165-224"""
+    return _weights_from_laplacian(points, triangles, "half_cotangent", sparse)
+
+
+def calculate_weights(points, triangles, method: str, sparse: bool = True):
+    """reference fem.py:227-256"""
+    method = method.lower()
+    if method == "uniform":
+        return adjacency_matrix(triangles, sparse=sparse).astype(float)
+    if method == "inv_euclidean":
+        return weights_inv_euclidean(points, triangles, sparse=sparse)
+    if method == "half_cotangent":
+        return weights_half_cotangent(points, triangles, sparse=sparse)
+    raise ValueError(
+        f"Unknown method ({method}). "
+        f"Supported methods are 'uniform', 'inv_euclidean', and 'half_cotangent'."
+    )
+
+
 def laplace_operator(points, triangles, masses: Optional[np.ndarray] = None, weight_method: str = "half_cotangent"):
     """reference fem.py:259-296 (``masses`` are always the lumped vertex areas)."""
     return _mesh(points, triangles, weight_method).operators.laplacian

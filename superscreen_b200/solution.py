@@ -65,6 +65,29 @@ class FilmSolution:
                 self._total_field = self._total_field + self.field_from_other_films
         return self._total_field
 
+    def is_close(self, other: "FilmSolution", rtol: float = 1e-4, atol: float = 1e-7) -> bool:
+        """reference solution.py:166-185"""
+        kw = dict(rtol=rtol, atol=atol)
+        return bool(np.allclose(self.stream, other.stream, **kw)
+                    and np.allclose(self.applied_field, other.applied_field, **kw)
+                    and np.allclose(self.self_field, other.self_field, **kw)
+                    and np.allclose(self.total_field, other.total_field, **kw))
+
+    def __eq__(self, other) -> bool:
+        """reference solution.py:187-199 (tolerance-based, like the reference)"""
+        if other is self:
+            return True
+        if not isinstance(other, FilmSolution):
+            return False
+        if (self.field_from_other_films is None) != (other.field_from_other_films is None):
+            return False
+        if self.field_from_other_films is not None and not np.allclose(self.field_from_other_films,
+                                                                       other.field_from_other_films):
+            return False
+        return self.is_close(other)
+
+    __hash__ = None
+
 
 _LOCATORS: Dict[int, Any] = {}
 
@@ -278,6 +301,32 @@ class Solution:
         total = np.sum(np.sum(J * unit_normals, axis=1) * edge_lengths)
         total = total * _u.conversion_factor(self.current_units, units)
         return _u.Quantity(total, units) if with_units else total
+
+    def equals(self, other, require_same_timestamp: bool = False) -> bool:
+        """reference solution.py:1089-1126 (solutions carry no creation time here, so
+        ``require_same_timestamp`` has no effect; devices are compared by name and polygon data)."""
+        if other is self:
+            return True
+        if not isinstance(other, Solution):
+            return False
+
+        def same_device(a, b):
+            if a.name != b.name or list(a.films) != list(b.films) or list(a.holes) != list(b.holes):
+                return False
+            for pa, pb in zip(list(a.films.values()) + list(a.holes.values()),
+                              list(b.films.values()) + list(b.holes.values())):
+                if pa.layer != pb.layer or not np.array_equal(pa.points, pb.points):
+                    return False
+            return True
+
+        if not (same_device(self.device, other.device) and self.field_units == other.field_units
+                and self.current_units == other.current_units
+                and self.circulating_currents == other.circulating_currents
+                and self.terminal_currents == other.terminal_currents
+                and self.applied_field_func == other.applied_field_func
+                and list(self.vortices) == list(other.vortices)):
+            return False
+        return self.film_solutions == other.film_solutions
 
     # ---------------------------------------------------------------- fluxoid
     def polygon_fluxoid(self, polygon_coords, *, film: str, interp_method: str = "linear",

@@ -21,7 +21,8 @@ from .. import units as _u
 from ..device import Device
 from ..solution import FilmSolution, Solution, Vortex
 from ..sources import ConstantField
-from .solve_film import LinearSystem, factorize_linear_systems, solve_film_device
+from .solve_film import (  # noqa: F401  (TerminalSystems, solve_film: names the reference module exposes)
+    LinearSystem, TerminalSystems, factorize_linear_systems, solve_film, solve_film_device)
 from .utils import FilmInfo, currents_to_floats, field_conversion_factor, make_film_info
 
 logger = logging.getLogger("solve")

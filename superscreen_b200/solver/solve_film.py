@@ -20,8 +20,9 @@ import numpy as np
 
 from .. import _lib
 from ..device import Device
+from ..geometry import close_curve, path_vectors  # noqa: F401  (names the reference module exposes)
 from ..solution import FilmSolution
-from .utils import FilmInfo
+from .utils import FilmInfo, stream_from_terminal_current  # noqa: F401
 
 logger = logging.getLogger("solve")
 

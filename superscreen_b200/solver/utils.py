@@ -16,7 +16,9 @@ import numpy as np
 
 from .. import units as _u
 from ..device import Device, Polygon
+from ..geometry import path_vectors  # noqa: F401  (names the reference module exposes)
 from ..mesh import Mesh
+from ..solution import Vortex  # noqa: F401
 
 logger = logging.getLogger("solve")
 

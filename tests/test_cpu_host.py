@@ -158,3 +158,27 @@ def test_with_lambda_shares_meshes():
     assert other.layers["layer"].Lambda == 0.4 and other.layers["layer"].z0 == 0.25
     assert device.layers["layer"].Lambda == 0.1
     assert other.meshes["film"] is sentinel and list(other.films) == ["film"]
+
+
+def test_solution_equality_helpers():
+    """FilmSolution.is_close / == (tolerance-based like the reference) and Solution.equals."""
+    from superscreen_b200.solution import FilmSolution, Solution
+
+    rng = np.random.default_rng(0)
+    n = 50
+    base = dict(stream=rng.standard_normal(n), current_density=rng.standard_normal((n, 2)),
+                applied_field=rng.standard_normal(n), self_field=rng.standard_normal(n))
+    a, b = FilmSolution(**base), FilmSolution(**{k: v.copy() for k, v in base.items()})
+    assert a == b and a.is_close(b)
+    c = FilmSolution(**{**base, "stream": base["stream"] + 1e-2})
+    assert a != c and not a.is_close(c)
+    d = FilmSolution(**base, field_from_other_films=np.zeros(n))
+    assert a != d and a != "not a solution"
+    device = sc.Device("d", layers=[sc.Layer("l", Lambda=1.0, z0=0.0)],
+                       films=[sc.Polygon("film", layer="l", points=box(2.0, points=4))])
+    f = sc.ConstantField(1.0)
+    kw = dict(device=device, applied_field_func=f, field_units="mT", current_units="uA")
+    s1, s2 = Solution(film_solutions={"film": a}, **kw), Solution(film_solutions={"film": b}, **kw)
+    assert s1.equals(s1) and s1.equals(s2) and not s1.equals(Solution(film_solutions={"film": c}, **kw))
+    assert not s1.equals(Solution(film_solutions={"film": a}, **{**kw, "field_units": "uT"}))
+    assert not s1.equals(42)

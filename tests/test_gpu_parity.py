@@ -107,6 +107,20 @@ def test_weight_methods(sc, golden):
         _check_csr(lap, g, f"out_laplacian_{method}")
     with pytest.raises(ValueError):
         sc.fem.laplace_operator(g["in_sites"], g["in_elements"], weight_method="nope")
+    # the edge-weight matrices themselves (reference fem.py:124-256), against the oracle
+    from oracle import port
+
+    for method in ("uniform", "inv_euclidean", "half_cotangent"):
+        w = sp.csr_matrix(sc.fem.calculate_weights(g["in_sites"], g["in_elements"], method))
+        ref = sp.csr_matrix(port.calculate_weights(g["in_sites"], g["in_elements"], method))
+        ref.eliminate_zeros()
+        w.sort_indices(); ref.sort_indices()
+        assert np.array_equal(w.indptr, ref.indptr) and np.array_equal(w.indices, ref.indices), method
+        assert rel_l2(w.data, ref.data) <= TOL_LOCAL, (method, rel_l2(w.data, ref.data))
+    dense = sc.fem.weights_half_cotangent(g["in_sites"], g["in_elements"], sparse=False)
+    assert isinstance(dense, np.ndarray) and dense.shape == (len(g["in_sites"]),) * 2
+    with pytest.raises(ValueError):
+        sc.fem.calculate_weights(g["in_sites"], g["in_elements"], "nope")
 
 
 def test_ring_solve_against_reference_golden(sc, golden):
