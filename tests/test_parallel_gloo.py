@@ -67,8 +67,21 @@ def _worker(rank, world, port, result_dict):
         j_shape = lambda n: (len(films[n].mesh.sites), 2)
         v_shape = lambda n: (len(films[n].mesh.sites),)
         iterations = int(g["in_iterations"])
+        # the per-film scope / join hooks (one CUDA stream per film in production) must wrap every
+        # owned film exactly once per step and be joined after every step
+        import contextlib
+
+        log = []
+
+        @contextlib.contextmanager
+        def film_scope(name):
+            log.append(("enter", name))
+            yield
+            log.append(("exit", name))
+
         per_iter = parallel.run_film_iterations(names, owners, comm, solve_fn, coupling_fn, zeros_fn, j_shape,
-                                                iterations)
+                                                iterations, film_scope=film_scope, join=lambda: log.append(("join",)))
+        assert log == [("enter", names[rank]), ("exit", names[rank]), ("join",)] * (iterations + 1)
         assert len(per_iter) == iterations + 1
         assert set(per_iter[0][0]) == {names[rank]}, "each rank solves only its own film"
         full = parallel.gather_film_results(per_iter, names, owners, comm,
