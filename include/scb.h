@@ -152,7 +152,9 @@ int scb_system_assemble(int64_t n, const double* sites, const double* weights, c
  * with Q_ij w_j = -q_ij w_j (i != j), Q_ii w_i = qdw_i.  v, out are [n, nrhs] row-major.
  * Replaces the hole slabs `_build_system_1d` @ g[hole] (solve_film.py:285-293,498-503),
  * `Q @ (weights * g)` (solve_film.py:565, with Lambda == NULL: kernel part only) and the
- * check_inversion product (solve_film.py:533-540). */
+ * check_inversion product (solve_film.py:533-540).  The dense part runs as tiled N-body sums on the
+ * fp64 CUDA cores, or for nrhs >= 16 as a DMMA GEMM whose kernel-matrix operand is evaluated on the
+ * fly in the mma fragment layout. */
 int scb_apply_operator(int64_t n, const double* sites, const double* weights, const double* qdw,
                        const double* Lambda, const int32_t* op_indptr, const int32_t* op_indices,
                        const double* laplacian, const double* T, int64_t n_src,
@@ -187,7 +189,9 @@ int scb_getrf_nopiv(int64_t n_pad, double* M, double* dinv, int32_t* info, scb_s
 int scb_getrf_sym_nopiv(int64_t n_pad, double* M, double* dinv, int32_t* info, scb_stream_t stream);
 
 /* Solves M X = B in place for nrhs right-hand sides, B[n_pad, nrhs] row-major, with the factors
- * and the `dinv` buffer produced by scb_getrf_nopiv (two persistent sweep kernels per 8 rhs). */
+ * and the `dinv` buffer produced by scb_getrf_nopiv / scb_getrf_sym_nopiv.  One right-hand side: two
+ * persistent flag-driven sweep kernels; 2..16: the same sweeps with DMMA block products (8 columns per
+ * pass); more: blocked right-looking substitution on DMMA (one launch per 128-row block step). */
 int scb_getrs_nopiv(int64_t n_pad, const double* LU, const double* dinv, int64_t nrhs, double* B,
                     scb_stream_t stream);
 
