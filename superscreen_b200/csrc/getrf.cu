@@ -316,7 +316,7 @@ trsm_kernel(double* __restrict__ M, int64_t ld, int64_t o, int ncol, const doubl
 // and, transposed, into the upper triangle of M (so getrs and lu_piv see an ordinary LU).
 __global__ void __launch_bounds__(256)
 trsm_sym_kernel(double* __restrict__ M, int64_t ld, int64_t o, const double* __restrict__ invU,
-                double* __restrict__ Lpack, double* __restrict__ Upack, int tile_chunks, int chunk0) {
+                double* __restrict__ Lpack, double* __restrict__ Upack, int tile_chunks, int chunk0, int tile0) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* As = reinterpret_cast<double*>(smem_raw);
   __shared__ double dU[NB];  // diagonal of U11
@@ -326,7 +326,7 @@ trsm_sym_kernel(double* __restrict__ M, int64_t ld, int64_t o, const double* __r
   const int64_t o2 = o + NB;
   if (tid < NB) dU[tid] = M[(o + tid) * ld + o + tid];
   double acc[4][4][2];
-  const int tile = blockIdx.x;
+  const int tile = blockIdx.x + tile0;  // 64-row tile below the diagonal block
   double* Atile = M + (o2 + (int64_t)tile * 64) * ld + o;
   double* Bs = As + 64 * TA_LD;
   gemm_k128<64, 128, 2, 4, 1>(Atile, ld, invU, NB, As, Bs, acc);  // ends after a __syncthreads: dU visible
@@ -1140,6 +1140,7 @@ static int g_diag_small = 1;
 static int g_diag_symb = 1;  // blocked LDL^T diagonal kernel in symmetric mode (SCB_DIAG_SYMB=0: sweep version)
 static int g_lookahead = 1;
 static int g_recursive_strips = 1;  // binary-tree schedule of the inner strip updates (SCB_LU_RECURSIVE=0: eager)
+static int g_split_panel = 1;  // symmetric LU: square of the outer panel on the chain, rows below on a 2nd stream (SCB_LU_SPLIT=0: off)
 static int g_lazy_strips = 0;  // left-looking inner strips: same flops, measured no faster (narrow grids)
 
 }  // namespace scb
@@ -1161,6 +1162,7 @@ static int lu_outer_blocks() {
 // stream): factorizations issued on different streams (independent films) overlap on the GPU
 struct LuStreams {
   cudaStream_t panel = nullptr;
+  cudaStream_t rest = nullptr;  // split panels: rows below the outer panel's diagonal square
   std::vector<cudaEvent_t> events;
   cudaEvent_t event(size_t i) {
     while (events.size() <= i) {
@@ -1231,6 +1233,7 @@ static int getrf_impl(int64_t n_pad, double* M, double* dinv, int32_t* info, scb
     if (const char* e = getenv("SCB_LU_LOOKAHEAD")) g_lookahead = atoi(e);
     if (const char* e = getenv("SCB_LU_LAZY")) g_lazy_strips = atoi(e);
     if (const char* e = getenv("SCB_LU_RECURSIVE")) g_recursive_strips = atoi(e);
+    if (const char* e = getenv("SCB_LU_SPLIT")) g_split_panel = atoi(e);
     g_attr_set[dev & 63] = true;
   }
   LuStreams* lsp;
@@ -1249,6 +1252,17 @@ static int getrf_impl(int64_t n_pad, double* M, double* dinv, int32_t* info, scb
     }
     sp = ls.panel;
   }
+  const bool split = sym && lookahead && g_split_panel && g_recursive_strips && !g_lazy_strips;
+  cudaStream_t sr = sp;
+  if (split) {
+    if (!ls.rest) {
+      int lo = 0, hi = 0;
+      SCB_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+      SCB_CUDA(cudaStreamCreateWithPriority(&ls.rest, cudaStreamNonBlocking, hi));
+    }
+    sr = ls.rest;
+  }
+  size_t ev = 0;
   SCB_CUDA(cudaMemsetAsync(info, 0, sizeof(int32_t), s));
   // ready flags / counters of scb_getrs_nopiv live behind the packed panels: start from zero
   SCB_CUDA(cudaMemsetAsync(dinv + lu_flags_offset(n_pad), 0, (nb + 16) * sizeof(double), s));
@@ -1260,6 +1274,65 @@ static int getrf_impl(int64_t n_pad, double* M, double* dinv, int32_t* info, scb
     const int64_t panel_end = (kb + q_eff) * NB;
     double* Lpack = pack_base + (P & 1) * pack_set;
     double* Upack = Lpack + n_pad * NB * q;
+    if (split) {
+      // Split panel (symmetric): the chain on `st` factors only the panel's diagonal square
+      // (diag -> the few column-panel tiles inside the square -> their strip tiles); the rows below
+      // the square follow on the second stream, block by block, without ever delaying the chain.
+      cudaEvent_t e_in = ls.event(ev++);
+      SCB_CUDA(cudaEventRecord(e_in, st));
+      SCB_CUDA(cudaStreamWaitEvent(sr, e_in, 0));
+      const int nt_below = (int)(nb - kb - q_eff);  // 128-row tiles below the outer panel
+      for (int i = 0; i < q_eff; i++) {
+        const int64_t k = kb + i;
+        const int64_t o = k * NB;
+        double* invL = dinv + k * 2 * NB * NB;
+        double* invU = invL + NB * NB;
+        const int inner_rem = q_eff - 1 - i;
+        if (g_diag_symb)
+          diag_kernel_symb<<<1, 256, diag_symb_smem, st>>>(M, n_pad, o, invL, invU, info, (int)k);
+        else
+          diag_kernel_small<true><<<1, 256, diag_small_smem, st>>>(M, n_pad, o, invL, invU, info, (int)k);
+        SCB_LAUNCH_CHECK();
+        if (inner_rem == 0 && nt_below == 0) break;
+        cudaEvent_t e_d = ls.event(ev++);
+        SCB_CUDA(cudaEventRecord(e_d, st));
+        if (inner_rem > 0) {
+          trsm_sym_kernel<<<2 * inner_rem, 256, trsm_smem, st>>>(M, n_pad, o, invU, Lpack, Upack, tile_chunks,
+                                                                 i * NCHUNK, 0);
+          SCB_LAUNCH_CHECK();
+        }
+        cudaEvent_t e_t = ls.event(ev++);
+        SCB_CUDA(cudaEventRecord(e_t, st));
+        if (nt_below > 0) {
+          SCB_CUDA(cudaStreamWaitEvent(sr, e_d, 0));
+          trsm_sym_kernel<<<2 * nt_below, 256, trsm_smem, sr>>>(M, n_pad, o, invU, Lpack, Upack, tile_chunks,
+                                                                i * NCHUNK, 2 * inner_rem);
+          SCB_LAUNCH_CHECK();
+        }
+        if (inner_rem > 0) {
+          int w = 1;
+          while (((i + 1) & w) == 0) w <<= 1;
+          const int k_lo = i + 1 - w;
+          const int c_lo = i + 1, c_hi = (i + 1 + w) < q_eff ? (i + 1 + w) : q_eff;
+          const int ncb = c_hi - c_lo;
+          const int64_t r0 = (kb + c_lo) * NB;
+          const int n_in = q_eff - c_lo;  // row tiles of the band inside the panel's square
+          update_kernel_t<true><<<dim3(2 * ncb, n_in), 256, upd_smem, st>>>(M, n_pad, r0, r0, Lpack, Upack, tile_chunks,
+                                                                           k_lo * NCHUNK, w * NCHUNK);
+          SCB_LAUNCH_CHECK();
+          if (nt_below > 0) {
+            SCB_CUDA(cudaStreamWaitEvent(sr, e_t, 0));
+            update_kernel_t<false><<<dim3(2 * ncb, nt_below), 256, upd_smem, sr>>>(
+                M, n_pad, panel_end, r0, Lpack, Upack, tile_chunks, k_lo * NCHUNK, w * NCHUNK);
+            SCB_LAUNCH_CHECK();
+          }
+        }
+      }
+      cudaEvent_t e_out = ls.event(ev++);
+      SCB_CUDA(cudaEventRecord(e_out, sr));
+      SCB_CUDA(cudaStreamWaitEvent(st, e_out, 0));
+      return SCB_OK;
+    }
     for (int i = 0; i < q_eff; i++) {
       const int64_t k = kb + i;
       const int64_t o = k * NB;
@@ -1289,7 +1362,7 @@ static int getrf_impl(int64_t n_pad, double* M, double* dinv, int32_t* info, scb
       SCB_LAUNCH_CHECK();
       if (nt == 0) break;
       if (sym)
-        trsm_sym_kernel<<<2 * nt, 256, trsm_smem, st>>>(M, n_pad, o, invU, Lpack, Upack, tile_chunks, i * NCHUNK);
+        trsm_sym_kernel<<<2 * nt, 256, trsm_smem, st>>>(M, n_pad, o, invU, Lpack, Upack, tile_chunks, i * NCHUNK, 0);
       else
         trsm_kernel<<<4 * nt, 256, trsm_smem, st>>>(M, n_pad, o, 2 * nt, invL, invU, Lpack, Upack, tile_chunks,
                                                     i * NCHUNK);
@@ -1356,7 +1429,6 @@ static int getrf_impl(int64_t n_pad, double* M, double* dinv, int32_t* info, scb
     stamps.push_back({what, panel, e});
   };
   const int64_t np = (nb + q - 1) / q;
-  size_t ev = 0;
   stamp("start", -1, s);
   if (lookahead) {
     cudaEvent_t e0 = ls.event(ev++);
