@@ -81,6 +81,52 @@ class Polygon:
     def extents(self) -> Tuple[float, float]:
         return tuple(np.ptp(self._points, axis=0))
 
+    @property
+    def area(self) -> float:
+        """Area enclosed by the polygon (shoelace formula; reference device/polygon.py:93-96)."""
+        from .geometry import signed_area
+
+        return float(abs(signed_area(self._points)))
+
+    def set_name(self, name: Optional[str]) -> "Polygon":
+        self.name = name
+        return self
+
+    def set_layer(self, layer: Optional[str]) -> "Polygon":
+        self.layer = layer
+        return self
+
+    def _origin(self, origin) -> np.ndarray:
+        if isinstance(origin, str):
+            if origin == "center":  # centre of the bounding box
+                return 0.5 * (self._points.min(axis=0) + self._points.max(axis=0))
+            if origin == "centroid":  # centre of mass of the enclosed area
+                p = self._points
+                cross = p[:-1, 0] * p[1:, 1] - p[1:, 0] * p[:-1, 1]
+                return ((p[:-1] + p[1:]) * cross[:, None]).sum(axis=0) / (3.0 * cross.sum())
+            raise ValueError(f"Unknown origin: {origin!r}.")
+        return np.asarray(origin, dtype=float)
+
+    def _mapped(self, points: np.ndarray, inplace: bool) -> "Polygon":
+        polygon = self if inplace else self.copy()
+        polygon._points = close_curve(orient_ccw(points))
+        return polygon
+
+    def translate(self, dx: float = 0.0, dy: float = 0.0, inplace: bool = False) -> "Polygon":
+        """reference device/polygon.py:251-270"""
+        return self._mapped(self._points + np.array([dx, dy], dtype=float), inplace)
+
+    def rotate(self, degrees: float, origin=(0.0, 0.0), inplace: bool = False) -> "Polygon":
+        """Counter-clockwise rotation about ``origin`` (reference device/polygon.py:226-249)."""
+        c, s_ = np.cos(np.radians(degrees)), np.sin(np.radians(degrees))
+        o = self._origin(origin)
+        return self._mapped((self._points - o) @ np.array([[c, s_], [-s_, c]]) + o, inplace)
+
+    def scale(self, xfact: float = 1.0, yfact: float = 1.0, origin=(0.0, 0.0), inplace: bool = False) -> "Polygon":
+        """reference device/polygon.py:272-300 (negative factors mirror the polygon)"""
+        o = self._origin(origin)
+        return self._mapped((self._points - o) * np.array([xfact, yfact], dtype=float) + o, inplace)
+
     _mask_cache: Dict[tuple, np.ndarray] = {}
 
     def contains_points(self, points, index: bool = False, radius: float = 0):
@@ -188,6 +234,33 @@ class Device:
         for p in polys:
             out[p.layer].append(p)
         return out
+
+    def get_polygons(self, polygon_type: Optional[str] = None, include_terminals: bool = True) -> List[Polygon]:
+        """All polygons of the device, or those of one kind (reference device/device.py:186-219)."""
+        kinds = {"film": list(self.films.values()), "hole": list(self.holes.values()),
+                 "abstract": list(self.abstract_regions.values()),
+                 "terminal": [t for ts in self.terminals.values() for t in ts]}
+        if polygon_type is not None:
+            polygon_type = polygon_type.lower()
+            if polygon_type not in kinds:
+                raise ValueError(f"Invalid polygon type: {polygon_type!r}.")
+            return kinds[polygon_type]
+        out = kinds["film"] + kinds["hole"] + kinds["abstract"]
+        return out + kinds["terminal"] if include_terminals else out
+
+    def poly_points(self, films: bool = True, holes: bool = True, abstract: bool = True) -> np.ndarray:
+        """Unique vertices of the selected polygons (reference device/device.py:221-240)."""
+        polys = (list(self.films.values()) if films else []) + (list(self.holes.values()) if holes else []) \
+            + (list(self.abstract_regions.values()) if abstract else [])
+        pts = np.concatenate([p.points for p in polys]) if polys else np.zeros((0, 2))
+        _, ix = np.unique(pts, axis=0, return_index=True)
+        return pts[np.sort(ix)]
+
+    def mesh_stats_dict(self) -> Dict[str, Dict[str, Union[int, float]]]:
+        """Per-film mesh statistics (reference device/device.py:487-497)."""
+        if not self.meshes:
+            raise ValueError("The device does not have a mesh.")
+        return {name: mesh.stats() for name, mesh in self.meshes.items()}
 
     def holes_by_film(self) -> Dict[str, List[Polygon]]:
         by_layer = self.polygons_by_layer("hole")

@@ -182,3 +182,37 @@ def test_solution_equality_helpers():
     assert s1.equals(s1) and s1.equals(s2) and not s1.equals(Solution(film_solutions={"film": c}, **kw))
     assert not s1.equals(Solution(film_solutions={"film": a}, **{**kw, "field_units": "uT"}))
     assert not s1.equals(42)
+
+
+def test_polygon_affine_helpers_and_device_queries():
+    """Small geometry conveniences mirrored from the reference (device/polygon.py:93-300,
+    device/device.py:186-240): numpy affine maps instead of shapely."""
+    sq = sc.Polygon("sq", layer="l", points=box(2.0, 1.0, points=4))
+    assert abs(sq.area - 2.0) < 1e-14
+    assert abs(sc.Polygon(points=circle(1.0, 400)).area - np.pi) < 1e-3
+    t = sq.translate(dx=1.0, dy=-2.0)
+    assert t is not sq and np.allclose(t.points.mean(axis=0) - sq.points.mean(axis=0), [1.0, -2.0])
+    r = sq.rotate(90.0)
+    assert np.allclose(sorted(np.ptp(r.points, axis=0)), [1.0, 2.0]) and abs(r.area - 2.0) < 1e-14
+    assert np.allclose(np.ptp(r.points, axis=0), [1.0, 2.0])          # extents swapped
+    c = sq.translate(3.0, 4.0).rotate(30.0, origin="centroid")
+    assert np.allclose(c._origin("centroid"), [3.0, 4.0]) and np.allclose(c._origin("center"), [3.0, 4.0])
+    s2 = sq.scale(xfact=-2.0, yfact=0.5)
+    assert abs(s2.area - 2.0) < 1e-14 and np.allclose(np.ptp(s2.points, axis=0), [4.0, 0.5])
+    from superscreen_b200.geometry import signed_area
+    assert signed_area(s2.points) > 0                                   # still counter-clockwise after mirroring
+    sq.translate(1.0, 0.0, inplace=True)
+    assert np.allclose(sq.points[:, 0].min(), 0.0)
+    assert sq.set_name("a").name == "a" and sq.set_layer("m").layer == "m"
+    with pytest.raises(ValueError):
+        sq.rotate(10.0, origin="nope")
+    device = sc.Device("d", layers=[sc.Layer("l", Lambda=1.0, z0=0.0)],
+                       films=[sc.Polygon("film", layer="l", points=box(4.0, points=4))],
+                       holes=[sc.Polygon("hole", layer="l", points=circle(1.0, 20))])
+    assert [p.name for p in device.get_polygons()] == ["film", "hole"]
+    assert [p.name for p in device.get_polygons("hole")] == ["hole"]
+    with pytest.raises(ValueError):
+        device.get_polygons("nope")
+    assert device.poly_points().shape == (4 + 20, 2) and device.poly_points(holes=False).shape == (4, 2)
+    with pytest.raises(ValueError):
+        device.mesh_stats_dict()
