@@ -248,7 +248,6 @@ def _run(model: "FactorizedModel", applied_fields, circ_by_film, vortex_flux, it
     # the films of one Jacobi step are independent and each is latency-bound (getrs sweeps, small
     # N-body launches): one side stream per owned film, joined after every step
     import contextlib
-    import os
 
     mine = [f for f in film_names if owners[f] == comm.rank]
     side = {}

@@ -10,9 +10,8 @@ self-field ``Q @ (w*g)`` on the device and downloads only O(n) vectors.
 from __future__ import annotations
 
 import contextlib
-import os
-
 import logging
+import os
 from dataclasses import dataclass, field
 from typing import Dict, Optional, Tuple, Union
 
@@ -226,8 +225,6 @@ def factorize_linear_systems(device: Device, film_info_dict: Dict[str, FilmInfo]
 
 def use_symmetric() -> bool:
     """Symmetric factorization for constant-Lambda films (default on; SCB_SYMMETRIC=0 disables)."""
-    import os
-
     return os.environ.get("SCB_SYMMETRIC", "1") != "0"
 
 
