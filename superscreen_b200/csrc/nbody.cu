@@ -379,6 +379,11 @@ extern "C" int scb_biot_savart(int kind, int64_t m, const double* tgt, int64_t n
   SCB_CHECK_ARG(m >= 0 && n >= 0 && nsets >= 1, "bad sizes");
   cudaStream_t s = (cudaStream_t)stream;
   const int64_t ocomp = kind == SCB_BS_VECTOR ? 3 : (kind == SCB_BS_VECTOR_POTENTIAL ? 2 : 1);
+  if (m == 0) return SCB_OK;  // no evaluation points: nothing to write
+  if (n == 0) {               // no sources: the field vanishes
+    SCB_CUDA(cudaMemsetAsync(out, 0, sizeof(double) * (size_t)(m * ocomp * nsets), s));
+    return SCB_OK;
+  }
   int64_t k = 0;
   while (k < nsets) {
     NbodyParams p{};

@@ -194,3 +194,21 @@ def test_many_rhs_tensor_core_substitution(sc, nrhs):
     assert float((out - cols).norm() / cols.norm()) <= 1e-13
     full = apply_operator(info, V)  # no gather list: every vertex is a source (V vanishes outside ix)
     assert float((full - cols).norm() / cols.norm()) <= 1e-13
+
+
+def test_empty_evaluation_sets(sc, golden):
+    """Edge cases of the field evaluation: no evaluation points and points that all lie in a film."""
+    g = golden("two_rings")
+    device = _two_ring_device(sc, g)
+    sol = sc.solve(device, applied_field=sc.ConstantField(0.3), circulating_currents={"lower_hole": 500.0})[0]
+    empty = sol.field_at_position(np.zeros((0, 3)), units="mT", with_units=False)
+    assert np.asarray(empty).shape == (0,)
+    from superscreen_b200.solution import biot_savart_2d
+
+    mesh = device.meshes["lower"]
+    out = biot_savart_2d(np.zeros(0), np.zeros(0), np.zeros(0), positions=mesh.sites,
+                         current_densities=sol.film_solutions["lower"].current_density, z0=0.0,
+                         areas=mesh.vertex_areas, vector=True)
+    assert out.shape == (0, 3)
+    one = sol.field_at_position(np.array([[0.1, 0.2, 3.0]]), units="mT", with_units=False)
+    assert np.asarray(one).shape in ((), (1,)) and np.isfinite(one).all()
