@@ -216,3 +216,19 @@ def test_polygon_affine_helpers_and_device_queries():
     assert device.poly_points().shape == (4 + 20, 2) and device.poly_points(holes=False).shape == (4, 2)
     with pytest.raises(ValueError):
         device.mesh_stats_dict()
+
+
+def test_c_abi_argument_errors_without_gpu():
+    """Argument validation happens before any CUDA call: bad sizes return a negative code and leave a
+    message in scb_last_error() (error behaviour) -- checkable without a device."""
+    lib = _lib.load_library()
+    rc = lib.scb_getrf_nopiv(100, None, None, None, None)          # n_pad not a multiple of 128
+    assert rc < 0 and b"128" in lib.scb_last_error()
+    rc = lib.scb_getrs_nopiv(128, None, None, 0, None, None)       # nrhs must be positive
+    assert rc < 0 and b"nrhs" in lib.scb_last_error()
+    rc = lib.scb_cdist(4, 0, 1, None, 1, None, None, None)         # dim must be 2 or 3
+    assert rc < 0 and b"dim" in lib.scb_last_error()
+    rc = lib.scb_biot_savart(1, -1, None, 0, None, None, None, 0.0, 1.0, 1, None, None)
+    assert rc < 0 and b"sizes" in lib.scb_last_error()
+    with pytest.raises(_lib.SCBError):
+        _lib.check(rc)
