@@ -7,8 +7,16 @@ assembly + LU + solve (the north-star "Q assembly + LU + solve").
 
 Prints ONE JSON line (see the task contract).  `value` is the device-resident wall time per
 solve, `e2e` the same through the public API with host buffers, `roofline` the LU's fp64
-TFLOP/s against the measured DMMA peak, `cpu_baseline` the oracle port on the host cores.
-Under torchrun every rank solves its own 20k film (weak scaling, no data-path collective).
+TFLOP/s against the DMMA issue rate measured in the same run, `cpu_baseline` the oracle port on
+the host cores.  Under torchrun every rank solves its own 20k film (weak scaling, no data-path
+collective), and the configurations that DO shard (BASELINE.json configs 4 and 5) are then run
+across the N ranks and reported under `sharded` (strong scaling, fixed total work):
+  c4_s            8 coupled rings x 5k vertices, 8 x 8 mutual-inductance matrix, iterations=5,
+                  one film factorization per rank, one all-gather of J per Jacobi step
+  c5_field_s      Solution.field_at_position on a 1000 x 1000 grid over a 60k-vertex film,
+                  evaluation points split over the ranks
+  lambda_sweep_s  4 Lambda values x 16 fields on the 60k film, one factorization per rank
+each checked in the run against the single-process result (`parity_vs_single_process`).
 """
 from __future__ import annotations
 
@@ -37,7 +45,7 @@ if ROOT not in sys.path:
 METRIC = "sc.solve wall time at 20k vertices (Q assembly + LU + solve)"
 WORKLOAD = ("C2: single square film box(10 um), ~20k-vertex jittered-hex Delaunay mesh, Lambda=0.1 um, "
             "uniform 1 mT; one independent film per GPU")
-FP64_DMMA_PEAK_TFLOPS = 37.0  # measured on this pool's B200 (profiles/r01_fp64_peaks.txt)
+FP64_DMMA_PEAK_FALLBACK = 37.0  # profiles/r01_fp64_peaks.txt; only used if the live measurement fails
 N_VERTICES = 20164
 SIDE = 10.0
 LAMBDA = 0.1
@@ -144,10 +152,6 @@ def cpu_reference_solve(sites, elements):
     return t, sol, len(interior)
 
 
-STAGE_EXPONENT = {"mesh_operators": 1.0, "Q_matrix": 2.0, "laplacian_toarray": 2.0, "build_system_2d": 2.0,
-                  "lu_factor": 3.0, "solve_film": 2.0}
-
-
 def cpu_threads():
     """Threads actually used by the CPU arm: min(numba threads, BLAS threads)."""
     try:
@@ -174,34 +178,43 @@ def warm_numba():
     port.q_matrix(p)
 
 
+def workload_config(sites, elements):
+    """The `config` object of BOTH arms (the reference arm must describe the identical workload)."""
+    from superscreen_b200.mesh import boundary_vertices_ccw
+
+    n, m = len(sites), len(elements)
+    n_int = n - len(boundary_vertices_ccw(elements))
+    return {"workload": WORKLOAD, "n_vertices": int(n), "n_triangles": int(m), "n_interior": int(n_int),
+            "n_pad": int(-(-n_int // 128) * 128),
+            "l2": "256 MiB buffer written between timed iterations (flushes the 126 MB L2)"}
+
+
 def run_reference_arm(args):
-    """--impl reference: bounded sample (smaller mesh of the same family), each stage scaled to
-    the full C2 size by its complexity exponent."""
+    """--impl reference: the reference's CPU path (oracle port: the Python reference and its
+    dependencies do not exist on the GPU box) on the SAME full-size C2 workload as the B200 arm,
+    all host cores, one full solve per step, `steps` and `warmup` honoured."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n_sample = 8000
-    sites, elements = make_workload(seed=0, n_vertices=n_sample)
+    sites, elements = make_workload(seed=0)
     warm_numba()
-    full_sites, _ = make_workload(seed=0)
-    scale_n = len(full_sites) / len(sites)
-    times = []
+    times, stages = [], []
     for it in range(args.warmup + args.steps):
         st, _, n_int = cpu_reference_solve(sites, elements)
-        scaled = sum(v * scale_n ** STAGE_EXPONENT[k] for k, v in st.items())
         if it >= args.warmup:
-            times.append(scaled)
+            times.append(float(sum(st.values())))
+            stages.append(st)
     value = float(np.mean(times))
-    sample = (f"{len(sites)}-vertex square of the same mesh family per step; every stage time scaled to "
-              f"{len(full_sites)} vertices by (n/n_s)^p, p=3 LU, 2 dense n^2 stages, 1 sparse operators")
+    sample = (f"the full C2 workload ({len(sites)} vertices, the B200 arm's rank-0 mesh), one complete solve per "
+              f"step, {args.steps} timed steps after {args.warmup} warm-up steps; oracle port of the reference "
+              "CPU path (numba + scipy/LAPACK), all host cores")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": value * 1e3, "higher_is_better": False,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "n_vertices": int(len(full_sites)),
-                   "implementation": "oracle port of the reference CPU path (the reference is pure Python with "
-                                     "dependencies that are absent on the GPU box and does not travel)"},
-        "cpu_baseline": {"value": value, "unit": "s", "cores": cpu_threads(), "kind": "port", "sample": sample},
+        "config": workload_config(sites, elements),
+        "cpu_baseline": {"value": value, "unit": "s", "cores": cpu_threads(), "kind": "port", "sample": sample,
+                         "stages_s": {k: float(np.mean([s_[k] for s_ in stages])) for k in stages[0]}},
         "e2e": {"value": value, "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -211,6 +224,55 @@ def run_reference_arm(args):
 # ------------------------------------------------------------------------------------------
 # B200 arm
 # ------------------------------------------------------------------------------------------
+def measure_dmma_peak(L, dev):
+    """fp64 tensor-core roofline denominator, measured in this run: issue rate of DMMA.8x8x4
+    (mma.sync m8n8k4 f64) from register-resident chains, 16 warps per SM, best of 5 launches."""
+    import ctypes
+
+    import torch
+
+    from superscreen_b200 import _lib
+
+    try:
+        scratch = torch.empty(int(L.scb_diag_scratch_elems()), dtype=torch.float64, device=dev)
+        flop = ctypes.c_double(0.0)
+        ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        best = None
+        for rep in range(6):
+            ea.record()
+            _lib.check(L.scb_diag_issue_rate(0, 20000, _lib.ptr(scratch), ctypes.byref(flop), _lib.stream_ptr()))
+            eb.record()
+            torch.cuda.synchronize()
+            ms = ea.elapsed_time(eb)
+            if rep > 0:
+                best = ms if best is None else min(best, ms)
+        tflops = flop.value / (best * 1e-3) * 1e-12
+        if not (20.0 < tflops < 80.0):
+            raise RuntimeError(f"implausible DMMA rate {tflops}")
+        return tflops, ("DMMA.8x8x4 issue rate measured in this run (scb_diag_issue_rate: 148 CTAs x 16 warps x 16 "
+                        "accumulator chains, best of 5); MEASURED_PEAKS.json has no fp64 entry")
+    except Exception as exc:  # noqa: BLE001
+        return FP64_DMMA_PEAK_FALLBACK, f"fallback (live measurement failed: {exc}); profiles/r01_fp64_peaks.txt"
+
+
+def load_ncu_evidence(symmetric: bool):
+    """`traffic` (dram bytes read + written per launch) and the ncu summary of the dominant LU launch,
+    from the newest committed profiles/r*_lu_dominant_launch.json (written from an `ncu --set full`
+    capture of `bench.py`); {"traffic": None} when there is none for this LU mode."""
+    import glob
+
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_lu_dominant_launch.json")), reverse=True):
+        try:
+            with open(path) as f:
+                rec = json.load(f)
+            rec = rec["symmetric" if symmetric else "general"]
+            out = {"traffic": rec.get("dram_bytes"), "dominant_launch": dict(rec, source=os.path.relpath(path, ROOT))}
+            return out
+        except Exception:  # noqa: BLE001
+            continue
+    return {"traffic": None}
+
+
 def run_b200_arm(args):
     import torch
     import torch.distributed as dist
@@ -382,42 +444,36 @@ def run_b200_arm(args):
     ms_per_step, e2e_s, getrf_ms = (float(v) for v in vals.cpu())
 
     # flops actually executed: n^3/3 for the symmetric factorization, 2 n^3/3 for the general one
+    config = workload_config(sites, elements)
+    assert config["n_interior"] == n_int and config["n_pad"] == n_pad
+    peak_tflops, peak_source = measure_dmma_peak(L, dev)
     lu_flops = ((1.0 if symmetric else 2.0) / 3.0) * float(n_int) ** 3
     lu_tflops = lu_flops / (getrf_ms * 1e-3) * 1e-12
     getrf_equiv_tflops = (2.0 / 3.0) * float(n_int) ** 3 / (getrf_ms * 1e-3) * 1e-12
+    roofline = {
+        "bound": "tensor", "achieved": lu_tflops, "peak": peak_tflops, "unit": "TFLOP/s",
+        "frac": lu_tflops / peak_tflops,
+        "kernel": ("scb_getrf_sym_nopiv" if symmetric else "scb_getrf_nopiv") + " = all launches of one "
+                  "factorization (update_kernel DMMA trailing updates + diag/trsm panel kernels, look-ahead on "
+                  "a second stream), timed live with CUDA events on the launching stream",
+        "work": ("1/3 * n_int^3 fp64 flop executed per symmetric factorization (a general getrf of the same "
+                 "matrix is 2/3 n^3: lu_getrf_equivalent_tflops)") if symmetric
+        else "2/3 * n_int^3 fp64 flop per factorization",
+        "peak_source": peak_source,
+    }
+    # DRAM traffic and the ncu view of the dominant launch come from a committed ncu capture of this
+    # command (profiles/), never from literals in this file; absent capture -> null
+    roofline.update(load_ncu_evidence(symmetric))
     line = {
         "metric": METRIC, "value": ms_per_step * 1e-3, "unit": "s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": False, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD,
-                   "n_vertices": int(n), "n_triangles": int(m), "n_interior": int(n_int), "n_pad": int(n_pad),
-                   "l2": "256 MiB buffer written between timed iterations (flushes the 126 MB L2)"},
+        "config": config,
         "stages_ms": {k: float(np.mean(v)) for k, v in stage_ms.items()},
         "solve_stage_kernels_ms": detail,
         "lu_tflops": lu_tflops, "lu_mode": "symmetric" if symmetric else "general",
         "lu_getrf_equivalent_tflops": getrf_equiv_tflops, "films_per_s": world / (ms_per_step * 1e-3),
-        "roofline": {"bound": "tensor", "achieved": lu_tflops, "peak": FP64_DMMA_PEAK_TFLOPS, "unit": "TFLOP/s",
-                     "frac": lu_tflops / FP64_DMMA_PEAK_TFLOPS,
-                     # DRAM bytes (read + write) of the dominant launch = the first K=1024 bulk trailing
-                     # update (ncu --set full, profiles/r01_update_kernel*_bulk_k1024_ncu.txt); most of it
-                     # are packed-operand re-reads that miss L2 (algorithmic C traffic: 2.59 / 5.14 GB)
-                     "traffic": 10.26e9 if symmetric else 25.6e9,
-                     "dominant_launch": (
-                         {"kernel": "scb::update_kernel_t<true> grid (280,140), 19740 lower-triangle tiles, K=1024",
-                          "flop": 331.2e9, "ms": 9.326, "achieved": 35.51, "frac": 35.51 / FP64_DMMA_PEAK_TFLOPS,
-                          "dmma_pipe_active_pct": 96.2, "source": "ncu, profiles/r01_update_kernel_tri_bulk_k1024_ncu.txt"}
-                         if symmetric else
-                         {"kernel": "scb::update_kernel_t<false> grid (280,140) K=1024", "flop": 657.7e9,
-                          "ms": 18.375, "achieved": 35.79, "frac": 35.79 / FP64_DMMA_PEAK_TFLOPS,
-                          "dmma_pipe_active_pct": 96.4, "source": "ncu, profiles/r01_update_kernel_bulk_k1024_ncu.txt"}),
-                     "kernel": ("scb_getrf_sym_nopiv" if symmetric else "scb_getrf_nopiv") + " = all launches of one factorization (update_kernel DMMA trailing "
-                               "updates + diag/trsm panel kernels, look-ahead on a second stream), timed live with "
-                               "CUDA events",
-                     "work": ("1/3 * n_int^3 fp64 flop executed per symmetric factorization (a general getrf "
-                              "of the same matrix is 2/3 n^3: lu_getrf_equivalent_tflops)") if symmetric
-                     else "2/3 * n_int^3 fp64 flop per factorization",
-                     "peak_source": "measured DMMA.8x8x4 issue rate on this pool's B200, "
-                                    "profiles/r01_fp64_peaks.txt (MEASURED_PEAKS.json has no fp64 entry)"},
+        "roofline": roofline,
         "e2e": {"value": e2e_s, "unit": "s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
         "gpu_launches": int(launches),
         "clocks": clocks,
@@ -431,10 +487,108 @@ def run_b200_arm(args):
                                 "sample": "the full C2 workload (same mesh), one repetition after numba warm-up",
                                 "stages_s": {k: float(v) for k, v in st.items()},
                                 "rel_l2_stream_gpu_vs_cpu": rel}
+    if not args.no_sharded:
+        torch.cuda.empty_cache()
+        line["sharded"] = run_sharded_legs(rank, world, dev)
     if rank == 0:
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_sharded_legs(rank, world, dev):
+    """BASELINE.json configs 4 and 5 across the N ranks (strong scaling: the total work is fixed,
+    the same keys are reported at every N), each compared in the run with the single-process result.
+    Times are device-synchronised wall times, barrier on both sides, max over ranks."""
+    import torch
+    import torch.distributed as dist
+
+    import superscreen_b200 as sc
+    from superscreen_b200 import configs, parallel
+
+    comm = parallel.DistComm() if world > 1 else None
+
+    def sync():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(fn):
+        sync()
+        t0 = time.perf_counter()
+        r = fn()
+        sync()
+        t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return r, float(t.item())
+
+    out = {"n_gpus": world, "scaling": "strong"}
+    parity = {}
+    # ---- C4: 8 coupled rings, 8 x 8 mutual-inductance matrix, iterations = 5 ----
+    device4, polys = configs.c4_ring_array(8, 5000)
+    ts = []
+    for rep in range(6):
+        M, t = timed(lambda: np.array(device4.mutual_inductance_matrix(polys, units="pH", iterations=5, comm=comm)))
+        ts.append(t)
+    out["c4_s"] = float(np.median(ts[1:]))
+    out["c4"] = {"films": 8, "vertices_per_film": int(len(device4.meshes["ring0"].sites)), "iterations": 5,
+                 "M00_pH": float(M[0, 0]), "M01_pH": float(M[0, 1]),
+                 "asymmetry": float(np.abs(M - M.T).max() / abs(M[0, 1]))}
+    M1 = M if world == 1 else np.array(device4.mutual_inductance_matrix(polys, units="pH", iterations=5))
+    parity["c4"] = float(np.abs(M - M1).max() / np.abs(M1).max())
+    del device4
+    torch.cuda.empty_cache()
+    # ---- C5: 60k-vertex film; field_at_position on a 1000 x 1000 grid, targets split over the ranks ----
+    device5, fields = configs.c5_large(60000)
+    model5, t_fact = timed(lambda: sc.factorize_model(device=device5, current_units="uA"))
+    n_int5 = len(model5.film_systems["film"].indices)
+    sol5 = sc.solve(model=model5, applied_field=sc.ConstantField(1.0))[0]
+    grid = configs.evaluation_grid(1000)
+    ts = []
+    for rep in range(4):
+        Bz, t = timed(lambda: parallel.field_at_position_sharded(sol5, grid, comm=comm, units="mT"))
+        ts.append(t)
+    out["c5_field_s"] = float(np.median(ts[1:]))
+    out["c5"] = {"vertices": int(len(device5.meshes["film"].sites)), "n_interior": int(n_int5),
+                 "targets": int(len(grid)), "factorize_s": t_fact,
+                 "gpairs_per_s": len(grid) * len(device5.meshes["film"].sites) / out["c5_field_s"] * 1e-9}
+    Bz1 = Bz if world == 1 else sol5.field_at_position(grid, units="mT", with_units=False)
+    parity["c5_field"] = float(np.linalg.norm(Bz - Bz1) / np.linalg.norm(Bz1))
+    # ---- C5 Lambda sweep: 4 factorizations x 16 fields, one Lambda per rank (round robin) ----
+    del model5, sol5
+    torch.cuda.empty_cache()
+    lams = list(configs.C5_LAMBDA_SWEEP)
+    mine = [lam for k, lam in enumerate(lams) if k % world == rank]
+
+    def one_lambda(lam):
+        m = sc.factorize_model(device=configs.with_lambda(device5, lam), current_units="uA")
+        sols = sc.solve_batch(model=m, applied_fields=[sc.ConstantField(float(f)) for f in fields[:16]])
+        g = sols[15][0].film_solutions["film"].stream
+        return [float(np.abs(g).max()), float(np.linalg.norm(g))]
+
+    res, t_sweep = timed(lambda: {lam: one_lambda(lam) for lam in mine})
+    out["lambda_sweep_s"] = t_sweep
+    if world > 1:
+        gathered = [None] * world
+        dist.all_gather_object(gathered, res)
+        allres = {k: v for d in gathered for k, v in d.items()}
+        # single-process check of a Lambda another rank factored
+        if rank == 0:
+            ref = one_lambda(lams[1])
+            parity["lambda_sweep"] = float(abs(ref[1] - allres[lams[1]][1]) / ref[1])
+        sync()
+    else:
+        allres = res
+        parity["lambda_sweep"] = 0.0
+    out["lambda_sweep"] = {"Lambdas": lams, "fields_per_Lambda": 16,
+                           "stream_max_and_norm": {str(k): allres[k] for k in lams}}
+    out["parity_vs_single_process"] = parity
+    if rank == 0:
+        bad = {k: v for k, v in parity.items() if not v <= 1e-12}
+        assert not bad, f"sharded results differ from the single-process ones: {bad}"
+    return out
 
 
 def main():
@@ -444,6 +598,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sharded", action="store_true", help="skip the sharded C4 / C5 legs")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

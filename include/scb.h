@@ -227,12 +227,32 @@ int scb_biot_savart(int kind, int64_t m, const double* tgt, int64_t n, const dou
                     const double* area, const double* J, double dz, double prefactor,
                     int64_t nsets, double* out, scb_stream_t stream);
 
+/* One Jacobi step of the film-to-film iteration for ONE target film (solver/solve.py:495-515: the
+ * sum of biot_savart_film_to_film over every other film) in a single launch.  The sources are the
+ * packed vertices of all films: src [n,3] = (x, y, z0 of the owning film's layer), area [n] (0 for
+ * padding rows), J [n, nsets, 2] (source-major: the layout the per-iteration J exchange delivers).
+ * Sources in [skip_lo, skip_hi) -- the target film's own segment -- are left out.
+ *   out[i, s] = prefactor * sum_j area_j (Jx[j,s] (y_i - y_j) - Jy[j,s] (x_i - x_j)) r_ij^-3,
+ *   r_ij^2 = (x_i - x_j)^2 + (y_i - y_j)^2 + (tgt_z - z_j)^2;   tgt [m,2], out [m, nsets]. */
+int scb_film_coupling(int64_t m, const double* tgt, double tgt_z, int64_t n, const double* src,
+                      const double* area, const double* J, int64_t skip_lo, int64_t skip_hi,
+                      double prefactor, int64_t nsets, double* out, scb_stream_t stream);
+
 /* ------------------------------------------------------------------------------------
  * Pairwise distances (K20): distance.py:5-84 cdist / (sq)euclidean_distance_2d/3d
  *   out[m, n] = |XA_i - XB_j|  (squared != 0: squared distance), dim = 2 or 3.  HBM-write bound.
  * ------------------------------------------------------------------------------------ */
 int scb_cdist(int dim, int squared, int64_t m, const double* XA, int64_t n, const double* XB,
               double* out, scb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * Diagnostics: roofline denominators measured in place (bench.py).  Launches a register-resident
+ * issue-rate loop of the fp64 tensor-core atom (kind 0: mma.sync m8n8k4 f64 = DMMA.8x8x4) or of DFMA
+ * (kind 1), one 512-thread CTA per SM.  *flop_host (HOST pointer, may be NULL) <- flop executed by the
+ * launch; the caller times the launch with CUDA events.  scratch: scb_diag_scratch_elems() doubles.
+ * ------------------------------------------------------------------------------------ */
+int scb_diag_issue_rate(int kind, int64_t iters, double* scratch, double* flop_host, scb_stream_t stream);
+int64_t scb_diag_scratch_elems(void);
 
 #ifdef __cplusplus
 }

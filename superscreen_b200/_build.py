@@ -10,7 +10,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libsc_b200.so")
-SOURCES = ["api.cu", "mesh_ops.cu", "nbody.cu", "assemble.cu", "getrf.cu", "getrs.cu", "spmv.cu"]
+SOURCES = ["api.cu", "mesh_ops.cu", "nbody.cu", "assemble.cu", "getrf.cu", "getrs.cu", "spmv.cu", "diag.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xptxas=-v",
@@ -24,19 +24,56 @@ def _nvcc() -> str:
     raise RuntimeError("nvcc not found")
 
 
+STAMP = LIB + ".stamp"
+ABI_VERSION = 200  # must equal scb_version() of the sources (csrc/api.cu)
+
+
+def source_digest() -> str:
+    """Content hash of everything the library is built from (sources, header, flags).  Content, not
+    mtimes: the tree is copied to the GPU box and checkouts reset timestamps."""
+    import hashlib
+
+    h = hashlib.blake2b(digest_size=16)
+    deps = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h")))
+    deps.append(os.path.join(os.path.dirname(HERE), "include", "scb.h"))
+    for d in deps:
+        h.update(os.path.basename(d).encode())
+        with open(d, "rb") as f:
+            h.update(f.read())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()
+
+
 def needs_build() -> bool:
-    if not os.path.exists(LIB):
+    """True when libsc_b200.so is missing or was built from other sources than the ones in the tree."""
+    if not os.path.exists(LIB) or not os.path.exists(STAMP):
         return True
-    t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [
-        os.path.join(os.path.dirname(HERE), "include", "scb.h")
-    ]
-    return any(os.path.getmtime(d) > t for d in deps)
+    try:
+        with open(STAMP) as f:
+            return f.read().strip() != source_digest()
+    except OSError:
+        return True
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
+    """Builds the library if needed.  Safe to call from several processes at once (torchrun ranks):
+    an exclusive file lock serialises the builders and the late-comers find an up-to-date library."""
     if not force and not needs_build():
         return LIB
+    import fcntl
+
+    os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
+    with open(os.path.join(HERE, "build", ".lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not needs_build():
+                return LIB
+            return _build_locked(verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(verbose: bool) -> str:
     nvcc = _nvcc()
     objs = []
     os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
@@ -56,8 +93,12 @@ def build(force: bool = False, verbose: bool = False) -> str:
         f.write("\n".join(log))
     if verbose:
         print("\n".join(log))
-    cmd = [nvcc, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]
+    tmp = LIB + f".tmp{os.getpid()}"
+    cmd = [nvcc, "-shared", "-o", tmp, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]
     subprocess.run(cmd, check=True, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    os.replace(tmp, LIB)  # atomic: a concurrent loader never maps a half-written file
+    with open(STAMP, "w") as f:
+        f.write(source_digest())
     return LIB
 
 

@@ -57,6 +57,10 @@ EXPORTS = {
     "scb_getrs_nopiv": (c_int, [c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
     "scb_spmv": (c_int, [c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_double, c_double, c_void_p, c_void_p]),
     "scb_biot_savart": (c_int, [c_int, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_double, c_double, c_int64, c_void_p, c_void_p]),
+    "scb_film_coupling": (c_int, [c_int64, c_void_p, c_double, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_int64,
+                                  c_double, c_int64, c_void_p, c_void_p]),
+    "scb_diag_issue_rate": (c_int, [c_int, c_int64, c_void_p, POINTER(c_double), c_void_p]),
+    "scb_diag_scratch_elems": (c_int64, []),
     "scb_cdist": (c_int, [c_int, c_int, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
 }
 
@@ -67,19 +71,21 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
     if _lib is not None and path is None:
         return _lib
     p = path or LIB_PATH
-    if not os.path.exists(p) and path is None:
-        # the library is built in-tree (python -m superscreen_b200._build); build it on first use
-        # when the sources are present but the artefact is not (fresh checkout with nvcc available)
-        try:
-            from . import _build
+    if path is None and not os.environ.get("SCB_LIB_PATH"):
+        # the library is built in-tree (python -m superscreen_b200._build).  (Re)build it when it is
+        # missing or stale with respect to csrc/ + include/scb.h (content hash, file-locked so that
+        # torchrun ranks do not race); a stale library that cannot be rebuilt is an error, never loaded.
+        from . import _build
 
-            _build.build()
-        except Exception as exc:  # noqa: BLE001
-            raise SCBError(
-                f"{p} not found and building it failed ({exc}). Run "
-                "`python -c 'import __graft_entry__ as g; g.build()'` (needs nvcc). "
-                "superscreen_b200 has no CPU fallback."
-            ) from exc
+        if _build.needs_build():
+            try:
+                _build.build()
+            except Exception as exc:  # noqa: BLE001
+                raise SCBError(
+                    f"{p} is missing or older than its sources and building it failed ({exc}). Run "
+                    "`python -c 'import __graft_entry__ as g; g.build()'` (needs nvcc). "
+                    "superscreen_b200 has no CPU fallback."
+                ) from exc
     if not os.path.exists(p):
         raise SCBError(
             f"{p} not found: the CUDA library has not been built. Run "
@@ -91,6 +97,10 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
         fn = getattr(lib, name)
         fn.restype = restype
         fn.argtypes = argtypes
+    from ._build import ABI_VERSION
+
+    if lib.scb_version() != ABI_VERSION:
+        raise SCBError(f"{p}: ABI version {lib.scb_version()} != expected {ABI_VERSION} (stale library?)")
     if path is None:
         _lib = lib
     return lib

@@ -320,6 +320,127 @@ int nbody_kernel_sum(int64_t m, const double* tgt, int64_t n, const double* src,
   return SCB_OK;
 }
 
+// ---------------------------------------------------------------------------------------
+// Film-to-film coupling of one Jacobi step (reference solver/solve.py:495-515) in ONE launch per
+// target film: the sources are the packed vertices of ALL films (x, y, z0 per vertex, zero-area
+// padding allowed), the target film's own segment [skip_lo, skip_hi) is left out, and `nsets`
+// current-density sets (batched right-hand sides) share every r^-3 evaluation.
+//   out[i, s] = prefactor * sum_{j not in skip} w_j (Jx[j,s] dy - Jy[j,s] dx) (dx^2 + dy^2 + dz_j^2)^-3/2
+// J is [n, ldj/2, 2] (source-major, as the J exchange delivers it), out is [m, ldo].
+// Same thread layout as nbody_kernel (SL source lanes per target, fixed-order butterfly), plus TPT
+// targets per thread: the 2 NR + 3 shared-memory operands of a source are loaded once for TPT pairs.
+// ---------------------------------------------------------------------------------------
+struct CouplingParams {
+  int64_t m;
+  const double* tgt;   // [m,2]
+  double tgt_z;
+  int64_t n;           // packed sources
+  const double* src;   // [n,3]
+  const double* area;  // [n]
+  const double* J;     // [n, ldj]  (ldj = 2 * nsets)
+  int64_t ldj;
+  int64_t set0;        // first set handled by this launch
+  int64_t skip_lo, skip_hi;
+  double prefactor;
+  double* out;         // [m, ldo]
+  int64_t ldo;
+};
+
+template <int SL, int NR, int TPT>
+__global__ void __launch_bounds__(256) film_coupling_kernel(CouplingParams p) {
+  __shared__ double sx[kTile], sy[kTile], sd[kTile];
+  __shared__ double spx[NR][kTile], spy[NR][kTile];
+  constexpr int TG = 256 / SL;  // target groups per CTA
+  const int tid = threadIdx.x;
+  const int sl = tid % SL;
+  const int64_t i0 = blockIdx.x * (int64_t)(TG * TPT) + tid / SL;
+  double tx[TPT], ty[TPT];
+#pragma unroll
+  for (int k = 0; k < TPT; k++) {
+    const int64_t i = i0 + k * TG;
+    tx[k] = i < p.m ? p.tgt[2 * i] : 0.0;
+    ty[k] = i < p.m ? p.tgt[2 * i + 1] : 0.0;
+  }
+  double acc[TPT][NR];
+#pragma unroll
+  for (int k = 0; k < TPT; k++)
+#pragma unroll
+    for (int r = 0; r < NR; r++) acc[k][r] = 0.0;
+
+#pragma unroll 1
+  for (int seg = 0; seg < 2; seg++) {
+    const int64_t lo = seg == 0 ? 0 : p.skip_hi;
+    const int64_t hi = seg == 0 ? p.skip_lo : p.n;
+    for (int64_t base = lo; base < hi; base += kTile) {
+      const int64_t j = base + tid;
+      __syncthreads();
+      if (j < hi) {
+        sx[tid] = p.src[3 * j];
+        sy[tid] = p.src[3 * j + 1];
+        const double dz = p.tgt_z - p.src[3 * j + 2];
+        sd[tid] = dz * dz;
+        const double w = p.area[j];
+        const double* Jj = p.J + j * p.ldj + 2 * p.set0;
+#pragma unroll
+        for (int r = 0; r < NR; r++) {
+          spx[r][tid] = w * Jj[2 * r];
+          spy[r][tid] = w * Jj[2 * r + 1];
+        }
+      }
+      __syncthreads();
+      const int cnt = (int)((hi - base) < kTile ? (hi - base) : kTile);
+#pragma unroll 2
+      for (int jj = sl; jj < cnt; jj += SL) {
+        const double xs = sx[jj], ys = sy[jj], ds = sd[jj];
+        double px[NR], py[NR];
+#pragma unroll
+        for (int r = 0; r < NR; r++) {
+          px[r] = spx[r][jj];
+          py[r] = spy[r][jj];
+        }
+#pragma unroll
+        for (int k = 0; k < TPT; k++) {
+          const double dx = tx[k] - xs, dy = ty[k] - ys;
+          const double k3 = inv_r3(fma(dx, dx, fma(dy, dy, ds)));
+          const double kdy = k3 * dy, kdx = k3 * dx;
+#pragma unroll
+          for (int r = 0; r < NR; r++) acc[k][r] = fma(px[r], kdy, fma(-py[r], kdx, acc[k][r]));
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int off = SL / 2; off > 0; off >>= 1) {
+#pragma unroll
+    for (int k = 0; k < TPT; k++)
+#pragma unroll
+      for (int r = 0; r < NR; r++) acc[k][r] += __shfl_xor_sync(0xffffffffu, acc[k][r], off);
+  }
+  if (sl != 0) return;
+#pragma unroll
+  for (int k = 0; k < TPT; k++) {
+    const int64_t i = i0 + k * TG;
+    if (i >= p.m) continue;
+#pragma unroll
+    for (int r = 0; r < NR; r++) p.out[i * p.ldo + p.set0 + r] = p.prefactor * acc[k][r];
+  }
+}
+
+template <int NR, int TPT>
+static int launch_coupling(const CouplingParams& p, cudaStream_t s) {
+  // small target sets (a film's own vertices): 32 source lanes per target so that 148 SMs are filled
+  const int64_t ctas32 = ceil_div(p.m, (256 / 32) * TPT);
+  if (ctas32 <= 148 * 8) {
+    film_coupling_kernel<32, NR, TPT><<<(unsigned)ctas32, 256, 0, s>>>(p);
+  } else if (ceil_div(p.m, (256 / 8) * TPT) <= 148 * 16) {
+    film_coupling_kernel<8, NR, TPT><<<(unsigned)ceil_div(p.m, (256 / 8) * TPT), 256, 0, s>>>(p);
+  } else {
+    film_coupling_kernel<1, NR, TPT><<<(unsigned)ceil_div(p.m, 256 * TPT), 256, 0, s>>>(p);
+  }
+  SCB_LAUNCH_CHECK();
+  return SCB_OK;
+}
+
 // out[i, j] = |XA_i - XB_j| (or its square): one thread per 2 adjacent columns, 128-bit stores
 template <int DIM>
 __global__ void cdist_kernel(int squared, int64_t m, const double* __restrict__ XA, int64_t n,
@@ -407,6 +528,33 @@ extern "C" int scb_biot_savart(int kind, int64_t m, const double* tgt, int64_t n
     }
     if (rc) return rc;
     k += step;
+  }
+  return SCB_OK;
+}
+
+extern "C" int scb_film_coupling(int64_t m, const double* tgt, double tgt_z, int64_t n, const double* src,
+                                 const double* area, const double* J, int64_t skip_lo, int64_t skip_hi,
+                                 double prefactor, int64_t nsets, double* out, scb_stream_t stream) {
+  SCB_CHECK_ARG(m >= 0 && n >= 0 && nsets >= 1, "bad sizes");
+  SCB_CHECK_ARG(0 <= skip_lo && skip_lo <= skip_hi && skip_hi <= n, "skip range must lie inside [0, n]");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (m == 0) return SCB_OK;
+  if (skip_lo == 0 && skip_hi == n) {  // no other film: the field vanishes
+    SCB_CUDA(cudaMemsetAsync(out, 0, sizeof(double) * (size_t)(m * nsets), s));
+    return SCB_OK;
+  }
+  CouplingParams p{};
+  p.m = m; p.tgt = tgt; p.tgt_z = tgt_z; p.n = n; p.src = src; p.area = area; p.J = J; p.ldj = 2 * nsets;
+  p.skip_lo = skip_lo; p.skip_hi = skip_hi; p.prefactor = prefactor; p.out = out; p.ldo = nsets;
+  int64_t k = 0;
+  while (k < nsets) {
+    p.set0 = k;
+    int rc;
+    if (nsets - k >= 8) { rc = launch_coupling<8, 2>(p, s); k += 8; }
+    else if (nsets - k >= 4) { rc = launch_coupling<4, 2>(p, s); k += 4; }
+    else if (nsets - k >= 2) { rc = launch_coupling<2, 2>(p, s); k += 2; }
+    else { rc = launch_coupling<1, 2>(p, s); k += 1; }
+    if (rc) return rc;
   }
   return SCB_OK;
 }

@@ -133,11 +133,14 @@ class Polygon:
         pts = np.atleast_2d(points)
         if len(pts) >= 16:
             # the same (polygon, points) query is repeated for every fluxoid / film-info evaluation;
-            # memoise on a content key (large point sets: shape, corner values and checksum)
+            # memoise on the full content (a digest of the float64 bytes for large point sets)
+            raw = np.ascontiguousarray(pts, dtype=float)
             if len(pts) >= 1024:
-                key = (self._points.tobytes(), pts.shape, float(pts[0, 0]), float(pts[-1, 1]), float(pts.sum()))
+                import hashlib
+
+                key = (self._points.tobytes(), pts.shape, hashlib.blake2b(raw.data, digest_size=16).digest())
             else:
-                key = (self._points.tobytes(), pts.shape, np.ascontiguousarray(pts, dtype=float).tobytes())
+                key = (self._points.tobytes(), pts.shape, raw.tobytes())
             mask = Polygon._mask_cache.get(key)
             if mask is None:
                 if len(Polygon._mask_cache) > 1024:
@@ -357,18 +360,33 @@ class Device:
         M = np.zeros((n_iter, n_holes, n_holes))
         films_by_hole = {h.name: film for film, hs in self.holes_by_film().items() for h in hs}
         model = factorize_model(device=self, current_units="mA", comm=comm)
+        # Multi-rank: every rank keeps only its own films' solutions (no replication of the results),
+        # evaluates the fluxoid rows of the holes in those films, and the small matrix is summed over
+        # the ranks -- M[i, j] only needs film(i)'s solution for the driven hole j.
+        sharded = comm is not None and comm.world > 1
         batch = solve_batch(
             model=model, applied_fields=[solve_kwargs.get("applied_field")] * len(hole_names),
             circulating_currents=[{name: 1.0} for name in hole_names],
             field_units=solve_kwargs.get("field_units", "mT"), iterations=solve_kwargs.get("iterations", 0),
-            check_inversion=solve_kwargs.get("check_inversion", False), last_only=not all_iterations)
+            check_inversion=solve_kwargs.get("check_inversion", False), last_only=not all_iterations,
+            gather=not sharded)
         to_units = _u.conversion_factor("H", units)
         for j, hole_name in enumerate(hole_names):
             for nn, solution in enumerate(batch[j][sl]):
                 for i, name in enumerate(hole_names):
+                    if films_by_hole[name] not in solution.film_solutions:
+                        continue  # another rank's film
                     fluxoid = solution.polygon_fluxoid(hole_polygon_mapping[name], film=films_by_hole[name],
                                                        units="Phi_0", with_units=False)
                     M[nn, i, j] = sum(fluxoid) * _u.PHI_0 / I_circ_A * to_units
+        if sharded:
+            import torch
+
+            dev = torch.device(f"cuda:{torch.cuda.current_device()}") if torch.cuda.is_available() \
+                else torch.device("cpu")
+            parts = torch.zeros((comm.world,) + M.shape, dtype=torch.float64, device=dev)
+            comm.all_gather_into(parts.view(comm.world, -1), torch.as_tensor(M).to(dev).reshape(1, -1))
+            M = parts.sum(dim=0).cpu().numpy()  # every entry is non-zero on exactly one rank
         result = [m for m in M]
         if not all_iterations:
             result = result[0]

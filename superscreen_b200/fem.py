@@ -91,17 +91,51 @@ def calculate_weights(points, triangles, method: str, sparse: bool = True):
 
 
 def laplace_operator(points, triangles, masses: Optional[np.ndarray] = None, weight_method: str = "half_cotangent"):
-    """reference fem.py:259-296 (``masses`` are always the lumped vertex areas)."""
-    return _mesh(points, triangles, weight_method).operators.laplacian
+    """reference fem.py:259-296.  The device builds ``inv(M) @ L`` with the lumped vertex areas as
+    ``M``; user-supplied ``masses`` replace them by a row rescaling ``diag(w / masses)``."""
+    import scipy.sparse as sp
+
+    mesh = _mesh(points, triangles, weight_method)
+    lap = mesh.operators.laplacian
+    if masses is None:
+        return lap
+    masses = np.asarray(masses, dtype=np.float64)
+    if masses.shape != (len(mesh.sites),):
+        raise ValueError(f"masses must have shape ({len(mesh.sites)},), got {masses.shape}.")
+    return sp.csr_array(sp.diags(mesh.vertex_areas / masses, format="csr") @ lap)
 
 
 def gradient_triangles(points, triangles, areas=None) -> Tuple:
-    """reference fem.py:299-347"""
-    ops = _mesh(points, triangles).operators
-    return ops.gradient_tri_x, ops.gradient_tri_y
+    """reference fem.py:299-347.  ``areas`` (pre-computed triangle areas) replace the device's own
+    areas in the ``1 / (2 area)`` factor by a row rescaling."""
+    import scipy.sparse as sp
+
+    mesh = _mesh(points, triangles)
+    ops = mesh.operators
+    Gx, Gy = ops.gradient_tri_x, ops.gradient_tri_y
+    if areas is None:
+        return Gx, Gy
+    areas = np.asarray(areas, dtype=np.float64)
+    if areas.shape != (len(mesh.elements),):
+        raise ValueError(f"areas must have shape ({len(mesh.elements)},), got {areas.shape}.")
+    scale = sp.diags(mesh.triangle_areas / areas, format="csr")
+    return sp.csr_array(scale @ Gx), sp.csr_array(scale @ Gy)
 
 
 def gradient_vertices(points, triangles, gradient_tri=None, areas=None) -> Tuple:
-    """reference fem.py:350-402"""
-    ops = _mesh(points, triangles).operators
+    """reference fem.py:350-402.  The device evaluates the star average of its own triangle
+    gradients; pre-computed ``gradient_tri`` / ``areas`` are accepted only when they agree with
+    those (they are an optimisation hint in the reference, not a different operator)."""
+    mesh = _mesh(points, triangles)
+    ops = mesh.operators
+    if areas is not None and not np.allclose(np.asarray(areas, dtype=float), mesh.triangle_areas, rtol=1e-12,
+                                             atol=0.0):
+        raise NotImplementedError("gradient_vertices: `areas` that differ from the mesh's triangle areas "
+                                  "are not supported.")
+    if gradient_tri is not None:
+        for given, own in zip(gradient_tri, (ops.gradient_tri_x, ops.gradient_tri_y)):
+            diff = abs(given - own)
+            if diff.shape != own.shape or (diff.nnz and diff.max() > 1e-12 * abs(own).max()):
+                raise NotImplementedError("gradient_vertices: a `gradient_tri` other than "
+                                          "gradient_triangles(points, triangles) is not supported.")
     return ops.gradient_x, ops.gradient_y

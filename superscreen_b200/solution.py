@@ -230,8 +230,9 @@ class Solution:
     def __init__(self, *, device: Device, film_solutions: Dict[str, FilmSolution], applied_field_func: Callable,
                  field_units: str, current_units: str, circulating_currents: Optional[Dict[str, float]] = None,
                  terminal_currents: Optional[Dict[str, float]] = None, vortices=None,
-                 solver: str = "superscreen_b200.solve"):
-        self.device = device.copy(with_mesh=True, copy_mesh=False)
+                 solver: str = "superscreen_b200.solve", _device_is_copy: bool = False):
+        # (the solver hands one private copy of the device to all the solutions of a call)
+        self.device = device if _device_is_copy else device.copy(with_mesh=True, copy_mesh=False)
         self.film_solutions = film_solutions
         self.applied_field_func = applied_field_func
         self.circulating_currents = circulating_currents or {}

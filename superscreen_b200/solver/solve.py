@@ -132,65 +132,49 @@ def factorize_model(*, device: Device, current_units: str, terminal_currents=Non
                            circulating_currents, vortices, current_units, comm)
 
 
-_PINNED = {}  # device index -> pinned staging buffer (float64), grown on demand
-
-
 def _to_host(t) -> np.ndarray:
-    """Device tensor -> host numpy array.  Large arrays go through a cached pinned staging buffer
-    (a pageable cudaMemcpy runs at a fraction of the PCIe/C2C rate)."""
+    """Device tensor -> host numpy array.  Large arrays are copied into a pinned tensor of torch's
+    caching host allocator (a pageable cudaMemcpy runs at a fraction of the PCIe/C2C rate) and
+    handed out as a view of it: no second host copy; the block returns to the cache when the last
+    view dies."""
     import torch
 
     t = t.contiguous()
-    if t.dtype != torch.float64 or t.numel() < (1 << 17):
+    if t.numel() < (1 << 15):
         return t.cpu().numpy()
-    key = t.device.index
-    buf = _PINNED.get(key)
-    if buf is None or buf.numel() < t.numel():
-        buf = torch.empty(max(t.numel(), 1 << 22), dtype=torch.float64, pin_memory=True)
-        _PINNED[key] = buf
-    stage = buf[: t.numel()].view(t.shape)
+    stage = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
     stage.copy_(t, non_blocking=True)
     torch.cuda.current_stream(t.device).synchronize()
-    return stage.numpy().copy()
+    return stage.numpy()
 
 
-def _to_solutions(device, film_names, results, applied_fields, others, field_conversion, kwargs_list):
-    """Device tensors (solver units) -> host FilmSolutions (reference solve_film.py:566-573).  One
-    device->host copy per array per film, shared by all batch entries; ``kwargs_list`` holds the
-    Solution keyword arguments of every batch entry (length 1 when not batched)."""
-    batched = next(iter(results.values()))[0].dim() == 2
-    host = {}
-    for name in film_names:
-        g, J, self_field = results[name]
-        applied = applied_fields[name] / field_conversion
-        self_field = self_field / field_conversion
-        other = None if others is None else others[name] / field_conversion
-        if batched:
-            # batch-major on the device, so that every batch entry is a contiguous host row (no per-entry copies)
-            g, applied, self_field = g.t(), applied.t(), self_field.t()
-            other = None if other is None else other.t()
-        host[name] = (_to_host(g), _to_host(J), _to_host(applied), _to_host(self_field),
-                      None if other is None else _to_host(other))
+def _solutions_from_host(device, host, film_names, host_fields, field_conversion, kwargs_list, batched):
+    """HostResults (parallel.ResultPacker) -> [[Solution per batch entry] per stored iterate]
+    (reference solve_film.py:566-573: fields are handed out in ``field_units``).  The arrays of the
+    FilmSolutions are views of the one downloaded buffer; the applied field never left the host."""
+    applied = {name: host_fields[name] / field_conversion for name in film_names}
+    shared = device.copy(with_mesh=True, copy_mesh=False)  # one copy shared by the solutions of this call
     out = []
-    for b, kwargs in enumerate(kwargs_list):
-        film_solutions = {}
-        for name in film_names:
-            g, J, applied, self_field, other = host[name]
-            if batched:
-                g, J, applied, self_field = g[b], J[b], applied[b], self_field[b]
-                other = None if other is None else other[b]
-            film_solutions[name] = FilmSolution(
-                stream=np.ascontiguousarray(g), current_density=np.ascontiguousarray(J),
-                applied_field=np.ascontiguousarray(applied), self_field=np.ascontiguousarray(self_field),
-                field_from_other_films=None if other is None else np.ascontiguousarray(other))
-        out.append(Solution(device=device, film_solutions=film_solutions, **kwargs))
+    for it in host.iterates:
+        row = []
+        for b, kwargs in enumerate(kwargs_list):
+            film_solutions = {}
+            for name in film_names:
+                g, J, self_field, other = host.film(it, b, name)
+                film_solutions[name] = FilmSolution(
+                    stream=g, current_density=J, applied_field=applied[name][b] if batched else applied[name],
+                    self_field=self_field, field_from_other_films=other)
+            row.append(Solution(device=shared, film_solutions=film_solutions, _device_is_copy=True, **kwargs))
+        out.append(row)
     return out
 
 
-def _evaluate_applied_field(applied_field, device, film_info, meshes, field_conversion):
+def _evaluate_applied_field(applied_field, device, film_info, meshes, field_conversion, films=None):
     """reference solver/solve.py:422-436 -> {film: host float64 (n,) in solver units}"""
     out = {}
     for film, mesh in meshes.items():
+        if films is not None and film not in films:
+            continue
         layer = device.layers[film_info[film].layer]
         z0 = layer.z0 * np.ones(len(mesh.sites))
         Hz_applied = np.squeeze(applied_field(mesh.sites[:, 0], mesh.sites[:, 1], z0) * field_conversion)
@@ -204,12 +188,39 @@ def _evaluate_applied_field(applied_field, device, film_info, meshes, field_conv
     return out
 
 
-def _run(model: "FactorizedModel", applied_fields, circ_by_film, vortex_flux, iterations, check_inversion):
-    """Runs the solve + film-to-film iterations on the device for single or batched right-hand
-    sides; returns the per-iteration results replicated on every rank."""
+def _packed_sources(model: "FactorizedModel", layout, z0s, dev):
+    """Static part of the film-to-film coupling: vertices (x, y, z0) and vertex areas of ALL films in
+    the packed layout of ``parallel.FilmLayout`` (padding rows: far away, zero area).  Built once per
+    model and device."""
     torch = _torch()
-    from ..parallel import Comm, film_owners, gather_film_results, run_film_iterations
+    cache = model.__dict__.setdefault("_packed_cache", {})
+    key = (str(dev), tuple(layout.films), layout.world)
+    hit = cache.get(key)
+    if hit is None:
+        src = torch.full((layout.total, 3), 1e30, dtype=torch.float64, device=dev)
+        area = torch.zeros(layout.total, dtype=torch.float64, device=dev)
+        for name in layout.films:
+            d = model.device.meshes[name]._data
+            lo, hi = layout.rows(name)
+            src[lo:hi, :2] = d.sites.to(dev)
+            src[lo:hi, 2] = z0s[name]
+            area[lo:hi] = d.t["vertex_areas"].to(dev)
+        hit = cache[key] = (src, area)
+    return hit
 
+
+def _run(model: "FactorizedModel", applied_fields, circ_by_film, vortex_flux, iterations, check_inversion,
+         field_conversion: float, batch: Optional[int] = None, last_only: bool = False, gather: bool = True):
+    """Runs the solve + film-to-film iterations on the device for single or batched right-hand
+    sides.  Everything stays on the device until the end: every owned film's result of every stored
+    iterate is packed into one buffer (``parallel.ResultPacker``), replicated over the ranks by one
+    all-gather if ``gather`` and downloaded once.  Returns ``parallel.HostResults``."""
+    torch = _torch()
+    import contextlib
+
+    from ..parallel import Comm, FilmLayout, ResultPacker, film_owners, run_film_iterations
+
+    L = _lib.lib()
     device = model.device
     comm = model.comm or Comm()
     film_names = list(device.films)
@@ -217,8 +228,11 @@ def _run(model: "FactorizedModel", applied_fields, circ_by_film, vortex_flux, it
     meshes = device.meshes
     film_info = model.film_info
     z0s = {name: float(device.layers[film_info[name].layer].z0) for name in film_names}
-    some = next(iter(applied_fields.values()))
-    batch = some.shape[1] if some.dim() == 2 else None
+    dev = next((t.device for t in applied_fields.values()), torch.device(f"cuda:{torch.cuda.current_device()}"))
+    layout = FilmLayout(film_names, {f: len(meshes[f].sites) for f in film_names}, owners, comm.world)
+    multi = len(film_names) >= 2 and iterations >= 1
+    n_solutions = iterations + 1 if multi else 1
+    iterates = [n_solutions - 1] if last_only else list(range(n_solutions))
 
     def solve_fn(name, other):
         return solve_film_device(
@@ -228,31 +242,27 @@ def _run(model: "FactorizedModel", applied_fields, circ_by_film, vortex_flux, it
             circulating_currents=None if circ_by_film is None else circ_by_film[name],
             terminal_systems=model.terminal_systems.get(name), device=device)
 
-    def coupling_fn(src_name, J_src, dst_name):
-        src, dst = meshes[src_name]._data, meshes[dst_name]._data
-        out = film_to_film_device(src.sites.to(dst.device), z0s[src_name], src.t["vertex_areas"].to(dst.device),
-                                  J_src.to(dst.device), dst.sites, z0s[dst_name])
-        return out.t().contiguous() if batch is not None else out
+    inv4pi = 1.0 / (4.0 * np.pi)
 
-    def zeros_fn(name):
-        return torch.zeros_like(applied_fields[name])
-
-    def j_shape(name):
-        n = len(meshes[name].sites)
-        return (batch, n, 2) if batch is not None else (n, 2)
-
-    def v_shape(name):
-        n = len(meshes[name].sites)
-        return (n, batch) if batch is not None else (n,)
+    def coupling_fn(dst, J_all):
+        # sum over every other film of biot_savart_film_to_film (reference solve.py:495-515): one launch
+        src, area = _packed_sources(model, layout, z0s, dev)
+        d = meshes[dst]._data
+        lo, hi = layout.rows(dst)
+        with torch.cuda.device(dev):
+            out = torch.empty((d.n, batch) if batch is not None else (d.n,), dtype=torch.float64, device=dev)
+            _lib.check(L.scb_film_coupling(d.n, _lib.ptr(d.sites), z0s[dst], layout.total, _lib.ptr(src),
+                                           _lib.ptr(area), _lib.ptr(J_all), lo, hi, inv4pi,
+                                           batch if batch is not None else 1, _lib.ptr(out), _lib.stream_ptr()))
+        return out
 
     # the films of one Jacobi step are independent and each is latency-bound (getrs sweeps, small
     # N-body launches): one side stream per owned film, joined after every step
-    import contextlib
-
-    mine = [f for f in film_names if owners[f] == comm.rank]
+    mine = layout.by_rank[comm.rank]
     side = {}
-    if len(mine) > 1 and int(os.environ.get("SCB_FILM_STREAMS", "8")) > 0:
-        pool = [torch.cuda.Stream(device=some.device) for _ in range(min(len(mine), int(os.environ.get("SCB_FILM_STREAMS", "8"))))]
+    n_side = int(os.environ.get("SCB_FILM_STREAMS", "8"))
+    if len(mine) > 1 and n_side > 0:
+        pool = [torch.cuda.Stream(device=dev) for _ in range(min(len(mine), n_side))]
         side = {f: pool[k % len(pool)] for k, f in enumerate(mine)}
 
     @contextlib.contextmanager
@@ -261,19 +271,24 @@ def _run(model: "FactorizedModel", applied_fields, circ_by_film, vortex_flux, it
         if st is None:
             yield
             return
-        st.wait_stream(torch.cuda.current_stream(some.device))
+        st.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(st):
             yield
 
     def join():
-        main = torch.cuda.current_stream(some.device)
+        main = torch.cuda.current_stream(dev)
         for st in set(side.values()):
             main.wait_stream(st)
 
-    per_iter = run_film_iterations(film_names, owners, comm, solve_fn, coupling_fn, zeros_fn, j_shape, iterations,
-                                   film_scope=film_scope, join=join)
-    return gather_film_results(per_iter, film_names, owners, comm,
-                               {"g": v_shape, "J": j_shape, "self": v_shape, "other": v_shape}, some)
+    with torch.cuda.device(dev):
+        if multi:
+            _packed_sources(model, layout, z0s, dev)  # (on the main stream, before the side streams start)
+        packer = ResultPacker(layout, comm, iterates, batch, torch.empty(0, dtype=torch.float64, device=dev))
+        j_like = torch.empty((0, batch, 2) if batch is not None else (0, 2), dtype=torch.float64, device=dev)
+        run_film_iterations(layout, comm, solve_fn, coupling_fn, iterations, film_scope=film_scope, join=join,
+                            on_result=packer.put, j_like=j_like)
+        packer.scale_fields(1.0 / field_conversion)
+        return packer.to_host(gather, to_numpy=_to_host)
 
 
 def _check_model_args(device, model, terminal_currents, circulating_currents, vortices, current_units):
@@ -317,24 +332,27 @@ def solve(device: Optional[Device] = None, *, model: Optional[FactorizedModel] =
     applied_field = applied_field or ConstantField(0)
     field_conversion = field_conversion_factor(field_units, current_units, length_units=length_units).magnitude
     host_fields = _evaluate_applied_field(applied_field, device, model.film_info, device.meshes, field_conversion)
-    applied_fields = {f: torch.as_tensor(h).to(device.meshes[f]._data.device) for f, h in host_fields.items()}
+    owned = _owned_films(model)
+    applied_fields = {f: torch.as_tensor(h).to(device.meshes[f]._data.device) for f, h in host_fields.items()
+                      if f in owned}
     # Phi_0 / mu_0 in [current_units * length_units]  (reference solve.py:441)
     vortex_flux = _u.PHI_0 / _u.MU_0 * _u.conversion_factor("A * m", f"({current_units}) * ({length_units})")
     solution_kwargs = dict(applied_field_func=applied_field, field_units=field_units, current_units=current_units,
                            circulating_currents=model.circulating_currents,
                            terminal_currents=model.terminal_currents, vortices=model.vortices, solver=_solver)
-    per_iter = _run(model, applied_fields, None, vortex_flux, iterations, check_inversion)
+    host = _run(model, applied_fields, None, vortex_flux, iterations, check_inversion, field_conversion)
     if not return_solutions:
         return None
     film_names = list(device.films)
-    return [_to_solutions(device, film_names, results, applied_fields, others, field_conversion,
-                          [solution_kwargs])[0] for results, others in per_iter]
+    per_iter = _solutions_from_host(device, host, film_names, host_fields, field_conversion, [solution_kwargs],
+                                    batched=False)
+    return [row[0] for row in per_iter]
 
 
 def solve_batch(*, model: FactorizedModel, applied_fields: Sequence[Optional[Callable]],
                 circulating_currents: Optional[Sequence[Dict[str, float]]] = None, field_units: str = "mT",
                 iterations: int = 0, check_inversion: bool = False, last_only: bool = False,
-                _solver: str = "superscreen_b200.solve_batch") -> List[List[Solution]]:
+                gather: bool = True, _solver: str = "superscreen_b200.solve_batch") -> List[List[Solution]]:
     """Solves B models that share one factorization in a single batched pass (multi-RHS getrs,
     multi-RHS matrix-free operator, one film-to-film exchange per iteration for the whole batch).
 
@@ -344,6 +362,9 @@ def solve_batch(*, model: FactorizedModel, applied_fields: Sequence[Optional[Cal
     ``solve(model=model_b, applied_field=applied_fields[b], iterations=iterations)`` where
     ``model_b`` has ``circulating_currents[b]`` (floats in ``model.current_units``).  With
     ``last_only`` only the final iterate is brought to the host (``out[b]`` has one element).
+    With a multi-rank model, ``gather=False`` skips the replication of the results: every rank's
+    solutions then hold only the films it owns (enough for per-film post-processing such as the
+    fluxoid rows of ``Device.mutual_inductance_matrix``).
     """
     torch = _torch()
     model = _check_model_args(None, model, None, None, None, None)
@@ -363,27 +384,40 @@ def solve_batch(*, model: FactorizedModel, applied_fields: Sequence[Optional[Cal
     length_units = device.length_units
     field_conversion = field_conversion_factor(field_units, current_units, length_units=length_units).magnitude
     funcs = [f or ConstantField(0) for f in applied_fields]
-    per_b = [_evaluate_applied_field(f, device, model.film_info, device.meshes, field_conversion) for f in funcs]
-    film_names = list(device.films)
+    owned = _owned_films(model)
+    film_names = [f for f in device.films if gather or f in owned]
+    per_b = [_evaluate_applied_field(f, device, model.film_info, device.meshes, field_conversion, films=film_names)
+             for f in funcs]
+    host_fields = {name: np.stack([h[name] for h in per_b], axis=0) for name in film_names}  # (B, n) per film
     dev_fields = {}
     circ_by_film = {}
     for name in film_names:
+        if name not in owned:
+            continue
         dev = device.meshes[name]._data.device
         # rows are contiguous on the host (fast stack + one H2D copy); the (n, nrhs) layout is made on the device
-        dev_fields[name] = torch.as_tensor(np.stack([h[name] for h in per_b], axis=0)).to(dev).t().contiguous()
+        dev_fields[name] = torch.as_tensor(host_fields[name]).to(dev).t().contiguous()
         circ_by_film[name] = {
             hole: torch.tensor([float(cc.get(hole, 0.0)) for cc in circulating_currents], dtype=torch.float64,
                                device=dev)
             for hole in model.film_info[name].hole_indices
         }
     vortex_flux = _u.PHI_0 / _u.MU_0 * _u.conversion_factor("A * m", f"({current_units}) * ({length_units})")
-    per_iter = _run(model, dev_fields, circ_by_film, vortex_flux, iterations, check_inversion)
+    host = _run(model, dev_fields, circ_by_film, vortex_flux, iterations, check_inversion, field_conversion,
+                batch=B, last_only=last_only, gather=gather)
     kwargs_list = [dict(applied_field_func=funcs[b], field_units=field_units, current_units=current_units,
                         circulating_currents=dict(circulating_currents[b]),
                         terminal_currents=model.terminal_currents, vortices=model.vortices, solver=_solver)
                    for b in range(B)]
-    if last_only:
-        per_iter = per_iter[-1:]
-    per_iter_solutions = [_to_solutions(device, film_names, results, dev_fields, others, field_conversion,
-                                        kwargs_list) for results, others in per_iter]
+    per_iter_solutions = _solutions_from_host(device, host, film_names, host_fields, field_conversion, kwargs_list,
+                                              batched=True)
     return [[it[b] for it in per_iter_solutions] for b in range(B)]
+
+
+def _owned_films(model: FactorizedModel):
+    """Names of the films whose systems this rank holds (all of them in a single process)."""
+    from ..parallel import Comm, film_owners
+
+    comm = model.comm or Comm()
+    owners = film_owners(list(model.device.films), comm)
+    return {f for f, r in owners.items() if r == comm.rank}

@@ -54,8 +54,18 @@ class LinearSystem:
 
     @property
     def A(self) -> np.ndarray:
-        """Dense A (n_int, n_int), re-assembled on demand (the LU overwrote the workspace)."""
+        """Dense A, re-assembled on demand: (n_int, n_int) for a factored system (the LU overwrote
+        the workspace), or the (n, len(indices)) column slab of ``_build_system_1d`` (reference
+        solve_film.py:285-293) for the hole / boundary systems, which are otherwise applied
+        matrix-free."""
         torch = _torch()
+        if self.n_pad == 0:
+            d = self.film_info.mesh._data
+            k = len(self.indices)
+            with torch.cuda.device(d.device):
+                E = torch.zeros(d.n, k, dtype=torch.float64, device=d.device)
+                E[self.indices_dev, torch.arange(k, device=d.device)] = 1.0
+                return apply_operator(self.film_info, E, src_idx=self.indices_dev).cpu().numpy()
         M = assemble_negA(self.film_info, self.indices_dev, len(self.indices), self.n_pad,
                           self.grad_Lambda_term if not isinstance(self.grad_Lambda_term, float) else None)[0]
         # (always the plain, unsymmetrised -A)
@@ -174,7 +184,11 @@ def factorize_linear_systems(device: Device, film_info_dict: Dict[str, FilmInfo]
                 system = LinearSystem(indices=indices, film_info=info, grad_Lambda_term=T if T is not None else 0.0,
                                       n_pad=n_pad, lu=M, dinv=dinv, indices_dev=ix_dev, margin=margin,
                                       sym_scale=sym_scale)
-                pending.append((film_name, system, lu_info, side))
+                # `pos`, `sym_full` and `T` are only read by kernels queued on the side stream: keep them
+                # referenced until the side streams have been joined (the caching allocator would
+                # otherwise hand their blocks to the next film's allocations on the caller's stream
+                # while the assembly is still pending)
+                pending.append((film_name, system, lu_info, side, (pos, sym_full, T)))
                 return system
 
             interior = info.interior_indices
@@ -203,7 +217,7 @@ def factorize_linear_systems(device: Device, film_info_dict: Dict[str, FilmInfo]
     for side in {id(p[3]): p[3] for p in pending if p[3] is not None}.values():
         with torch.cuda.device(side.device):
             torch.cuda.current_stream(side.device).wait_stream(side)
-    for film_name, system, lu_info, _ in pending:
+    for film_name, system, lu_info, _, _keepalive in pending:
         flag = int(lu_info.item())
         mm = float(system.margin.min().item())
         if flag != 0:
@@ -296,7 +310,7 @@ def solve_film_device(*, film_info: FilmInfo, film_system: LinearSystem, hole_sy
     ``applied_field`` is ``(n,)`` or, for a batch of B right-hand sides sharing the factorization,
     ``(n, B)``; ``circulating_currents`` (default: ``film_info.circulating_currents``) maps hole
     names to a float or to a ``(B,)`` tensor.  Returns ``(g, J, self_field)`` with shapes
-    ``(n,), (n, 2), (n,)`` or ``(n, B), (B, n, 2), (n, B)``.
+    ``(n,), (n, 2), (n,)`` or ``(n, B), (n, B, 2), (n, B)``.
     """
     torch = _torch()
     info = film_info
@@ -364,6 +378,13 @@ def solve_film_device(*, film_info: FilmInfo, film_system: LinearSystem, hole_sy
                     gf = gf + lu_solve(film_system, r)
                     r = residual(gf)
             err = float((r.abs().max() / scale).item())
+            if film_system.refine and err > 1e-10:
+                # the factors were only a preconditioner (system not provably dominant) and the
+                # refinement did not converge: never hand back an unconverged stream function
+                raise np.linalg.LinAlgError(
+                    f"Film {info.name!r}: iterative refinement against the unpivoted LU stalled at a relative "
+                    f"residual of {err:.3e} (> 1e-10); factorize with pivoting (SCB_PIVOT=1)."
+                )
             if err > 1e-8:
                 logger.warning(
                     f"Unable to solve for stream function in {info.name!r}), "
@@ -383,10 +404,8 @@ def solve_film_device(*, film_info: FilmInfo, film_system: LinearSystem, hole_sy
             g[ix] += gv[:, None] if batched else gv
         # J = curl(g z) = [dg/dy, -dg/dx]
         Jx, Jy = spmv(d, "gradient_y", g), spmv(d, "gradient_x", g, alpha=-1.0)
-        if batched:
-            J = torch.stack([Jx.t(), Jy.t()], dim=2).contiguous()  # (B, n, 2)
-        else:
-            J = torch.stack([Jx, Jy], dim=1)
+        # (n, 2), or (n, B, 2) for a batch: source-major, the layout of the film-to-film exchange
+        J = torch.stack([Jx, Jy], dim=2 if batched else 1)
         if transport:
             # _biot_savart_within_film on per-triangle current densities (solve_film.py:557-562)
             J_tri = torch.stack([spmv(d, "gtri_y", g), spmv(d, "gtri_x", g, alpha=-1.0)], dim=1).contiguous()

@@ -57,15 +57,25 @@ def _worker(rank, world, port, result_dict):
             return (torch.from_numpy(fs.stream), torch.from_numpy(np.ascontiguousarray(fs.current_density)),
                     torch.from_numpy(fs.self_field * conv))
 
-        def coupling_fn(src, J, dst):
-            out = oracle.biot_savart_film_to_film(
-                films[src].mesh.sites, float(films[src].z0), films[src].mesh.vertex_areas,
-                np.ascontiguousarray(J.numpy()), films[dst].mesh.sites, float(films[dst].z0))
-            return torch.from_numpy(out)
+        sizes = {n: len(films[n].mesh.sites) for n in names}
+        layout = parallel.FilmLayout(names, sizes, owners, world)
+        assert layout.chunk == max(sizes.values()) and layout.total == world * layout.chunk
+        assert layout.rows("upper") == (layout.chunk, layout.chunk + sizes["upper"])
+        assert layout.local_rows("upper") == (0, sizes["upper"])
 
-        zeros_fn = lambda n: torch.zeros(len(films[n].mesh.sites), dtype=torch.float64)
-        j_shape = lambda n: (len(films[n].mesh.sites), 2)
-        v_shape = lambda n: (len(films[n].mesh.sites),)
+        def coupling_fn(dst, J_all):
+            # the packed J of ALL films arrives in one all-gather; sum the fields of the other films
+            assert tuple(J_all.shape) == (layout.total, 2)
+            acc = np.zeros(sizes[dst])
+            for src in names:
+                if src == dst:
+                    continue
+                lo, hi = layout.rows(src)
+                acc += oracle.biot_savart_film_to_film(
+                    films[src].mesh.sites, float(films[src].z0), films[src].mesh.vertex_areas,
+                    np.ascontiguousarray(J_all[lo:hi].numpy()), films[dst].mesh.sites, float(films[dst].z0))
+            return torch.from_numpy(acc)
+
         iterations = int(g["in_iterations"])
         # the per-film scope / join hooks (one CUDA stream per film in production) must wrap every
         # owned film exactly once per step and be joined after every step
@@ -79,25 +89,42 @@ def _worker(rank, world, port, result_dict):
             yield
             log.append(("exit", name))
 
-        per_iter = parallel.run_film_iterations(names, owners, comm, solve_fn, coupling_fn, zeros_fn, j_shape,
-                                                iterations, film_scope=film_scope, join=lambda: log.append(("join",)))
+        ncoll = {"n": 0}
+        orig = comm.all_gather_into
+
+        def counting(out, send):
+            ncoll["n"] += 1
+            return orig(out, send)
+
+        comm.all_gather_into = counting
+        packer = parallel.ResultPacker(layout, comm, list(range(iterations + 1)), None,
+                                       torch.zeros(1, dtype=torch.float64))
+        per_iter = parallel.run_film_iterations(layout, comm, solve_fn, coupling_fn, iterations,
+                                                film_scope=film_scope, join=lambda: log.append(("join",)),
+                                                on_result=packer.put)
+        assert ncoll["n"] == iterations, "exactly one collective per Jacobi step"
         assert log == [("enter", names[rank]), ("exit", names[rank]), ("join",)] * (iterations + 1)
         assert len(per_iter) == iterations + 1
         assert set(per_iter[0][0]) == {names[rank]}, "each rank solves only its own film"
-        full = parallel.gather_film_results(per_iter, names, owners, comm,
-                                            {"g": v_shape, "J": j_shape, "self": v_shape, "other": v_shape},
-                                            torch.zeros(1, dtype=torch.float64))
+        packer.scale_fields(1.0 / conv)
+        local = packer.to_host(gather=False)
+        assert local.films() == [names[rank]]
+        full = packer.to_host(gather=True)
+        assert ncoll["n"] == iterations + 1, "results are replicated by ONE all-gather after the last step"
+        assert full.films() == names
         errs = []
         rel = lambda a, b: float(np.linalg.norm(a - b) / np.linalg.norm(b))
-        for it, (results, others) in enumerate(full):
-            assert set(results) == set(names)
+        for it in range(iterations + 1):
             for n in names:
-                gg, J, sf = results[n]
-                errs.append(rel(gg.numpy(), g[f"out_it{it}_{n}_stream"]))
-                errs.append(rel(J.numpy(), g[f"out_it{it}_{n}_J"]))
-                errs.append(rel(sf.numpy() / conv, g[f"out_it{it}_{n}_self_field"]))
-                if others is not None:
-                    errs.append(rel(others[n].numpy() / conv, g[f"out_it{it}_{n}_other"]))
+                gg, J, sf, other = full.film(it, 0, n)
+                assert gg.flags.c_contiguous and J.flags.c_contiguous
+                errs.append(rel(gg, g[f"out_it{it}_{n}_stream"]))
+                errs.append(rel(J, g[f"out_it{it}_{n}_J"]))
+                errs.append(rel(sf, g[f"out_it{it}_{n}_self_field"]))
+                if it > 0:
+                    errs.append(rel(other, g[f"out_it{it}_{n}_other"]))
+                else:
+                    assert other is None
         # target sharding + ragged all-gather
         m = 11
         lo, hi, sizes = parallel.sharded_targets(m, comm)
@@ -125,5 +152,9 @@ def test_split_and_single_process_comm():
     comm = parallel.Comm()
     assert parallel.film_owners(["a", "b", "c"], comm) == {"a": 0, "b": 0, "c": 0}
     t = torch.ones(3)
-    assert parallel.exchange_films({"a": t}, {"a": 0}, {"a": (3,)}, comm, t)["a"] is t
+    assert parallel.all_gather_chunks_equal(t, comm) is t
+    layout = parallel.FilmLayout(["a", "b", "c"], {"a": 5, "b": 7, "c": 2}, {"a": 0, "b": 1, "c": 0}, 2)
+    assert layout.by_rank == [["a", "c"], ["b"]] and layout.chunk == 7 and layout.total == 14
+    assert layout.rows("a") == (0, 5) and layout.rows("c") == (5, 7) and layout.rows("b") == (7, 14)
+    assert layout.local_rows("c") == (5, 7) and layout.local_rows("b") == (0, 7)
     assert isinstance(parallel.default_comm(), parallel.Comm)

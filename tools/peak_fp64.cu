@@ -9,6 +9,9 @@
 #include <cusolverDn.h>
 
 #define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %d\n", cudaGetErrorString(e), __LINE__); exit(1);} } while (0)
+// every kernel launch is checked: a configuration that cannot launch (too many registers for the
+// block size) must not be reported as a throughput
+#define LAUNCH_OK() CK(cudaGetLastError())
 
 template <int NACC>
 __global__ void dmma_kernel(double* out, int iters) {
@@ -51,13 +54,14 @@ int main() {
   int nsm = p.multiProcessorCount;
   double* out; CK(cudaMalloc(&out, sizeof(double) * nsm * 8 * 1024));
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-  for (int warps : {4, 8, 16, 32}) {
+  for (int warps : {4, 8, 16}) {  // (32 warps x 16 accumulator pairs do not fit the register file)
     int iters = 20000;
     dmma_kernel<16><<<nsm, warps * 32>>>(out, 100);
+    LAUNCH_OK();
     CK(cudaDeviceSynchronize());
     float best = 1e30f;
     for (int r = 0; r < 3; r++) {
-      cudaEventRecord(e0); dmma_kernel<16><<<nsm, warps * 32>>>(out, iters); cudaEventRecord(e1);
+      cudaEventRecord(e0); dmma_kernel<16><<<nsm, warps * 32>>>(out, iters); LAUNCH_OK(); cudaEventRecord(e1);
       CK(cudaEventSynchronize(e1)); float ms; cudaEventElapsedTime(&ms, e0, e1); if (ms < best) best = ms;
     }
     double flops = 2.0 * 8 * 8 * 4 * 16.0 * iters * warps * nsm;
@@ -66,10 +70,11 @@ int main() {
   for (int warps : {8, 16, 32}) {
     int iters = 20000;
     dfma_kernel<16><<<nsm, warps * 32>>>(out, 100);
+    LAUNCH_OK();
     CK(cudaDeviceSynchronize());
     float best = 1e30f;
     for (int r = 0; r < 3; r++) {
-      cudaEventRecord(e0); dfma_kernel<16><<<nsm, warps * 32>>>(out, iters); cudaEventRecord(e1);
+      cudaEventRecord(e0); dfma_kernel<16><<<nsm, warps * 32>>>(out, iters); LAUNCH_OK(); cudaEventRecord(e1);
       CK(cudaEventSynchronize(e1)); float ms; cudaEventElapsedTime(&ms, e0, e1); if (ms < best) best = ms;
     }
     double flops = 2.0 * 32 * 16.0 * iters * warps * nsm;
@@ -79,7 +84,7 @@ int main() {
   {
     cudaEventRecord(e0);
     int launches = 0;
-    for (; launches < 40; launches++) dmma_kernel<16><<<nsm, 512>>>(out, 200000);
+    for (; launches < 40; launches++) { dmma_kernel<16><<<nsm, 512>>>(out, 200000); LAUNCH_OK(); }
     cudaEventRecord(e1); CK(cudaEventSynchronize(e1)); float ms; cudaEventElapsedTime(&ms, e0, e1);
     double flops = 2.0 * 256 * 16.0 * 200000 * 16 * nsm * launches;
     printf("DMMA sustained (%.0f ms): %.2f TFLOP/s\n", ms, flops / ms * 1e-9);
