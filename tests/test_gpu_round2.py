@@ -1,0 +1,254 @@
+"""GPU parity tests added in round 2: the many-RHS tensor-core paths and the packed film-to-film
+coupling against scipy / the CPU oracle (not against other kernels of this repo), the BASELINE
+configurations closer to their full sizes, and the full-size C2 film against the oracle together
+with bit-reproducibility of the symmetric factorization at 20k vertices."""
+import numpy as np
+import pytest
+
+from conftest import rel_l2
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-8
+
+
+@pytest.fixture(scope="module")
+def sc():
+    import torch
+
+    assert torch.cuda.is_available()
+    import superscreen_b200 as sc
+
+    return sc
+
+
+def _square_device(sc, n_vertices, seed=3, Lambda=0.1):
+    from superscreen_b200 import configs
+
+    return configs.c2_square(n_vertices, seed=seed, Lambda=Lambda)
+
+
+# ----------------------------------------------------------------------------------------
+# many right-hand sides against scipy / the dense oracle operator
+# ----------------------------------------------------------------------------------------
+def test_many_rhs_against_scipy_and_dense_kernel(sc):
+    """64 right-hand sides at > 6k vertices: scb_getrs_nopiv (blocked DMMA substitution) against
+    scipy.linalg.lu_solve(lu_factor(-A), H) -- the reference's own call (solve_film.py:279,530) -- and the
+    64-column matrix-free operator (kernel_gemm_kernel) against the oracle's dense Q @ (w * G)."""
+    import scipy.linalg as la
+    import torch
+
+    from oracle import port
+    from superscreen_b200.solver.solve_film import apply_operator, lu_solve
+
+    device = _square_device(sc, 6400)
+    mesh = device.meshes["film"]
+    model = sc.factorize_model(device=device, current_units="uA")
+    system, info = model.film_systems["film"], model.film_info["film"]
+    n_int, n = len(system.indices), len(mesh.sites)
+    assert n_int > 6000
+    rng = np.random.default_rng(7)
+    for nrhs in (64, 9):
+        H = rng.normal(size=(n_int, nrhs))
+        x = lu_solve(system, torch.as_tensor(H).cuda()).cpu().numpy()
+        A = system.A  # dense -A re-assembled by the device; checked against the oracle below
+        ref = la.lu_solve(la.lu_factor(-A), H)
+        assert rel_l2(x, ref) <= 1e-10, (nrhs, rel_l2(x, ref))
+    # the dense system matrix itself, against the oracle's build_system_2d
+    omesh = port.build_mesh(mesh.sites, mesh.elements)
+    Aref = port.build_system_2d(omesh.Q, omesh.vertex_areas, np.full(n, 0.1), omesh.laplacian.toarray(), 0,
+                                system.indices)
+    assert rel_l2(A, Aref) <= 1e-12
+    # matrix-free Q @ (w * G) with 64 columns (tensor-core kernel GEMM) and 5 columns (CUDA cores)
+    for ncol in (64, 5):
+        G = rng.normal(size=(n, ncol))
+        out = apply_operator(info, torch.as_tensor(G).cuda(), with_sparse=False).cpu().numpy()
+        ref = omesh.Q @ (omesh.vertex_areas[:, None] * G)
+        assert rel_l2(out, ref) <= 1e-11, (ncol, rel_l2(out, ref))
+
+
+def test_film_coupling_kernel_against_oracle(sc):
+    """scb_film_coupling (one launch per target film over the packed sources of all films, own segment
+    skipped, zero-area padding rows) against the sum of the oracle's biot_savart_film_to_film."""
+    import torch
+
+    from oracle import port
+    from superscreen_b200 import _lib
+
+    L = _lib.lib()
+    rng = np.random.default_rng(2)
+    sizes = [700, 333, 1201]
+    zs = [0.0, 0.5, 0.5]
+    films = [(rng.uniform(-3, 3, (n, 2)) + 7.0 * k, rng.uniform(0.01, 0.02, n)) for k, n in enumerate(sizes)]
+    pad = 57  # padding rows after every film (what a rank-major layout with unequal chunks produces)
+    total = sum(sizes) + pad * len(sizes)
+    for nsets in (1, 3, 8, 13):
+        src = np.full((total, 3), 1e30)
+        area = np.zeros(total)
+        J = np.zeros((total, nsets, 2))
+        rows = []
+        o = 0
+        for (xy, w), z in zip(films, zs):
+            n = len(xy)
+            src[o:o + n, :2], src[o:o + n, 2], area[o:o + n] = xy, z, w
+            J[o:o + n] = rng.normal(size=(n, nsets, 2))
+            rows.append((o, o + n))
+            o += n + pad
+        d = lambda a: torch.as_tensor(np.ascontiguousarray(a)).cuda()
+        src_d, area_d, J_d = d(src), d(area), d(J if nsets > 1 else J[:, 0, :])
+        for k, ((xy, _), z) in enumerate(zip(films, zs)):
+            lo, hi = rows[k]
+            tgt_d = d(xy)
+            out = torch.empty((len(xy), nsets) if nsets > 1 else (len(xy),), dtype=torch.float64, device="cuda")
+            _lib.check(L.scb_film_coupling(len(xy), _lib.ptr(tgt_d), z, total, _lib.ptr(src_d), _lib.ptr(area_d),
+                                           _lib.ptr(J_d), lo, hi, 1.0 / (4 * np.pi), nsets, _lib.ptr(out),
+                                           _lib.stream_ptr()))
+            got = out.cpu().numpy().reshape(len(xy), nsets)
+            for s in range(nsets):
+                ref = np.zeros(len(xy))
+                for j, ((sxy, sw), sz) in enumerate(zip(films, zs)):
+                    if j == k:
+                        continue
+                    a, b = rows[j]
+                    ref += port.biot_savart_film_to_film(sxy, sz, sw, np.ascontiguousarray(J[a:b, s, :]), xy, z)
+                assert rel_l2(got[:, s], ref) <= 1e-12, (nsets, k, s)
+    # a film alone in the layout sees no other film
+    out = torch.ones(sizes[0], dtype=torch.float64, device="cuda")
+    _lib.check(L.scb_film_coupling(sizes[0], _lib.ptr(d(films[0][0])), 0.0, sizes[0], _lib.ptr(d(src[:sizes[0]])),
+                                   _lib.ptr(d(area[:sizes[0]])), _lib.ptr(d(J[:sizes[0], 0, :])), 0, sizes[0],
+                                   1.0, 1, _lib.ptr(out), _lib.stream_ptr()))
+    assert float(out.abs().max()) == 0.0
+
+
+# ----------------------------------------------------------------------------------------
+# BASELINE configurations closer to full size
+# ----------------------------------------------------------------------------------------
+def _oracle_films(sc, device, circulating=None):
+    from test_gpu_configs import oracle_films
+
+    return oracle_films(sc, device, circulating)
+
+
+def test_c3_susceptometer_3k_per_film(sc):
+    from oracle import port
+    from superscreen_b200 import configs
+    from superscreen_b200.geometry import close_curve, points_in_polygon
+    from test_gpu_configs import compare
+
+    device, polygons = configs.c3_susceptometer(n_vertices=3000)
+    assert min(len(m.sites) for m in device.meshes.values()) >= 2900
+    films = _oracle_films(sc, device)
+    model = sc.factorize_model(device=device, current_units="uA", circulating_currents={"fc_center": "1 mA"})
+    sols = sc.solve(model=model, iterations=5)
+    osols = port.solve(films, lambda x, y, z: 0 * x, circulating_currents={"fc_center": 1000.0}, iterations=5)
+    for it in range(6):
+        compare(sols[it], osols[it], list(device.films))
+    by_name = {f.name: f for f in films}
+    fl = sols[-1].hole_fluxoid("pl_center", points=polygons["pl_center"], with_units=False)
+    of, osup = port.polygon_fluxoid(by_name["pl"], osols[-1]["pl"], close_curve(polygons["pl_center"]),
+                                    lambda p, q: points_in_polygon(p, q))
+    assert abs(sum(fl) - (of + osup)) <= TOL * abs(of + osup)
+
+
+def test_c4_eight_rings(sc):
+    """All 8 rings of C4 (2 x 4 grid, pitch 12 um), 8 x 8 mutual-inductance matrix with iterations=3,
+    against one oracle solve per driven hole."""
+    from oracle import port
+    from superscreen_b200 import configs
+    from superscreen_b200.geometry import close_curve, points_in_polygon
+
+    device, polygons = configs.c4_ring_array(n_rings=8, n_vertices=1500)
+    M = np.array(device.mutual_inductance_matrix(polygons, units="pH", iterations=3))
+    assert M.shape == (8, 8)
+    films = _oracle_films(sc, device)
+    by_name = {f.name: f for f in films}
+    holes = list(device.holes)
+    conv_mA = 1e-3 / port.MU_0 * 1e-3
+    Mref = np.zeros_like(M)
+    for j, hole in enumerate(holes):
+        osol = port.solve(films, lambda x, y, z: 0 * x, circulating_currents={hole: 1.0}, iterations=3,
+                          field_conversion=conv_mA)[-1]
+        for i, name in enumerate(holes):
+            film = by_name[f"ring{i}"]
+            f, s = port.polygon_fluxoid(film, osol[film.name], close_curve(polygons[name]),
+                                        lambda p, q: points_in_polygon(p, q), current_to_A=1e-3)
+            Mref[i, j] = (f + s) * port.PHI_0 / 1e-3 * 1e12
+    assert np.abs(M - Mref).max() <= TOL * np.abs(Mref).max()
+    assert np.abs(M - M.T).max() <= 0.10 * np.abs(M[0, 1])
+
+
+def test_lambda_sweep_case(sc):
+    """One point of the C5 Lambda sweep (configs.with_lambda: shared device-resident mesh, new
+    factorization) with a 16-field batch, against the oracle."""
+    from oracle import port
+    from superscreen_b200 import configs
+
+    device, fields = configs.c5_large(n_vertices=4000)
+    mesh = device.meshes["film"]
+    omesh = port.build_mesh(mesh.sites, mesh.elements)
+    interior = np.setdiff1d(np.arange(len(mesh.sites)), omesh.boundary_indices)
+    conv = port.field_conversion_mT_to_uA_per_um()
+    for lam in (0.05, 0.4):
+        model = sc.factorize_model(device=configs.with_lambda(device, lam), current_units="uA")
+        assert np.array_equal(interior, model.film_systems["film"].indices)
+        batch = sc.solve_batch(model=model, applied_fields=[sc.ConstantField(float(f)) for f in fields[:16]])
+        film = port.OracleFilm(name="film", mesh=omesh, z0=0.0, Lambda=np.full(len(mesh.sites), lam),
+                               interior_indices=interior, hole_indices={})
+        port.factorize_film(film, keep_A=False)
+        for b in (0, 15):
+            ref = port.solve_film(film, np.full(len(mesh.sites), fields[b] * conv), {}, conv)
+            fs = batch[b][0].film_solutions["film"]
+            assert rel_l2(fs.stream, ref.stream) <= TOL
+            assert rel_l2(fs.current_density, ref.current_density) <= TOL
+            assert rel_l2(fs.total_field, ref.total_field) <= TOL
+
+
+# ----------------------------------------------------------------------------------------
+# full-size C2 against the oracle, and bit-reproducibility at 20k
+# ----------------------------------------------------------------------------------------
+def test_c2_full_size_against_oracle_and_reproducible(sc):
+    import torch
+
+    from oracle import port
+    from superscreen_b200 import _lib
+    from superscreen_b200.solver.solve_film import assemble_negA
+
+    device = _square_device(sc, 20164, seed=0)
+    mesh = device.meshes["film"]
+    n = len(mesh.sites)
+    assert n > 20000
+    model = sc.factorize_model(device=device, current_units="uA")
+    fs = sc.solve(model=model, applied_field=sc.ConstantField(1.0))[0].film_solutions["film"]
+    # ---- oracle: the reference CPU path on the identical mesh (about 12 s on the GPU box's host) ----
+    omesh = port.build_mesh(mesh.sites, mesh.elements)
+    interior = np.setdiff1d(np.arange(n), omesh.boundary_indices)
+    assert np.array_equal(interior, model.film_systems["film"].indices)
+    film = port.OracleFilm(name="film", mesh=omesh, z0=0.0, Lambda=np.full(n, 0.1), interior_indices=interior,
+                           hole_indices={})
+    port.factorize_film(film, keep_A=False)
+    conv = port.field_conversion_mT_to_uA_per_um()
+    ref = port.solve_film(film, np.full(n, conv), {}, conv)
+    assert rel_l2(fs.stream, ref.stream) <= TOL
+    assert rel_l2(fs.current_density, ref.current_density) <= TOL
+    assert rel_l2(fs.self_field, ref.self_field) <= TOL
+    del film, omesh
+    # ---- bit-reproducibility of the symmetric factorization at the full size, 3 repetitions ----
+    L = _lib.lib()
+    system, info = model.film_systems["film"], model.film_info["film"]
+    assert system.sym_scale is not None, "constant Lambda takes the symmetric factorization"
+    d = mesh._data
+    sym_full = torch.sqrt(d.t["vertex_areas"])
+    first = None
+    for rep in range(3):
+        M, _ = assemble_negA(info, system.indices_dev, len(system.indices), system.n_pad, None,
+                             sym_scale_full=sym_full)
+        dinv = torch.empty_like(system.dinv)
+        flag = torch.zeros(1, dtype=torch.int32, device="cuda")
+        _lib.check(L.scb_getrf_sym_nopiv(system.n_pad, _lib.ptr(M), _lib.ptr(dinv), _lib.ptr(flag), _lib.stream_ptr()))
+        torch.cuda.synchronize()
+        assert int(flag.item()) == 0
+        if first is None:
+            first = M
+            assert torch.equal(M, system.lu), "re-factorization differs from the model's factors"
+        else:
+            assert torch.equal(M, first), f"symmetric LU not bit-reproducible at 20k (repetition {rep})"
+        del dinv
