@@ -313,6 +313,7 @@ def run_b200_arm(args):
     lu_ws = torch.empty(n_pad, n_pad, dtype=torch.float64, device=dev)
     dinv = torch.empty(int(L.scb_getrf_dinv_bytes(n_pad)) // 8, dtype=torch.float64, device=dev)
     lu_info = torch.zeros(1, dtype=torch.int32, device=dev)
+    pos_d = torch.empty(n, dtype=torch.int32, device=dev)  # vertex -> system row map left by the assembly
     l2_flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device=dev)  # > 126 MB L2
 
     ev = {k: (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
@@ -339,14 +340,14 @@ def run_b200_arm(args):
         # constant Lambda: same choice as factorize_linear_systems -- the diagonally similar symmetric
         # form S = D (-A) D^-1, D = sqrt(w), factored by the symmetric LU (half the flops)
         sym_full = torch.sqrt(data.t["vertex_areas"]) if symmetric else None
-        assemble_negA(info, ix_d, n_int, n_pad, None, out=lu_ws, sym_scale_full=sym_full)
+        assemble_negA(info, ix_d, n_int, n_pad, None, out=lu_ws, sym_scale_full=sym_full, pos=pos_d)
         if record: ev["assemble"][1].record(stream)
         if record: ev["getrf"][0].record(stream)
         getrf = L.scb_getrf_sym_nopiv if symmetric else L.scb_getrf_nopiv
         _lib.check(getrf(n_pad, _lib.ptr(lu_ws), _lib.ptr(dinv), _lib.ptr(lu_info), _lib.stream_ptr()))
         if record: ev["getrf"][1].record(stream)
         system = LinearSystem(indices=interior, film_info=info, n_pad=n_pad, lu=lu_ws, dinv=dinv, indices_dev=ix_d,
-                              sym_scale=None if sym_full is None else sym_full[ix_d].contiguous())
+                              sym_scale=None if sym_full is None else sym_full[ix_d].contiguous(), pos=pos_d)
         if record: ev["solve"][0].record(stream)
         out = solve_film_device(film_info=info, film_system=system, hole_systems={}, applied_field=H_d,
                                 vortex_flux=0.0)

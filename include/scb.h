@@ -203,6 +203,22 @@ int scb_spmv(int64_t nrows, const int32_t* indptr, const int32_t* indices, const
              int64_t nrhs, const double* x, double alpha, double beta, double* y,
              scb_stream_t stream);
 
+/* Fused steps of one film solve (solver/solve_film.py:526-531,556); all arrays are [rows, nrhs]
+ * row-major.
+ *   scb_solve_rhs:  B[r, c] = (applied[ix[r], c] + other[ix[r], c] - ha_eff[ix[r], c]) * scale[r] for
+ *       r < n_int and 0 for the padding rows n_int <= r < n_pad  (h = Hz_applied[ix] - Ha_eff[ix], in the
+ *       symmetrised system scaled by D).  other, ha_eff, scale may be NULL.
+ *   scb_solve_stream:  g[i, c] = g0[i, c] + (pos[i] >= 0 ? X[pos[i], c] / scale[pos[i]] : 0)  (g[ix] += gf on
+ *       top of the hole / transport boundary values g0; pos = the vertex -> system-row map that
+ *       scb_system_assemble leaves in pos_scratch, -1 outside the system).  scale, g0 may be NULL.
+ *   scb_current_density:  J[i, c, :] = ((gradient_y g)[i, c], -(gradient_x g)[i, c])  in one pass. */
+int scb_solve_rhs(int64_t n_int, int64_t n_pad, const int64_t* ix, int64_t nrhs, const double* applied,
+                  const double* other, const double* ha_eff, const double* scale, double* B, scb_stream_t stream);
+int scb_solve_stream(int64_t n, int64_t nrhs, const int32_t* pos, const double* X, const double* scale,
+                     const double* g0, double* g, scb_stream_t stream);
+int scb_current_density(int64_t n, const int32_t* op_indptr, const int32_t* op_indices, const double* gradient_x,
+                        const double* gradient_y, int64_t nrhs, const double* g, double* J, scb_stream_t stream);
+
 /* ------------------------------------------------------------------------------------
  * Biot-Savart family (K15-K18, rows a14, a15, a17, a18)
  * ------------------------------------------------------------------------------------ */

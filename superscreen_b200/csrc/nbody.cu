@@ -1,18 +1,22 @@
-// Tiled fp64 N-body style pair sums (K13, K15-K18 and the row sums of the kernel matrix).
+// Tiled fp64 N-body style pair sums (K13, K15-K18, the row sums of the kernel matrix and the
+// film-to-film coupling of the Jacobi iteration).
 //
-// One templated kernel: a CTA owns 256/SL targets; its threads are laid out as
-// (target, source-lane) with SL source lanes per target inside one warp.  Sources are staged
-// through shared memory in tiles of 256; each thread walks the tile entries congruent to its
-// source lane and the SL partial sums of a target are combined with a fixed-order warp-shuffle
-// butterfly, so results are deterministic and no float atomics are used.  SL is chosen from the
-// number of targets so that small target sets (film-to-film, row sums at 2k-60k vertices) still
-// fill 148 SMs, while million-point field evaluations run one target per thread.
+// One templated kernel.  A thread owns TPT = 2 targets (coalesced: target k of thread t in CTA b is
+// (b * TPT + k) * 256 + t); the sources are staged through shared memory in tiles of 256 and every
+// thread walks the whole tile, so all lanes of a warp read the SAME shared-memory word (broadcast,
+// one wavefront per load) and the operands of a source are loaded once for TPT pairs.
+// Parallelism for small target sets (a film's own vertices: 2k-60k targets) comes from splitting
+// the SOURCES over gridDim.y CTAs, never from sub-dividing a warp: the partial sums go to a
+// stream-ordered scratch buffer [split][target][acc] and a second tiny kernel adds them in split
+// order.  Split count and chunk size depend only on (m, n), so results are bit-reproducible and no
+// float atomics are used.  Million-point field evaluations run unsplit.
 //
-// fp64 CUDA-core bound: ~20 DFMA-class operations per pair.
+// fp64 CUDA-core bound: ~16-20 DFMA-class operations per pair.
 //
 // Reference kernels restated (file:line under /root/reference/superscreen):
 //   distance.py:87-115 + device/mesh.py:454-458 (row sums / Q @ (w*g))
-//   solver/solve.py:28-73 biot_savart_film_to_film, solver/solve_film.py:393-437
+//   solver/solve.py:28-73 biot_savart_film_to_film (+ its sum over films, :495-515),
+//   solver/solve_film.py:393-437
 //   sources/current.py:13-110 _biot_savart_2d_z/_vector, solution.py:917-928 vector potential
 #include "scb_common.cuh"
 
@@ -24,11 +28,12 @@ enum : int {
   NB_VECTOR = SCB_BS_VECTOR,
   NB_VECPOT = SCB_BS_VECTOR_POTENTIAL,
   NB_BOUNDARY = SCB_BS_BOUNDARY,
-  NB_KERNEL = 16,  // sum_{j != i} q_ij * payload_j[r], r < NR   (in-plane, 1/r^3)
+  NB_KERNEL = 16,    // sum_{j != i} q_ij * payload_j[r], r < NR   (in-plane, 1/r^3)
+  NB_COUPLING = 17,  // film-to-film over the packed sources of all films (scb_film_coupling)
 };
 
 constexpr int kTile = 256;
-constexpr int kMaxNR = 4;
+constexpr int TPT = 2;  // targets per thread
 
 struct NbodyParams {
   int64_t m;              // targets
@@ -37,123 +42,43 @@ struct NbodyParams {
   const double* src;      // [*,2] or [*,3] (indexed through src_idx when given)
   const int64_t* src_idx; // optional gather list for NB_KERNEL
   const double* area;     // [*] per-source weight
-  const double* J;        // [*,2] (biot-savart) or v [*, ldv] (NB_KERNEL)
-  int64_t ldv;            // row stride of v / out for NB_KERNEL
-  int64_t rhs0;           // first rhs column handled by this launch (NB_KERNEL)
-  double dz2;             // film-to-film
+  const double* J;        // [*,2] (biot-savart), v [*, ldv] (NB_KERNEL), [n, ldv] (NB_COUPLING, ldv = 2 nsets)
+  int64_t ldv;            // row stride of v / J
+  int64_t ldo;            // row stride of out (NB_KERNEL: = ldv; NB_COUPLING: nsets)
+  int64_t rhs0;           // first rhs column / current-density set handled by this launch
+  double dz2;             // film-to-film: squared layer distance
+  double tgt_z;           // NB_COUPLING: z of the target film
+  int64_t skip_lo, skip_len;  // NB_COUPLING: sources [skip_lo, skip_lo + skip_len) are left out
   double prefactor;
   double* out;
   int accumulate;
+  int64_t chunk;          // sources per CTA; gridDim.y CTAs cover the sources
+  double* partial;        // [gridDim.y][m][NACC] partial sums when gridDim.y > 1
 };
 
-template <int KIND>
+template <int KIND, int NR>
 struct Traits {
   static constexpr int tdim = (KIND == NB_Z || KIND == NB_VECTOR || KIND == NB_VECPOT) ? 3 : 2;
-  static constexpr int nacc = KIND == NB_VECTOR ? 4 : (KIND == NB_VECPOT ? 2 : (KIND == NB_Z ? 2 : 1));
+  // NR = right-hand sides (NB_KERNEL) or current-density sets sharing the geometry (film-to-film)
+  static constexpr bool multi = KIND == NB_KERNEL || KIND == NB_FILM_TO_FILM || KIND == NB_COUPLING;
+  static constexpr int nacc = multi ? NR : (KIND == NB_VECTOR ? 4 : (KIND == NB_VECPOT || KIND == NB_Z ? 2 : 1));
+  static constexpr int npay = KIND == NB_KERNEL ? NR : (multi ? 2 * NR : 2);
+  static constexpr bool has_sz = tdim == 3 || KIND == NB_COUPLING;
 };
 
-template <int KIND, int SL, int NR>
-__global__ void __launch_bounds__(256) nbody_kernel(NbodyParams p) {
-  constexpr int TD = Traits<KIND>::tdim;
-  // NR = right-hand sides (NB_KERNEL) or current-density sets sharing the geometry (NB_FILM_TO_FILM)
-  constexpr int NACC = (KIND == NB_KERNEL || KIND == NB_FILM_TO_FILM) ? NR : Traits<KIND>::nacc;
-  constexpr int NPAY = KIND == NB_KERNEL ? NR : (KIND == NB_FILM_TO_FILM ? 2 * NR : 2);
-  __shared__ double sx[kTile], sy[kTile], sz[TD == 3 ? kTile : 1];
-  __shared__ double spay[NPAY][kTile];
-
-  const int tid = threadIdx.x;
-  const int sl = tid % SL;
-  const int64_t i = blockIdx.x * (int64_t)(256 / SL) + tid / SL;
-  const bool active = i < p.m;
-  double tx = 0, ty = 0, tz = 0;
-  if (active) {
-    tx = p.tgt[TD * i];
-    ty = p.tgt[TD * i + 1];
-    if (TD == 3) tz = p.tgt[TD * i + 2];
-  }
-  double acc[NACC];
-#pragma unroll
-  for (int a = 0; a < NACC; a++) acc[a] = 0.0;
-
-  for (int64_t base = 0; base < p.n; base += kTile) {
-    const int64_t j = base + tid;
-    __syncthreads();
-    if (j < p.n) {
-      const int64_t js = p.src_idx ? p.src_idx[j] : j;
-      sx[tid] = p.src[TD * js];
-      sy[tid] = p.src[TD * js + 1];
-      if (TD == 3) sz[tid] = p.src[TD * js + 2];
-      const double w = p.area[js];
-      if (KIND == NB_KERNEL) {
-#pragma unroll
-        for (int r = 0; r < NR; r++) spay[r][tid] = p.J ? w * p.J[js * p.ldv + p.rhs0 + r] : w;
-      } else if (KIND == NB_FILM_TO_FILM) {
-#pragma unroll
-        for (int r = 0; r < NR; r++) {
-          spay[2 * r][tid] = w * p.J[(r * p.n + js) * 2];
-          spay[2 * r + 1][tid] = w * p.J[(r * p.n + js) * 2 + 1];
-        }
-      } else {
-        spay[0][tid] = w * p.J[2 * js];
-        spay[1][tid] = w * p.J[2 * js + 1];
-      }
-    }
-    __syncthreads();
-    const int cnt = (int)((p.n - base) < kTile ? (p.n - base) : kTile);
-#pragma unroll 4
-    for (int jj = sl; jj < cnt; jj += SL) {
-      const double dx = tx - sx[jj];
-      const double dy = ty - sy[jj];
-      double r2 = dx * dx + dy * dy;
-      double dzv = 0.0;
-      if (TD == 3) {
-        dzv = tz - sz[jj];
-        r2 += dzv * dzv;
-      } else if (KIND == NB_FILM_TO_FILM) {
-        r2 += p.dz2;
-      }
-      if (KIND == NB_VECPOT) {
-        const double inv = inv_r1(r2);
-        acc[0] += spay[0][jj] * inv;
-        acc[1] += spay[1][jj] * inv;
-      } else {
-        double k3 = inv_r3(r2);
-        if (KIND == NB_KERNEL) {
-          k3 = r2 > 0.0 ? k3 : 0.0;  // q_ii = 0 (distance.py:104-105)
-#pragma unroll
-          for (int r = 0; r < NR; r++) acc[r] += spay[r][jj] * k3;
-        } else if (KIND == NB_FILM_TO_FILM) {
-#pragma unroll
-          for (int r = 0; r < NR; r++) acc[r] += (spay[2 * r][jj] * dy - spay[2 * r + 1][jj] * dx) * k3;
-        } else if (KIND == NB_BOUNDARY) {
-          acc[0] -= (spay[0][jj] * dx + spay[1][jj] * dy) * k3;
-        } else if (KIND == NB_Z) {
-          acc[0] += k3 * spay[0][jj] * dy;  // Jx_dy
-          acc[1] += k3 * spay[1][jj] * dx;  // Jy_dx
-        } else {                            // NB_VECTOR
-          const double px = k3 * spay[0][jj], py = k3 * spay[1][jj];
-          acc[0] += px * dy;   // Jx_dy
-          acc[1] += py * dx;   // Jy_dx
-          acc[2] += px * dzv;  // Jx_dz
-          acc[3] += py * dzv;  // Jy_dz
-        }
-      }
-    }
-  }
-  // fixed-order butterfly over the SL source lanes
-#pragma unroll
-  for (int off = SL / 2; off > 0; off >>= 1) {
-#pragma unroll
-    for (int a = 0; a < NACC; a++) acc[a] += __shfl_xor_sync(0xffffffffu, acc[a], off);
-  }
-  if (!active || sl != 0) return;
+// final value(s) of target i from its complete sums
+template <int KIND, int NR>
+__device__ __forceinline__ void nbody_store(const NbodyParams& p, int64_t i, const double (&acc)[Traits<KIND, NR>::nacc]) {
   const double pf = p.prefactor;
   if (KIND == NB_KERNEL) {
 #pragma unroll
     for (int r = 0; r < NR; r++) {
-      double* o = p.out + i * p.ldv + p.rhs0 + r;
+      double* o = p.out + i * p.ldo + p.rhs0 + r;
       *o = p.accumulate ? *o + pf * acc[r] : pf * acc[r];
     }
+  } else if (KIND == NB_COUPLING) {
+#pragma unroll
+    for (int r = 0; r < NR; r++) p.out[i * p.ldo + p.rhs0 + r] = pf * acc[r];
   } else if (KIND == NB_Z) {
     p.out[i] = pf * (acc[0] - acc[1]);
   } else if (KIND == NB_VECTOR) {
@@ -172,18 +97,198 @@ __global__ void __launch_bounds__(256) nbody_kernel(NbodyParams p) {
 }
 
 template <int KIND, int NR>
-static int launch_nbody(const NbodyParams& p, cudaStream_t s) {
-  if (p.m == 0) return SCB_OK;
-  // enough CTAs for >= ~4 waves of 148 SMs when possible
-  const int64_t want = 148 * 4;
-  if (p.m * 32 / 256 <= want && p.n >= 32) {
-    nbody_kernel<KIND, 32, NR><<<(unsigned)ceil_div(p.m, 8), 256, 0, s>>>(p);
-  } else if (p.m * 8 / 256 <= want * 2 && p.n >= 8) {
-    nbody_kernel<KIND, 8, NR><<<(unsigned)ceil_div(p.m, 32), 256, 0, s>>>(p);
-  } else {
-    nbody_kernel<KIND, 1, NR><<<(unsigned)ceil_div(p.m, 256), 256, 0, s>>>(p);
+__global__ void __launch_bounds__(256) nbody_kernel(NbodyParams p) {
+  using T = Traits<KIND, NR>;
+  constexpr int TD = T::tdim;
+  constexpr int NACC = T::nacc;
+  constexpr int NPAY = T::npay;
+  __shared__ double sx[kTile], sy[kTile], sz[T::has_sz ? kTile : 1];
+  __shared__ double spay[NPAY][kTile];
+
+  const int tid = threadIdx.x;
+  int64_t ti[TPT];
+  double tx[TPT], ty[TPT], tz[TPT];
+#pragma unroll
+  for (int k = 0; k < TPT; k++) {
+    ti[k] = (blockIdx.x * (int64_t)TPT + k) * 256 + tid;
+    const bool ok = ti[k] < p.m;
+    tx[k] = ok ? p.tgt[TD * ti[k]] : 0.0;
+    ty[k] = ok ? p.tgt[TD * ti[k] + 1] : 0.0;
+    tz[k] = (ok && TD == 3) ? p.tgt[TD * ti[k] + 2] : 0.0;
   }
+  double acc[TPT][NACC];
+#pragma unroll
+  for (int k = 0; k < TPT; k++)
+#pragma unroll
+    for (int a = 0; a < NACC; a++) acc[k][a] = 0.0;
+
+  // this CTA's slice of the (virtual, skip range removed) source index space
+  const int64_t n_eff = p.n - (KIND == NB_COUPLING ? p.skip_len : 0);
+  const int64_t lo = blockIdx.y * p.chunk;
+  const int64_t hi = (lo + p.chunk) < n_eff ? (lo + p.chunk) : n_eff;
+  for (int64_t base = lo; base < hi; base += kTile) {
+    const int64_t v = base + tid;
+    __syncthreads();
+    if (v < hi) {
+      const int64_t j = (KIND == NB_COUPLING && v >= p.skip_lo) ? v + p.skip_len : v;
+      const int64_t js = p.src_idx ? p.src_idx[j] : j;
+      const double w = p.area[js];
+      if (KIND == NB_COUPLING) {
+        sx[tid] = p.src[3 * js];
+        sy[tid] = p.src[3 * js + 1];
+        const double dz = p.tgt_z - p.src[3 * js + 2];
+        sz[tid] = dz * dz;
+        const double* Jj = p.J + js * p.ldv + 2 * p.rhs0;
+#pragma unroll
+        for (int r = 0; r < NR; r++) {
+          spay[2 * r][tid] = w * Jj[2 * r];
+          spay[2 * r + 1][tid] = w * Jj[2 * r + 1];
+        }
+      } else {
+        sx[tid] = p.src[TD * js];
+        sy[tid] = p.src[TD * js + 1];
+        if (TD == 3) sz[tid] = p.src[TD * js + 2];
+        if (KIND == NB_KERNEL) {
+#pragma unroll
+          for (int r = 0; r < NR; r++) spay[r][tid] = p.J ? w * p.J[js * p.ldv + p.rhs0 + r] : w;
+        } else if (KIND == NB_FILM_TO_FILM) {
+#pragma unroll
+          for (int r = 0; r < NR; r++) {
+            spay[2 * r][tid] = w * p.J[(r * p.n + js) * 2];
+            spay[2 * r + 1][tid] = w * p.J[(r * p.n + js) * 2 + 1];
+          }
+        } else {
+          spay[0][tid] = w * p.J[2 * js];
+          spay[1][tid] = w * p.J[2 * js + 1];
+        }
+      }
+    }
+    __syncthreads();
+    const int cnt = (int)((hi - base) < kTile ? (hi - base) : kTile);
+#pragma unroll 2
+    for (int jj = 0; jj < cnt; jj++) {
+      const double xs = sx[jj], ys = sy[jj];
+      const double zs = T::has_sz ? sz[jj] : 0.0;
+      double pay[NPAY];
+#pragma unroll
+      for (int q = 0; q < NPAY; q++) pay[q] = spay[q][jj];
+#pragma unroll
+      for (int k = 0; k < TPT; k++) {
+        const double dx = tx[k] - xs, dy = ty[k] - ys;
+        double r2 = fma(dx, dx, dy * dy);
+        double dzv = 0.0;
+        if (TD == 3) {
+          dzv = tz[k] - zs;
+          r2 = fma(dzv, dzv, r2);
+        } else if (KIND == NB_COUPLING) {
+          r2 += zs;
+        } else if (KIND == NB_FILM_TO_FILM) {
+          r2 += p.dz2;
+        }
+        if (KIND == NB_VECPOT) {
+          const double inv = inv_r1(r2);
+          acc[k][0] = fma(pay[0], inv, acc[k][0]);
+          acc[k][1] = fma(pay[1], inv, acc[k][1]);
+        } else {
+          double k3 = inv_r3(r2);
+          if (KIND == NB_KERNEL) {
+            k3 = r2 > 0.0 ? k3 : 0.0;  // q_ii = 0 (distance.py:104-105)
+#pragma unroll
+            for (int r = 0; r < NR; r++) acc[k][r] = fma(pay[r], k3, acc[k][r]);
+          } else if (KIND == NB_FILM_TO_FILM || KIND == NB_COUPLING) {
+            const double kdy = k3 * dy, kdx = k3 * dx;
+#pragma unroll
+            for (int r = 0; r < NR; r++) acc[k][r] = fma(pay[2 * r], kdy, fma(-pay[2 * r + 1], kdx, acc[k][r]));
+          } else if (KIND == NB_BOUNDARY) {
+            acc[k][0] = fma(-k3, fma(pay[0], dx, pay[1] * dy), acc[k][0]);
+          } else if (KIND == NB_Z) {
+            acc[k][0] = fma(k3 * pay[0], dy, acc[k][0]);  // Jx_dy
+            acc[k][1] = fma(k3 * pay[1], dx, acc[k][1]);  // Jy_dx
+          } else {                                        // NB_VECTOR
+            const double px = k3 * pay[0], py = k3 * pay[1];
+            acc[k][0] = fma(px, dy, acc[k][0]);   // Jx_dy
+            acc[k][1] = fma(py, dx, acc[k][1]);   // Jy_dx
+            acc[k][2] = fma(px, dzv, acc[k][2]);  // Jx_dz
+            acc[k][3] = fma(py, dzv, acc[k][3]);  // Jy_dz
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < TPT; k++) {
+    if (ti[k] >= p.m) continue;
+    if (gridDim.y == 1) {
+      nbody_store<KIND, NR>(p, ti[k], acc[k]);
+    } else {
+      double* o = p.partial + ((int64_t)blockIdx.y * p.m + ti[k]) * NACC;
+#pragma unroll
+      for (int a = 0; a < NACC; a++) o[a] = acc[k][a];
+    }
+  }
+}
+
+// adds the per-split partial sums of a target in split order and stores the final value(s)
+template <int KIND, int NR>
+__global__ void nbody_reduce_kernel(NbodyParams p, int nsplit) {
+  constexpr int NACC = Traits<KIND, NR>::nacc;
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= p.m) return;
+  double acc[NACC];
+#pragma unroll
+  for (int a = 0; a < NACC; a++) acc[a] = 0.0;
+  for (int y = 0; y < nsplit; y++) {
+    const double* o = p.partial + ((int64_t)y * p.m + i) * NACC;
+#pragma unroll
+    for (int a = 0; a < NACC; a++) acc[a] += o[a];
+  }
+  nbody_store<KIND, NR>(p, i, acc);
+}
+
+static bool g_pool_set[64] = {};
+
+template <int KIND, int NR>
+static int launch_nbody(NbodyParams p, cudaStream_t s) {
+  if (p.m == 0) return SCB_OK;
+  constexpr int NACC = Traits<KIND, NR>::nacc;
+  const int64_t n_eff = p.n - (KIND == NB_COUPLING ? p.skip_len : 0);
+  const int64_t ctas_x = ceil_div(p.m, 256 * TPT);
+  // One balanced wave: every CTA does the same amount of work, so the source range is split until the
+  // grid just fills the resident-CTA capacity of the device (a CTA keeps at least one source tile).
+  static int capacity = 0;  // per instantiation; all devices of a node are identical
+  if (capacity == 0) {
+    int per_sm = 0, sms = 0, dev = 0;
+    SCB_CUDA(cudaGetDevice(&dev));
+    SCB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nbody_kernel<KIND, NR>, 256, 0));
+    SCB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    capacity = per_sm * sms > 0 ? per_sm * sms : 148;
+  }
+  int64_t split = capacity / ctas_x;
+  const int64_t max_split = n_eff / kTile;
+  if (split > max_split) split = max_split;
+  if (split < 1) split = 1;
+  p.chunk = n_eff > 0 ? ceil_div(n_eff, split) : 1;
+  split = n_eff > 0 ? ceil_div(n_eff, p.chunk) : 1;
+  p.partial = nullptr;
+  if (split > 1) {
+    int dev = 0;
+    SCB_CUDA(cudaGetDevice(&dev));
+    if (!g_pool_set[dev & 63]) {  // keep freed scratch in the stream-ordered pool instead of returning it to the OS
+      cudaMemPool_t pool;
+      SCB_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
+      uint64_t keep = ~0ull;
+      SCB_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+      g_pool_set[dev & 63] = true;
+    }
+    SCB_CUDA(cudaMallocAsync(&p.partial, sizeof(double) * (size_t)(split * p.m * NACC), s));
+  }
+  nbody_kernel<KIND, NR><<<dim3((unsigned)ctas_x, (unsigned)split), 256, 0, s>>>(p);
   SCB_LAUNCH_CHECK();
+  if (split > 1) {
+    nbody_reduce_kernel<KIND, NR><<<(unsigned)ceil_div(p.m, 128), 128, 0, s>>>(p, (int)split);
+    SCB_LAUNCH_CHECK();
+    SCB_CUDA(cudaFreeAsync(p.partial, s));
+  }
   return SCB_OK;
 }
 
@@ -297,7 +402,7 @@ int nbody_kernel_sum(int64_t m, const double* tgt, int64_t n, const double* src,
                      int64_t nrhs, double prefactor, double* out, int accumulate, cudaStream_t s) {
   NbodyParams p{};
   p.m = m; p.tgt = tgt; p.n = n; p.src = src; p.src_idx = src_idx; p.area = w; p.J = v;
-  p.ldv = ldv; p.prefactor = prefactor; p.out = out; p.accumulate = accumulate;
+  p.ldv = ldv; p.ldo = ldv; p.prefactor = prefactor; p.out = out; p.accumulate = accumulate;
   int64_t r = 0;
   // 16 or more right-hand sides: tensor-core GEMM against the on-the-fly kernel matrix
   while (v != nullptr && nrhs - r >= 16) {
@@ -317,127 +422,6 @@ int nbody_kernel_sum(int64_t m, const double* tgt, int64_t n, const double* src,
     else { rc = launch_nbody<NB_KERNEL, 1>(p, s); r += 1; }
     if (rc) return rc;
   }
-  return SCB_OK;
-}
-
-// ---------------------------------------------------------------------------------------
-// Film-to-film coupling of one Jacobi step (reference solver/solve.py:495-515) in ONE launch per
-// target film: the sources are the packed vertices of ALL films (x, y, z0 per vertex, zero-area
-// padding allowed), the target film's own segment [skip_lo, skip_hi) is left out, and `nsets`
-// current-density sets (batched right-hand sides) share every r^-3 evaluation.
-//   out[i, s] = prefactor * sum_{j not in skip} w_j (Jx[j,s] dy - Jy[j,s] dx) (dx^2 + dy^2 + dz_j^2)^-3/2
-// J is [n, ldj/2, 2] (source-major, as the J exchange delivers it), out is [m, ldo].
-// Same thread layout as nbody_kernel (SL source lanes per target, fixed-order butterfly), plus TPT
-// targets per thread: the 2 NR + 3 shared-memory operands of a source are loaded once for TPT pairs.
-// ---------------------------------------------------------------------------------------
-struct CouplingParams {
-  int64_t m;
-  const double* tgt;   // [m,2]
-  double tgt_z;
-  int64_t n;           // packed sources
-  const double* src;   // [n,3]
-  const double* area;  // [n]
-  const double* J;     // [n, ldj]  (ldj = 2 * nsets)
-  int64_t ldj;
-  int64_t set0;        // first set handled by this launch
-  int64_t skip_lo, skip_hi;
-  double prefactor;
-  double* out;         // [m, ldo]
-  int64_t ldo;
-};
-
-template <int SL, int NR, int TPT>
-__global__ void __launch_bounds__(256) film_coupling_kernel(CouplingParams p) {
-  __shared__ double sx[kTile], sy[kTile], sd[kTile];
-  __shared__ double spx[NR][kTile], spy[NR][kTile];
-  constexpr int TG = 256 / SL;  // target groups per CTA
-  const int tid = threadIdx.x;
-  const int sl = tid % SL;
-  const int64_t i0 = blockIdx.x * (int64_t)(TG * TPT) + tid / SL;
-  double tx[TPT], ty[TPT];
-#pragma unroll
-  for (int k = 0; k < TPT; k++) {
-    const int64_t i = i0 + k * TG;
-    tx[k] = i < p.m ? p.tgt[2 * i] : 0.0;
-    ty[k] = i < p.m ? p.tgt[2 * i + 1] : 0.0;
-  }
-  double acc[TPT][NR];
-#pragma unroll
-  for (int k = 0; k < TPT; k++)
-#pragma unroll
-    for (int r = 0; r < NR; r++) acc[k][r] = 0.0;
-
-#pragma unroll 1
-  for (int seg = 0; seg < 2; seg++) {
-    const int64_t lo = seg == 0 ? 0 : p.skip_hi;
-    const int64_t hi = seg == 0 ? p.skip_lo : p.n;
-    for (int64_t base = lo; base < hi; base += kTile) {
-      const int64_t j = base + tid;
-      __syncthreads();
-      if (j < hi) {
-        sx[tid] = p.src[3 * j];
-        sy[tid] = p.src[3 * j + 1];
-        const double dz = p.tgt_z - p.src[3 * j + 2];
-        sd[tid] = dz * dz;
-        const double w = p.area[j];
-        const double* Jj = p.J + j * p.ldj + 2 * p.set0;
-#pragma unroll
-        for (int r = 0; r < NR; r++) {
-          spx[r][tid] = w * Jj[2 * r];
-          spy[r][tid] = w * Jj[2 * r + 1];
-        }
-      }
-      __syncthreads();
-      const int cnt = (int)((hi - base) < kTile ? (hi - base) : kTile);
-#pragma unroll 2
-      for (int jj = sl; jj < cnt; jj += SL) {
-        const double xs = sx[jj], ys = sy[jj], ds = sd[jj];
-        double px[NR], py[NR];
-#pragma unroll
-        for (int r = 0; r < NR; r++) {
-          px[r] = spx[r][jj];
-          py[r] = spy[r][jj];
-        }
-#pragma unroll
-        for (int k = 0; k < TPT; k++) {
-          const double dx = tx[k] - xs, dy = ty[k] - ys;
-          const double k3 = inv_r3(fma(dx, dx, fma(dy, dy, ds)));
-          const double kdy = k3 * dy, kdx = k3 * dx;
-#pragma unroll
-          for (int r = 0; r < NR; r++) acc[k][r] = fma(px[r], kdy, fma(-py[r], kdx, acc[k][r]));
-        }
-      }
-    }
-  }
-#pragma unroll
-  for (int off = SL / 2; off > 0; off >>= 1) {
-#pragma unroll
-    for (int k = 0; k < TPT; k++)
-#pragma unroll
-      for (int r = 0; r < NR; r++) acc[k][r] += __shfl_xor_sync(0xffffffffu, acc[k][r], off);
-  }
-  if (sl != 0) return;
-#pragma unroll
-  for (int k = 0; k < TPT; k++) {
-    const int64_t i = i0 + k * TG;
-    if (i >= p.m) continue;
-#pragma unroll
-    for (int r = 0; r < NR; r++) p.out[i * p.ldo + p.set0 + r] = p.prefactor * acc[k][r];
-  }
-}
-
-template <int NR, int TPT>
-static int launch_coupling(const CouplingParams& p, cudaStream_t s) {
-  // small target sets (a film's own vertices): 32 source lanes per target so that 148 SMs are filled
-  const int64_t ctas32 = ceil_div(p.m, (256 / 32) * TPT);
-  if (ctas32 <= 148 * 8) {
-    film_coupling_kernel<32, NR, TPT><<<(unsigned)ctas32, 256, 0, s>>>(p);
-  } else if (ceil_div(p.m, (256 / 8) * TPT) <= 148 * 16) {
-    film_coupling_kernel<8, NR, TPT><<<(unsigned)ceil_div(p.m, (256 / 8) * TPT), 256, 0, s>>>(p);
-  } else {
-    film_coupling_kernel<1, NR, TPT><<<(unsigned)ceil_div(p.m, 256 * TPT), 256, 0, s>>>(p);
-  }
-  SCB_LAUNCH_CHECK();
   return SCB_OK;
 }
 
@@ -543,17 +527,17 @@ extern "C" int scb_film_coupling(int64_t m, const double* tgt, double tgt_z, int
     SCB_CUDA(cudaMemsetAsync(out, 0, sizeof(double) * (size_t)(m * nsets), s));
     return SCB_OK;
   }
-  CouplingParams p{};
-  p.m = m; p.tgt = tgt; p.tgt_z = tgt_z; p.n = n; p.src = src; p.area = area; p.J = J; p.ldj = 2 * nsets;
-  p.skip_lo = skip_lo; p.skip_hi = skip_hi; p.prefactor = prefactor; p.out = out; p.ldo = nsets;
+  NbodyParams p{};
+  p.m = m; p.tgt = tgt; p.tgt_z = tgt_z; p.n = n; p.src = src; p.area = area; p.J = J; p.ldv = 2 * nsets;
+  p.skip_lo = skip_lo; p.skip_len = skip_hi - skip_lo; p.prefactor = prefactor; p.out = out; p.ldo = nsets;
   int64_t k = 0;
   while (k < nsets) {
-    p.set0 = k;
+    p.rhs0 = k;
     int rc;
-    if (nsets - k >= 8) { rc = launch_coupling<8, 2>(p, s); k += 8; }
-    else if (nsets - k >= 4) { rc = launch_coupling<4, 2>(p, s); k += 4; }
-    else if (nsets - k >= 2) { rc = launch_coupling<2, 2>(p, s); k += 2; }
-    else { rc = launch_coupling<1, 2>(p, s); k += 1; }
+    if (nsets - k >= 8) { rc = launch_nbody<NB_COUPLING, 8>(p, s); k += 8; }
+    else if (nsets - k >= 4) { rc = launch_nbody<NB_COUPLING, 4>(p, s); k += 4; }
+    else if (nsets - k >= 2) { rc = launch_nbody<NB_COUPLING, 2>(p, s); k += 2; }
+    else { rc = launch_nbody<NB_COUPLING, 1>(p, s); k += 1; }
     if (rc) return rc;
   }
   return SCB_OK;

@@ -224,6 +224,50 @@ def biot_savart_2d(x, y, z, *, positions, current_densities, z0: float = 0, area
         return _to_host(out)
 
 
+class _FluxoidGeometry(NamedTuple):
+    """Everything of ``polygon_fluxoid`` that depends only on (mesh, film, polygon)."""
+
+    ix: np.ndarray            # mesh vertices inside the polygon
+    w_ix: np.ndarray          # their vertex areas
+    tri_vertices: np.ndarray  # (q, 3) vertices of the triangle containing every polygon point
+    bary: np.ndarray          # (q, 3) barycentric weights
+    valid: np.ndarray         # (q,) polygon point lies in the film and in the mesh
+    dl: np.ndarray            # (q - 1, 2) polygon edge vectors
+    Lambda_poly: np.ndarray   # (q,) Lambda at the polygon points
+
+
+_FLUXOID_GEOMETRY: Dict[tuple, Any] = {}
+
+
+def _fluxoid_geometry(device: Device, film: str, mesh, polygon_coords) -> _FluxoidGeometry:
+    """The fluxoid of the same polygon is evaluated for many solutions on the same mesh (every
+    column / iterate of a mutual-inductance matrix): index sets and interpolation weights are
+    memoised per (mesh, film polygon, fluxoid polygon)."""
+    polygon = polygon_coords if isinstance(polygon_coords, Polygon) else Polygon(points=polygon_coords)
+    points = polygon.points
+    film_poly = device.films[film]
+    Lambda = device.layers[film_poly.layer].Lambda
+    key = (id(mesh), points.tobytes(), film_poly.points.tobytes(), None if callable(Lambda) else float(Lambda))
+    hit = _FLUXOID_GEOMETRY.get(key)
+    if hit is not None and hit[0] is mesh and (not callable(Lambda) or hit[1] is Lambda):
+        return hit[2]
+    if not film_poly.contains_points(points).all():
+        raise ValueError(f"The polygon is not contained within the film ({film!r}).")
+    ix = np.where(polygon.contains_points(mesh.sites))[0]
+    ok, tri, w = _locate(mesh.sites, mesh.elements, points, 16)
+    valid = ok & film_poly.contains_points(points)
+    if callable(Lambda):
+        Lambda_poly = np.asarray(Lambda(points[:, 0], points[:, 1]), dtype=float) * np.ones(len(points))
+    else:
+        Lambda_poly = float(Lambda) * np.ones(len(points))
+    geo = _FluxoidGeometry(ix=ix, w_ix=mesh.vertex_areas[ix], tri_vertices=mesh.elements[tri], bary=w,
+                           valid=valid, dl=np.diff(points, axis=0), Lambda_poly=Lambda_poly)
+    if len(_FLUXOID_GEOMETRY) > 256:
+        _FLUXOID_GEOMETRY.clear()
+    _FLUXOID_GEOMETRY[key] = (mesh, Lambda, geo)
+    return geo
+
+
 class Solution:
     """reference solution.py:201-260 (container) + post-processing methods."""
 
@@ -334,26 +378,23 @@ class Solution:
                         units: Optional[str] = "Phi_0", with_units: bool = True) -> Fluxoid:
         """reference solution.py:484-563"""
         device = self.device
+        if interp_method != "linear":
+            raise NotImplementedError("Only linear interpolation is available.")
         if units is None:
             units = f"({self.field_units}) * ({device.length_units}) ** 2"
-        polygon = polygon_coords if isinstance(polygon_coords, Polygon) else Polygon(points=polygon_coords)
-        points = polygon.points
-        if not device.films[film].contains_points(points).all():
-            raise ValueError(f"The polygon is not contained within the film ({film!r}).")
         mesh = device.meshes[film]
-        ix = polygon.contains_points(mesh.sites)
-        flux = np.einsum("i, i ->", self.film_solutions[film].total_field[ix], mesh.vertex_areas[ix])
+        geo = _fluxoid_geometry(device, film, mesh, polygon_coords)
+        fs = self.film_solutions[film]
+        flux = np.einsum("i, i ->", fs.total_field[geo.ix], geo.w_ix)
         flux_units = f"({self.field_units}) * ({device.length_units}) ** 2"
         flux_part = flux * _flux_conversion(flux_units, units)
         J_units = f"({self.current_units}) / ({device.length_units})"
-        J_poly = self.interp_current_density(points, film=film, method=interp_method, units=J_units)
-        Lambda = device.layers[device.films[film].layer].Lambda
-        if callable(Lambda):
-            Lambda_poly = np.asarray(Lambda(points[:, 0], points[:, 1]), dtype=float) * np.ones(len(points))
-        else:
-            Lambda_poly = float(Lambda) * np.ones(len(points))
-        dl = np.diff(points, axis=0)
-        int_J = np.trapezoid(Lambda_poly[:-1] * np.sum(J_poly[:-1] * dl, axis=1))
+        # J at the polygon vertices: linear interpolation on the mesh, zero outside the film / mesh
+        # (interp_current_density, reference solution.py:278-319, on cached barycentric weights)
+        J_poly = np.einsum("qk,qkc->qc", geo.bary, fs.current_density[geo.tri_vertices])
+        J_poly[~geo.valid] = 0
+        J_poly[~np.isfinite(J_poly).all(axis=1)] = 0
+        int_J = np.trapezoid(geo.Lambda_poly[:-1] * np.sum(J_poly[:-1] * geo.dl, axis=1))
         # mu_0 * [J_units * length^2]
         si = _u.MU_0 * int_J * _u.conversion_factor(f"({J_units}) * ({device.length_units}) ** 2", "A * m")
         supercurrent_part = si * _u.conversion_factor("Wb", units)

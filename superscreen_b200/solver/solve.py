@@ -22,7 +22,7 @@ from ..device import Device
 from ..solution import FilmSolution, Solution, Vortex
 from ..sources import ConstantField
 from .solve_film import (  # noqa: F401  (TerminalSystems, solve_film: names the reference module exposes)
-    LinearSystem, TerminalSystems, factorize_linear_systems, solve_film, solve_film_device)
+    LinearSystem, TerminalSystems, factorize_linear_systems, hole_boundary_state, solve_film, solve_film_device)
 from .utils import FilmInfo, currents_to_floats, field_conversion_factor, make_film_info
 
 logger = logging.getLogger("solve")
@@ -234,13 +234,20 @@ def _run(model: "FactorizedModel", applied_fields, circ_by_film, vortex_flux, it
     n_solutions = iterations + 1 if multi else 1
     iterates = [n_solutions - 1] if last_only else list(range(n_solutions))
 
+    hole_states = {}  # hole boundary values + their effective field: constant over the iterations
+
     def solve_fn(name, other):
+        circ = None if circ_by_film is None else circ_by_film[name]
+        if name not in hole_states:
+            info = film_info[name]
+            hole_states[name] = hole_boundary_state(
+                info, model.hole_systems[name], info.circulating_currents if circ is None else circ,
+                applied_fields[name]) if model.hole_systems[name] else (None, None)
         return solve_film_device(
             film_info=film_info[name], film_system=model.film_systems[name],
             hole_systems=model.hole_systems[name], applied_field=applied_fields[name], vortex_flux=vortex_flux,
-            field_from_other_films=other, check_inversion=check_inversion,
-            circulating_currents=None if circ_by_film is None else circ_by_film[name],
-            terminal_systems=model.terminal_systems.get(name), device=device)
+            field_from_other_films=other, check_inversion=check_inversion, circulating_currents=circ,
+            terminal_systems=model.terminal_systems.get(name), device=device, hole_state=hole_states[name])
 
     inv4pi = 1.0 / (4.0 * np.pi)
 

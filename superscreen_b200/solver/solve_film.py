@@ -51,6 +51,7 @@ class LinearSystem:
     refine: bool = False  # not provably dominant -> iterative refinement in every solve
     # symmetric mode: the factors are those of S = D (-A) D^-1, D = diag(sym_scale) = sqrt(w[indices])
     sym_scale: object = field(repr=False, default=None)
+    pos: object = field(repr=False, default=None)  # torch int32 (n,): mesh vertex -> row of this system, -1 outside
 
     @property
     def A(self) -> np.ndarray:
@@ -183,7 +184,7 @@ def factorize_linear_systems(device: Device, film_info_dict: Dict[str, FilmInfo]
                     _lib.check(getrf(n_pad, _lib.ptr(M), _lib.ptr(dinv), _lib.ptr(lu_info), _lib.stream_ptr()))
                 system = LinearSystem(indices=indices, film_info=info, grad_Lambda_term=T if T is not None else 0.0,
                                       n_pad=n_pad, lu=M, dinv=dinv, indices_dev=ix_dev, margin=margin,
-                                      sym_scale=sym_scale)
+                                      sym_scale=sym_scale, pos=pos)
                 # `pos`, `sym_full` and `T` are only read by kernels queued on the side stream: keep them
                 # referenced until the side streams have been joined (the caching allocator would
                 # otherwise hand their blocks to the next film's allocations on the caller's stream
@@ -300,97 +301,136 @@ def spmv(d, key: str, x, alpha: float = 1.0):
     return y if x.dim() == 2 else y[:, 0]
 
 
+def hole_boundary_state(film_info: FilmInfo, hole_systems: Dict[str, LinearSystem], circ, like):
+    """Hole boundary conditions (reference solve_film.py:493-503): ``g0[hole] = I_circ`` and the
+    effective field ``Ha_eff = -sum_k A[:, hole_k] @ g0[hole_k]`` (matrix-free).  Depends only on the
+    circulating currents, not on the applied field: evaluated once per solve call and shared by all
+    film-to-film iterations.  ``like`` gives the shape ``(n,)`` / ``(n, B)``.  Returns ``(g0, Ha_eff)``
+    or ``(None, None)`` when no hole carries a current."""
+    torch = _torch()
+    batched = like.dim() == 2
+    g0 = None
+    for name, s in hole_systems.items():
+        cur = circ.get(name, 0)
+        if torch.is_tensor(cur):
+            if g0 is None:
+                g0 = torch.zeros_like(like)
+            g0[s.indices_dev] += cur.to(like.dtype)[None, :] if batched else cur.to(like.dtype)
+        elif cur:
+            if g0 is None:
+                g0 = torch.zeros_like(like)
+            g0[s.indices_dev] += float(cur)
+    if g0 is None:
+        return None, None
+    src = torch.cat([s.indices_dev for s in hole_systems.values()])
+    return g0, -apply_operator(film_info, g0, src_idx=src)
+
+
 def solve_film_device(*, film_info: FilmInfo, film_system: LinearSystem, hole_systems: Dict[str, LinearSystem],
                       applied_field, vortex_flux: float, field_from_other_films=None,
                       check_inversion: bool = False, circulating_currents=None, terminal_systems=None,
-                      device: Optional[Device] = None):
+                      device: Optional[Device] = None, hole_state=None):
     """Device-side body of ``solve_film`` (reference solve_film.py:483-565): all arguments and
     results are device tensors in solver units.
 
     ``applied_field`` is ``(n,)`` or, for a batch of B right-hand sides sharing the factorization,
     ``(n, B)``; ``circulating_currents`` (default: ``film_info.circulating_currents``) maps hole
-    names to a float or to a ``(B,)`` tensor.  Returns ``(g, J, self_field)`` with shapes
-    ``(n,), (n, 2), (n,)`` or ``(n, B), (n, B, 2), (n, B)``.
+    names to a float or to a ``(B,)`` tensor.  ``hole_state`` = ``hole_boundary_state(...)`` if the
+    caller has it already.  Returns ``(g, J, self_field)`` with shapes ``(n,), (n, 2), (n,)`` or
+    ``(n, B), (n, B, 2), (n, B)``.
     """
     torch = _torch()
+    L = _lib.lib()
     info = film_info
     d = info.mesh._data
     circ = info.circulating_currents if circulating_currents is None else circulating_currents
     batched = applied_field.dim() == 2
+    nrhs = applied_field.shape[1] if batched else 1
+    transport = terminal_systems is not None
     with torch.cuda.device(d.device):
-        Hz = applied_field if field_from_other_films is None else applied_field + field_from_other_films
-        g = torch.zeros_like(Hz)
-        Ha_eff = None
-        # hole boundary conditions: g[hole] = I_circ; Ha_eff = -sum_k A[:, hole_k] @ g[hole_k]
-        if hole_systems:
-            any_current = False
-            for name, s in hole_systems.items():
-                cur = circ.get(name, 0)
-                if torch.is_tensor(cur):
-                    g[s.indices_dev] += cur.to(g.dtype)[None, :] if batched else cur.to(g.dtype)
-                    any_current = True
-                elif cur:
-                    g[s.indices_dev] += float(cur)
-                    any_current = True
-            if any_current:
-                src = torch.cat([s.indices_dev for s in hole_systems.values()])
-                Ha_eff = -apply_operator(info, g, src_idx=src)
-        transport = terminal_systems is not None
-        if transport:
-            # reference solve_film.py:505-524
-            if batched:
-                raise NotImplementedError("Batched right-hand sides are not supported for terminal films.")
-            g_transport = solve_for_terminal_current_stream(device, info, terminal_systems,
-                                                            info.terminal_currents or {})
-            g = g + g_transport
-            b = terminal_systems.boundary.indices_dev
-            boundary_sites = d.sites[b]
-            boundary_stream = g_transport[b]
-            centers = (0.5 * (boundary_sites + torch.roll(boundary_sites, -1, dims=0))).contiguous()
-            boundary_stream = 0.5 * (boundary_stream + torch.roll(boundary_stream, -1, dims=0))
-            dr = torch.roll(boundary_sites, -1, dims=0) - boundary_sites  # edges of the closed curve
-            lengths = torch.linalg.norm(dr, dim=1)
-            normals = (torch.stack([dr[:, 1], -dr[:, 0]], dim=1) / lengths[:, None]).contiguous()
-            Ha_transport = torch.empty(d.n, dtype=torch.float64, device=d.device)
-            # _get_boundary_effective_field (solve_film.py:393-412): kind 4, area = stream * length
-            _lib.check(_lib.lib().scb_biot_savart(
-                4, d.n, _lib.ptr(d.sites), int(b.numel()), _lib.ptr(centers),
-                _lib.ptr((boundary_stream * lengths).contiguous()), _lib.ptr(normals), 0.0, 1.0 / (4.0 * np.pi), 1,
-                _lib.ptr(Ha_transport), _lib.stream_ptr()))
-            Ha_eff = Ha_transport if Ha_eff is None else Ha_eff + Ha_transport
-        ix = film_system.indices_dev
-        h = Hz[ix] if Ha_eff is None else Hz[ix] - Ha_eff[ix]
-        gf = lu_solve(film_system, h)
-        if film_system.refine or check_inversion:
-            # residual of (-A) gf = h through the matrix-free operator (reference check_inversion,
-            # solve_film.py:533-540); refinement steps when the LU is only a preconditioner
-            def residual(x):
-                full = torch.zeros_like(Hz)
-                full[ix] = x
-                return h + apply_operator(info, full, src_idx=ix)[ix]
+        if hole_state is None:
+            hole_state = hole_boundary_state(info, hole_systems, circ, applied_field) if hole_systems \
+                else (None, None)
+        g0, Ha_eff = hole_state
+        if not (transport or film_system.refine or check_inversion):
+            # the common case in four fused steps: right-hand side, triangular solves, stream function,
+            # current density (one kernel each instead of ~20 gather / scatter / elementwise launches)
+            n_int, n_pad = len(film_system.indices), film_system.n_pad
+            if film_system.pos is None:  # (a system that was not built by factorize_linear_systems)
+                pos = torch.full((d.n,), -1, dtype=torch.int32, device=d.device)
+                pos[film_system.indices_dev] = torch.arange(n_int, dtype=torch.int32, device=d.device)
+                film_system.pos = pos
+            B = torch.empty((n_pad, nrhs), dtype=torch.float64, device=d.device)
+            applied_c = applied_field.contiguous()
+            other_c = None if field_from_other_films is None else field_from_other_films.contiguous()
+            s = _lib.stream_ptr()
+            _lib.check(L.scb_solve_rhs(n_int, n_pad, _lib.ptr(film_system.indices_dev), nrhs, _lib.ptr(applied_c),
+                                       _lib.ptr(other_c), _lib.ptr(Ha_eff), _lib.ptr(film_system.sym_scale),
+                                       _lib.ptr(B), s))
+            _lib.check(L.scb_getrs_nopiv(n_pad, _lib.ptr(film_system.lu), _lib.ptr(film_system.dinv), nrhs,
+                                         _lib.ptr(B), s))
+            g = torch.empty_like(applied_c)
+            _lib.check(L.scb_solve_stream(d.n, nrhs, _lib.ptr(film_system.pos), _lib.ptr(B),
+                                          _lib.ptr(film_system.sym_scale), _lib.ptr(g0), _lib.ptr(g), s))
+        else:
+            Hz = applied_field if field_from_other_films is None else applied_field + field_from_other_films
+            g = torch.zeros_like(Hz) if g0 is None else g0.clone()
+            if transport:
+                # reference solve_film.py:505-524
+                if batched:
+                    raise NotImplementedError("Batched right-hand sides are not supported for terminal films.")
+                g_transport = solve_for_terminal_current_stream(device, info, terminal_systems,
+                                                                info.terminal_currents or {})
+                g = g + g_transport
+                b = terminal_systems.boundary.indices_dev
+                boundary_sites = d.sites[b]
+                boundary_stream = g_transport[b]
+                centers = (0.5 * (boundary_sites + torch.roll(boundary_sites, -1, dims=0))).contiguous()
+                boundary_stream = 0.5 * (boundary_stream + torch.roll(boundary_stream, -1, dims=0))
+                dr = torch.roll(boundary_sites, -1, dims=0) - boundary_sites  # edges of the closed curve
+                lengths = torch.linalg.norm(dr, dim=1)
+                normals = (torch.stack([dr[:, 1], -dr[:, 0]], dim=1) / lengths[:, None]).contiguous()
+                Ha_transport = torch.empty(d.n, dtype=torch.float64, device=d.device)
+                # _get_boundary_effective_field (solve_film.py:393-412): kind 4, area = stream * length
+                _lib.check(L.scb_biot_savart(
+                    4, d.n, _lib.ptr(d.sites), int(b.numel()), _lib.ptr(centers),
+                    _lib.ptr((boundary_stream * lengths).contiguous()), _lib.ptr(normals), 0.0, 1.0 / (4.0 * np.pi), 1,
+                    _lib.ptr(Ha_transport), _lib.stream_ptr()))
+                Ha_eff = Ha_transport if Ha_eff is None else Ha_eff + Ha_transport
+            ix = film_system.indices_dev
+            h = Hz[ix] if Ha_eff is None else Hz[ix] - Ha_eff[ix]
+            gf = lu_solve(film_system, h)
+            if film_system.refine or check_inversion:
+                # residual of (-A) gf = h through the matrix-free operator (reference check_inversion,
+                # solve_film.py:533-540); refinement steps when the LU is only a preconditioner
+                def residual(x):
+                    full = torch.zeros_like(Hz)
+                    full[ix] = x
+                    return h + apply_operator(info, full, src_idx=ix)[ix]
 
-            r = residual(gf)
-            scale = h.abs().max().clamp_min(1e-300)
-            if film_system.refine:
-                for _ in range(5):
-                    if float((r.abs().max() / scale).item()) <= 1e-13:
-                        break
-                    gf = gf + lu_solve(film_system, r)
-                    r = residual(gf)
-            err = float((r.abs().max() / scale).item())
-            if film_system.refine and err > 1e-10:
-                # the factors were only a preconditioner (system not provably dominant) and the
-                # refinement did not converge: never hand back an unconverged stream function
-                raise np.linalg.LinAlgError(
-                    f"Film {info.name!r}: iterative refinement against the unpivoted LU stalled at a relative "
-                    f"residual of {err:.3e} (> 1e-10); factorize with pivoting (SCB_PIVOT=1)."
-                )
-            if err > 1e-8:
-                logger.warning(
-                    f"Unable to solve for stream function in {info.name!r}), "
-                    f"maximum error {r.abs().max().item():.3e} (relative {err:.3e})."
-                )
-        g[ix] += gf
+                r = residual(gf)
+                scale = h.abs().max().clamp_min(1e-300)
+                if film_system.refine:
+                    for _ in range(5):
+                        if float((r.abs().max() / scale).item()) <= 1e-13:
+                            break
+                        gf = gf + lu_solve(film_system, r)
+                        r = residual(gf)
+                err = float((r.abs().max() / scale).item())
+                if film_system.refine and err > 1e-10:
+                    # the factors were only a preconditioner (system not provably dominant) and the
+                    # refinement did not converge: never hand back an unconverged stream function
+                    raise np.linalg.LinAlgError(
+                        f"Film {info.name!r}: iterative refinement against the unpivoted LU stalled at a relative "
+                        f"residual of {err:.3e} (> 1e-10); factorize with pivoting (SCB_PIVOT=1)."
+                    )
+                if err > 1e-8:
+                    logger.warning(
+                        f"Unable to solve for stream function in {info.name!r}), "
+                        f"maximum error {r.abs().max().item():.3e} (relative {err:.3e})."
+                    )
+            g[ix] += gf
+        ix = film_system.indices_dev
         for vortex in info.vortices:
             # K[:, j] = -lu_solve(lu(-A), e_j): one right-hand side instead of eye(n)
             # (reference solve_film.py:541-554)
@@ -402,15 +442,18 @@ def solve_film_device(*, film_info: FilmInfo, film_system: LinearSystem, hole_sy
             Kj = -lu_solve(film_system, e)
             gv = vortex_flux * vortex.nPhi0 * Kj / d.t["vertex_areas"][j_device]
             g[ix] += gv[:, None] if batched else gv
-        # J = curl(g z) = [dg/dy, -dg/dx]
-        Jx, Jy = spmv(d, "gradient_y", g), spmv(d, "gradient_x", g, alpha=-1.0)
-        # (n, 2), or (n, B, 2) for a batch: source-major, the layout of the film-to-film exchange
-        J = torch.stack([Jx, Jy], dim=2 if batched else 1)
+        # J = curl(g z) = [dg/dy, -dg/dx]: (n, 2), or (n, B, 2) for a batch (source-major, the layout
+        # of the film-to-film exchange)
+        g = g.contiguous()
+        J = torch.empty((d.n, nrhs, 2) if batched else (d.n, 2), dtype=torch.float64, device=d.device)
+        _lib.check(L.scb_current_density(d.n, _lib.ptr(d.t["op_indptr"]), _lib.ptr(d.t["op_indices"]),
+                                         _lib.ptr(d.t["gradient_x"]), _lib.ptr(d.t["gradient_y"]), nrhs, _lib.ptr(g),
+                                         _lib.ptr(J), _lib.stream_ptr()))
         if transport:
             # _biot_savart_within_film on per-triangle current densities (solve_film.py:557-562)
             J_tri = torch.stack([spmv(d, "gtri_y", g), spmv(d, "gtri_x", g, alpha=-1.0)], dim=1).contiguous()
             self_field = torch.empty(d.n, dtype=torch.float64, device=d.device)
-            _lib.check(_lib.lib().scb_biot_savart(
+            _lib.check(L.scb_biot_savart(
                 0, d.n, _lib.ptr(d.sites), d.m, _lib.ptr(d.t["centroids"]), _lib.ptr(d.t["triangle_areas"]),
                 _lib.ptr(J_tri), 0.0, 1.0 / (4.0 * np.pi), 1, _lib.ptr(self_field), _lib.stream_ptr()))
         else:

@@ -10,6 +10,7 @@ with ``ast`` into (scale, dimension-vector) pairs over [length, mass, time, curr
 from __future__ import annotations
 
 import ast
+import functools
 import math
 import re
 from typing import Tuple, Union
@@ -98,7 +99,12 @@ def parse(expr: str) -> Tuple[float, np.ndarray]:
     """``"1 mA"``, ``"uA / um"``, ``"mT * um ** 2"``, ``"Phi_0 / A"`` -> (SI scale, dims)."""
     if isinstance(expr, Unit):
         return expr.scale, expr.dims
-    text = str(expr).strip().replace("^", "**")
+    return _parse_text(str(expr))
+
+
+@functools.lru_cache(maxsize=512)
+def _parse_text(text: str) -> Tuple[float, np.ndarray]:
+    text = text.strip().replace("^", "**")
     # implicit multiplication between a leading number and a unit: "1 mA" -> "1 * mA"
     text = re.sub(r"^([-+]?[0-9.]+(?:[eE][-+]?[0-9]+)?)\s+(?=[A-Za-zµμ])", r"\1 * ", text)
     text = text.replace("µ", "u").replace("μ", "u")
