@@ -188,6 +188,18 @@ int scb_getrf_nopiv(int64_t n_pad, double* M, double* dinv, int32_t* info, scb_s
  * factorization of the symmetric matrix, exactly as scb_getrf_nopiv would produce. */
 int scb_getrf_sym_nopiv(int64_t n_pad, double* M, double* dinv, int32_t* info, scb_stream_t stream);
 
+/* The same factorization WITH partial (row) pivoting, P M = L U -- what the reference's
+ * scipy.linalg.lu_factor (LAPACK dgetrf) computes -- for systems that are not provably safe without it
+ * (general systems whose `margin` from scb_system_assemble is not positive).  Per 128-column panel the
+ * pivot rows are found on a scratch copy (maximum magnitude over all rows below the diagonal, ties to the
+ * lower row index), the interchanges are applied to the full rows, and the panel is then factored and
+ * applied by the unpivoted kernels (K = 128 trailing updates on DMMA).  piv (device int32[n_pad]):
+ * LAPACK-style, row k was interchanged with row piv[k] (0-based).  perm (device int32[n_pad]): row r of
+ * P M is row perm[r] of M, i.e. solve M x = h as scb_getrs_nopiv on B[r] = h[perm[r]].  The identity
+ * padding block is never interchanged with real rows.  info as for scb_getrf_nopiv. */
+int scb_getrf_piv(int64_t n_pad, double* M, double* dinv, int32_t* piv, int32_t* perm, int32_t* info,
+                  scb_stream_t stream);
+
 /* Solves M X = B in place for nrhs right-hand sides, B[n_pad, nrhs] row-major, with the factors
  * and the `dinv` buffer produced by scb_getrf_nopiv / scb_getrf_sym_nopiv.  One right-hand side: two
  * persistent flag-driven sweep kernels; 2..16: the same sweeps with DMMA block products (8 columns per

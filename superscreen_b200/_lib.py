@@ -54,6 +54,7 @@ EXPORTS = {
     "scb_getrf_dinv_bytes": (c_int64, [c_int64]),
     "scb_getrf_nopiv": (c_int, [c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "scb_getrf_sym_nopiv": (c_int, [c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "scb_getrf_piv": (c_int, [c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "scb_getrs_nopiv": (c_int, [c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
     "scb_spmv": (c_int, [c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_double, c_double, c_void_p, c_void_p]),
     "scb_solve_rhs": (c_int, [c_int64, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),

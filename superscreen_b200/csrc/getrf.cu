@@ -1135,6 +1135,172 @@ diag_kernel_symb(double* __restrict__ M, int64_t ld, int64_t o, double* __restri
   SCB_STAMP(7);
 }
 
+// ---------------------------------------------------------------------------------------
+// Partial (row) pivoting -- the fallback for systems that are not provably safe without it
+// (reference: scipy.linalg.lu_factor = LAPACK dgetrf at solver/solve_film.py:232,253,279 always
+// pivots).  The pivot rows of a 128-column panel are found on a scratch copy of the panel
+// (rows o .. n, ping-pong buffers X -> Y, one launch per column so that every column's pivot is the
+// maximum over ALL rows below the diagonal, exactly LAPACK's choice up to ties); the interchanges
+// are then applied to the full rows of M and the panel is factored by the same unpivoted kernels
+// as above -- on the permuted rows that is the identical elimination.
+// ---------------------------------------------------------------------------------------
+constexpr int PR = 64;  // panel rows per CTA of the pivot search
+
+struct PivCand {
+  double a;   // |value|
+  int32_t r;  // row relative to the panel origin
+};
+
+// larger magnitude wins; ties (and NaN-free equality) go to the smaller row: deterministic
+__device__ __forceinline__ bool piv_better(double a, int32_t r, double b, int32_t q) {
+  return a > b || (a == b && r < q);
+}
+
+// CTA-wide argmax of (a, r) over 256 threads; result valid in thread 0
+__device__ __forceinline__ void piv_block_argmax(double& a, int32_t& r, double* sa, int32_t* sr) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    const double b = __shfl_xor_sync(0xffffffffu, a, off);
+    const int32_t q = __shfl_xor_sync(0xffffffffu, r, off);
+    if (piv_better(b, q, a, r)) { a = b; r = q; }
+  }
+  if (lane == 0) { sa[warp] = a; sr[warp] = r; }
+  __syncthreads();
+  if (tid == 0) {
+    for (int w8 = 1; w8 < 8; w8++)
+      if (piv_better(sa[w8], sr[w8], a, r)) { a = sa[w8]; r = sr[w8]; }
+  }
+}
+
+// step -1: Y <- panel of M (rows o .., columns o .. o+127), candidates of column 0
+__global__ void __launch_bounds__(256)
+piv_init_kernel(const double* __restrict__ M, int64_t ld, int64_t o, int64_t nrows, double* __restrict__ Y,
+                PivCand* __restrict__ cand_out) {
+  __shared__ double sa[8];
+  __shared__ int32_t sr[8];
+  const int tid = threadIdx.x;
+  const int64_t r0 = (int64_t)blockIdx.x * PR;
+  double best = -1.0;
+  int32_t brow = 0x7fffffff;
+  for (int idx = tid; idx < PR * 64; idx += 256) {  // 64 double2 per row
+    const int64_t r = r0 + (idx >> 6);
+    const int c = (idx & 63) * 2;
+    if (r < nrows) {
+      const double2 v = *reinterpret_cast<const double2*>(M + (o + r) * ld + o + c);
+      *reinterpret_cast<double2*>(Y + r * NB + c) = v;
+      if (c == 0 && piv_better(fabs(v.x), (int32_t)r, best, brow)) { best = fabs(v.x); brow = (int32_t)r; }
+    }
+  }
+  piv_block_argmax(best, brow, sa, sr);
+  if (tid == 0) cand_out[blockIdx.x] = PivCand{best, brow};
+}
+
+// step j (0 .. 127): pivot of column j from the candidates of the previous launch; rows j+1 .. of
+// X with rows (j, p) interchanged are eliminated into Y (columns j+1 ..), candidates of column j+1
+__global__ void __launch_bounds__(256)
+piv_step_kernel(const double* __restrict__ X, double* __restrict__ Y, int64_t nrows, int j, int ncand,
+                const PivCand* __restrict__ cand_in, PivCand* __restrict__ cand_out, int64_t o,
+                int32_t* __restrict__ piv, int32_t* __restrict__ info) {
+  __shared__ double sa[8];
+  __shared__ int32_t sr[8];
+  __shared__ double prow[NB];
+  __shared__ int32_t s_p;
+  __shared__ double s_rp;
+  const int tid = threadIdx.x;
+  // ---- pivot of column j: reduce the per-CTA candidates (every CTA does it redundantly) ----
+  double a = -1.0;
+  int32_t p = 0x7fffffff;
+  for (int k = tid; k < ncand; k += 256) {
+    const PivCand c = cand_in[k];
+    if (piv_better(c.a, c.r, a, p)) { a = c.a; p = c.r; }
+  }
+  piv_block_argmax(a, p, sa, sr);
+  if (tid == 0) {
+    s_p = p;
+    const bool bad = !(a > 0.0 && isfinite(a));
+    if (blockIdx.x == 0) {
+      piv[o + j] = (int32_t)(o + (bad ? j : p));
+      if (bad) atomicCAS(info, 0, (int32_t)(o + j + 1));
+    }
+    if (bad) s_p = j;  // singular column: no interchange, the diagonal kernel reports it as well
+  }
+  __syncthreads();
+  p = s_p;
+  if (j == NB - 1) return;
+  // pivot row (row p of X) -> shared, and 1 / pivot
+  if (tid < NB) prow[tid] = X[(int64_t)p * NB + tid];
+  __syncthreads();
+  if (tid == 0) s_rp = 1.0 / prow[j];
+  __syncthreads();
+  const double rp = s_rp;
+  // ---- eliminate my rows: thread (tr, tc) -> rows tr + 8 k, columns 4 tc .. 4 tc + 3 ----
+  const int tr = tid >> 5, tc = tid & 31;
+  const int c0 = 4 * tc;
+  const int64_t r0 = (int64_t)blockIdx.x * PR;
+  double best = -1.0;
+  int32_t brow = 0x7fffffff;
+  if (c0 + 3 > j) {  // this thread owns at least one column right of j
+    for (int k = 0; k < PR / 8; k++) {
+      const int64_t r = r0 + tr + 8 * k;
+      if (r <= j || r >= nrows) continue;
+      const int64_t src = (r == p) ? j : r;  // after the interchange position p holds old row j
+      const double l = X[src * NB + j] * rp;
+      const double4 x = *reinterpret_cast<const double4*>(X + src * NB + c0);
+      double v[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+      for (int e = 0; e < 4; e++) {
+        const int c = c0 + e;
+        if (c > j) {
+          v[e] = fma(-l, prow[c], v[e]);
+          if (c == j + 1 && piv_better(fabs(v[e]), (int32_t)r, best, brow)) { best = fabs(v[e]); brow = (int32_t)r; }
+        }
+      }
+      *reinterpret_cast<double4*>(Y + r * NB + c0) = make_double4(v[0], v[1], v[2], v[3]);
+    }
+  }
+  piv_block_argmax(best, brow, sa, sr);
+  if (tid == 0) cand_out[blockIdx.x] = PivCand{best, brow};
+}
+
+// perm <- identity
+__global__ void perm_init_kernel(int64_t n, int32_t* __restrict__ perm) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) perm[i] = (int32_t)i;
+}
+
+// applies the 128 interchanges of panel o to the full rows of M (one thread per column, the
+// interchanges in order) and to the running permutation
+__global__ void __launch_bounds__(256)
+laswp_kernel(double* __restrict__ M, int64_t ld, int64_t o, const int32_t* __restrict__ piv,
+             int32_t* __restrict__ perm) {
+  __shared__ int32_t sp[NB];
+  const int tid = threadIdx.x;
+  if (tid < NB) sp[tid] = piv[o + tid];
+  __syncthreads();
+  const int64_t c = blockIdx.x * (int64_t)blockDim.x + tid;
+  if (c < ld) {
+    for (int j = 0; j < NB; j++) {
+      const int64_t p = sp[j];
+      if (p != o + j) {
+        const double a = M[(o + j) * ld + c], b = M[p * ld + c];
+        M[(o + j) * ld + c] = b;
+        M[p * ld + c] = a;
+      }
+    }
+  }
+  if (blockIdx.x == 0 && tid == 0) {
+    for (int j = 0; j < NB; j++) {
+      const int64_t p = sp[j];
+      if (p != o + j) {
+        const int32_t t = perm[o + j];
+        perm[o + j] = perm[p];
+        perm[p] = t;
+      }
+    }
+  }
+}
+
 static bool g_attr_set[64] = {};  // kernel attributes are per device
 static int g_diag_small = 1;
 static int g_diag_symb = 1;  // blocked LDL^T diagonal kernel in symmetric mode (SCB_DIAG_SYMB=0: sweep version)
@@ -1506,6 +1672,84 @@ static int getrf_impl(int64_t n_pad, double* M, double* dinv, int32_t* info, scb
     for (auto& st : stamps) cudaEventDestroy(st.e);
   }
   return SCB_OK;
+}
+
+// Right-looking LU with partial pivoting, one level of blocking (NB = 128): per panel the pivot
+// search (129 small launches), the row interchanges, then the unpivoted diagonal / panel-solve /
+// trailing-update kernels of the fast path with K = 128.  A fallback: ~25 TFLOP/s instead of ~32.
+static int getrf_piv_impl(int64_t n_pad, double* M, double* dinv, int32_t* piv, int32_t* perm, int32_t* info,
+                          scb_stream_t stream) {
+  SCB_CHECK_ARG(n_pad > 0 && n_pad % NB == 0, "n_pad must be a positive multiple of 128");
+  SCB_CHECK_ARG(piv != nullptr && perm != nullptr, "piv and perm are required");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int64_t nb = n_pad / NB;
+  const int q = lu_outer_blocks();
+  const int tile_chunks = q * NCHUNK;
+  double* pack_base = dinv + nb * 2 * NB * NB;
+  const int64_t pack_set = 2 * n_pad * NB * q;
+  double* Lpack = pack_base;
+  double* Upack = Lpack + n_pad * NB * q;
+  // scratch of the pivot search: the second pack set (unused by the one-level algorithm)
+  double* X = pack_base + pack_set;
+  double* Y = X + n_pad * NB;
+  PivCand* cand0 = reinterpret_cast<PivCand*>(Y + n_pad * NB);
+  const int64_t max_cand = (n_pad + PR - 1) / PR;
+  PivCand* cand1 = cand0 + max_cand;
+  SCB_CHECK_ARG(2 * n_pad * NB + 4 * max_cand <= pack_set, "factorization workspace too small for pivoting");
+  const int diag_small_smem = 3 * QN * QLD * sizeof(double);
+  const int trsm_smem = kTrsmSmemDoubles * sizeof(double);
+  const int upd_smem = 2 * sizeof(UpdateStage);
+  int dev = 0;
+  SCB_CUDA(cudaGetDevice(&dev));
+  static bool attr_set[64] = {};
+  if (!attr_set[dev & 63]) {
+    SCB_CUDA(cudaFuncSetAttribute(diag_kernel_small<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, diag_small_smem));
+    SCB_CUDA(cudaFuncSetAttribute(update_kernel_t<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, upd_smem));
+    SCB_CUDA(cudaFuncSetAttribute(trsm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, trsm_smem));
+    SCB_CUDA(cudaFuncSetAttribute(update_kernel_t<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    attr_set[dev & 63] = true;
+  }
+  SCB_CUDA(cudaMemsetAsync(info, 0, sizeof(int32_t), s));
+  SCB_CUDA(cudaMemsetAsync(dinv + lu_flags_offset(n_pad), 0, (nb + 16) * sizeof(double), s));
+  perm_init_kernel<<<(unsigned)ceil_div(n_pad, 256), 256, 0, s>>>(n_pad, perm);
+  SCB_LAUNCH_CHECK();
+  for (int64_t k = 0; k < nb; k++) {
+    const int64_t o = k * NB;
+    const int64_t nrows = n_pad - o;
+    const int ncta = (int)((nrows + PR - 1) / PR);
+    // 1. pivot rows of this panel
+    piv_init_kernel<<<ncta, 256, 0, s>>>(M, n_pad, o, nrows, X, cand0);
+    SCB_LAUNCH_CHECK();
+    double *src = X, *dst = Y;
+    PivCand *cin = cand0, *cout = cand1;
+    for (int j = 0; j < NB; j++) {
+      piv_step_kernel<<<ncta, 256, 0, s>>>(src, dst, nrows, j, ncta, cin, cout, o, piv, info);
+      SCB_LAUNCH_CHECK();
+      double* t = src; src = dst; dst = t;
+      PivCand* c = cin; cin = cout; cout = c;
+    }
+    // 2. interchanges on the full rows
+    laswp_kernel<<<(unsigned)ceil_div(n_pad, 256), 256, 0, s>>>(M, n_pad, o, piv, perm);
+    SCB_LAUNCH_CHECK();
+    // 3. the panel, unpivoted, on the permuted rows
+    double* invL = dinv + k * 2 * NB * NB;
+    double* invU = invL + NB * NB;
+    diag_kernel_small<false><<<1, 256, diag_small_smem, s>>>(M, n_pad, o, invL, invU, info, (int)k);
+    SCB_LAUNCH_CHECK();
+    const int nt = (int)(nb - k - 1);
+    if (nt == 0) break;
+    trsm_kernel<<<4 * nt, 256, trsm_smem, s>>>(M, n_pad, o, 2 * nt, invL, invU, Lpack, Upack, tile_chunks, 0);
+    SCB_LAUNCH_CHECK();
+    update_kernel_t<false><<<dim3(2 * nt, nt), 256, upd_smem, s>>>(M, n_pad, o + NB, o + NB, Lpack, Upack, tile_chunks,
+                                                                  0, NCHUNK);
+    SCB_LAUNCH_CHECK();
+  }
+  return SCB_OK;
+}
+
+extern "C" int scb_getrf_piv(int64_t n_pad, double* M, double* dinv, int32_t* piv, int32_t* perm, int32_t* info,
+                             scb_stream_t stream) {
+  return getrf_piv_impl(n_pad, M, dinv, piv, perm, info, stream);
 }
 
 extern "C" int scb_getrf_nopiv(int64_t n_pad, double* M, double* dinv, int32_t* info, scb_stream_t stream) {

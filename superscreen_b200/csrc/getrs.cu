@@ -1,46 +1,35 @@
-// Multi-RHS triangular solves with the no-pivot LU (K12): scipy.linalg.lu_solve at
+// Multi-RHS triangular solves with the LU factors (K12): scipy.linalg.lu_solve at
 // solver/solve_film.py:367,388,530,545.
 //
 // One PERSISTENT kernel per sweep (forward L y = b, backward U x = y).  The factor is processed in
-// 128-row blocks; CTAs grab blocks in sweep order from an atomic work counter (so a CTA only ever
-// waits for blocks that are already owned by running or finished CTAs: deadlock-free without
-// co-residency assumptions).  For its block i a CTA streams the block row of the factor,
+// 128-row blocks; CTAs grab (block, column-chain) work items in sweep order from an atomic counter (so
+// a CTA only ever waits for items that are already owned by running or finished CTAs: deadlock-free
+// without co-residency assumptions).  For its block i a CTA streams the block row of the factor,
 //     acc_i = b_i - sum_{j before i} F_ij x_j ,
 // waiting on a per-block ready flag before it touches x_j, then finishes the block with the stored
 // inverse of the diagonal block, x_i = inv(F_ii) acc_i, publishes x_i (threadfence + flag) and grabs
-// the next block.  The critical chain per block is flag -> one 128x128 GEMV whose factor rows are
-// already in registers -> one 128x128 GEMV from L2-prefetched data -> flag; all the HBM traffic
-// (8 n^2 bytes for both sweeps at nrhs <= 8) streams off the chain.
+// the next item.  What sits on the critical chain of a block is kept minimal:
+//   * the factor tile F_ij is in registers BEFORE the flag of x_j is awaited, and the inverse of the
+//     diagonal block was staged into shared memory when the block was grabbed;
+//   * one right-hand side: the 16 row sums of a warp are reduced together by a transposing butterfly
+//     (16 shuffles instead of 16 x 5);
+//   * several right-hand sides: both 128x128 products of a block run on the fp64 tensor cores
+//     (mma.sync m8n8k4, SASS DMMA), 8 or 16 columns per chain, and all the column chains of a
+//     launch advance CONCURRENTLY (work item = (block, chain), chains of the same block row are
+//     grabbed back to back so that they share the factor tiles in L2).
+// The ready flags live in a stream-ordered scratch allocation that is zeroed per sweep (no epochs:
+// the launch sequence is replayable, e.g. from a CUDA graph).
 #include "scb_common.cuh"
 
 namespace scb {
 
-int64_t lu_flags_offset(int64_t n_pad);  // getrf.cu
-
 constexpr int NB = SCB_LU_BLOCK;
+constexpr int DLDS = NB + 4;  // row stride of the shared copy of inv(F_ii): conflict-free A fragments
 
 __device__ __forceinline__ void dmma_rhs(double& d0, double& d1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
                : "+d"(d0), "+d"(d1)
                : "d"(a), "d"(b));
-}
-
-// one warp: acc[c] = sum_q a[q] * xs[lane + 32 q][c], reduced over the warp
-template <int RT>
-__device__ __forceinline__ void row_dot(const double (&a)[4], const double (*xs)[RT + 1], int lane,
-                                        double (&acc)[RT]) {
-#pragma unroll
-  for (int c = 0; c < RT; c++) {
-    double s = 0.0;
-#pragma unroll
-    for (int q = 0; q < 4; q++) s += a[q] * xs[lane + 32 * q][c];
-    acc[c] = s;
-  }
-#pragma unroll
-  for (int c = 0; c < RT; c++) {
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], off);
-  }
 }
 
 __device__ __forceinline__ void prefetch_tile_l2(const double* tile, int64_t ld_bytes, int warp, int lane) {
@@ -53,18 +42,76 @@ __device__ __forceinline__ void prefetch_tile_l2(const double* tile, int64_t ld_
   }
 }
 
-// RT: right-hand sides per pass.  lower = 1: forward sweep with L (unit diagonal handled through the
-// stored inverse), lower = 0: backward sweep with U.
-template <int RT>
-__global__ void __launch_bounds__(256)
-trsv_sweep_kernel(const double* __restrict__ F, int64_t ld, const double* __restrict__ dinv, int64_t nb,
-                  int lower, int64_t nrhs, int64_t r0, double* __restrict__ B, int* __restrict__ flags,
-                  int* __restrict__ counter, int epoch) {
-  __shared__ double xs[NB][RT + 1];
-  __shared__ double bs[NB][RT + 1];
+// inv(F_ii) (128 x 128, row stride 128) -> shared [128][DLDS]
+__device__ __forceinline__ void stage_inverse(double* __restrict__ dsm, const double* __restrict__ dblk) {
+#pragma unroll 8
+  for (int idx = threadIdx.x; idx < NB * NB / 2; idx += 256) {
+    const int r = idx >> 6, c = (idx & 63) * 2;
+    const double2 v = *reinterpret_cast<const double2*>(dblk + r * NB + c);
+    *reinterpret_cast<double2*>(&dsm[r * DLDS + c]) = v;
+  }
+}
+
+__device__ __forceinline__ void wait_flag(const int* flag) {
+  if (threadIdx.x == 0) {
+    while (*reinterpret_cast<const volatile int*>(flag) == 0) {
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+// Sums 16 per-lane values over the 32 lanes of a warp with a transposing butterfly: 16 shuffles.
+// On return lane L holds the total of value (L >> 1) & 15 (both lanes of a pair hold it).
+__device__ __forceinline__ double reduce16(double (&a)[16], int lane) {
+  {
+    const bool up = lane & 16;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      const double send = up ? a[k] : a[k + 8];
+      const double keep = up ? a[k + 8] : a[k];
+      a[k] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+  }
+  {
+    const bool up = lane & 8;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const double send = up ? a[k] : a[k + 4];
+      const double keep = up ? a[k + 4] : a[k];
+      a[k] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+  }
+  {
+    const bool up = lane & 4;
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+      const double send = up ? a[k] : a[k + 2];
+      const double keep = up ? a[k + 2] : a[k];
+      a[k] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+  }
+  {
+    const bool up = lane & 2;
+    const double send = up ? a[0] : a[1];
+    const double keep = up ? a[1] : a[0];
+    a[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  }
+  return a[0] + __shfl_xor_sync(0xffffffffu, a[0], 1);
+}
+
+// ---------------------------------------------------------------------------------------
+// one right-hand side.  Warp w owns rows w + 8 k (k < 16) of the block; after reduce16 lane L holds
+// the value of row w + 8 (L >> 1).
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256, 1)
+trsv_sweep_kernel(const double* __restrict__ F, int64_t ld, const double* __restrict__ dinv, int64_t nb, int lower,
+                  double* __restrict__ B, int* __restrict__ flags, int* __restrict__ counter) {
+  extern __shared__ __align__(16) double dsm[];  // [NB][DLDS]
+  __shared__ double xs[NB];
   __shared__ int s_p;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int nr = (int)((nrhs - r0) < RT ? (nrhs - r0) : RT);
+  const int myrow = warp + 8 * (lane >> 1);
   const int64_t ldb = ld * (int64_t)sizeof(double);
   for (;;) {
     __syncthreads();
@@ -73,16 +120,9 @@ trsv_sweep_kernel(const double* __restrict__ F, int64_t ld, const double* __rest
     const int p = s_p;  // position in sweep order
     if (p >= nb) break;
     const int64_t i = lower ? p : nb - 1 - p;
-    const double* dblk = dinv + i * 2 * NB * NB + (lower ? 0 : NB * NB);
-    prefetch_tile_l2(dblk, NB * sizeof(double), warp, lane);
-    // right-hand side entries of my 16 rows (lane c < nr holds column c)
-    double bval[16];
-#pragma unroll
-    for (int rr = 0; rr < 16; rr++) bval[rr] = lane < nr ? B[(i * NB + warp + 8 * rr) * nrhs + r0 + lane] : 0.0;
-    if (p > 0) {
-      const int64_t j0 = lower ? 0 : nb - 1;
-      prefetch_tile_l2(F + i * NB * ld + j0 * NB, ldb, warp, lane);
-    }
+    if (p > 0) prefetch_tile_l2(F + i * NB * ld + (lower ? 0 : nb - 1) * NB, ldb, warp, lane);
+    stage_inverse(dsm, dinv + i * 2 * NB * NB + (lower ? 0 : NB * NB));
+    double bval = B[i * NB + myrow];
     for (int q = 0; q < p; q++) {
       const int64_t j = lower ? q : nb - 1 - q;
       // factor rows first (independent of x_j), next tile into L2, then wait for x_j
@@ -93,213 +133,88 @@ trsv_sweep_kernel(const double* __restrict__ F, int64_t ld, const double* __rest
 #pragma unroll
         for (int k = 0; k < 4; k++) fa[rr][k] = Frow[lane + 32 * k];
       }
-      if (q + 1 < p) {
-        const int64_t jn = lower ? q + 1 : nb - 2 - q;
-        prefetch_tile_l2(F + i * NB * ld + jn * NB, ldb, warp, lane);
-      }
-      if (tid == 0) {
-        while (*reinterpret_cast<volatile int*>(flags + j) != epoch) {
-        }
-        __threadfence();
-      }
+      if (q + 1 < p) prefetch_tile_l2(F + i * NB * ld + (lower ? q + 1 : nb - 2 - q) * NB, ldb, warp, lane);
+      wait_flag(flags + j);
+      if (tid < NB) xs[tid] = __ldcg(&B[j * NB + tid]);
       __syncthreads();
-      for (int idx = tid; idx < NB * RT; idx += 256) {
-        const int r = idx / RT, c = idx % RT;
-        xs[r][c] = c < nr ? __ldcg(&B[(j * NB + r) * nrhs + r0 + c]) : 0.0;
-      }
-      __syncthreads();
+      double s[16];
+      const double x0 = xs[lane], x1 = xs[lane + 32], x2 = xs[lane + 64], x3 = xs[lane + 96];
+#pragma unroll
+      for (int rr = 0; rr < 16; rr++) s[rr] = fma(fa[rr][3], x3, fma(fa[rr][2], x2, fma(fa[rr][1], x1, fa[rr][0] * x0)));
+      bval -= reduce16(s, lane);
+      __syncthreads();  // xs is rewritten for the next tile
+    }
+    // finish: x_i = inv(F_ii) acc_i with the inverse already in shared memory
+    if ((lane & 1) == 0) xs[myrow] = bval;
+    __syncthreads();  // (also orders stage_inverse's stores before the reads below)
+    {
+      double s[16];
+      const double x0 = xs[lane], x1 = xs[lane + 32], x2 = xs[lane + 64], x3 = xs[lane + 96];
 #pragma unroll
       for (int rr = 0; rr < 16; rr++) {
-        double accv[RT];
-        row_dot<RT>(fa[rr], xs, lane, accv);
-        double v = 0.0;
-#pragma unroll
-        for (int c = 0; c < RT; c++) v = (lane == c) ? accv[c] : v;
-        bval[rr] -= v;
+        const double* Drow = dsm + (warp + 8 * rr) * DLDS;
+        s[rr] = fma(Drow[lane + 96], x3, fma(Drow[lane + 64], x2, fma(Drow[lane + 32], x1, Drow[lane] * x0)));
       }
-    }
-    // finish: x_i = inv(F_ii) acc_i
-#pragma unroll
-    for (int rr = 0; rr < 16; rr++)
-      if (lane < RT) bs[warp + 8 * rr][lane] = bval[rr];
-    double da[16][4];
-#pragma unroll
-    for (int rr = 0; rr < 16; rr++) {
-      const double* Drow = dblk + (int64_t)(warp + 8 * rr) * NB;
-#pragma unroll
-      for (int k = 0; k < 4; k++) da[rr][k] = Drow[lane + 32 * k];
-    }
-    __syncthreads();
-#pragma unroll
-    for (int rr = 0; rr < 16; rr++) {
-      double accv[RT];
-      row_dot<RT>(da[rr], bs, lane, accv);
-      if (lane < nr) {
-        double v = 0.0;
-#pragma unroll
-        for (int c = 0; c < RT; c++) v = (lane == c) ? accv[c] : v;
-        B[(i * NB + warp + 8 * rr) * nrhs + r0 + lane] = v;
-      }
+      const double v = reduce16(s, lane);
+      if ((lane & 1) == 0) B[i * NB + myrow] = v;
     }
     // publish: the barrier orders every thread's x_i stores before thread 0's fence (cumulative at
-    // gpu scope), which orders them before the flag store -- one fence per block instead of 257
+    // gpu scope), which orders them before the flag store
     __syncthreads();
     if (tid == 0) {
       __threadfence();
-      *reinterpret_cast<volatile int*>(flags + i) = epoch;
+      *reinterpret_cast<volatile int*>(flags + i) = 1;
     }
   }
 }
 
 // ---------------------------------------------------------------------------------------
-// Many right-hand sides (nrhs > 16): blocked right-looking substitution on the fp64 tensor cores.
-// One launch per 128-row block step k; CTA (column chunk of 16 right-hand sides, row tile i):
-//     B_i -= F_ik X_k                                  (128x128 times 128x16, DMMA)
-// and the CTA of the NEXT block of the sweep goes on to solve it with the stored inverse of its
-// diagonal block, X_i = inv(F_ii) B_i, so the next launch finds X_{k+1} in place.  Step k = -1
-// only solves the first block.  The flops (4 n^2 nrhs) run at tensor rate and every factor tile
-// is read once per column chunk; the chain per block is one launch + two 128x128x16 products.
+// RC = 8 or 16 right-hand sides per chain on the fp64 tensor cores.  Work item p -> block p / nchains,
+// chain p % nchains (columns c_base + RC * chain ..).  Warp w owns rows 16 w .. 16 w + 15 of the block:
+// C fragments (rows 16 w + 8 rt + g, columns 8 ct + 2 t, + 1), A fragments of the factor tile loaded
+// straight from global memory before the ready flag of x_j is awaited.
 // ---------------------------------------------------------------------------------------
-constexpr int RC = 16;        // right-hand sides per CTA
-constexpr int XLD = RC + 4;   // row stride of the shared X / Y tiles (conflict-free B fragments)
-
-
-// acc[rt][ct] (rows warp*16 + rt*8 + g, columns ct*8 + 2t, +1) += sign * A[128 x 128] * Xs[128 x RC]
-__device__ __forceinline__ void tile_product(const double* __restrict__ A, int64_t lda, const double* __restrict__ Xs,
-                                             double sign, double (&acc)[2][2][2]) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int g = lane >> 2, t = lane & 3;
-  const double* A0 = A + (int64_t)(warp * 16 + g) * lda + t;
-  const double* A1 = A0 + 8 * lda;
-  // all A fragments of half the K range are requested before the first DMMA (latency-bound loads)
-#pragma unroll 1
-  for (int kh = 0; kh < NB / 4; kh += 16) {
-    double a0[16], a1[16];
-#pragma unroll
-    for (int u = 0; u < 16; u++) {
-      a0[u] = __ldg(A0 + (kh + u) * 4);
-      a1[u] = __ldg(A1 + (kh + u) * 4);
-    }
-#pragma unroll
-    for (int u = 0; u < 16; u++) {
-      const int ks = kh + u;
-      const double b0 = Xs[(ks * 4 + t) * XLD + g];
-      const double b1 = Xs[(ks * 4 + t) * XLD + 8 + g];
-      const double x0 = sign * a0[u], x1 = sign * a1[u];
-      dmma_rhs(acc[0][0][0], acc[0][0][1], x0, b0);
-      dmma_rhs(acc[0][1][0], acc[0][1][1], x0, b1);
-      dmma_rhs(acc[1][0][0], acc[1][0][1], x1, b0);
-      dmma_rhs(acc[1][1][0], acc[1][1][1], x1, b1);
-    }
-  }
-}
-
-__global__ void __launch_bounds__(256)
-trsm_rhs_step_kernel(const double* __restrict__ F, int64_t ld, const double* __restrict__ dinv, int64_t nb,
-                     int lower, int64_t k, int64_t nrhs, double* __restrict__ B) {
-  __shared__ double Xs[NB * XLD];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int g = lane >> 2, t = lane & 3;
-  const int64_t c0 = (int64_t)blockIdx.x * RC;
-  // row tile of this CTA: the blocks after k in sweep order (k < 0: only the first block is solved)
-  const int64_t first = lower ? 0 : nb - 1;
-  const int64_t i = k < 0 ? first : (lower ? k + 1 + blockIdx.y : k - 1 - (int64_t)blockIdx.y);
-  const bool solve_here = blockIdx.y == 0;
-  double acc[2][2][2];
-  double* Bi = B + i * NB * nrhs;
-  if (solve_here) {
-    // the two tiles on the critical path of this and of the next step: into L2 ahead of use
-    prefetch_tile_l2(dinv + i * 2 * NB * NB + (lower ? 0 : NB * NB), NB * sizeof(double), warp, lane);
-    const int64_t inext = lower ? i + 1 : i - 1;
-    if (inext >= 0 && inext < nb)
-      prefetch_tile_l2(F + inext * NB * ld + i * NB, ld * (int64_t)sizeof(double), warp, lane);
-  }
-  // C fragments = B_i chunk (columns beyond nrhs read as zero and are never stored)
-#pragma unroll
-  for (int rt = 0; rt < 2; rt++)
-#pragma unroll
-    for (int ct = 0; ct < 2; ct++)
-#pragma unroll
-      for (int e = 0; e < 2; e++) {
-        const int64_t c = c0 + ct * 8 + 2 * t + e;
-        acc[rt][ct][e] = c < nrhs ? Bi[(int64_t)(warp * 16 + rt * 8 + g) * nrhs + c] : 0.0;
-      }
-  if (k >= 0) {
-    const double* Bk = B + k * NB * nrhs;
-    for (int idx = tid; idx < NB * RC; idx += 256) {
-      const int r = idx / RC, c = idx % RC;
-      Xs[r * XLD + c] = (c0 + c) < nrhs ? Bk[(int64_t)r * nrhs + c0 + c] : 0.0;
-    }
-    __syncthreads();
-    tile_product(F + i * NB * ld + k * NB, ld, Xs, -1.0, acc);
-  }
-  if (solve_here) {
-    __syncthreads();  // everyone is done reading Xs
-#pragma unroll
-    for (int rt = 0; rt < 2; rt++)
-#pragma unroll
-      for (int ct = 0; ct < 2; ct++)
-#pragma unroll
-        for (int e = 0; e < 2; e++) {
-          Xs[(warp * 16 + rt * 8 + g) * XLD + ct * 8 + 2 * t + e] = acc[rt][ct][e];
-          acc[rt][ct][e] = 0.0;
-        }
-    __syncthreads();
-    tile_product(dinv + i * 2 * NB * NB + (lower ? 0 : NB * NB), NB, Xs, 1.0, acc);
-  }
-#pragma unroll
-  for (int rt = 0; rt < 2; rt++)
-#pragma unroll
-    for (int ct = 0; ct < 2; ct++)
-#pragma unroll
-      for (int e = 0; e < 2; e++) {
-        const int64_t c = c0 + ct * 8 + 2 * t + e;
-        if (c < nrhs) Bi[(int64_t)(warp * 16 + rt * 8 + g) * nrhs + c] = acc[rt][ct][e];
-      }
-}
-
-// ---------------------------------------------------------------------------------------
-// 2..8 right-hand sides: the same persistent flag-driven sweep, but the two 128x128 products per
-// block run on the fp64 tensor cores (mma.sync m8n8k4: the 8 right-hand sides are exactly one n
-// tile), so there is no warp-shuffle reduction on the critical chain.  Warp w owns rows
-// 16 w .. 16 w + 15 of the block; the A fragments of the factor tile are loaded straight from
-// global memory before the ready flag of x_j is awaited.
-// ---------------------------------------------------------------------------------------
-constexpr int XP = 12;  // row stride of the shared x tile: conflict-free B fragments
-
-__global__ void __launch_bounds__(256)
-trsv_sweep_dmma_kernel(const double* __restrict__ F, int64_t ld, const double* __restrict__ dinv, int64_t nb,
-                       int lower, int64_t nrhs, int64_t r0, double* __restrict__ B, int* __restrict__ flags,
-                       int* __restrict__ counter, int epoch) {
-  __shared__ double xs[NB * XP];
+template <int RC>
+__global__ void __launch_bounds__(256, 1)
+trsm_sweep_dmma_kernel(const double* __restrict__ F, int64_t ld, const double* __restrict__ dinv, int64_t nb,
+                       int lower, int64_t nrhs, int64_t c_base, int nchains, double* __restrict__ B,
+                       int* __restrict__ flags, int* __restrict__ counter) {
+  constexpr int XP = RC + 4;   // row stride of the shared x tile: conflict-free B fragments
+  constexpr int CT = RC / 8;   // 8-column tiles per chain
+  extern __shared__ __align__(16) double smem[];
+  double* dsm = smem;              // [NB][DLDS]
+  double* xs = smem + NB * DLDS;   // [NB][XP]
   __shared__ int s_p;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
-  const int nr = (int)((nrhs - r0) < 8 ? (nrhs - r0) : 8);
   const int64_t ldb = ld * (int64_t)sizeof(double);
+  const int64_t nitems = nb * nchains;
   for (;;) {
     __syncthreads();
     if (tid == 0) s_p = atomicAdd(counter, 1);
     __syncthreads();
-    const int p = s_p;  // position in sweep order
-    if (p >= nb) break;
+    const int64_t item = s_p;
+    if (item >= nitems) break;
+    const int p = (int)(item / nchains);  // position of the block in sweep order
+    const int ch = (int)(item % nchains);
     const int64_t i = lower ? p : nb - 1 - p;
-    const double* dblk = dinv + i * 2 * NB * NB + (lower ? 0 : NB * NB);
-    prefetch_tile_l2(dblk, NB * sizeof(double), warp, lane);
-    // C fragments: rows 16 warp + 8 rt + g, columns 2t, 2t + 1 of the right-hand side block
-    double acc[2][2];
+    const int64_t c0 = c_base + (int64_t)ch * RC;
+    const int nr = (int)((nrhs - c0) < RC ? (nrhs - c0) : RC);
+    int* cflags = flags + (int64_t)ch * nb;
+    if (p > 0) prefetch_tile_l2(F + i * NB * ld + (lower ? 0 : nb - 1) * NB, ldb, warp, lane);
+    stage_inverse(dsm, dinv + i * 2 * NB * NB + (lower ? 0 : NB * NB));
+    double acc[2][CT][2];
 #pragma unroll
     for (int rt = 0; rt < 2; rt++)
 #pragma unroll
-      for (int e = 0; e < 2; e++)
-        acc[rt][e] = (2 * t + e) < nr ? B[(i * NB + warp * 16 + rt * 8 + g) * nrhs + r0 + 2 * t + e] : 0.0;
-    if (p > 0) {
-      const int64_t j0 = lower ? 0 : nb - 1;
-      prefetch_tile_l2(F + i * NB * ld + j0 * NB, ldb, warp, lane);
-    }
+      for (int ct = 0; ct < CT; ct++)
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+          const int c = ct * 8 + 2 * t + e;
+          acc[rt][ct][e] = c < nr ? B[(i * NB + warp * 16 + rt * 8 + g) * nrhs + c0 + c] : 0.0;
+        }
     for (int q = 0; q < p; q++) {
       const int64_t j = lower ? q : nb - 1 - q;
-      // A fragments of the factor tile first (independent of x_j), next tile into L2, then wait
       double a[2][NB / 4];
 #pragma unroll
       for (int rt = 0; rt < 2; rt++) {
@@ -307,64 +222,69 @@ trsv_sweep_dmma_kernel(const double* __restrict__ F, int64_t ld, const double* _
 #pragma unroll
         for (int ks = 0; ks < NB / 4; ks++) a[rt][ks] = Frow[ks * 4];
       }
-      if (q + 1 < p) {
-        const int64_t jn = lower ? q + 1 : nb - 2 - q;
-        prefetch_tile_l2(F + i * NB * ld + jn * NB, ldb, warp, lane);
-      }
-      if (tid == 0) {
-        while (*reinterpret_cast<volatile int*>(flags + j) != epoch) {
-        }
-        __threadfence();
-      }
-      __syncthreads();
-      for (int idx = tid; idx < NB * 8; idx += 256) {
-        const int r = idx >> 3, c = idx & 7;
-        xs[r * XP + c] = c < nr ? __ldcg(&B[(j * NB + r) * nrhs + r0 + c]) : 0.0;
+      if (q + 1 < p) prefetch_tile_l2(F + i * NB * ld + (lower ? q + 1 : nb - 2 - q) * NB, ldb, warp, lane);
+      wait_flag(cflags + j);
+      for (int idx = tid; idx < NB * RC; idx += 256) {
+        const int r = idx / RC, c = idx % RC;
+        xs[r * XP + c] = c < nr ? __ldcg(&B[(j * NB + r) * nrhs + c0 + c]) : 0.0;
       }
       __syncthreads();
 #pragma unroll
       for (int ks = 0; ks < NB / 4; ks++) {
-        const double b = xs[(ks * 4 + t) * XP + g];
-        dmma_rhs(acc[0][0], acc[0][1], -a[0][ks], b);
-        dmma_rhs(acc[1][0], acc[1][1], -a[1][ks], b);
+#pragma unroll
+        for (int ct = 0; ct < CT; ct++) {
+          const double b = xs[(ks * 4 + t) * XP + ct * 8 + g];
+          dmma_rhs(acc[0][ct][0], acc[0][ct][1], -a[0][ks], b);
+          dmma_rhs(acc[1][ct][0], acc[1][ct][1], -a[1][ks], b);
+        }
+      }
+      __syncthreads();  // xs is rewritten for the next tile
+    }
+    // finish: x_i = inv(F_ii) acc_i, A fragments from the shared copy of the inverse
+#pragma unroll
+    for (int rt = 0; rt < 2; rt++)
+#pragma unroll
+      for (int ct = 0; ct < CT; ct++)
+#pragma unroll
+        for (int e = 0; e < 2; e++) xs[(warp * 16 + rt * 8 + g) * XP + ct * 8 + 2 * t + e] = acc[rt][ct][e];
+    __syncthreads();
+    double out[2][CT][2];
+#pragma unroll
+    for (int rt = 0; rt < 2; rt++)
+#pragma unroll
+      for (int ct = 0; ct < CT; ct++) out[rt][ct][0] = out[rt][ct][1] = 0.0;
+    const double* D0 = dsm + (warp * 16 + g) * DLDS + t;
+    const double* D1 = D0 + 8 * DLDS;
+#pragma unroll 8
+    for (int ks = 0; ks < NB / 4; ks++) {
+      const double a0 = D0[ks * 4], a1 = D1[ks * 4];
+#pragma unroll
+      for (int ct = 0; ct < CT; ct++) {
+        const double b = xs[(ks * 4 + t) * XP + ct * 8 + g];
+        dmma_rhs(out[0][ct][0], out[0][ct][1], a0, b);
+        dmma_rhs(out[1][ct][0], out[1][ct][1], a1, b);
       }
     }
-    // finish: x_i = inv(F_ii) acc_i
-    double da[2][NB / 4];
-#pragma unroll
-    for (int rt = 0; rt < 2; rt++) {
-      const double* Drow = dblk + (int64_t)(warp * 16 + rt * 8 + g) * NB + t;
-#pragma unroll
-      for (int ks = 0; ks < NB / 4; ks++) da[rt][ks] = Drow[ks * 4];
-    }
-    __syncthreads();  // everyone is done with the x tile of the last product
 #pragma unroll
     for (int rt = 0; rt < 2; rt++)
 #pragma unroll
-      for (int e = 0; e < 2; e++) xs[(warp * 16 + rt * 8 + g) * XP + 2 * t + e] = acc[rt][e];
-    __syncthreads();
-    double out[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+      for (int ct = 0; ct < CT; ct++)
 #pragma unroll
-    for (int ks = 0; ks < NB / 4; ks++) {
-      const double b = xs[(ks * 4 + t) * XP + g];
-      dmma_rhs(out[0][0], out[0][1], da[0][ks], b);
-      dmma_rhs(out[1][0], out[1][1], da[1][ks], b);
-    }
-#pragma unroll
-    for (int rt = 0; rt < 2; rt++)
-#pragma unroll
-      for (int e = 0; e < 2; e++)
-        if ((2 * t + e) < nr) B[(i * NB + warp * 16 + rt * 8 + g) * nrhs + r0 + 2 * t + e] = out[rt][e];
+        for (int e = 0; e < 2; e++) {
+          const int c = ct * 8 + 2 * t + e;
+          if (c < nr) B[(i * NB + warp * 16 + rt * 8 + g) * nrhs + c0 + c] = out[rt][ct][e];
+        }
     __syncthreads();
     if (tid == 0) {
       __threadfence();
-      *reinterpret_cast<volatile int*>(flags + i) = epoch;
+      *reinterpret_cast<volatile int*>(cflags + i) = 1;
     }
   }
 }
 
-static int g_epoch = 0;
-static int g_capacity[64][2] = {};  // resident CTAs per device for RT = 1 / 8
+constexpr int kMaxChains = 8;  // column chains advanced concurrently by one launch
+static int g_sms[64] = {};
+static bool g_attr[64] = {};
 
 }  // namespace scb
 
@@ -378,48 +298,46 @@ extern "C" int scb_getrs_nopiv(int64_t n_pad, const double* LU, const double* di
   const int64_t nb = n_pad / NB;
   int dev = 0;
   SCB_CUDA(cudaGetDevice(&dev));
-  const int which = nrhs == 1 ? 0 : 1;
-  int& cap = g_capacity[dev & 63][which];
-  if (cap == 0) {
-    int per_sm = 0, sms = 0;
-    if (which == 0)
-      SCB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trsv_sweep_kernel<1>, 256, 0));
-    else
-      SCB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trsv_sweep_dmma_kernel, 256, 0));
-    SCB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    cap = per_sm * sms;
-    if (cap < 1) cap = 1;
+  const int smem1 = NB * DLDS * sizeof(double);
+  const int smem8 = (NB * DLDS + NB * (8 + 4)) * sizeof(double);
+  const int smem16 = (NB * DLDS + NB * (16 + 4)) * sizeof(double);
+  if (!g_attr[dev & 63]) {
+    SCB_CUDA(cudaFuncSetAttribute(trsv_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1));
+    SCB_CUDA(cudaFuncSetAttribute(trsm_sweep_dmma_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem8));
+    SCB_CUDA(cudaFuncSetAttribute(trsm_sweep_dmma_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem16));
+    SCB_CUDA(cudaDeviceGetAttribute(&g_sms[dev & 63], cudaDevAttrMultiProcessorCount, dev));
+    cudaMemPool_t pool;  // keep the freed flag scratch in the stream-ordered pool
+    SCB_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
+    uint64_t keep = ~0ull;
+    SCB_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    g_attr[dev & 63] = true;
   }
-  if (nrhs > 16) {
-    // (up to 16 right-hand sides two passes of the flag-driven DMMA sweep are faster)
-    // tensor-core path: one launch per block step and sweep direction
-    const unsigned ncc = (unsigned)((nrhs + RC - 1) / RC);
-    for (int lower = 1; lower >= 0; lower--) {
-      trsm_rhs_step_kernel<<<dim3(ncc, 1), 256, 0, s>>>(LU, n_pad, dinv, nb, lower, -1, nrhs, B);
-      SCB_LAUNCH_CHECK();
-      for (int64_t q = 0; q + 1 < nb; q++) {
-        const int64_t k = lower ? q : nb - 1 - q;
-        trsm_rhs_step_kernel<<<dim3(ncc, (unsigned)(nb - 1 - q)), 256, 0, s>>>(LU, n_pad, dinv, nb, lower, k, nrhs, B);
-        SCB_LAUNCH_CHECK();
-      }
-    }
-    return SCB_OK;
-  }
-  // integer scratch behind the packed panels of the factorization workspace
-  int* flags = reinterpret_cast<int*>(const_cast<double*>(dinv) + lu_flags_offset(n_pad));
-  int* counters = flags + nb;  // [0]: work counter
-  const int grid = (int)(nb < cap ? nb : cap);
-  const int RTv = which == 0 ? 1 : 8;
+  const int sms = g_sms[dev & 63] > 0 ? g_sms[dev & 63] : 148;  // one CTA per SM (shared-memory bound)
+  // column chains: one right-hand side, one chain of 8, or chains of 16 (at most kMaxChains per pass)
+  const int rc = nrhs == 1 ? 1 : (nrhs <= 8 ? 8 : 16);
+  const int64_t chains_total = (nrhs + rc - 1) / rc;
+  const int64_t max_chains = chains_total < kMaxChains ? chains_total : kMaxChains;
+  int* scratch = nullptr;  // [max_chains][nb] ready flags + work counter
+  const size_t scratch_bytes = sizeof(int) * (size_t)(max_chains * nb + 1);
+  SCB_CUDA(cudaMallocAsync(&scratch, scratch_bytes, s));
+  int* counter = scratch + max_chains * nb;
   for (int lower = 1; lower >= 0; lower--) {
-    for (int64_t r0 = 0; r0 < nrhs; r0 += RTv) {
-      const int epoch = ++g_epoch;
-      SCB_CUDA(cudaMemsetAsync(counters, 0, sizeof(int), s));
-      if (which == 0)
-        trsv_sweep_kernel<1><<<grid, 256, 0, s>>>(LU, n_pad, dinv, nb, lower, nrhs, r0, B, flags, counters, epoch);
+    for (int64_t ch0 = 0; ch0 < chains_total; ch0 += kMaxChains) {
+      const int nchains = (int)((chains_total - ch0) < kMaxChains ? (chains_total - ch0) : kMaxChains);
+      SCB_CUDA(cudaMemsetAsync(scratch, 0, scratch_bytes, s));
+      const int64_t items = nb * nchains;
+      const int grid = (int)(items < sms ? items : sms);
+      if (rc == 1)
+        trsv_sweep_kernel<<<grid, 256, smem1, s>>>(LU, n_pad, dinv, nb, lower, B, scratch, counter);
+      else if (rc == 8)
+        trsm_sweep_dmma_kernel<8><<<grid, 256, smem8, s>>>(LU, n_pad, dinv, nb, lower, nrhs, ch0 * rc, nchains, B,
+                                                           scratch, counter);
       else
-        trsv_sweep_dmma_kernel<<<grid, 256, 0, s>>>(LU, n_pad, dinv, nb, lower, nrhs, r0, B, flags, counters, epoch);
+        trsm_sweep_dmma_kernel<16><<<grid, 256, smem16, s>>>(LU, n_pad, dinv, nb, lower, nrhs, ch0 * rc, nchains, B,
+                                                             scratch, counter);
       SCB_LAUNCH_CHECK();
     }
   }
+  SCB_CUDA(cudaFreeAsync(scratch, s));
   return SCB_OK;
 }

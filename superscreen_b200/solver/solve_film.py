@@ -52,6 +52,11 @@ class LinearSystem:
     # symmetric mode: the factors are those of S = D (-A) D^-1, D = diag(sym_scale) = sqrt(w[indices])
     sym_scale: object = field(repr=False, default=None)
     pos: object = field(repr=False, default=None)  # torch int32 (n,): mesh vertex -> row of this system, -1 outside
+    # pivoted factorization (scb_getrf_piv): P (-A) = L U.  piv: LAPACK-style interchanges (int32, n_pad),
+    # perm: int64 (n_int,) with row r of P(-A) = row perm[r] of -A, rhs_indices_dev = indices_dev[perm]
+    piv: object = field(repr=False, default=None)
+    perm: object = field(repr=False, default=None)
+    rhs_indices_dev: object = field(repr=False, default=None)
 
     @property
     def A(self) -> np.ndarray:
@@ -75,7 +80,8 @@ class LinearSystem:
 
     @property
     def lu_piv(self) -> Tuple[np.ndarray, np.ndarray]:
-        """(lu, piv) of ``-A`` in scipy.linalg.lu_factor layout; piv is the identity (no pivoting).
+        """(lu, piv) of ``-A`` in scipy.linalg.lu_factor layout; piv is the identity unless the system
+        was factored with partial pivoting (``scb_getrf_piv``).
         In symmetric mode the stored factors belong to S = D (-A) D^-1; since
         -A = (D^-1 L D)(D^-1 U D) with D^-1 L D still unit lower triangular, they are rescaled
         element-wise on the way out."""
@@ -83,6 +89,8 @@ class LinearSystem:
         lu = self.lu[:n, :n]
         if self.sym_scale is not None:
             lu = lu * (self.sym_scale[None, :] / self.sym_scale[:, None])
+        if self.piv is not None:  # partial pivoting: the interchanges, exactly scipy's `piv`
+            return lu.cpu().numpy(), self.piv[:n].cpu().numpy().astype(np.int32)
         return lu.cpu().numpy(), np.arange(n, dtype=np.int32)
 
 
@@ -174,17 +182,33 @@ def factorize_linear_systems(device: Device, film_info_dict: Dict[str, FilmInfo]
                 dinv = torch.empty(int(L.scb_getrf_dinv_bytes(n_pad)) // 8, dtype=torch.float64, device=d.device)
                 lu_info = torch.zeros(1, dtype=torch.int32, device=d.device)
                 sym_scale = None if sym_full is None else sym_full[ix_dev].contiguous()
-                getrf = L.scb_getrf_sym_nopiv if sym_full is not None else L.scb_getrf_nopiv
                 side = side_streams[len(pending) % len(side_streams)] if side_streams else None
                 if side is not None:
                     side.wait_stream(torch.cuda.current_stream(d.device))
+                piv = perm = rhs_ix = None
                 with torch.cuda.stream(side) if side is not None else contextlib.nullcontext():
                     assemble_negA(info, ix_dev, n_int, n_pad, T, out=M, want_margin=True, sym_scale_full=sym_full,
                                   pos=pos, margin=margin)
-                    _lib.check(getrf(n_pad, _lib.ptr(M), _lib.ptr(dinv), _lib.ptr(lu_info), _lib.stream_ptr()))
+                    # Pivoting (SCB_PIVOT=auto): the symmetrised constant-Lambda system is definite and
+                    # needs none; a general system gets LAPACK-style partial pivoting when its rows are
+                    # not provably diagonally dominant (sign-indefinite grad-Lambda term)
+                    use_piv = False
+                    if sym_full is None:
+                        mode = pivot_mode()
+                        use_piv = mode == "1" or (mode == "auto" and float(margin.min().item()) <= 0.0)
+                    if use_piv:
+                        piv = torch.empty(n_pad, dtype=torch.int32, device=d.device)
+                        perm32 = torch.empty(n_pad, dtype=torch.int32, device=d.device)
+                        _lib.check(L.scb_getrf_piv(n_pad, _lib.ptr(M), _lib.ptr(dinv), _lib.ptr(piv), _lib.ptr(perm32),
+                                                   _lib.ptr(lu_info), _lib.stream_ptr()))
+                        perm = perm32[:n_int].to(torch.int64)
+                        rhs_ix = ix_dev[perm]
+                    else:
+                        getrf = L.scb_getrf_sym_nopiv if sym_full is not None else L.scb_getrf_nopiv
+                        _lib.check(getrf(n_pad, _lib.ptr(M), _lib.ptr(dinv), _lib.ptr(lu_info), _lib.stream_ptr()))
                 system = LinearSystem(indices=indices, film_info=info, grad_Lambda_term=T if T is not None else 0.0,
                                       n_pad=n_pad, lu=M, dinv=dinv, indices_dev=ix_dev, margin=margin,
-                                      sym_scale=sym_scale, pos=pos)
+                                      sym_scale=sym_scale, pos=pos, piv=piv, perm=perm, rhs_indices_dev=rhs_ix)
                 # `pos`, `sym_full` and `T` are only read by kernels queued on the side stream: keep them
                 # referenced until the side streams have been joined (the caching allocator would
                 # otherwise hand their blocks to the next film's allocations on the caller's stream
@@ -223,9 +247,12 @@ def factorize_linear_systems(device: Device, film_info_dict: Dict[str, FilmInfo]
         mm = float(system.margin.min().item())
         if flag != 0:
             raise np.linalg.LinAlgError(
-                f"Film {film_name!r}: zero or non-finite pivot at row {flag - 1} in the unpivoted LU."
+                f"Film {film_name!r}: zero or non-finite pivot at row {flag - 1} of the LU factorization."
             )
-        if mm <= 0:
+        if system.piv is not None:
+            # partial pivoting: padding rows must not have been interchanged with real ones
+            logger.info(f"Film {film_name!r}: factored with partial pivoting (margin lower bound {mm:.3e}).")
+        elif mm <= 0:
             # dominance can fail for non-Delaunay (smoothed) meshes or strongly
             # inhomogeneous Lambda.  The unpivoted factors are then used as a preconditioner:
             # every solve is iteratively refined against the matrix-free operator and the
@@ -236,6 +263,13 @@ def factorize_linear_systems(device: Device, film_info_dict: Dict[str, FilmInfo]
                 f"(margin lower bound {mm:.3e}); solves will use iterative refinement."
             )
     return film_systems, hole_systems, terminal_systems
+
+
+def pivot_mode() -> str:
+    """SCB_PIVOT: 'auto' (default: partial pivoting for general systems whose rows are not provably
+    diagonally dominant), '1' (every general system), '0' (never: unpivoted LU + iterative refinement)."""
+    mode = os.environ.get("SCB_PIVOT", "auto").lower()
+    return mode if mode in ("auto", "0", "1") else "auto"
 
 
 def use_symmetric() -> bool:
@@ -274,6 +308,8 @@ def lu_solve(system: LinearSystem, h):
     nrhs = h2.shape[1]
     with torch.cuda.device(system.lu.device):
         B = torch.zeros(system.n_pad, nrhs, dtype=torch.float64, device=system.lu.device)
+        if system.perm is not None:  # P (-A) x = P h
+            h2 = h2[system.perm]
         # symmetric mode: (-A) x = h  <=>  S (D x) = D h
         B[:n_int] = h2 if system.sym_scale is None else h2 * system.sym_scale[:, None]
         _lib.check(L.scb_getrs_nopiv(system.n_pad, _lib.ptr(system.lu), _lib.ptr(system.dinv), nrhs, _lib.ptr(B),
@@ -364,7 +400,8 @@ def solve_film_device(*, film_info: FilmInfo, film_system: LinearSystem, hole_sy
             applied_c = applied_field.contiguous()
             other_c = None if field_from_other_films is None else field_from_other_films.contiguous()
             s = _lib.stream_ptr()
-            _lib.check(L.scb_solve_rhs(n_int, n_pad, _lib.ptr(film_system.indices_dev), nrhs, _lib.ptr(applied_c),
+            rhs_ix = film_system.indices_dev if film_system.rhs_indices_dev is None else film_system.rhs_indices_dev
+            _lib.check(L.scb_solve_rhs(n_int, n_pad, _lib.ptr(rhs_ix), nrhs, _lib.ptr(applied_c),
                                        _lib.ptr(other_c), _lib.ptr(Ha_eff), _lib.ptr(film_system.sym_scale),
                                        _lib.ptr(B), s))
             _lib.check(L.scb_getrs_nopiv(n_pad, _lib.ptr(film_system.lu), _lib.ptr(film_system.dinv), nrhs,
@@ -417,7 +454,7 @@ def solve_film_device(*, film_info: FilmInfo, film_system: LinearSystem, hole_sy
                         gf = gf + lu_solve(film_system, r)
                         r = residual(gf)
                 err = float((r.abs().max() / scale).item())
-                if film_system.refine and err > 1e-10:
+                if film_system.refine and not err <= 1e-10:  # (NaN counts as not converged)
                     # the factors were only a preconditioner (system not provably dominant) and the
                     # refinement did not converge: never hand back an unconverged stream function
                     raise np.linalg.LinAlgError(

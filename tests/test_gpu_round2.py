@@ -252,3 +252,106 @@ def test_c2_full_size_against_oracle_and_reproducible(sc):
         else:
             assert torch.equal(M, first), f"symmetric LU not bit-reproducible at 20k (repetition {rep})"
         del dinv
+
+
+# ----------------------------------------------------------------------------------------
+# partial pivoting (scb_getrf_piv)
+# ----------------------------------------------------------------------------------------
+def _vanishing_pivot_device(sc, n_vertices=900):
+    """A square film whose Lambda(x, y) = s (eps + ramp) is tuned so that the LEADING diagonal entry of the
+    system matrix cancels: A_00 = Q_00 w_0 - Lambda_0 lap_00 - (grad Lambda . grad)_00 = 0.  The matrix is
+    well conditioned (cond ~ 2e4) and LAPACK's pivoted LU solves it to 1e-13; an unpivoted elimination
+    divides by a pivot of rounding size."""
+    from superscreen_b200.geometry import box
+    from superscreen_b200.synthetic import square_mesh
+
+    sites, elements = square_mesh(10.0, n_vertices, seed=4)
+    mesh = sc.Mesh.from_triangulation(sites, elements)
+    ops = mesh.operators
+    interior = np.setdiff1d(np.arange(len(sites)), mesh.boundary_indices)
+    i0 = int(interior[0])
+    gx, gy, lap = ops.gradient_x.tocsr(), ops.gradient_y.tocsr(), ops.laplacian.tocsr()
+    d = np.array([gx[i0, i0], gy[i0, i0]])
+    d /= np.linalg.norm(d)
+    x0, y0 = sites[i0]
+    eps = 1e-3
+    shape = lambda x, y: eps + np.clip((x - x0) * d[0] + (y - y0) * d[1], 0.0, None)
+    Lh = shape(sites[:, 0], sites[:, 1])
+    T00 = (gx @ Lh)[i0] * gx[i0, i0] + (gy @ Lh)[i0] * gy[i0, i0]
+    c0 = Lh[i0] * lap[i0, i0] + T00
+    assert c0 > 0
+    qdw0 = ops.Q_diagonal[i0] * mesh.vertex_areas[i0]
+    s = qdw0 / c0
+    device = sc.Device("vanishing_pivot", layers=[sc.Layer("layer", Lambda=lambda x, y: s * shape(x, y), z0=0.0)],
+                       films=[sc.Polygon("film", layer="layer", points=box(10.0, points=4))])
+    device.set_meshes({"film": mesh})
+    return device, s * Lh, interior
+
+
+def _oracle_solution(device, Lambda, interior, field_mT=1.0):
+    from oracle import port
+
+    mesh = device.meshes["film"]
+    film = port.OracleFilm(name="film", mesh=port.build_mesh(mesh.sites, mesh.elements), z0=0.0, Lambda=Lambda,
+                           interior_indices=interior, hole_indices={})
+    port.factorize_film(film)
+    conv = port.field_conversion_mT_to_uA_per_um()
+    return film, port.solve_film(film, np.full(len(mesh.sites), field_mT * conv), {}, conv)
+
+
+def test_pivoted_factorization_on_vanishing_leading_pivot(sc, monkeypatch):
+    import scipy.linalg as la
+
+    device, Lambda, interior = _vanishing_pivot_device(sc)
+    film, ref = _oracle_solution(device, Lambda, interior)
+    assert abs(film.A[0, 0]) <= 1e-10 * np.abs(film.A[0]).max(), "the construction should cancel the leading pivot"
+    # without pivoting the path must fail loudly (zero pivot, or refinement that cannot converge)
+    monkeypatch.setenv("SCB_PIVOT", "0")
+    with pytest.raises(np.linalg.LinAlgError):
+        model = sc.factorize_model(device=device, current_units="uA")
+        sc.solve(model=model, applied_field=sc.ConstantField(1.0))
+    # default (auto): the non-dominant general system is factored with partial pivoting
+    monkeypatch.delenv("SCB_PIVOT")
+    model = sc.factorize_model(device=device, current_units="uA")
+    system = model.film_systems["film"]
+    assert system.piv is not None and not system.refine
+    fs = sc.solve(model=model, applied_field=sc.ConstantField(1.0))[0].film_solutions["film"]
+    assert rel_l2(fs.stream, ref.stream) <= TOL
+    assert rel_l2(fs.current_density, ref.current_density) <= TOL
+    assert rel_l2(fs.self_field, ref.self_field) <= TOL
+    # lu_piv is a scipy-compatible (lu, piv) pair of -A: scipy's own lu_solve accepts it
+    lu, piv = system.lu_piv
+    assert piv.dtype == np.int32 and (piv != np.arange(len(piv))).any()
+    rng = np.random.default_rng(0)
+    h = rng.normal(size=len(piv))
+    x_scipy = la.lu_solve((lu, piv), h)
+    x_ref = la.lu_solve(film.lu_piv, h)
+    assert rel_l2(x_scipy, x_ref) <= 1e-9
+    # every pivot is the column maximum below the diagonal: |L| <= 1, as LAPACK guarantees
+    assert np.abs(np.tril(lu, -1)).max() <= 1.0 + 1e-12
+    # batched right-hand sides go through the same row permutation
+    batch = sc.solve_batch(model=model, applied_fields=[sc.ConstantField(f) for f in (1.0, -2.0, 0.5)])
+    assert rel_l2(batch[1][0].film_solutions["film"].stream, -2.0 * ref.stream) <= TOL
+
+
+def test_forced_pivoting_matches_unpivoted_and_oracle(sc, monkeypatch):
+    """SCB_PIVOT=1 on a well-behaved inhomogeneous film (golden square_inhomogeneous): same answer as the
+    unpivoted general LU and as the live-reference golden solution."""
+    from oracle import port
+    from superscreen_b200 import configs
+
+    device = configs.c2_square(2500, seed=9, Lambda=0.1)
+    mesh = device.meshes["film"]
+    lam = lambda x, y: 0.1 * (1.0 + 0.5 * np.sin(x) * np.cos(0.7 * y))
+    device.layers["layer"].Lambda = lam
+    interior = np.setdiff1d(np.arange(len(mesh.sites)), mesh.boundary_indices)
+    _, ref = _oracle_solution(device, lam(mesh.sites[:, 0], mesh.sites[:, 1]), interior, field_mT=0.3)
+    out = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("SCB_PIVOT", mode)
+        model = sc.factorize_model(device=device, current_units="uA")
+        assert (model.film_systems["film"].piv is not None) == (mode == "1")
+        out[mode] = sc.solve(model=model, applied_field=sc.ConstantField(0.3))[0].film_solutions["film"]
+        assert rel_l2(out[mode].stream, ref.stream) <= TOL
+        assert rel_l2(out[mode].total_field, ref.total_field) <= TOL
+    assert rel_l2(out["1"].stream, out["0"].stream) <= 1e-11
