@@ -17,7 +17,12 @@
 //     (mma.sync m8n8k4, SASS DMMA), 8 or 16 columns per chain, and all the column chains of a
 //     launch advance CONCURRENTLY (work item = (block, chain), chains of the same block row are
 //     grabbed back to back so that they share the factor tiles in L2).
-// The ready flags live in a stream-ordered scratch allocation that is zeroed per sweep (no epochs:
+//   * no memory fence on the chain: a finished x entry is published as a 16-byte packet {value, tag}
+//     written with ONE 128-bit store and read with 128-bit volatile loads (value and tag arrive
+//     together, as in decoupled look-back scans), so the data validates itself.  A per-block flag,
+//     stored right behind the packets WITHOUT a fence, only keeps the CTAs that have caught up with
+//     the head of the chain from polling with all their threads (one thread per CTA spins on it).
+// Packets and flags live in a stream-ordered scratch allocation that is zeroed per sweep (no epochs:
 // the launch sequence is replayable, e.g. from a CUDA graph).
 #include "scb_common.cuh"
 
@@ -52,13 +57,38 @@ __device__ __forceinline__ void stage_inverse(double* __restrict__ dsm, const do
   }
 }
 
-__device__ __forceinline__ void wait_flag(const int* flag) {
+// a published solution entry: value and ready tag in one naturally aligned 16-byte word
+struct __align__(16) Packet {
+  double value;
+  unsigned long long tag;
+};
+
+__device__ __forceinline__ void publish(Packet* p, double v) {
+  asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};\n" ::"l"(p), "l"(__double_as_longlong(v)), "l"(1ull)
+               : "memory");
+}
+
+// one thread of the CTA spins on the (unfenced) block flag; the packets behind it validate themselves
+__device__ __forceinline__ void wait_block(const int* flag) {
   if (threadIdx.x == 0) {
     while (*reinterpret_cast<const volatile int*>(flag) == 0) {
     }
-    __threadfence();
   }
   __syncthreads();
+}
+__device__ __forceinline__ void signal_block(int* flag) {
+  __syncthreads();  // every thread has issued its packet stores
+  if (threadIdx.x == 0) *reinterpret_cast<volatile int*>(flag) = 1;
+}
+
+// spins until the packet has been published and returns its value (the 128-bit load delivers value
+// and tag together)
+__device__ __forceinline__ double consume(const Packet* p) {
+  unsigned long long v, tag;
+  do {
+    asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];\n" : "=l"(v), "=l"(tag) : "l"(p) : "memory");
+  } while (tag == 0ull);
+  return __longlong_as_double((long long)v);
 }
 
 // Sums 16 per-lane values over the 32 lanes of a warp with a transposing butterfly: 16 shuffles.
@@ -106,7 +136,8 @@ __device__ __forceinline__ double reduce16(double (&a)[16], int lane) {
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256, 1)
 trsv_sweep_kernel(const double* __restrict__ F, int64_t ld, const double* __restrict__ dinv, int64_t nb, int lower,
-                  double* __restrict__ B, int* __restrict__ flags, int* __restrict__ counter) {
+                  double* __restrict__ B, Packet* __restrict__ packets, int* __restrict__ flags,
+                  int* __restrict__ counter) {
   extern __shared__ __align__(16) double dsm[];  // [NB][DLDS]
   __shared__ double xs[NB];
   __shared__ int s_p;
@@ -134,8 +165,8 @@ trsv_sweep_kernel(const double* __restrict__ F, int64_t ld, const double* __rest
         for (int k = 0; k < 4; k++) fa[rr][k] = Frow[lane + 32 * k];
       }
       if (q + 1 < p) prefetch_tile_l2(F + i * NB * ld + (lower ? q + 1 : nb - 2 - q) * NB, ldb, warp, lane);
-      wait_flag(flags + j);
-      if (tid < NB) xs[tid] = __ldcg(&B[j * NB + tid]);
+      wait_block(flags + j);
+      if (tid < NB) xs[tid] = consume(packets + j * NB + tid);
       __syncthreads();
       double s[16];
       const double x0 = xs[lane], x1 = xs[lane + 32], x2 = xs[lane + 64], x3 = xs[lane + 96];
@@ -156,15 +187,12 @@ trsv_sweep_kernel(const double* __restrict__ F, int64_t ld, const double* __rest
         s[rr] = fma(Drow[lane + 96], x3, fma(Drow[lane + 64], x2, fma(Drow[lane + 32], x1, Drow[lane] * x0)));
       }
       const double v = reduce16(s, lane);
-      if ((lane & 1) == 0) B[i * NB + myrow] = v;
+      if ((lane & 1) == 0) {
+        publish(packets + i * NB + myrow, v);
+        B[i * NB + myrow] = v;
+      }
     }
-    // publish: the barrier orders every thread's x_i stores before thread 0's fence (cumulative at
-    // gpu scope), which orders them before the flag store
-    __syncthreads();
-    if (tid == 0) {
-      __threadfence();
-      *reinterpret_cast<volatile int*>(flags + i) = 1;
-    }
+    signal_block(flags + i);
   }
 }
 
@@ -174,12 +202,16 @@ trsv_sweep_kernel(const double* __restrict__ F, int64_t ld, const double* __rest
 // C fragments (rows 16 w + 8 rt + g, columns 8 ct + 2 t, + 1), A fragments of the factor tile loaded
 // straight from global memory before the ready flag of x_j is awaited.
 // ---------------------------------------------------------------------------------------
-template <int RC>
+// PACKETS: x travels in self-validating packets behind an unfenced flag (single chain: measured faster);
+// otherwise the consumers read x from B behind a fenced flag (several concurrent chains: the packet
+// traffic of all the chains at the head of the sweep measured slower than two fences per block).
+template <int RC, bool PACKETS>
 __global__ void __launch_bounds__(256, 1)
 trsm_sweep_dmma_kernel(const double* __restrict__ F, int64_t ld, const double* __restrict__ dinv, int64_t nb,
                        int lower, int64_t nrhs, int64_t c_base, int nchains, double* __restrict__ B,
-                       int* __restrict__ flags, int* __restrict__ counter) {
-  constexpr int XP = RC + 4;   // row stride of the shared x tile: conflict-free B fragments
+                       Packet* __restrict__ packets, int* __restrict__ flags, int* __restrict__ counter) {
+  constexpr int XP = RC + 4;
+  constexpr int PK = NB * RC / 256;  // packets consumed per thread and tile   // row stride of the shared x tile: conflict-free B fragments
   constexpr int CT = RC / 8;   // 8-column tiles per chain
   extern __shared__ __align__(16) double smem[];
   double* dsm = smem;              // [NB][DLDS]
@@ -200,6 +232,7 @@ trsm_sweep_dmma_kernel(const double* __restrict__ F, int64_t ld, const double* _
     const int64_t i = lower ? p : nb - 1 - p;
     const int64_t c0 = c_base + (int64_t)ch * RC;
     const int nr = (int)((nrhs - c0) < RC ? (nrhs - c0) : RC);
+    Packet* cpackets = packets + (int64_t)ch * nb * (NB * RC);  // [nb][NB][RC] of this chain
     int* cflags = flags + (int64_t)ch * nb;
     if (p > 0) prefetch_tile_l2(F + i * NB * ld + (lower ? 0 : nb - 1) * NB, ldb, warp, lane);
     stage_inverse(dsm, dinv + i * 2 * NB * NB + (lower ? 0 : NB * NB));
@@ -223,10 +256,37 @@ trsm_sweep_dmma_kernel(const double* __restrict__ F, int64_t ld, const double* _
         for (int ks = 0; ks < NB / 4; ks++) a[rt][ks] = Frow[ks * 4];
       }
       if (q + 1 < p) prefetch_tile_l2(F + i * NB * ld + (lower ? q + 1 : nb - 2 - q) * NB, ldb, warp, lane);
-      wait_flag(cflags + j);
-      for (int idx = tid; idx < NB * RC; idx += 256) {
-        const int r = idx / RC, c = idx % RC;
-        xs[r * XP + c] = c < nr ? __ldcg(&B[(j * NB + r) * nrhs + c0 + c]) : 0.0;
+      if (PACKETS) {
+        wait_block(cflags + j);
+        // all of this thread's packets are requested together; (rare) retry until every tag is set
+        const Packet* pk = cpackets + j * (NB * RC) + tid;
+        unsigned long long v[PK], tg[PK];
+        bool ready;
+        do {
+          ready = true;
+#pragma unroll
+          for (int k = 0; k < PK; k++) {
+            asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];\n" : "=l"(v[k]), "=l"(tg[k]) : "l"(pk + 256 * k) : "memory");
+          }
+#pragma unroll
+          for (int k = 0; k < PK; k++) ready = ready && (tg[k] != 0ull);
+        } while (!ready);
+#pragma unroll
+        for (int k = 0; k < PK; k++) {
+          const int idx = tid + 256 * k;
+          xs[(idx / RC) * XP + idx % RC] = __longlong_as_double((long long)v[k]);
+        }
+      } else {
+        if (tid == 0) {
+          while (*reinterpret_cast<const volatile int*>(cflags + j) == 0) {
+          }
+          __threadfence();
+        }
+        __syncthreads();
+        for (int idx = tid; idx < NB * RC; idx += 256) {
+          const int r = idx / RC, c = idx % RC;
+          xs[r * XP + c] = c < nr ? __ldcg(&B[(j * NB + r) * nrhs + c0 + c]) : 0.0;
+        }
       }
       __syncthreads();
 #pragma unroll
@@ -272,12 +332,20 @@ trsm_sweep_dmma_kernel(const double* __restrict__ F, int64_t ld, const double* _
 #pragma unroll
         for (int e = 0; e < 2; e++) {
           const int c = ct * 8 + 2 * t + e;
-          if (c < nr) B[(i * NB + warp * 16 + rt * 8 + g) * nrhs + c0 + c] = out[rt][ct][e];
+          const int r = warp * 16 + rt * 8 + g;
+          if (PACKETS) publish(cpackets + i * (NB * RC) + r * RC + c, out[rt][ct][e]);  // (columns >= nr: zeros)
+          if (c < nr) B[(i * NB + r) * nrhs + c0 + c] = out[rt][ct][e];
         }
-    __syncthreads();
-    if (tid == 0) {
-      __threadfence();
-      *reinterpret_cast<volatile int*>(cflags + i) = 1;
+    if (PACKETS) {
+      signal_block(cflags + i);
+    } else {
+      // the barrier orders every thread's x_i stores before thread 0's fence (cumulative at gpu scope),
+      // which orders them before the flag store
+      __syncthreads();
+      if (tid == 0) {
+        __threadfence();
+        *reinterpret_cast<volatile int*>(cflags + i) = 1;
+      }
     }
   }
 }
@@ -303,8 +371,8 @@ extern "C" int scb_getrs_nopiv(int64_t n_pad, const double* LU, const double* di
   const int smem16 = (NB * DLDS + NB * (16 + 4)) * sizeof(double);
   if (!g_attr[dev & 63]) {
     SCB_CUDA(cudaFuncSetAttribute(trsv_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1));
-    SCB_CUDA(cudaFuncSetAttribute(trsm_sweep_dmma_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem8));
-    SCB_CUDA(cudaFuncSetAttribute(trsm_sweep_dmma_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem16));
+    SCB_CUDA(cudaFuncSetAttribute(trsm_sweep_dmma_kernel<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem8));
+    SCB_CUDA(cudaFuncSetAttribute(trsm_sweep_dmma_kernel<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem16));
     SCB_CUDA(cudaDeviceGetAttribute(&g_sms[dev & 63], cudaDevAttrMultiProcessorCount, dev));
     cudaMemPool_t pool;  // keep the freed flag scratch in the stream-ordered pool
     SCB_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
@@ -317,10 +385,14 @@ extern "C" int scb_getrs_nopiv(int64_t n_pad, const double* LU, const double* di
   const int rc = nrhs == 1 ? 1 : (nrhs <= 8 ? 8 : 16);
   const int64_t chains_total = (nrhs + rc - 1) / rc;
   const int64_t max_chains = chains_total < kMaxChains ? chains_total : kMaxChains;
-  int* scratch = nullptr;  // [max_chains][nb] ready flags + work counter
-  const size_t scratch_bytes = sizeof(int) * (size_t)(max_chains * nb + 1);
+  // [max_chains][nb][128][rc] solution packets + [max_chains][nb] block flags + work counter
+  const size_t packet_bytes = rc == 16 ? 0 : sizeof(Packet) * (size_t)(max_chains * nb * NB * rc);
+  const size_t scratch_bytes = packet_bytes + sizeof(int) * (size_t)(max_chains * nb + 4);
+  char* scratch = nullptr;
   SCB_CUDA(cudaMallocAsync(&scratch, scratch_bytes, s));
-  int* counter = scratch + max_chains * nb;
+  Packet* packets = reinterpret_cast<Packet*>(scratch);
+  int* flags = reinterpret_cast<int*>(scratch + packet_bytes);
+  int* counter = flags + max_chains * nb;
   for (int lower = 1; lower >= 0; lower--) {
     for (int64_t ch0 = 0; ch0 < chains_total; ch0 += kMaxChains) {
       const int nchains = (int)((chains_total - ch0) < kMaxChains ? (chains_total - ch0) : kMaxChains);
@@ -328,13 +400,13 @@ extern "C" int scb_getrs_nopiv(int64_t n_pad, const double* LU, const double* di
       const int64_t items = nb * nchains;
       const int grid = (int)(items < sms ? items : sms);
       if (rc == 1)
-        trsv_sweep_kernel<<<grid, 256, smem1, s>>>(LU, n_pad, dinv, nb, lower, B, scratch, counter);
+        trsv_sweep_kernel<<<grid, 256, smem1, s>>>(LU, n_pad, dinv, nb, lower, B, packets, flags, counter);
       else if (rc == 8)
-        trsm_sweep_dmma_kernel<8><<<grid, 256, smem8, s>>>(LU, n_pad, dinv, nb, lower, nrhs, ch0 * rc, nchains, B,
-                                                           scratch, counter);
+        trsm_sweep_dmma_kernel<8, true><<<grid, 256, smem8, s>>>(LU, n_pad, dinv, nb, lower, nrhs, ch0 * rc, nchains, B,
+                                                           packets, flags, counter);
       else
-        trsm_sweep_dmma_kernel<16><<<grid, 256, smem16, s>>>(LU, n_pad, dinv, nb, lower, nrhs, ch0 * rc, nchains, B,
-                                                             scratch, counter);
+        trsm_sweep_dmma_kernel<16, false><<<grid, 256, smem16, s>>>(LU, n_pad, dinv, nb, lower, nrhs, ch0 * rc, nchains, B,
+                                                             packets, flags, counter);
       SCB_LAUNCH_CHECK();
     }
   }
