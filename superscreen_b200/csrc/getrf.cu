@@ -379,6 +379,15 @@ __device__ __forceinline__ double fast_rcp(double a) {
   return fma(r, e, r);
 }
 
+// seed r0 (relative error e = 1 - a r0, |e| ~ 2^-23) and one third-order step: 1/a = r0 (1 + e + e^2 + O(e^3)),
+// three dependent FMAs instead of four
+__device__ __forceinline__ double fast_rcp_halley(double a) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(a));
+  const double e = fma(-a, r, 1.0);
+  return fma(r, fma(e, e, e), r);
+}
+
 // two Newton steps (what the compiler's own fp64 division uses on the MUFU.RCP64H seed)
 __device__ __forceinline__ double fast_rcp2(double a) {
   double r;
@@ -910,18 +919,24 @@ __device__ __forceinline__ int ldl64_blocked(double* __restrict__ S, double* __r
         for (int c = 0; c <= r; c++) a[r][c] = S[(k0 + r) * QLD + k0 + c];
 #pragma unroll
       for (int j = 0; j < 8; j++) {
+        // The 8 pivots are a chain of dependent fp64 operations (~25 cycles each): keep it short.
+        // The products a[r][j] a[c][j] do not depend on 1 / d_j, so after the reciprocal (seed + 3
+        // dependent FMAs) every trailing entry, the next pivot included, is ONE FMA away.
         const double djj = a[j][j];
-        const double rjj = fast_rcp2(djj);
-        // trailing lower triangle: a[r][c] -= (a[r][j] / d_j) * a[c][j]
+        double pr[8][8];
+#pragma unroll
+        for (int r = j + 1; r < 8; r++)
+#pragma unroll
+          for (int c = j + 1; c <= r; c++) pr[r][c] = a[r][j] * a[c][j];
+        const double rjj = fast_rcp_halley(djj);
 #pragma unroll
         for (int r = j + 1; r < 8; r++) {
-          const double l = a[r][j] * rjj;
 #pragma unroll
-          for (int c = j + 1; c <= r; c++) a[r][c] = fma(-l, a[c][j], a[r][c]);
-          // column j of row r is final: store it now (off the dependency chain)
+          for (int c = j + 1; c <= r; c++) a[r][c] = fma(-pr[r][c], rjj, a[r][c]);
+          // column j of row r is final: store it (off the dependency chain)
           if (lane == 8 + r) {
-            S[(k0 + r) * QLD + k0 + j] = l;            // L[r][j]
-            S[(k0 + j) * QLD + k0 + r] = a[r][j];      // U[j][r] = d_j L[r][j]
+            S[(k0 + r) * QLD + k0 + j] = a[r][j] * rjj;  // L[r][j]
+            S[(k0 + j) * QLD + k0 + r] = a[r][j];        // U[j][r] = d_j L[r][j]
           }
         }
         if (lane == j) {
@@ -1434,7 +1449,8 @@ static int getrf_impl(int64_t n_pad, double* M, double* dinv, int32_t* info, scb
   SCB_CUDA(cudaMemsetAsync(dinv + lu_flags_offset(n_pad), 0, (nb + 16) * sizeof(double), s));
 
   // factorization of outer panel P (inner blocks kb .. kb+q_eff-1) on stream st, packs -> set (P & 1)
-  auto factor_panel = [&](int64_t P, cudaStream_t st) -> int {
+  // rest_ready: event after which the rows below the panel's square are up to date (split panels)
+  auto factor_panel = [&](int64_t P, cudaStream_t st, cudaEvent_t rest_ready) -> int {
     const int64_t kb = P * q;
     const int q_eff = (int)((nb - kb) < q ? (nb - kb) : q);
     const int64_t panel_end = (kb + q_eff) * NB;
@@ -1447,6 +1463,7 @@ static int getrf_impl(int64_t n_pad, double* M, double* dinv, int32_t* info, scb
       cudaEvent_t e_in = ls.event(ev++);
       SCB_CUDA(cudaEventRecord(e_in, st));
       SCB_CUDA(cudaStreamWaitEvent(sr, e_in, 0));
+      if (rest_ready) SCB_CUDA(cudaStreamWaitEvent(sr, rest_ready, 0));
       const int nt_below = (int)(nb - kb - q_eff);  // 128-row tiles below the outer panel
       for (int i = 0; i < q_eff; i++) {
         const int64_t k = kb + i;
@@ -1476,17 +1493,22 @@ static int getrf_impl(int64_t n_pad, double* M, double* dinv, int32_t* info, scb
           SCB_LAUNCH_CHECK();
         }
         if (inner_rem > 0) {
-          int w = 1;
-          while (((i + 1) & w) == 0) w <<= 1;
-          const int k_lo = i + 1 - w;
-          const int c_lo = i + 1, c_hi = (i + 1 + w) < q_eff ? (i + 1 + w) : q_eff;
-          const int ncb = c_hi - c_lo;
-          const int64_t r0 = (kb + c_lo) * NB;
-          const int n_in = q_eff - c_lo;  // row tiles of the band inside the panel's square
-          update_kernel_t<true><<<dim3(2 * ncb, n_in), 256, upd_smem, st>>>(M, n_pad, r0, r0, Lpack, Upack, tile_chunks,
-                                                                           k_lo * NCHUNK, w * NCHUNK);
+          // Inside the square (the latency-critical chain): eager right-looking updates, K = 128 -- every
+          // launch is short (4 k-chunks per CTA) and the next diagonal block is ready right after it.
+          const int64_t r1 = (kb + i + 1) * NB;
+          update_kernel_t<true><<<dim3(2 * inner_rem, inner_rem), 256, upd_smem, st>>>(
+              M, n_pad, r1, r1, Lpack, Upack, tile_chunks, i * NCHUNK, NCHUNK);
           SCB_LAUNCH_CHECK();
+          // Rows below the square (throughput work on the second stream): recursive (binary-tree)
+          // schedule -- after inner block i the w = 2^tz(i+1) block columns that follow receive the last
+          // w inner panels at once, so most of these flops run with K = 256 / 512.
           if (nt_below > 0) {
+            int w = 1;
+            while (((i + 1) & w) == 0) w <<= 1;
+            const int k_lo = i + 1 - w;
+            const int c_lo = i + 1, c_hi = (i + 1 + w) < q_eff ? (i + 1 + w) : q_eff;
+            const int ncb = c_hi - c_lo;
+            const int64_t r0 = (kb + c_lo) * NB;
             SCB_CUDA(cudaStreamWaitEvent(sr, e_t, 0));
             update_kernel_t<false><<<dim3(2 * ncb, nt_below), 256, upd_smem, sr>>>(
                 M, n_pad, panel_end, r0, Lpack, Upack, tile_chunks, k_lo * NCHUNK, w * NCHUNK);
@@ -1601,7 +1623,7 @@ static int getrf_impl(int64_t n_pad, double* M, double* dinv, int32_t* info, scb
     SCB_CUDA(cudaEventRecord(e0, s));
     SCB_CUDA(cudaStreamWaitEvent(sp, e0, 0));
   }
-  if (int rc = factor_panel(0, sp)) return rc;
+  if (int rc = factor_panel(0, sp, nullptr)) return rc;
   stamp("chain_end", 0, sp);
   for (int64_t P = 0; P < np; P++) {
     const int64_t kb = P * q;
@@ -1619,7 +1641,25 @@ static int getrf_impl(int64_t n_pad, double* M, double* dinv, int32_t* info, scb
     }
     // A: the L-shaped strip that panel P+1 lives in (rows e0..e1 x all columns, rows below x cols e0..e1)
     const int nt0 = (int)((n_pad - e0) / NB), ntp = (int)((e1 - e0) / NB), nt1 = (int)((n_pad - e1) / NB);
-    if (sym) {
+    cudaEvent_t rest_ready = nullptr;
+    if (sym && split) {
+      // symmetric, split panels: the square of panel P+1 first -- its factorization (a latency-bound
+      // chain) starts as soon as these 72 tiles are done and runs concurrently with the update of
+      // the rows below the square, which only the second (rows-below) stream of the panel waits for
+      update_kernel_t<true><<<dim3(2 * ntp, ntp), 256, upd_smem, s>>>(M, n_pad, e0, e0, Lpack, Upack, tile_chunks, 0,
+                                                                       nchunks);
+      SCB_LAUNCH_CHECK();
+      if (nt1 > 0) {
+        cudaEvent_t e_sq = ls.event(ev++);
+        SCB_CUDA(cudaEventRecord(e_sq, s));
+        SCB_CUDA(cudaStreamWaitEvent(sp, e_sq, 0));
+        update_kernel_t<false><<<dim3(2 * ntp, nt1), 256, upd_smem, s>>>(M, n_pad, e1, e0, Lpack, Upack, tile_chunks, 0,
+                                                                          nchunks);
+        SCB_LAUNCH_CHECK();
+        rest_ready = ls.event(ev++);
+        SCB_CUDA(cudaEventRecord(rest_ready, s));
+      }
+    } else if (sym) {
       // symmetric: one launch for the whole column strip of panel P+1 (its own square and everything below)
       dim3 g12(2 * ntp, nt0);
       update_kernel_t<true><<<g12, 256, upd_smem, s>>>(M, n_pad, e0, e0, Lpack, Upack, tile_chunks, 0, nchunks);
@@ -1636,12 +1676,12 @@ static int getrf_impl(int64_t n_pad, double* M, double* dinv, int32_t* info, scb
       }
     }
     stamp("strip_end", P + 1, s);
-    if (lookahead) {  // panel P+1 can be factored as soon as its strip is up to date
+    if (lookahead && !rest_ready) {  // panel P+1 can be factored as soon as its strip is up to date
       cudaEvent_t e = ls.event(ev++);
       SCB_CUDA(cudaEventRecord(e, s));
       SCB_CUDA(cudaStreamWaitEvent(sp, e, 0));
     }
-    if (int rc = factor_panel(P + 1, sp)) return rc;
+    if (int rc = factor_panel(P + 1, sp, rest_ready)) return rc;
     stamp("chain_end", P + 1, sp);
     // B: the rest of the trailing block, concurrently with the factorization of panel P+1
     if (nt1 > 0) {
