@@ -917,6 +917,7 @@ __device__ __forceinline__ int ldl64_blocked(double* __restrict__ S, double* __r
       for (int r = 0; r < 8; r++)
 #pragma unroll
         for (int c = 0; c <= r; c++) a[r][c] = S[(k0 + r) * QLD + k0 + c];
+      __syncwarp();  // every lane has read the tile before single lanes overwrite entries of it
 #pragma unroll
       for (int j = 0; j < 8; j++) {
         // The 8 pivots are a chain of dependent fp64 operations (~25 cycles each): keep it short.

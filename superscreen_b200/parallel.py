@@ -353,4 +353,9 @@ def field_at_position_sharded(solution, positions, *, zs=None, comm: Optional[Co
         return np.asarray(local)
     dev = torch.device(f"cuda:{torch.cuda.current_device()}") if torch.cuda.is_available() else torch.device("cpu")
     chunk = torch.as_tensor(np.ascontiguousarray(np.asarray(local, dtype=np.float64))).to(dev)
-    return comm.all_gather_chunks(chunk, sizes).cpu().numpy()
+    full = comm.all_gather_chunks(chunk, sizes)
+    if full.is_cuda:
+        from .solver.solve import _to_host
+
+        return _to_host(full)  # pinned staging: the full result is 8 bytes x m on every rank
+    return full.cpu().numpy()

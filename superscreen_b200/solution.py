@@ -191,7 +191,9 @@ def biot_savart_2d(x, y, z, *, positions, current_densities, z0: float = 0, area
                    current_units: str = "uA", vector: bool = True, device_tensors: Optional[dict] = None):
     """Field (tesla) of a current sheet at ``(x, y, z)`` (reference sources/current.py:113-196).
     ``areas`` is required (the Delaunay fallback of the reference, current.py:186-189, is host-side
-    meshing and out of scope)."""
+    meshing and out of scope).  ``device_tensors``: optional dict that keeps the uploaded source arrays
+    (SI units) between calls on the same current sheet -- ``Solution.field_at_position`` evaluates many
+    target sets against one solution."""
     import torch
 
     L = _lib.lib()
@@ -205,16 +207,24 @@ def biot_savart_2d(x, y, z, *, positions, current_densities, z0: float = 0, area
     np.multiply(x, to_meter, out=ev[:, 0])
     np.multiply(y, to_meter, out=ev[:, 1])
     np.multiply(z, to_meter, out=ev[:, 2])  # (a length-1 z broadcasts)
-    positions, current_densities = np.atleast_2d(positions, current_densities)
-    J = np.ascontiguousarray(current_densities * to_amp_per_meter, dtype=np.float64)
-    pos = positions * to_meter
-    zz = z0 * np.ones(len(pos)) * to_meter
-    ar = np.ascontiguousarray(np.asarray(areas) * to_meter**2, dtype=np.float64)
-    pos3 = np.ascontiguousarray(np.concatenate([pos, zz[:, None]], axis=1), dtype=np.float64)
-    m, n = len(ev), len(pos3)
+    m = len(ev)
     with torch.cuda.device(dev):
+        src_key = ("sources", str(dev))
+        src = None if device_tensors is None else device_tensors.get(src_key)
+        if src is None:
+            positions, current_densities = np.atleast_2d(positions, current_densities)
+            J = np.ascontiguousarray(current_densities * to_amp_per_meter, dtype=np.float64)
+            pos = positions * to_meter
+            zz = z0 * np.ones(len(pos)) * to_meter
+            ar = np.ascontiguousarray(np.asarray(areas) * to_meter**2, dtype=np.float64)
+            pos3 = np.ascontiguousarray(np.concatenate([pos, zz[:, None]], axis=1), dtype=np.float64)
+            src = tuple(torch.as_tensor(a).to(dev) for a in (pos3, ar, J))
+            if device_tensors is not None:
+                device_tensors[src_key] = src
+        pos_d, ar_d, J_d = src
+        n = int(pos_d.shape[0])
         # keep the uploads referenced until the result has been read back (stream-ordered use)
-        ev_d, pos_d, ar_d, J_d = (torch.as_tensor(a).to(dev) for a in (ev, pos3, ar, J))
+        ev_d = torch.as_tensor(ev).to(dev)
         out = torch.empty((m, 3) if vector else (m,), dtype=torch.float64, device=dev)
         _lib.check(L.scb_biot_savart(2 if vector else 1, m, _lib.ptr(ev_d), n, _lib.ptr(pos_d), _lib.ptr(ar_d),
                                      _lib.ptr(J_d), 0.0, _MU0_BIOT_SAVART / (4 * np.pi), 1, _lib.ptr(out),
@@ -243,14 +253,15 @@ def _fluxoid_geometry(device: Device, film: str, mesh, polygon_coords) -> _Fluxo
     """The fluxoid of the same polygon is evaluated for many solutions on the same mesh (every
     column / iterate of a mutual-inductance matrix): index sets and interpolation weights are
     memoised per (mesh, film polygon, fluxoid polygon)."""
-    polygon = polygon_coords if isinstance(polygon_coords, Polygon) else Polygon(points=polygon_coords)
-    points = polygon.points
     film_poly = device.films[film]
     Lambda = device.layers[film_poly.layer].Lambda
-    key = (id(mesh), points.tobytes(), film_poly.points.tobytes(), None if callable(Lambda) else float(Lambda))
+    raw = polygon_coords.points if isinstance(polygon_coords, Polygon) else np.asarray(polygon_coords, dtype=float)
+    key = (id(mesh), raw.tobytes(), film_poly.points.tobytes(), None if callable(Lambda) else float(Lambda))
     hit = _FLUXOID_GEOMETRY.get(key)
     if hit is not None and hit[0] is mesh and (not callable(Lambda) or hit[1] is Lambda):
         return hit[2]
+    polygon = polygon_coords if isinstance(polygon_coords, Polygon) else Polygon(points=polygon_coords)
+    points = polygon.points  # closed and counter-clockwise (reference device/polygon.py:67-77)
     if not film_poly.contains_points(points).all():
         raise ValueError(f"The polygon is not contained within the film ({film!r}).")
     ix = np.where(polygon.contains_points(mesh.sites))[0]
@@ -286,6 +297,16 @@ class Solution:
         self._current_units = current_units
         self._solver = solver
         self._time_created = dt.datetime.now()
+
+    def _source_cache(self, film: str) -> dict:
+        """Device copies of a film's current sheet (sites, areas, J in SI units) for repeated field
+        evaluations; dropped when the film's current density array is replaced."""
+        cache = self.__dict__.setdefault("_bs_sources", {})
+        J = self.film_solutions[film].current_density
+        entry = cache.get(film)
+        if entry is None or entry.get("J_ref") is not J:
+            entry = cache[film] = {"J_ref": J}
+        return entry
 
     field_units = property(lambda self: self._field_units)
     current_units = property(lambda self: self._current_units)
@@ -450,12 +471,14 @@ class Solution:
                 field_from_film = biot_savart_2d(
                     positions[:, 0], positions[:, 1], zs, positions=mesh.sites, areas=mesh.vertex_areas,
                     current_densities=self.film_solutions[name].current_density, z0=layer.z0,
-                    length_units=device.length_units, current_units=self.current_units, vector=vector)
+                    length_units=device.length_units, current_units=self.current_units, vector=vector,
+                    device_tensors=self._source_cache(name))
             elif out.any():
                 field_from_film[out] = biot_savart_2d(
                     positions[out, 0], positions[out, 1], zs[out], positions=mesh.sites, areas=mesh.vertex_areas,
                     current_densities=self.film_solutions[name].current_density, z0=layer.z0,
-                    length_units=device.length_units, current_units=self.current_units, vector=vector)
+                    length_units=device.length_units, current_units=self.current_units, vector=vector,
+                    device_tensors=self._source_cache(name))
             fields[name] = convert_field(field_from_film, units, old_units="tesla", with_units=with_units)
         if return_sum:
             return sum(fields.values())

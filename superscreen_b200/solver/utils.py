@@ -135,20 +135,33 @@ def make_film_info(*, device: Device, vortices: Sequence, circulating_currents: 
                     f"London penetration depth; the thin-film assumption may not be valid."
                 )
             london_lambda = _evaluate(london_lambda, x, y)[:, np.newaxis]
-        hole_indices = {
-            hole.name: hole.contains_points(mesh.sites, index=True).astype(np.int64)
-            for hole in holes_by_film[name]
-        }
-        in_hole = np.zeros(len(mesh.sites), dtype=bool)
-        if hole_indices:
-            in_hole[np.concatenate(list(hole_indices.values()))] = True
+        # index sets (reference solver/utils.py:271-304) depend only on the mesh and the polygons:
+        # memoised per device, so that repeated factorizations (Lambda sweeps, one model per
+        # mutual-inductance call) do not redo the point-in-polygon tests
+        geo_key = (id(mesh), film.points.tobytes(), tuple(h.points.tobytes() for h in holes_by_film[name]),
+                   name in device.terminals)
+        cache = device.__dict__.setdefault("_film_geometry_cache", {})
+        hit = cache.get(name)
+        if hit is not None and hit[0] == geo_key and hit[1] is mesh:
+            hole_indices, in_hole, boundary_indices, interior_indices = hit[2]
+        else:
+            hole_indices = {
+                hole.name: hole.contains_points(mesh.sites, index=True).astype(np.int64)
+                for hole in holes_by_film[name]
+            }
+            in_hole = np.zeros(len(mesh.sites), dtype=bool)
+            if hole_indices:
+                in_hole[np.concatenate(list(hole_indices.values()))] = True
+            if name in device.terminals:
+                boundary_indices = device.boundary_vertices(name)  # ordered counter-clockwise
+            else:
+                boundary_indices = mesh.boundary_indices
+            keep = film.contains_points(mesh.sites).copy()
+            keep[boundary_indices] = False
+            interior_indices = np.where(keep)[0].astype(np.int64)  # == setdiff1d(in film, boundary), ascending
+            cache[name] = (geo_key, mesh, (hole_indices, in_hole, boundary_indices, interior_indices))
         circ = {h: c for h, c in circulating_currents.items() if h in hole_indices}
         lambda_info = LambdaInfo(film=name, Lambda=Lambda, london_lambda=london_lambda, thickness=layer.thickness)
-        if name in device.terminals:
-            boundary_indices = device.boundary_vertices(name)  # ordered counter-clockwise
-        else:
-            boundary_indices = mesh.boundary_indices
-        interior_indices = np.setdiff1d(film.contains_points(mesh.sites, index=True), boundary_indices).astype(np.int64)
         info = FilmInfo(
             name=name, layer=layer.name, lambda_info=lambda_info, vortices=tuple(vortices_by_film[name]),
             interior_indices=interior_indices, boundary_indices=boundary_indices, hole_indices=hole_indices,

@@ -122,6 +122,17 @@ class Unit:
 
 def conversion_factor(old: str, new: str) -> float:
     """Multiply a magnitude in ``old`` units by this to express it in ``new`` units."""
+    if isinstance(old, str) and isinstance(new, str):
+        return _conversion_factor_text(old, new)
+    return _conversion_factor(old, new)
+
+
+@functools.lru_cache(maxsize=1024)
+def _conversion_factor_text(old: str, new: str) -> float:
+    return _conversion_factor(old, new)
+
+
+def _conversion_factor(old, new) -> float:
     so, do = parse(old)
     sn, dn = parse(new)
     if not np.allclose(do, dn):
