@@ -66,15 +66,21 @@ class DistComm(Comm):
         return tensor
 
     def all_gather_chunks(self, chunk, sizes: Sequence[int]):
-        """Concatenation over ranks of per-rank chunks with (possibly different) leading sizes."""
+        """Concatenation over ranks of per-rank chunks with (possibly different) leading sizes: one
+        flat all-gather of the chunks padded to the largest size."""
         import torch
 
         m = max(sizes)
-        pad = torch.zeros((m,) + tuple(chunk.shape[1:]), dtype=chunk.dtype, device=chunk.device)
-        pad[: chunk.shape[0]] = chunk
-        out = [torch.empty_like(pad) for _ in range(self.world)]
-        _dist().all_gather(out, pad, group=self.group)
-        return torch.cat([o[:s] for o, s in zip(out, sizes)], dim=0)
+        if chunk.shape[0] == m:
+            pad = chunk.contiguous()
+        else:
+            pad = torch.zeros((m,) + tuple(chunk.shape[1:]), dtype=chunk.dtype, device=chunk.device)
+            pad[: chunk.shape[0]] = chunk
+        out = torch.empty((self.world * m,) + tuple(chunk.shape[1:]), dtype=chunk.dtype, device=chunk.device)
+        self.all_gather_into(out, pad)
+        if all(s_ == m for s_ in sizes):
+            return out
+        return torch.cat([out[r * m: r * m + s_] for r, s_ in enumerate(sizes)], dim=0)
 
     def all_gather_into(self, out, send) -> None:
         """out[(world * k, ...)] <- concatenation over ranks of send[(k, ...)] (one collective)."""
