@@ -101,3 +101,98 @@ def evaluation_grid(n: int = 1000, half_width: float = 7.5, z: float = 1.0) -> n
     xs = np.linspace(-half_width, half_width, n)
     X, Y = np.meshgrid(xs, xs)
     return np.column_stack([X.ravel(), Y.ravel(), np.full(X.size, z)])
+
+
+# ----------------------------------------------------------------------------------------------
+# IBM scanning-SQUID susceptometers (the only physically validated numbers the reference publishes:
+# field-coil <-> pickup-loop mutual inductance 69 +- 7 Phi_0/A ("small", 100 nm pickup loop) and
+# 166 +- 4 Phi_0/A ("medium", 300 nm), docs/notebooks/scanning-squid.ipynb cell 3; Rev. Sci. Instrum.
+# 87, 093702 (2016) Table 1).  Coordinates restated from docs/notebooks/squids/ibm/{small,medium}.py,
+# layer stack from docs/notebooks/squids/ibm/layers.py (align="middle"), `with_terminals=False` route of
+# docs/notebooks/squids/mutuals.py:52-55 (closed field coil, circulating current in `fc_center`).
+# ----------------------------------------------------------------------------------------------
+def ibm_squid_layers(london_lambda: float = 0.08, z0: float = 0.0, d_BE: float = 0.16, d_I1: float = 0.15,
+                     d_W1: float = 0.10, d_I2: float = 0.13, d_W2: float = 0.20):
+    z_W2 = z0 + d_W2 / 2
+    z_W1 = z_W2 + d_I2 + d_W1 / 2
+    z_BE = z_W1 + d_I1 + d_BE / 2
+    return [Layer("W2", london_lambda=london_lambda, thickness=d_W2, z0=z_W2),
+            Layer("W1", london_lambda=london_lambda, thickness=d_W1, z0=z_W1),
+            Layer("BE", london_lambda=london_lambda, thickness=d_BE, z0=z_BE)]
+
+
+def _keyhole(radius: float, half_width: float, y_bottom: float, points: int = 160) -> np.ndarray:
+    """Counter-clockwise ring: a circle of ``radius`` about the origin whose bottom opens into a slot
+    ``|x| <= half_width`` reaching down to ``y_bottom``."""
+    a0 = np.arcsin(half_width / radius)
+    t = np.linspace(-np.pi / 2 + a0, 3 * np.pi / 2 - a0, points)
+    arc = radius * np.stack([np.cos(t), np.sin(t)], axis=1)   # from the right slot edge around to the left one
+    ys = np.linspace(arc[-1, 1], y_bottom, 40)[1:]
+    left = np.stack([np.full(len(ys), -half_width), ys], axis=1)
+    bottom = np.stack([np.linspace(-half_width, half_width, 12)[1:-1], np.full(10, y_bottom)], axis=1)
+    right = np.stack([np.full(len(ys), half_width), ys[::-1]], axis=1)
+    return np.concatenate([arc, left, bottom, right], axis=0)
+
+
+def ibm_susceptometer(size: str = "small", n_vertices: int = 4000, seed: int = 0, attach_meshes: bool = True):
+    """IBM susceptometer with a closed field coil -> (device, {"pl_center": fluxoid ring}).
+
+    Every film gets its own mesh: a jittered-hex Delaunay mesh of the film's bounding box (8 % margin)
+    with the rings of the film and of its holes embedded as vertices (`synthetic.make_mesh`)."""
+    if size == "small":
+        pl_length, ri_pl, ro_pl, ri_fc, ro_fc = 2.5, 0.1, 0.3, 0.5, 1.0125
+        pl_center = Polygon("pl_center", layer="W1", points=box(0.20, pl_length, center=(0, -pl_length / 2 + ri_pl)))
+        pl = Polygon("pl", layer="W1", points=box(2 * ro_pl, pl_length + ro_pl,
+                                                  center=(0, -(pl_length + 0.3) / 2 + 3 * ri_pl))).union(
+            np.array([[-0.30, -1.10], [-0.385, -1.7], [-0.64, -2.57], [+0.62, -2.57], [+0.35, -1.67], [+0.30, -1.15]]))
+        pl_shield1 = Polygon("pl_shield1", layer="W2", points=np.array(
+            [[+0.35, -ri_pl], [-0.35, -ri_pl], [-0.98, -2.65], [-1.05, -2.80], [+1.05, -2.80], [+0.98, -2.65]]))
+        pl_shield2 = Polygon("pl_shield2", layer="BE", points=np.array(
+            [[+0.5, -1.5 - ri_pl], [-0.5, -1.5 - ri_pl], [-0.84, -2.70], [+0.84, -2.70]]))
+        fc = Polygon("fc", layer="BE", points=circle(ro_fc, center=(0, 0.01))).union(np.array(
+            [[2.30, -0.35], [2.00, -0.04], [1.19, 0.54], [0.60, 0.80], [0.40, -0.9], [1.1, -1.30], [1.35, -1.9]]))
+        fc_shield = Polygon("fc_shield", layer="W1", points=np.array(
+            [[2.5, -0.45], [2.15, -0.15], [2.00, -0.04], [1.31, 0.43], [0.81, -0.08], [0.66, -1.23], [1.25, -2.65]]))
+        fc_center = Polygon("fc_center", layer="BE", points=circle(ri_fc)).union(np.array(
+            [[1.7, -0.47], [0.95, 0.02], [0.6, 0.11], [0.4, 0.28], [0.33, -0.34], [0.69, -0.44], [1.4, -0.9]]))
+        # fluxoid contour half way between the slot-shaped hole and the outline of the pickup loop
+        ring = box(0.40, 2.65, points=240, center=(0.0, -1.125))
+        name = "ibm_100nm"
+    elif size == "medium":
+        pl_length, ri_pl, ro_pl, ri_fc, ro_fc = 2.2, 0.3, 0.5, 1.0, 1.5
+        pl_center = Polygon("pl_center", layer="W1", points=circle(ri_pl)).union(
+            box(0.2, pl_length, center=(0, -pl_length / 2 - 0.9 * ri_pl)))
+        pl = Polygon("pl", layer="W1", points=circle(ro_pl)).union(
+            np.array([[+0.3, -0.4], [-0.3, -0.4], [-0.87, -2.8], [+0.85, -2.8]]))
+        pl_shield2 = Polygon("pl_shield2", layer="BE", points=np.array(
+            [[+0.75, -(2.3 - ri_pl)], [-0.75, -(2.3 - ri_pl)], [-0.99, -3.0], [+0.96, -3.0]]))
+        pl_shield1 = Polygon("pl_shield1", layer="W2", points=np.array(
+            [[+0.3, -0.4], [-0.3, -0.4], [-1.0, -2.7], [-1.2, -3.2], [+1.2, -3.2], [+1.0, -2.7]]))
+        fc_center = Polygon("fc_center", layer="BE", points=circle(ri_fc)).union(np.array(
+            [[2.2, -1.2], [1.7, -0.45], [0.97, 0.0], [0.8, -0.5], [1.23, -0.78], [1.4, -0.9], [1.85, -1.55]]))
+        fc = Polygon("fc", layer="BE", points=circle(ro_fc)).union(np.array(
+            [[3.0, -1.05], [2.0, 0.0], [1.68, 0.2], [1.2, 0.52], [0.85, -1.18], [1.12, -1.35], [1.55, -2.35]]))
+        fc_shield = Polygon("fc_shield", layer="W1", points=np.array(
+            [[3.25, -1.25], [2.96, -0.9], [2.0, 0.0], [1.67, 0.19], [1.11, -0.37], [0.9, -1.4], [1.5, -2.9]]))
+        ring = _keyhole(0.40, 0.17, -(pl_length + 0.9 * ri_pl) - 0.08)
+        name = "ibm_300nm"
+    else:
+        raise ValueError(f"Unknown susceptometer size {size!r} (small | medium).")
+    films = [fc, fc_shield, pl_shield1, pl_shield2, pl]
+    holes = [pl_center, fc_center]
+    device = Device(name, layers=ibm_squid_layers(), films=films, holes=holes, length_units="um")
+    holes_by_film = device.holes_by_film()
+    meshes = {}
+    for k, film in enumerate(films):
+        pts = film.points
+        lo, hi = pts.min(axis=0), pts.max(axis=0)
+        c, ext = 0.5 * (lo + hi), (hi - lo) * 1.08
+        rings = [r[:-1] for r in film.rings]
+        for hole in holes_by_film[film.name]:
+            rings += [r[:-1] for r in hole.rings]
+        meshes[film.name] = make_mesh(box(ext[0], ext[1], points=4, center=tuple(c)), target_vertices=n_vertices,
+                                      embedded=rings, seed=seed + k)
+    if not attach_meshes:  # (host-only use: the triangulations without the device-built operators)
+        return device, {"pl_center": ring}, meshes
+    device.set_meshes(meshes)
+    return device, {"pl_center": ring}

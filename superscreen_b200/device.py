@@ -127,6 +127,20 @@ class Polygon:
         o = self._origin(origin)
         return self._mapped((self._points - o) * np.array([xfact, yfact], dtype=float) + o, inplace)
 
+    def union(self, *others) -> "Polygon":
+        """Union with other polygons / coordinate arrays (reference device/polygon.py:302-340) as a
+        ``CompositePolygon`` (membership tests only, no outline)."""
+        return CompositePolygon(self.name, layer=self.layer, add=[self._points] + _rings_of(others))
+
+    def difference(self, *others) -> "Polygon":
+        """This polygon minus others (reference device/polygon.py:378-435), as a ``CompositePolygon``."""
+        return CompositePolygon(self.name, layer=self.layer, add=[self._points], sub=_rings_of(others))
+
+    @property
+    def rings(self) -> List[np.ndarray]:
+        """The closed ring(s) that make up the polygon."""
+        return [self._points]
+
     _mask_cache: Dict[tuple, np.ndarray] = {}
 
     def contains_points(self, points, index: bool = False, radius: float = 0):
@@ -162,6 +176,85 @@ class Polygon:
 
     def __repr__(self):
         return f"Polygon(name={self.name!r}, layer={self.layer!r}, points=<{len(self._points)} x 2>)"
+
+
+class CompositePolygon(Polygon):
+    """Union / difference of simple polygons, as far as the solve path needs it: membership tests.
+
+    Stands in for the shapely-backed ``Polygon.union`` / ``Polygon.difference`` of the reference
+    (device/polygon.py:302-435).  The resulting outline is never computed: a point is inside when it is
+    inside any of the ``add`` rings and inside none of the ``sub`` rings, which is all that
+    ``make_film_info`` (index sets), ``holes_by_film`` and the fluxoid checks ask of a film or hole.
+    ``points`` is the concatenation of the closed ``add`` rings (a point cloud that covers the outline,
+    NOT one ordered ring); ``rings`` gives the individual closed rings, e.g. for meshing."""
+
+    def __init__(self, name: Optional[str] = None, *, layer: Optional[str] = None, add, sub=()):
+        self.name = name
+        self.layer = layer
+        self._add = [close_curve(orient_ccw(np.asarray(r, dtype=float))) for r in add]
+        self._sub = [close_curve(orient_ccw(np.asarray(r, dtype=float))) for r in sub]
+        if not self._add:
+            raise ValueError("A composite polygon needs at least one ring.")
+        self._points = np.concatenate(self._add, axis=0)
+
+    @property
+    def rings(self) -> List[np.ndarray]:
+        return list(self._add)
+
+    @property
+    def cut_rings(self) -> List[np.ndarray]:
+        return list(self._sub)
+
+    @property
+    def area(self) -> float:
+        raise NotImplementedError("The area of a composite polygon is not available (no outline is computed).")
+
+    def _mapped(self, points, inplace):
+        raise NotImplementedError("Affine maps of composite polygons are not supported; transform the parts.")
+
+    def contains_points(self, points, index: bool = False, radius: float = 0):
+        pts = np.atleast_2d(points)
+        mask = np.zeros(len(pts), dtype=bool)
+        for ring in self._add:
+            mask |= Polygon.contains_points(_ring_polygon(ring), pts)
+        for ring in self._sub:
+            mask &= ~Polygon.contains_points(_ring_polygon(ring), pts)
+        return np.where(mask)[0] if index else mask
+
+    def union(self, *others) -> "CompositePolygon":
+        return CompositePolygon(self.name, layer=self.layer, add=self._add + _rings_of(others), sub=self._sub)
+
+    def difference(self, *others) -> "CompositePolygon":
+        return CompositePolygon(self.name, layer=self.layer, add=self._add, sub=self._sub + _rings_of(others))
+
+    def copy(self) -> "CompositePolygon":
+        return CompositePolygon(self.name, layer=self.layer, add=[r.copy() for r in self._add],
+                                sub=[r.copy() for r in self._sub])
+
+    def __repr__(self):
+        return (f"CompositePolygon(name={self.name!r}, layer={self.layer!r}, "
+                f"rings={len(self._add)}, cut_rings={len(self._sub)})")
+
+
+def _ring_polygon(ring: np.ndarray) -> Polygon:
+    """A plain Polygon over an already closed, counter-clockwise ring (no re-normalisation)."""
+    new = object.__new__(Polygon)
+    new.name, new.layer, new._points = None, None, ring
+    return new
+
+
+def _rings_of(items) -> List[np.ndarray]:
+    rings = []
+    for it in items:
+        if isinstance(it, CompositePolygon):
+            if it.cut_rings:
+                raise NotImplementedError("Cannot combine with a composite polygon that has cut-outs.")
+            rings.extend(it.rings)
+        elif isinstance(it, Polygon):
+            rings.append(it.points)
+        else:
+            rings.append(np.asarray(it, dtype=float))
+    return rings
 
 
 def _as_dict(items):
