@@ -380,6 +380,19 @@ class Device:
             d.meshes = self.meshes
         return d
 
+    def to_hdf5(self, path_or_group, save_mesh: bool = True, compress: bool = True) -> None:
+        """reference device/device.py:936-977"""
+        from . import io as _io
+
+        _io.device_to_hdf5(self, path_or_group, save_mesh=save_mesh, compress=compress)
+
+    @staticmethod
+    def from_hdf5(path_or_group) -> "Device":
+        """reference device/device.py:979-1016"""
+        from . import io as _io
+
+        return _io.device_from_hdf5(path_or_group)
+
     # ---- meshes are inputs (mesh generation is out of scope, SURVEY.md section 2a) ----
     def set_meshes(self, meshes: Dict[str, Union[Mesh, Tuple[np.ndarray, np.ndarray]]]) -> None:
         """Attach one triangulation per film: ``{film: Mesh | (sites, elements)}``."""

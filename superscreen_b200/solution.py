@@ -65,6 +65,19 @@ class FilmSolution:
                 self._total_field = self._total_field + self.field_from_other_films
         return self._total_field
 
+    def to_hdf5(self, h5group) -> None:
+        """reference solution.py:132-143"""
+        from . import io as _io
+
+        _io.film_solution_to_hdf5(self, h5group)
+
+    @staticmethod
+    def from_hdf5(h5group) -> "FilmSolution":
+        """reference solution.py:145-164"""
+        from . import io as _io
+
+        return _io.film_solution_from_hdf5(h5group)
+
     def is_close(self, other: "FilmSolution", rtol: float = 1e-4, atol: float = 1e-7) -> bool:
         """reference solution.py:166-185"""
         kw = dict(rtol=rtol, atol=atol)
@@ -297,6 +310,41 @@ class Solution:
         self._current_units = current_units
         self._solver = solver
         self._time_created = dt.datetime.now()
+
+    @property
+    def version_info(self) -> Dict[str, str]:
+        if getattr(self, "_version_info", None) is None:
+            from . import io as _io
+
+            self._version_info = _io.version_info()
+        return self._version_info
+
+    def to_hdf5(self, path_or_group, device_path: Optional[str] = None, compress: bool = True) -> None:
+        """reference solution.py:936-978"""
+        from . import io as _io
+
+        _io.solution_to_hdf5(self, path_or_group, device_path=device_path, compress=compress)
+
+    @staticmethod
+    def from_hdf5(path_or_group) -> "Solution":
+        """reference solution.py:980-1029"""
+        from . import io as _io
+
+        return _io.solution_from_hdf5(path_or_group)
+
+    @staticmethod
+    def save_solutions(solutions, path_or_group, compress: bool = True) -> None:
+        """reference solution.py:1031-1063"""
+        from . import io as _io
+
+        _io.save_solutions(solutions, path_or_group, compress=compress)
+
+    @staticmethod
+    def load_solutions(path_or_group):
+        """reference solution.py:1065-1087"""
+        from . import io as _io
+
+        return _io.load_solutions(path_or_group)
 
     def _source_cache(self, film: str) -> dict:
         """Device copies of a film's current sheet (sites, areas, J in SI units) for repeated field

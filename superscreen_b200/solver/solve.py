@@ -64,7 +64,7 @@ def film_to_film_device(src_sites, src_z0: float, src_areas, src_J, tgt_sites, t
 
 @dataclass
 class FactorizedModel:
-    """reference solver/solve.py:76-220 (HDF5 persistence is out of scope)."""
+    """reference solver/solve.py:76-220"""
 
     device: Device
     film_info: Dict[str, FilmInfo]
@@ -102,6 +102,20 @@ class FactorizedModel:
 
     def copy(self) -> "FactorizedModel":
         return copy.copy(self)
+
+    def to_hdf5(self, h5group) -> None:
+        """reference solver/solve.py:102-132 (same groups, datasets and attributes; ``superscreen_b200.io``)"""
+        from .. import io as _io
+
+        _io.model_to_hdf5(self, h5group)
+
+    @staticmethod
+    def from_hdf5(h5group, comm=None) -> "FactorizedModel":
+        """reference solver/solve.py:134-180; operators and factors are rebuilt on the GPU from the stored
+        triangulations."""
+        from .. import io as _io
+
+        return _io.model_from_hdf5(h5group, comm=comm)
 
 
 def factorize_model(*, device: Device, current_units: str, terminal_currents=None, circulating_currents=None,
@@ -331,8 +345,6 @@ def solve(device: Optional[Device] = None, *, model: Optional[FactorizedModel] =
     if log_level is not None:
         logging.basicConfig(level=log_level)
     model = _check_model_args(device, model, terminal_currents, circulating_currents, vortices, current_units)
-    if save_path is not None:
-        raise NotImplementedError("HDF5 persistence is a 'next' row of the hot-path scope (SURVEY.md 8f.3).")
     device = model.device
     current_units = model.current_units
     length_units = device.length_units
@@ -353,7 +365,14 @@ def solve(device: Optional[Device] = None, *, model: Optional[FactorizedModel] =
     film_names = list(device.films)
     per_iter = _solutions_from_host(device, host, film_names, host_fields, field_conversion, [solution_kwargs],
                                     batched=False)
-    return [row[0] for row in per_iter]
+    solutions = [row[0] for row in per_iter]
+    if save_path is not None:
+        # reference solve.py:475-480,541-543: the device once in the root group, solution i in group str(i)
+        # with a soft link to it (an HDF5 file path needs h5py; an open group works without)
+        from .. import io as _io
+
+        _io.save_solutions(solutions, save_path)
+    return solutions
 
 
 def solve_batch(*, model: FactorizedModel, applied_fields: Sequence[Optional[Callable]],

@@ -78,6 +78,12 @@ class LinearSystem:
         n = len(self.indices)
         return (-M[:n, :n]).cpu().numpy()
 
+    def to_hdf5(self, h5group) -> None:
+        """reference solver/solve_film.py:37-51"""
+        from .. import io as _io
+
+        _io.linear_system_to_hdf5(self, h5group)
+
     @property
     def lu_piv(self) -> Tuple[np.ndarray, np.ndarray]:
         """(lu, piv) of ``-A`` in scipy.linalg.lu_factor layout; piv is the identity unless the system

@@ -69,6 +69,12 @@ class FilmInfo:
     # device-resident state (torch tensors), filled by make_film_info
     dev: Dict[str, object] = field(repr=False, default_factory=dict)
 
+    def to_hdf5(self, h5group) -> None:
+        """reference solver/utils.py:134-164"""
+        from .. import io as _io
+
+        _io.film_info_to_hdf5(self, h5group)
+
     @property
     def weights(self) -> np.ndarray:
         return self.mesh.operators.weights

@@ -386,3 +386,51 @@ def test_ibm_susceptometer_mutual_inductance(sc, size, measured, sigma):
         M2 = sum(sols[-1].hole_fluxoid("pl_center", points=box(0.44, 2.68, points=240, center=(0.0, -1.125)),
                                        with_units=False)) / 1e-3
         assert abs(M2 - M[-1]) <= 0.05 * abs(M[-1]), (M2, M[-1])
+
+
+# ----------------------------------------------------------------------------------------
+# persistence: the reference's HDF5 layout for a factorized model (io.py), through the group protocol
+# ----------------------------------------------------------------------------------------
+def test_factorized_model_hdf5_layout_roundtrip(sc):
+    import scipy.linalg as la
+
+    from superscreen_b200 import configs
+    from superscreen_b200 import io as scio
+
+    device, _ = configs.c1_ring(900)
+    model = sc.factorize_model(device=device, current_units="uA", circulating_currents={"ring_hole": "1 mA"},
+                               vortices=[sc.Vortex(x=3.0, y=0.2, film="ring")])
+    g = scio.MemoryGroup()
+    model.to_hdf5(g)
+    # reference solver/solve.py:102-132
+    assert set(g.keys()) == {"device", "film_info", "film_systems", "hole_systems", "terminal_systems",
+                             "terminal_currents", "circulating_currents", "vortices"}
+    assert g.attrs["current_units"] == "uA" and g["circulating_currents"].attrs["ring_hole"] == 1000.0
+    fsys = g["film_systems"]["ring"]
+    assert set(fsys.keys()) == {"A", "indices", "lu", "piv"} and fsys.attrs["grad_Lambda_term"] == 0.0
+    A, lu, piv = np.array(fsys["A"]), np.array(fsys["lu"]), np.array(fsys["piv"])
+    n_int = len(model.film_systems["ring"].indices)
+    assert A.shape == (n_int, n_int) and lu.shape == (n_int, n_int) and piv.dtype == np.int32
+    # the stored factors are scipy-compatible factors of -A (solver/solve_film.py:279)
+    h = np.random.default_rng(0).normal(size=n_int)
+    assert rel_l2(la.lu_solve((lu, piv), h), np.linalg.solve(-A, h)) <= 1e-10
+    hsys = g["hole_systems"]["ring"]["ring_hole"]
+    assert set(hsys.keys()) == {"A", "indices"} and np.array(hsys["A"]).shape == (len(device.meshes["ring"].sites),
+                                                                                  len(np.array(hsys["indices"])))
+    info = g["film_info"]["ring"]
+    assert {"lambda_info", "vortices", "interior_indices", "boundary_indices", "hole_indices", "in_hole",
+            "circulating_currents", "weights", "kernel", "laplacian"} <= set(info.keys())
+    n = len(device.meshes["ring"].sites)
+    assert np.array(info["kernel"]).shape == (n, n) and np.array(info["laplacian"]).shape == (n, n)
+    assert set(g["device"]["mesh"]["ring"].keys()) == {"sites", "elements"}
+    # load: operators and factors are rebuilt on the GPU; the solutions agree bit for bit
+    back = sc.FactorizedModel.from_hdf5(g)
+    assert back.circulating_currents == {"ring_hole": 1000.0} and len(back.vortices["ring"]) == 1
+    a = sc.solve(model=model, applied_field=sc.ConstantField(0.4))[0].film_solutions["ring"]
+    store = scio.MemoryGroup()
+    b = sc.solve(model=back, applied_field=sc.ConstantField(0.4), save_path=store)[0].film_solutions["ring"]
+    assert np.array_equal(a.stream, b.stream) and np.array_equal(a.self_field, b.self_field)
+    # solve(save_path=...) wrote the reference's file layout: /device + one group per iterate
+    assert set(store.keys()) == {"device", "0"}
+    c = sc.Solution.load_solutions(store)[0].film_solutions["ring"]
+    assert np.array_equal(c.stream, a.stream)
