@@ -143,3 +143,28 @@ def stream_ptr() -> int:
 
 def launch_count() -> int:
     return int(load_library().scb_launch_count())
+
+
+_NVTX = os.environ.get("SCB_NVTX", "0") not in ("", "0")
+
+
+class nvtx_range:
+    """NVTX range around a stage of the path (``SCB_NVTX=1``; a no-op otherwise): mesh operators,
+    film info, per-film assembly + factorization, every Jacobi step, result download."""
+
+    def __init__(self, name: str):
+        self.name = name
+
+    def __enter__(self):
+        if _NVTX:
+            import torch
+
+            torch.cuda.nvtx.range_push(self.name)
+        return self
+
+    def __exit__(self, *exc):
+        if _NVTX:
+            import torch
+
+            torch.cuda.nvtx.range_pop()
+        return False

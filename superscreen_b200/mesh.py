@@ -288,7 +288,8 @@ class Mesh:
         elements = np.ascontiguousarray(elements, dtype=np.int64)
         if elements.min() < 0 or elements.max() >= len(sites):
             raise ValueError("elements reference vertices outside of sites")
-        data = DeviceMeshData(sites, elements, weight_method=weight_method, device=device)
+        with _lib.nvtx_range("scb.mesh_operators"):
+            data = DeviceMeshData(sites, elements, weight_method=weight_method, device=device)
         return Mesh(data, sites, elements, build_operators=build_operators)
 
     # lazily downloaded arrays (same names as the reference attributes)

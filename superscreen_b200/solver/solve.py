@@ -134,14 +134,16 @@ def factorize_model(*, device: Device, current_units: str, terminal_currents=Non
     vortices = vortices or []
     if not device.meshes:
         raise ValueError("The device does not have a mesh. Call device.make_mesh() to generate it.")
-    film_info = make_film_info(device=device, vortices=vortices, circulating_currents=circulating_currents,
-                               terminal_currents=terminal_currents)
+    with _lib.nvtx_range("scb.make_film_info"):
+        film_info = make_film_info(device=device, vortices=vortices, circulating_currents=circulating_currents,
+                                   terminal_currents=terminal_currents)
     from ..parallel import Comm, film_owners
 
     comm = comm or Comm()
     owners = film_owners(list(device.films), comm)
     owned = {f for f, r in owners.items() if r == comm.rank}
-    film_systems, hole_systems, terminal_systems = factorize_linear_systems(device, film_info, owned=owned)
+    with _lib.nvtx_range("scb.factorize_linear_systems"):
+        film_systems, hole_systems, terminal_systems = factorize_linear_systems(device, film_info, owned=owned)
     return FactorizedModel(device, film_info, film_systems, hole_systems, terminal_systems, terminal_currents,
                            circulating_currents, vortices, current_units, comm)
 
@@ -251,6 +253,10 @@ def _run(model: "FactorizedModel", applied_fields, circ_by_film, vortex_flux, it
     hole_states = {}  # hole boundary values + their effective field: constant over the iterations
 
     def solve_fn(name, other):
+        with _lib.nvtx_range(f"scb.solve_film[{name}]"):
+            return _solve_fn(name, other)
+
+    def _solve_fn(name, other):
         circ = None if circ_by_film is None else circ_by_film[name]
         if name not in hole_states:
             info = film_info[name]
@@ -266,6 +272,10 @@ def _run(model: "FactorizedModel", applied_fields, circ_by_film, vortex_flux, it
     inv4pi = 1.0 / (4.0 * np.pi)
 
     def coupling_fn(dst, J_all):
+        with _lib.nvtx_range(f"scb.film_coupling[{dst}]"):
+            return _coupling_fn(dst, J_all)
+
+    def _coupling_fn(dst, J_all):
         # sum over every other film of biot_savart_film_to_film (reference solve.py:495-515): one launch
         src, area = _packed_sources(model, layout, z0s, dev)
         d = meshes[dst]._data
@@ -306,10 +316,12 @@ def _run(model: "FactorizedModel", applied_fields, circ_by_film, vortex_flux, it
             _packed_sources(model, layout, z0s, dev)  # (on the main stream, before the side streams start)
         packer = ResultPacker(layout, comm, iterates, batch, torch.empty(0, dtype=torch.float64, device=dev))
         j_like = torch.empty((0, batch, 2) if batch is not None else (0, 2), dtype=torch.float64, device=dev)
-        run_film_iterations(layout, comm, solve_fn, coupling_fn, iterations, film_scope=film_scope, join=join,
-                            on_result=packer.put, j_like=j_like)
+        with _lib.nvtx_range("scb.film_iterations"):
+            run_film_iterations(layout, comm, solve_fn, coupling_fn, iterations, film_scope=film_scope, join=join,
+                                on_result=packer.put, j_like=j_like)
         packer.scale_fields(1.0 / field_conversion)
-        return packer.to_host(gather, to_numpy=_to_host)
+        with _lib.nvtx_range("scb.results_to_host"):
+            return packer.to_host(gather, to_numpy=_to_host)
 
 
 def _check_model_args(device, model, terminal_currents, circulating_currents, vortices, current_units):

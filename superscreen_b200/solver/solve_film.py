@@ -192,7 +192,8 @@ def factorize_linear_systems(device: Device, film_info_dict: Dict[str, FilmInfo]
                 if side is not None:
                     side.wait_stream(torch.cuda.current_stream(d.device))
                 piv = perm = rhs_ix = None
-                with torch.cuda.stream(side) if side is not None else contextlib.nullcontext():
+                with (torch.cuda.stream(side) if side is not None else contextlib.nullcontext()), \
+                        _lib.nvtx_range(f"scb.assemble+getrf[{film_name}, n={n_int}]"):
                     assemble_negA(info, ix_dev, n_int, n_pad, T, out=M, want_margin=True, sym_scale_full=sym_full,
                                   pos=pos, margin=margin)
                     # Pivoting (SCB_PIVOT=auto): the symmetrised constant-Lambda system is definite and
