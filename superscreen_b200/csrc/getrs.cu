@@ -382,6 +382,8 @@ extern "C" int scb_getrs_nopiv(int64_t n_pad, const double* LU, const double* di
   }
   const int sms = g_sms[dev & 63] > 0 ? g_sms[dev & 63] : 148;  // one CTA per SM (shared-memory bound)
   // column chains: one right-hand side, one chain of 8, or chains of 16 (at most kMaxChains per pass)
+  // (measured at 20k, 64 right-hand sides: 4 fenced chains of 16 columns 5.2 ms; 8 packet chains of 8 columns
+  //  6.5 ms; 16-column chains streamed through a cp.async shared-memory pipeline 5.7 ms)
   const int rc = nrhs == 1 ? 1 : (nrhs <= 8 ? 8 : 16);
   const int64_t chains_total = (nrhs + rc - 1) / rc;
   const int64_t max_chains = chains_total < kMaxChains ? chains_total : kMaxChains;
@@ -405,8 +407,8 @@ extern "C" int scb_getrs_nopiv(int64_t n_pad, const double* LU, const double* di
         trsm_sweep_dmma_kernel<8, true><<<grid, 256, smem8, s>>>(LU, n_pad, dinv, nb, lower, nrhs, ch0 * rc, nchains, B,
                                                            packets, flags, counter);
       else
-        trsm_sweep_dmma_kernel<16, false><<<grid, 256, smem16, s>>>(LU, n_pad, dinv, nb, lower, nrhs, ch0 * rc, nchains, B,
-                                                             packets, flags, counter);
+        trsm_sweep_dmma_kernel<16, false><<<grid, 256, smem16, s>>>(LU, n_pad, dinv, nb, lower, nrhs, ch0 * rc, nchains,
+                                                                    B, packets, flags, counter);
       SCB_LAUNCH_CHECK();
     }
   }

@@ -13,6 +13,7 @@ ap.add_argument("--n", type=int, default=20164)
 ap.add_argument("--reps", type=int, default=1)
 ap.add_argument("--nrhs", type=int, default=1)
 ap.add_argument("--sym", type=int, default=1)
+ap.add_argument("--piv", type=int, default=0, help="1: time scb_getrf_piv (partial pivoting) instead")
 args = ap.parse_args()
 L = _lib.lib()
 sites, elements = square_mesh(10.0, args.n, seed=0)
@@ -59,19 +60,27 @@ for rep in range(args.reps):
     assemble_negA(info, ix, n_int, n_pad, None, out=M, sym_scale_full=sym_full)
     torch.cuda.synchronize()
     e0.record()
-    fn = L.scb_getrf_sym_nopiv if args.sym else L.scb_getrf_nopiv
-    _lib.check(fn(n_pad, _lib.ptr(M), _lib.ptr(dinv), _lib.ptr(flag), _lib.stream_ptr()))
+    if args.piv:
+        piv = torch.empty(n_pad, dtype=torch.int32, device="cuda"); perm = torch.empty(n_pad, dtype=torch.int32, device="cuda")
+        _lib.check(L.scb_getrf_piv(n_pad, _lib.ptr(M), _lib.ptr(dinv), _lib.ptr(piv), _lib.ptr(perm), _lib.ptr(flag), _lib.stream_ptr()))
+    else:
+        fn = L.scb_getrf_sym_nopiv if args.sym else L.scb_getrf_nopiv
+        _lib.check(fn(n_pad, _lib.ptr(M), _lib.ptr(dinv), _lib.ptr(flag), _lib.stream_ptr()))
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
     fl = (1/3 if args.sym else 2/3) * n_int**3
-    print(f"getrf sym={args.sym} n_int={n_int} n_pad={n_pad}: {ms:.2f} ms  {fl/ms*1e-9:.2f} TFLOP/s executed  ({(2/3)*n_int**3/ms*1e-9:.2f} getrf-equivalent)  info={int(flag.item())}")
+    print(f"getrf sym={args.sym} piv={args.piv} n_int={n_int} n_pad={n_pad}: {ms:.2f} ms  {fl/ms*1e-9:.2f} TFLOP/s executed  ({(2/3)*n_int**3/ms*1e-9:.2f} getrf-equivalent)  info={int(flag.item())}")
 if args.stage == "getrs":
     system = LinearSystem(indices=info.interior_indices, film_info=info, n_pad=n_pad, lu=M, dinv=dinv, indices_dev=ix,
                           sym_scale=None if sym_full is None else sym_full[ix].contiguous())
     h = torch.randn(n_int, args.nrhs, dtype=torch.float64, device="cuda")
+    ts = []
     for rep in range(args.reps + 1):
         e0.record(); x = lu_solve(system, h); e1.record(); torch.cuda.synchronize()
-        print(f"getrs nrhs={args.nrhs}: {e0.elapsed_time(e1):.3f} ms")
+        ts.append(e0.elapsed_time(e1))
+        print(f"getrs nrhs={args.nrhs}: {ts[-1]:.3f} ms")
+    if len(ts) >= 5:
+        print(f"getrs nrhs={args.nrhs} n_pad={n_pad}: steady state (median of the last {len(ts) - 3} calls) {float(np.median(ts[3:])):.3f} ms")
     # consistency with the single-RHS flag-driven sweeps on a few columns
     cols = sorted(set([0, args.nrhs // 2, args.nrhs - 1]))
     ref = torch.stack([lu_solve(system, h[:, c].contiguous()) for c in cols], dim=1)
