@@ -9,7 +9,7 @@ for p in $parts; do case $p in
 launches)
   $NCU --metrics gpu__time_duration.sum -c 4000 --csv --log-file $out/bench_launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-sharded > $out/bench_under_ncu.log 2>&1 ;;
 lu)
-  $NCU --set full -k regex:update_kernel_tILb1 -c 18 -f -o $out/lu_update_tri python tools/run_stage.py --stage getrf --n 20164 --sym 1 > $out/lu_update_tri.log 2>&1; raw $out/lu_update_tri.ncu-rep
+  $NCU --set full --kernel-name-base mangled -k regex:update_kernel_tILb1 -c 18 -f -o $out/lu_update_tri python tools/run_stage.py --stage getrf --n 20164 --sym 1 > $out/lu_update_tri.log 2>&1; raw $out/lu_update_tri.ncu-rep
   $NCU --set full -k regex:diag_kernel_symb -s 20 -c 1 -f -o $out/lu_diag python tools/run_stage.py --stage getrf --n 20164 --sym 1 > $out/lu_diag.log 2>&1; raw $out/lu_diag.ncu-rep ;;
 assemble)
   $NCU --set full -k regex:assemble_dense -c 1 -f -o $out/assemble_dense python tools/run_stage.py --stage getrf --n 20164 --sym 1 > $out/assemble.log 2>&1; raw $out/assemble_dense.ncu-rep ;;
