@@ -116,7 +116,7 @@ template <bool TRI>
 __global__ void __launch_bounds__(256, 2)
 update_kernel_t(double* __restrict__ M, int64_t ld, int64_t row0, int64_t col0,
                 const double* __restrict__ Lpack, const double* __restrict__ Upack, int tile_chunks,
-                int chunk0, int nchunks) {
+                int chunk0, int nchunks, int kBand) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   UpdateStage* stage = reinterpret_cast<UpdateStage*>(smem_raw);
   __shared__ uint64_t bars[2];
@@ -128,7 +128,22 @@ update_kernel_t(double* __restrict__ M, int64_t ld, int64_t row0, int64_t col0,
 
   // tile coordinates.  TRI: the region is square and only the tiles that intersect its lower
   // triangle are updated (row tile by owns column tiles 0 .. 2 by + 1); the others exit at once.
-  const int by = blockIdx.y, bx = blockIdx.x;
+  // Raster order: the hardware issues CTAs with blockIdx.x fastest, i.e. one row tile (one L tile)
+  // against ALL column tiles -- at 20k that is 280 U tiles = 143 MB per row, more than the L2 holds, so
+  // every U tile came from DRAM once per row tile (10.1 GB per launch for 2.9 GB algorithmic).  The linear
+  // CTA index is therefore re-mapped to bands of kBand (16) row tiles, column-major inside a band: the
+  // resident wave works on kBand L tiles (16 MB) and ~20 U tiles, and a U tile is fetched from DRAM once
+  // per band.  Same tiles, same arithmetic per tile: results are bit-identical.
+  int by = blockIdx.y, bx = blockIdx.x;
+  if (kBand > 1 && (int)gridDim.y > 1) {
+    const int gx = gridDim.x, gy = gridDim.y;
+    const int64_t id = (int64_t)blockIdx.y * gx + blockIdx.x;
+    const int band = (int)(id / ((int64_t)kBand * gx));
+    const int band_rows = (gy - band * kBand) < kBand ? (gy - band * kBand) : kBand;
+    const int rem = (int)(id - (int64_t)band * kBand * gx);
+    bx = rem / band_rows;
+    by = band * kBand + rem % band_rows;
+  }
   if (TRI && bx > 2 * by + 1) return;
   // packed operands are indexed by ABSOLUTE 128-row / 64-column tile and by chunk slot
   const double* Ltile = Lpack + ((row0 >> 7) + by) * ((int64_t)tile_chunks * A_CHUNK) + (int64_t)chunk0 * A_CHUNK;
@@ -180,6 +195,15 @@ update_kernel_t(double* __restrict__ M, int64_t ld, int64_t row0, int64_t col0,
 #pragma unroll
         for (int j = 0; j < 4; j++) dmma(acc[i][j][0], acc[i][j][1], a[i], b[j]);
     }
+    // The stage that was just read through the generic proxy (LDS) is about to be overwritten through
+    // the async proxy (the next bulk copy): accesses through different proxies are NOT ordered by
+    // bar.sync alone.  Every reader therefore issues a generic->async proxy fence before the barrier.
+    // Without it the kernel was not reproducible: rarely (a few tiles per launch at 20k, more often for
+    // the short K = 128 launches) the operand fragments of a warp came out wrong in units of 32-byte
+    // shared-memory sectors, i.e. LU entries off by 1e-8 .. 1e-5 relative and run-to-run different
+    // factors (tools/lu_kernel_determinism.cu: identical inputs, bitwise comparison; 0 differences
+    // in every configuration with the fence, hundreds to thousands of words without it).
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
     __syncthreads();
     if (tid == 0 && c + 2 < nchunks) {
       mbar_expect_tx(&bars[st], kStageBytes);
@@ -264,7 +288,7 @@ __global__ void __launch_bounds__(256)
 trsm_kernel(double* __restrict__ M, int64_t ld, int64_t o, int ncol, const double* __restrict__ invL,
             const double* __restrict__ invU, double* __restrict__ Lpack, double* __restrict__ Upack,
             int tile_chunks, int chunk0) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   double* As = reinterpret_cast<double*>(smem_raw);
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
@@ -317,7 +341,7 @@ trsm_kernel(double* __restrict__ M, int64_t ld, int64_t o, int ncol, const doubl
 __global__ void __launch_bounds__(256)
 trsm_sym_kernel(double* __restrict__ M, int64_t ld, int64_t o, const double* __restrict__ invU,
                 double* __restrict__ Lpack, double* __restrict__ Upack, int tile_chunks, int chunk0, int tile0) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   double* As = reinterpret_cast<double*>(smem_raw);
   __shared__ double dU[NB];  // diagonal of U11
   const int tid = threadIdx.x;
@@ -401,7 +425,7 @@ __device__ __forceinline__ double fast_rcp2(double a) {
 __global__ void __launch_bounds__(512, 1)
 diag_kernel(double* __restrict__ M, int64_t ld, int64_t o, double* __restrict__ invL,
             double* __restrict__ invU, int32_t* __restrict__ info, int block_index) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   double* D = reinterpret_cast<double*>(smem_raw);  // [128][129] finished L / U entries
   __shared__ double rowb[2][NB];                    // register row j
   __shared__ double colb[2][NB];                    // register column j
@@ -722,7 +746,7 @@ template <bool SYM>
 __global__ void __launch_bounds__(256, 2)
 diag_kernel_small(double* __restrict__ M, int64_t ld, int64_t o, double* __restrict__ invL,
                   double* __restrict__ invU, int32_t* __restrict__ info, int block_index) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   double* S0 = reinterpret_cast<double*>(smem_raw);
   double* S1 = S0 + QN * QLD;
   double* S2 = S1 + QN * QLD;
@@ -1060,7 +1084,7 @@ __device__ __forceinline__ void emit_inverses_symb(const double* __restrict__ SL
 __global__ void __launch_bounds__(256, 2)
 diag_kernel_symb(double* __restrict__ M, int64_t ld, int64_t o, double* __restrict__ invL,
                  double* __restrict__ invU, int32_t* __restrict__ info, int block_index) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   double* S0 = reinterpret_cast<double*>(smem_raw);
   double* S1 = S0 + QN * QLD;
   double* S2 = S1 + QN * QLD;
@@ -1324,6 +1348,10 @@ static int g_lookahead = 1;
 static int g_recursive_strips = 1;  // binary-tree schedule of the inner strip updates (SCB_LU_RECURSIVE=0: eager)
 static int g_split_panel = 1;  // symmetric LU: square of the outer panel on the chain, rows below on a 2nd stream (SCB_LU_SPLIT=0: off)
 static int g_lazy_strips = 0;  // left-looking inner strips: same flops, measured no faster (narrow grids)
+static int g_inner_la = 0;     // split panels: block-level look-ahead inside the square (SCB_LU_INNER_LA=1; measured: no gain)
+static int g_tail_q = 0;       // outer-panel width (in 128-blocks) used for the last g_tail_blocks blocks (0: same q)
+static int g_tail_blocks = 0;
+static int g_band = 16;        // raster order of the update kernel: row tiles per band (SCB_LU_BAND=0: hardware order)
 
 }  // namespace scb
 
@@ -1345,6 +1373,7 @@ static int lu_outer_blocks() {
 struct LuStreams {
   cudaStream_t panel = nullptr;
   cudaStream_t rest = nullptr;  // split panels: rows below the outer panel's diagonal square
+  cudaStream_t square = nullptr;  // split panels: the columns of the square that are not next on the chain
   std::vector<cudaEvent_t> events;
   cudaEvent_t event(size_t i) {
     while (events.size() <= i) {
@@ -1416,6 +1445,10 @@ static int getrf_impl(int64_t n_pad, double* M, double* dinv, int32_t* info, scb
     if (const char* e = getenv("SCB_LU_LAZY")) g_lazy_strips = atoi(e);
     if (const char* e = getenv("SCB_LU_RECURSIVE")) g_recursive_strips = atoi(e);
     if (const char* e = getenv("SCB_LU_SPLIT")) g_split_panel = atoi(e);
+    if (const char* e = getenv("SCB_LU_INNER_LA")) g_inner_la = atoi(e);
+    if (const char* e = getenv("SCB_LU_TAIL_Q")) g_tail_q = atoi(e);
+    if (const char* e = getenv("SCB_LU_TAIL_BLOCKS")) g_tail_blocks = atoi(e);
+    if (const char* e = getenv("SCB_LU_BAND")) g_band = atoi(e);
     g_attr_set[dev & 63] = true;
   }
   LuStreams* lsp;
@@ -1444,16 +1477,46 @@ static int getrf_impl(int64_t n_pad, double* M, double* dinv, int32_t* info, scb
     }
     sr = ls.rest;
   }
+  const bool inner_la = split && g_inner_la;
+  cudaStream_t sq = sp;
+  if (inner_la) {
+    if (!ls.square) {
+      int lo = 0, hi = 0;
+      SCB_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+      SCB_CUDA(cudaStreamCreateWithPriority(&ls.square, cudaStreamNonBlocking, hi));
+    }
+    sq = ls.square;
+  }
   size_t ev = 0;
   SCB_CUDA(cudaMemsetAsync(info, 0, sizeof(int32_t), s));
   // ready flags / counters of scb_getrs_nopiv live behind the packed panels: start from zero
   SCB_CUDA(cudaMemsetAsync(dinv + lu_flags_offset(n_pad), 0, (nb + 16) * sizeof(double), s));
 
+  // Outer panels: q blocks each; optionally narrower panels (SCB_LU_TAIL_Q) for the last
+  // SCB_LU_TAIL_BLOCKS blocks, where the trailing block is too small to hide a q-block chain.
+  std::vector<int64_t> pk;  // first 128-block of every outer panel
+  std::vector<int> pq;      // blocks in it
+  {
+    const int qt = (g_tail_q > 0 && g_tail_q < q) ? g_tail_q : q;
+    const int64_t tail0 = (qt < q && g_tail_blocks > 0 && g_tail_blocks < nb) ? nb - g_tail_blocks : nb;
+    int64_t k = 0;
+    while (k < nb) {
+      int w = k < tail0 ? q : qt;
+      if (k < tail0 && k + w > tail0) w = (int)(tail0 - k);
+      if (k + w > nb) w = (int)(nb - k);
+      pk.push_back(k);
+      pq.push_back(w);
+      k += w;
+    }
+  }
+  const int64_t np = (int64_t)pk.size();
+
   // factorization of outer panel P (inner blocks kb .. kb+q_eff-1) on stream st, packs -> set (P & 1)
   // rest_ready: event after which the rows below the panel's square are up to date (split panels)
   auto factor_panel = [&](int64_t P, cudaStream_t st, cudaEvent_t rest_ready) -> int {
-    const int64_t kb = P * q;
-    const int q_eff = (int)((nb - kb) < q ? (nb - kb) : q);
+    if (P >= np) return SCB_OK;
+    const int64_t kb = pk[P];
+    const int q_eff = pq[P];
     const int64_t panel_end = (kb + q_eff) * NB;
     double* Lpack = pack_base + (P & 1) * pack_set;
     double* Upack = Lpack + n_pad * NB * q;
@@ -1466,6 +1529,7 @@ static int getrf_impl(int64_t n_pad, double* M, double* dinv, int32_t* info, scb
       SCB_CUDA(cudaStreamWaitEvent(sr, e_in, 0));
       if (rest_ready) SCB_CUDA(cudaStreamWaitEvent(sr, rest_ready, 0));
       const int nt_below = (int)(nb - kb - q_eff);  // 128-row tiles below the outer panel
+      cudaEvent_t e_sq_prev = nullptr;  // look-ahead: the square's other columns have received inner panel i - 1
       for (int i = 0; i < q_eff; i++) {
         const int64_t k = kb + i;
         const int64_t o = k * NB;
@@ -1497,9 +1561,29 @@ static int getrf_impl(int64_t n_pad, double* M, double* dinv, int32_t* info, scb
           // Inside the square (the latency-critical chain): eager right-looking updates, K = 128 -- every
           // launch is short (4 k-chunks per CTA) and the next diagonal block is ready right after it.
           const int64_t r1 = (kb + i + 1) * NB;
-          update_kernel_t<true><<<dim3(2 * inner_rem, inner_rem), 256, upd_smem, st>>>(
-              M, n_pad, r1, r1, Lpack, Upack, tile_chunks, i * NCHUNK, NCHUNK);
-          SCB_LAUNCH_CHECK();
+          if (inner_la) {
+            // Block-level look-ahead: the chain updates only the block column it factors next (2 x inner_rem
+            // CTAs, so it never queues behind its own wide launches for SM slots held by bulk CTAs); the
+            // other columns of the square receive inner panel i on a third stream and are awaited one
+            // step later.  Per tile the inner panels are still applied in ascending order.
+            if (e_sq_prev) SCB_CUDA(cudaStreamWaitEvent(st, e_sq_prev, 0));
+            update_kernel_t<false><<<dim3(2, inner_rem), 256, upd_smem, st>>>(
+                M, n_pad, r1, r1, Lpack, Upack, tile_chunks, i * NCHUNK, NCHUNK, g_band);
+            SCB_LAUNCH_CHECK();
+            e_sq_prev = nullptr;
+            if (inner_rem > 1) {
+              SCB_CUDA(cudaStreamWaitEvent(sq, e_t, 0));
+              update_kernel_t<true><<<dim3(2 * (inner_rem - 1), inner_rem - 1), 256, upd_smem, sq>>>(
+                  M, n_pad, r1 + NB, r1 + NB, Lpack, Upack, tile_chunks, i * NCHUNK, NCHUNK, g_band);
+              SCB_LAUNCH_CHECK();
+              e_sq_prev = ls.event(ev++);
+              SCB_CUDA(cudaEventRecord(e_sq_prev, sq));
+            }
+          } else {
+            update_kernel_t<true><<<dim3(2 * inner_rem, inner_rem), 256, upd_smem, st>>>(
+                M, n_pad, r1, r1, Lpack, Upack, tile_chunks, i * NCHUNK, NCHUNK, g_band);
+            SCB_LAUNCH_CHECK();
+          }
           // Rows below the square (throughput work on the second stream): recursive (binary-tree)
           // schedule -- after inner block i the w = 2^tz(i+1) block columns that follow receive the last
           // w inner panels at once, so most of these flops run with K = 256 / 512.
@@ -1512,7 +1596,7 @@ static int getrf_impl(int64_t n_pad, double* M, double* dinv, int32_t* info, scb
             const int64_t r0 = (kb + c_lo) * NB;
             SCB_CUDA(cudaStreamWaitEvent(sr, e_t, 0));
             update_kernel_t<false><<<dim3(2 * ncb, nt_below), 256, upd_smem, sr>>>(
-                M, n_pad, panel_end, r0, Lpack, Upack, tile_chunks, k_lo * NCHUNK, w * NCHUNK);
+                M, n_pad, panel_end, r0, Lpack, Upack, tile_chunks, k_lo * NCHUNK, w * NCHUNK, g_band);
             SCB_LAUNCH_CHECK();
           }
         }
@@ -1532,11 +1616,11 @@ static int getrf_impl(int64_t n_pad, double* M, double* dinv, int32_t* info, scb
         // left-looking inside the outer panel: bring block column i and block row i up to date
         // with ALL previous inner panels at once (K = 128 i) right before they are factored
         dim3 gc(2, nt + 1);  // rows [o, n) x cols [o, o+128)
-        update_kernel_t<false><<<gc, 256, upd_smem, st>>>(M, n_pad, o, o, Lpack, Upack, tile_chunks, 0, i * NCHUNK);
+        update_kernel_t<false><<<gc, 256, upd_smem, st>>>(M, n_pad, o, o, Lpack, Upack, tile_chunks, 0, i * NCHUNK, g_band);
         SCB_LAUNCH_CHECK();
         if (nt > 0 && !sym) {  // (symmetric: the row panel is mirrored from the column panel)
           dim3 gr(2 * nt, 1);  // rows [o, o+128) x cols [o+128, n)
-          update_kernel_t<false><<<gr, 256, upd_smem, st>>>(M, n_pad, o, o + NB, Lpack, Upack, tile_chunks, 0, i * NCHUNK);
+          update_kernel_t<false><<<gr, 256, upd_smem, st>>>(M, n_pad, o, o + NB, Lpack, Upack, tile_chunks, 0, i * NCHUNK, g_band);
           SCB_LAUNCH_CHECK();
         }
       }
@@ -1572,16 +1656,16 @@ static int getrf_impl(int64_t n_pad, double* M, double* dinv, int32_t* info, scb
         dim3 ga(2 * ncb, nrt);
         if (sym)
           update_kernel_t<true><<<ga, 256, upd_smem, st>>>(M, n_pad, r0, r0, Lpack, Upack, tile_chunks, k_lo * NCHUNK,
-                                                           w * NCHUNK);
+                                                           w * NCHUNK, g_band);
         else
           update_kernel_t<false><<<ga, 256, upd_smem, st>>>(M, n_pad, r0, r0, Lpack, Upack, tile_chunks, k_lo * NCHUNK,
-                                                            w * NCHUNK);
+                                                            w * NCHUNK, g_band);
         SCB_LAUNCH_CHECK();
         const int ncright = nrt - ncb;                    // 128-column blocks right of the band
         if (ncright > 0 && !sym) {
           dim3 gb(2 * ncright, ncb);
           update_kernel_t<false><<<gb, 256, upd_smem, st>>>(M, n_pad, r0, r0 + (int64_t)ncb * NB, Lpack, Upack,
-                                                            tile_chunks, k_lo * NCHUNK, w * NCHUNK);
+                                                            tile_chunks, k_lo * NCHUNK, w * NCHUNK, g_band);
           SCB_LAUNCH_CHECK();
         }
       } else if (inner_rem > 0 && !g_lazy_strips) {
@@ -1589,16 +1673,16 @@ static int getrf_impl(int64_t n_pad, double* M, double* dinv, int32_t* info, scb
         dim3 ga(2 * inner_rem, nt);
         if (sym)  // (tiles above the block diagonal of the panel's own square are never read)
           update_kernel_t<true><<<ga, 256, upd_smem, st>>>(M, n_pad, o + NB, o + NB, Lpack, Upack, tile_chunks,
-                                                           i * NCHUNK, NCHUNK);
+                                                           i * NCHUNK, NCHUNK, g_band);
         else
           update_kernel_t<false><<<ga, 256, upd_smem, st>>>(M, n_pad, o + NB, o + NB, Lpack, Upack, tile_chunks,
-                                                            i * NCHUNK, NCHUNK);
+                                                            i * NCHUNK, NCHUNK, g_band);
         SCB_LAUNCH_CHECK();
         const int nright = nt - inner_rem;
         if (nright > 0 && !sym) {  // (symmetric: the row strip is never read)
           dim3 gb(2 * nright, inner_rem);
           update_kernel_t<false><<<gb, 256, upd_smem, st>>>(M, n_pad, o + NB, panel_end, Lpack, Upack, tile_chunks,
-                                                   i * NCHUNK, NCHUNK);
+                                                   i * NCHUNK, NCHUNK, g_band);
           SCB_LAUNCH_CHECK();
         }
       }
@@ -1617,7 +1701,6 @@ static int getrf_impl(int64_t n_pad, double* M, double* dinv, int32_t* info, scb
     cudaEventRecord(e, st);
     stamps.push_back({what, panel, e});
   };
-  const int64_t np = (nb + q - 1) / q;
   stamp("start", -1, s);
   if (lookahead) {
     cudaEvent_t e0 = ls.event(ev++);
@@ -1627,11 +1710,11 @@ static int getrf_impl(int64_t n_pad, double* M, double* dinv, int32_t* info, scb
   if (int rc = factor_panel(0, sp, nullptr)) return rc;
   stamp("chain_end", 0, sp);
   for (int64_t P = 0; P < np; P++) {
-    const int64_t kb = P * q;
-    const int q_eff = (int)((nb - kb) < q ? (nb - kb) : q);
+    const int64_t kb = pk[P];
+    const int q_eff = pq[P];
     const int64_t e0 = (kb + q_eff) * NB;  // first row/col after panel P
     if (e0 >= n_pad) break;
-    const int64_t e1 = (e0 + (int64_t)q * NB) < n_pad ? (e0 + (int64_t)q * NB) : n_pad;  // end of panel P+1
+    const int64_t e1 = e0 + (int64_t)pq[P + 1] * NB;  // end of panel P+1
     const double* Lpack = pack_base + (P & 1) * pack_set;
     const double* Upack = Lpack + n_pad * NB * q;
     const int nchunks = q_eff * NCHUNK;
@@ -1648,14 +1731,14 @@ static int getrf_impl(int64_t n_pad, double* M, double* dinv, int32_t* info, scb
       // chain) starts as soon as these 72 tiles are done and runs concurrently with the update of
       // the rows below the square, which only the second (rows-below) stream of the panel waits for
       update_kernel_t<true><<<dim3(2 * ntp, ntp), 256, upd_smem, s>>>(M, n_pad, e0, e0, Lpack, Upack, tile_chunks, 0,
-                                                                       nchunks);
+                                                                       nchunks, g_band);
       SCB_LAUNCH_CHECK();
       if (nt1 > 0) {
         cudaEvent_t e_sq = ls.event(ev++);
         SCB_CUDA(cudaEventRecord(e_sq, s));
         SCB_CUDA(cudaStreamWaitEvent(sp, e_sq, 0));
         update_kernel_t<false><<<dim3(2 * ntp, nt1), 256, upd_smem, s>>>(M, n_pad, e1, e0, Lpack, Upack, tile_chunks, 0,
-                                                                          nchunks);
+                                                                          nchunks, g_band);
         SCB_LAUNCH_CHECK();
         rest_ready = ls.event(ev++);
         SCB_CUDA(cudaEventRecord(rest_ready, s));
@@ -1663,16 +1746,16 @@ static int getrf_impl(int64_t n_pad, double* M, double* dinv, int32_t* info, scb
     } else if (sym) {
       // symmetric: one launch for the whole column strip of panel P+1 (its own square and everything below)
       dim3 g12(2 * ntp, nt0);
-      update_kernel_t<true><<<g12, 256, upd_smem, s>>>(M, n_pad, e0, e0, Lpack, Upack, tile_chunks, 0, nchunks);
+      update_kernel_t<true><<<g12, 256, upd_smem, s>>>(M, n_pad, e0, e0, Lpack, Upack, tile_chunks, 0, nchunks, g_band);
       SCB_LAUNCH_CHECK();
     } else {
       // rows of panel P+1: all columns to the right
       dim3 g1(2 * nt0, ntp);
-      update_kernel_t<false><<<g1, 256, upd_smem, s>>>(M, n_pad, e0, e0, Lpack, Upack, tile_chunks, 0, nchunks);
+      update_kernel_t<false><<<g1, 256, upd_smem, s>>>(M, n_pad, e0, e0, Lpack, Upack, tile_chunks, 0, nchunks, g_band);
       SCB_LAUNCH_CHECK();
       if (nt1 > 0) {
         dim3 g2(2 * ntp, nt1);
-        update_kernel_t<false><<<g2, 256, upd_smem, s>>>(M, n_pad, e1, e0, Lpack, Upack, tile_chunks, 0, nchunks);
+        update_kernel_t<false><<<g2, 256, upd_smem, s>>>(M, n_pad, e1, e0, Lpack, Upack, tile_chunks, 0, nchunks, g_band);
         SCB_LAUNCH_CHECK();
       }
     }
@@ -1688,10 +1771,10 @@ static int getrf_impl(int64_t n_pad, double* M, double* dinv, int32_t* info, scb
     if (nt1 > 0) {
       if (sym) {  // tiles on / below the diagonal only
         update_kernel_t<true><<<dim3(2 * nt1, nt1), 256, upd_smem, s>>>(M, n_pad, e1, e1, Lpack, Upack, tile_chunks, 0,
-                                                                         nchunks);
+                                                                         nchunks, g_band);
       } else {
         dim3 g3(2 * nt1, nt1);
-        update_kernel_t<false><<<g3, 256, upd_smem, s>>>(M, n_pad, e1, e1, Lpack, Upack, tile_chunks, 0, nchunks);
+        update_kernel_t<false><<<g3, 256, upd_smem, s>>>(M, n_pad, e1, e1, Lpack, Upack, tile_chunks, 0, nchunks, g_band);
       }
       SCB_LAUNCH_CHECK();
       stamp("bulk_end", P, s);
@@ -1782,7 +1865,7 @@ static int getrf_piv_impl(int64_t n_pad, double* M, double* dinv, int32_t* piv, 
     trsm_kernel<<<4 * nt, 256, trsm_smem, s>>>(M, n_pad, o, 2 * nt, invL, invU, Lpack, Upack, tile_chunks, 0);
     SCB_LAUNCH_CHECK();
     update_kernel_t<false><<<dim3(2 * nt, nt), 256, upd_smem, s>>>(M, n_pad, o + NB, o + NB, Lpack, Upack, tile_chunks,
-                                                                  0, NCHUNK);
+                                                                  0, NCHUNK, g_band);
     SCB_LAUNCH_CHECK();
   }
   return SCB_OK;

@@ -30,7 +30,8 @@ for rep in range(reps):
     torch.cuda.synchronize()
     outs.append(torch.tril(M) if os.environ.get("SCB_SYM_DEBUG") else M)
 nb = n_pad // 128
-tag = f"n={n} sym={sym} dbg={os.environ.get('SCB_SYM_DEBUG','0')} la={os.environ.get('SCB_LU_LOOKAHEAD','1')}"
+print("checksums (int64 sum of the bit patterns):", [int(o.view(torch.int64).sum().item()) for o in outs])
+tag = f"n={n} sym={sym} dbg={os.environ.get('SCB_SYM_DEBUG','0')} la={os.environ.get('SCB_LU_LOOKAHEAD','1')} band={os.environ.get('SCB_LU_BAND','16')}"
 for rep in range(1, reps):
     D = (outs[rep] - outs[0]).abs().view(nb, 128, nb, 128).amax(dim=(1, 3)).cpu().numpy()
     bad = np.argwhere(D > 0)
