@@ -295,6 +295,24 @@ def test_lu_bit_reproducible_on_identical_input(sc, symmetric):
     Lf[torch.arange(len(rows), device="cuda"), rows] = 1.0
     err = float((Lf @ torch.triu(first) - S[rows]).abs().max() / S.abs().max())
     assert err <= 1e-12, err
+    # the flag-driven substitution sweeps (1 / 8 / 64 right-hand sides) must reproduce themselves as well
+    dinv = torch.zeros(int(L.scb_getrf_dinv_bytes(n_pad)) // 8, dtype=torch.float64, device="cuda")
+    M = S.clone()
+    _lib.check(getrf(n_pad, _lib.ptr(M), _lib.ptr(dinv), _lib.ptr(flag), _lib.stream_ptr()))
+    g = torch.Generator(device="cuda").manual_seed(1)
+    for nrhs in (1, 8, 64):
+        B0 = torch.randn(n_pad, nrhs, dtype=torch.float64, device="cuda", generator=g)
+        outs = []
+        for rep in range(3):
+            B = B0.clone()
+            _lib.check(L.scb_getrs_nopiv(n_pad, _lib.ptr(M), _lib.ptr(dinv), nrhs, _lib.ptr(B), _lib.stream_ptr()))
+            torch.cuda.synchronize()
+            outs.append(B)
+        assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2]), f"getrs nrhs={nrhs} not reproducible"
+        # residual of the triangular solves against the factors: (L U) x = b
+        x = outs[0]
+        r = torch.tril(M, -1) @ (torch.triu(M) @ x) + torch.triu(M) @ x - B0
+        assert float(r.abs().max() / B0.abs().max()) <= 1e-9
 
 
 # ----------------------------------------------------------------------------------------
