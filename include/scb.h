@@ -107,6 +107,37 @@ int scb_mesh_smooth(int64_t n, const double* sites, const int32_t* adj_indptr, c
                     scb_stream_t stream);
 
 /* ------------------------------------------------------------------------------------
+ * Mesh generation (row f4): the reference calls meshpy / Triangle in device/utils.py:17-136
+ * (generate_mesh: points + boundary facets -> refined Delaunay mesh, refined until `min_points` /
+ * `max_edge_length` hold).  Here: quasi-uniform point cloud + Delaunay triangulation on the device.
+ * ------------------------------------------------------------------------------------ */
+
+/* inside[i] (uint8) <- even-odd rule of points[i] = (x, y) against `nrings` closed rings (ring r =
+ * ring_vertices[ring_ptr[r] .. ring_ptr[r + 1]), implicitly closed); outer boundary + holes of a region. */
+int scb_points_in_rings(int64_t m, const double* points, int nrings, const int64_t* ring_ptr,
+                        const double* ring_vertices, uint8_t* inside, scb_stream_t stream);
+
+/* Jittered hexagonal lattice: point (ix, iy), ix < nx, iy < ny, at
+ *   (x0 + (ix + (iy & 1) / 2) h, y0 + iy h sqrt(3) / 2) + jitter * h * U(-1, 1)^2
+ * (counter-based generator of (seed, point index): the same on every device and launch geometry).
+ * points <- f64[nx * ny, 2]; keep[i] (uint8) <- 1 iff the point lies in the region (even-odd over the
+ * rings) and farther than min_dist from every one of the `nfixed` fixed (polygon) points. */
+int scb_lattice_points(int64_t nx, int64_t ny, double x0, double y0, double h, double jitter, uint64_t seed,
+                       int nrings, const int64_t* ring_ptr, const double* ring_vertices, int64_t nfixed,
+                       const double* fixed, double min_dist, double* points, uint8_t* keep,
+                       scb_stream_t stream);
+
+/* Delaunay triangulation of n points in general position (what scipy.spatial.Delaunay / Triangle
+ * compute for the same points).  (x0, y0, cell, ncx, ncy): a uniform grid that covers the points
+ * (cell width of the order of the point spacing).  triangles <- int64[<= max_triangles, 3],
+ * counter-clockwise, smallest vertex first, ordered by that vertex and then counter-clockwise around
+ * it starting at its smallest neighbour: a deterministic function of the point array.
+ * info (device, int64[4]) <- { number of triangles found (may exceed max_triangles: call again),
+ *   points whose Voronoi cell overflowed, points whose triangle list overflowed, 0 }. */
+int scb_delaunay(int64_t n, const double* points, double x0, double y0, double cell, int32_t ncx, int32_t ncy,
+                 int64_t max_triangles, int64_t* triangles, int64_t* info, scb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
  * Kernel matrix pieces and system assembly  (K1-K3, K8-K10, K19, rows a1-a3, a9-a11)
  *   distance.py:87-115 q_matrix, device/mesh.py:434-458 Q_matrix,
  *   solver/utils.py:290-297 (dense casts, never materialised here),

@@ -8,7 +8,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import POINTER, Structure, c_char_p, c_double, c_int, c_int32, c_int64, c_uint8, c_void_p
+from ctypes import POINTER, Structure, c_char_p, c_double, c_int, c_int32, c_int64, c_uint8, c_uint64, c_void_p
 from typing import Optional
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -66,6 +66,11 @@ EXPORTS = {
     "scb_diag_issue_rate": (c_int, [c_int, c_int64, c_void_p, POINTER(c_double), c_void_p]),
     "scb_diag_scratch_elems": (c_int64, []),
     "scb_cdist": (c_int, [c_int, c_int, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
+    "scb_points_in_rings": (c_int, [c_int64, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "scb_lattice_points": (c_int, [c_int64, c_int64, c_double, c_double, c_double, c_double, c_uint64, c_int, c_void_p,
+                                   c_void_p, c_int64, c_void_p, c_double, c_void_p, c_void_p, c_void_p]),
+    "scb_delaunay": (c_int, [c_int64, c_void_p, c_double, c_double, c_double, c_int32, c_int32, c_int64, c_void_p,
+                             c_void_p, c_void_p]),
 }
 
 

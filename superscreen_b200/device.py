@@ -168,6 +168,17 @@ class Polygon:
             return np.where(mask)[0]
         return mask
 
+    def make_mesh(self, min_points: Optional[int] = None, max_edge_length: Optional[float] = None,
+                  convex_hull: bool = False, smooth: int = 0, build_operators: bool = False, **meshpy_kwargs):
+        """Creates a :class:`Mesh` for the polygon on the GPU (reference device/polygon.py:192-224)."""
+        from . import meshgen
+        from .mesh import Mesh as _Mesh
+
+        points, triangles = meshgen.generate_mesh(self.points, min_points=min_points, max_edge_length=max_edge_length,
+                                                  convex_hull=convex_hull, **meshpy_kwargs)
+        mesh = _Mesh.from_triangulation(points, triangles, build_operators=build_operators and not smooth)
+        return mesh.smooth(smooth, build_operators=build_operators) if smooth else mesh
+
     def copy(self) -> "Polygon":
         # the stored points are already closed and counter-clockwise: skip the constructor's normalisation
         new = object.__new__(Polygon)
@@ -404,12 +415,73 @@ class Device:
             out[name] = m if isinstance(m, Mesh) else Mesh.from_triangulation(*m)
         self.meshes = out
 
-    def make_mesh(self, target_vertices: Union[int, Dict[str, int]] = 2000, buffer_factor: float = 0.05,
-                  seed: int = 0, smooth: int = 0) -> None:
-        """Synthetic stand-in for ``Device.make_mesh`` (reference device/device.py:383-471): meshes
-        the bounding disk/box of each film (convex outlines only) with ``synthetic.make_mesh``;
-        ``smooth`` Laplacian-smoothing sweeps are applied on the device like the reference's
-        ``smooth`` argument (device/device.py:463-467 -> Mesh.smooth)."""
+    def make_mesh(self, buffer_factor: Union[float, Dict[str, float], None] = 0.05,
+                  buffer: Union[float, Dict[str, float], None] = None, join_style: str = "mitre",
+                  min_points: Union[int, Dict[str, int], None] = None,
+                  max_edge_length: Union[float, Dict[str, float], None] = None, preserve_boundary: bool = False,
+                  smooth: Union[int, Dict[str, int]] = 0, *, target_vertices: Union[int, Dict[str, int], None] = None,
+                  seed: int = 0, **meshpy_kwargs) -> None:
+        """Generates the triangular mesh of every film (reference device/device.py:383-471; same
+        arguments).  Runs on the GPU (``meshgen.generate_mesh``: point cloud + Delaunay triangulation on
+        the device, refined until ``min_points`` / ``max_edge_length`` hold).  As in the reference, the
+        mesh of a film covers the film polygon plus a buffer region (``buffer`` in length units, or
+        ``buffer_factor`` times the largest film dimension) unless the film has terminals or the buffer is
+        0; the polygons of the holes / abstract regions inside the film become mesh vertices.  The buffered
+        boundary is the convex hull of the film offset outward with mitre joins (the reference buffers the
+        polygon itself with shapely, rounded joins -- the vacuum region differs, the film does not).
+        ``smooth``: Laplacian-smoothing sweeps on the device (device/device.py:463-467 -> Mesh.smooth).
+
+        ``target_vertices=...`` selects the host-side synthetic generator of the benchmark
+        configurations instead (``synthetic.make_mesh``: scipy Delaunay, convex outlines only; runs
+        without a GPU)."""
+        if target_vertices is not None:
+            return self._make_mesh_synthetic(target_vertices, buffer_factor if buffer_factor is not None else 0.0,
+                                             seed, smooth if not isinstance(smooth, dict) else 0)
+        from . import meshgen
+
+        films = self.films
+
+        def per_film(v):
+            return v if isinstance(v, dict) else {name: v for name in films}
+
+        buffer_factor, buffer, min_points = per_film(buffer_factor), per_film(buffer), per_film(min_points)
+        max_edge_length, smooth = per_film(max_edge_length), per_film(smooth)
+        holes_by_layer = self.polygons_by_layer("hole")
+        abs_by_layer = self.polygons_by_layer("abstract")
+        meshes = {}
+        for k, (name, film) in enumerate(films.items()):
+            film_terminals = self.terminals.get(name)
+            film_ring = film.points[:-1]
+            coords, embedded = [film_ring], []
+            for poly in holes_by_layer.get(film.layer, []) + abs_by_layer.get(film.layer, []):
+                if film.contains_points(poly.points).all():
+                    coords.append(poly.points[:-1])
+                    embedded.append(poly.points[:-1])
+            if film_terminals or buffer.get(name) == 0 or (buffer_factor.get(name) is None and buffer.get(name) is None) \
+                    or (buffer.get(name) is None and buffer_factor.get(name) == 0):
+                boundary = film_ring
+            else:
+                size = buffer[name] if buffer.get(name) is not None else buffer_factor[name] * max(film.extents)
+                hull = meshgen.convex_hull_ring(film_ring)
+                boundary = meshgen.offset_convex_ring(hull, float(size))
+                # (reference: Polygon(points=buffered).resample(len(film.points)))
+                per = np.linalg.norm(np.roll(boundary, -1, axis=0) - boundary, axis=1).sum()
+                boundary = meshgen._resample_ring(boundary, per / max(len(film_ring), 8))
+                coords.append(boundary)
+                embedded.append(film_ring)
+            points, triangles = meshgen.generate_mesh(
+                meshgen.ensure_unique(np.concatenate(coords, axis=0)), min_points=min_points.get(name),
+                max_edge_length=max_edge_length.get(name), boundary=boundary, convex_hull=False,
+                preserve_boundary=preserve_boundary or bool(film_terminals), seed=seed + k, embedded=embedded,
+                **meshpy_kwargs)
+            mesh = Mesh.from_triangulation(points, triangles, build_operators=not smooth.get(name))
+            meshes[name] = mesh.smooth(smooth[name]) if smooth.get(name) else mesh
+        self.meshes = meshes
+
+    def _make_mesh_synthetic(self, target_vertices: Union[int, Dict[str, int]], buffer_factor: float, seed: int,
+                             smooth: int) -> None:
+        """Host-side generator of the benchmark / parity configurations: meshes the (scaled) convex outline
+        of each film with ``synthetic.make_mesh`` (jittered lattice + scipy Delaunay)."""
         from .synthetic import make_mesh
 
         holes_by_film = self.holes_by_film()

@@ -232,3 +232,33 @@ def test_c_abi_argument_errors_without_gpu():
     assert rc < 0 and b"sizes" in lib.scb_last_error()
     with pytest.raises(_lib.SCBError):
         _lib.check(rc)
+
+
+def test_meshgen_host_geometry_helpers():
+    """Host-side pieces of the device mesh generator (no GPU): hull, mitre offset, ring resampling,
+    duplicate removal, boundary conformity check; the generator itself refuses to run without a GPU."""
+    from superscreen_b200 import _lib, meshgen
+    from superscreen_b200.geometry import signed_area
+
+    ell = np.array([[0, 0], [6, 0], [6, 2], [2, 2], [2, 5], [0, 5]], dtype=float)
+    hull = meshgen.convex_hull_ring(ell)
+    assert signed_area(hull) > 0 and len(hull) == 5 and {tuple(p) for p in hull} == {(0, 0), (6, 0), (6, 2), (2, 5), (0, 5)}
+    sq = np.array([[0, 0], [2, 0], [2, 1], [0, 1]], dtype=float)
+    off = meshgen.offset_convex_ring(sq, 0.5)
+    assert np.allclose(sorted(map(tuple, off)), sorted([(-0.5, -0.5), (2.5, -0.5), (2.5, 1.5), (-0.5, 1.5)]))
+    res = meshgen._resample_ring(sq, 0.5)
+    assert len(res) == 12 and {tuple(p) for p in sq} <= {tuple(p) for p in res}
+    assert np.allclose(np.linalg.norm(np.roll(res, -1, axis=0) - res, axis=1), 0.5)
+    dup = np.array([[0, 0], [1, 0], [0, 0], [1, 1], [1, 0]], dtype=float)
+    assert np.array_equal(meshgen.ensure_unique(dup), np.array([[0, 0], [1, 0], [1, 1]], dtype=float))
+    # two triangles tiling the unit square: conforming to the square, not to a bigger one
+    pts = np.array([[0, 0], [1, 0], [1, 1], [0, 1]], dtype=float)
+    tri = np.array([[0, 1, 2], [0, 2, 3]])
+    assert meshgen.boundary_is_conforming(pts, tri, [pts])
+    assert not meshgen.boundary_is_conforming(pts, tri, [2 * pts])
+    assert abs(meshgen.min_triangle_angle(pts, tri) - 45.0) < 1e-9
+    import torch
+
+    if not torch.cuda.is_available():
+        with pytest.raises(_lib.SCBError):
+            meshgen.generate_mesh(ell, min_points=100)
