@@ -246,15 +246,25 @@ trsm_sweep_dmma_kernel(const double* __restrict__ F, int64_t ld, const double* _
           const int c = ct * 8 + 2 * t + e;
           acc[rt][ct][e] = c < nr ? B[(i * NB + warp * 16 + rt * 8 + g) * nrhs + c0 + c] : 0.0;
         }
-    for (int q = 0; q < p; q++) {
-      const int64_t j = lower ? q : nb - 1 - q;
-      double a[2][NB / 4];
+    // The A fragments of a factor tile are fetched in two halves (k < 64, k >= 64) that are software
+    // pipelined across tiles: while one half feeds the tensor cores the other one is in flight, so the
+    // global-memory latency of a tile (the CTA is alone on its SM) hides behind the previous tile's DMMAs
+    // and the wait for x_j instead of preceding every tile.
+    constexpr int HK = NB / 8;  // k4 steps per half
+    double aA[2][HK], aB[2][HK];
+    const double* Frow0 = F + (i * NB + warp * 16 + g) * ld + t;  // row of rt = 0; rt = 1: + 8 ld
+    auto load_half = [&](double (&dst)[2][HK], int64_t jt, int half) {
 #pragma unroll
       for (int rt = 0; rt < 2; rt++) {
-        const double* Frow = F + (i * NB + warp * 16 + rt * 8 + g) * ld + j * NB + t;
+        const double* Fr = Frow0 + (int64_t)rt * 8 * ld + jt * NB + half * (NB / 2);
 #pragma unroll
-        for (int ks = 0; ks < NB / 4; ks++) a[rt][ks] = Frow[ks * 4];
+        for (int ks = 0; ks < HK; ks++) dst[rt][ks] = Fr[ks * 4];
       }
+    };
+    if (p > 0) load_half(aA, lower ? 0 : nb - 1, 0);
+    for (int q = 0; q < p; q++) {
+      const int64_t j = lower ? q : nb - 1 - q;
+      load_half(aB, j, 1);
       if (q + 1 < p) prefetch_tile_l2(F + i * NB * ld + (lower ? q + 1 : nb - 2 - q) * NB, ldb, warp, lane);
       if (PACKETS) {
         wait_block(cflags + j);
@@ -290,12 +300,22 @@ trsm_sweep_dmma_kernel(const double* __restrict__ F, int64_t ld, const double* _
       }
       __syncthreads();
 #pragma unroll
-      for (int ks = 0; ks < NB / 4; ks++) {
+      for (int ks = 0; ks < HK; ks++) {
 #pragma unroll
         for (int ct = 0; ct < CT; ct++) {
           const double b = xs[(ks * 4 + t) * XP + ct * 8 + g];
-          dmma_rhs(acc[0][ct][0], acc[0][ct][1], -a[0][ks], b);
-          dmma_rhs(acc[1][ct][0], acc[1][ct][1], -a[1][ks], b);
+          dmma_rhs(acc[0][ct][0], acc[0][ct][1], -aA[0][ks], b);
+          dmma_rhs(acc[1][ct][0], acc[1][ct][1], -aA[1][ks], b);
+        }
+      }
+      if (q + 1 < p) load_half(aA, lower ? q + 1 : nb - 2 - q, 0);  // first half of the next tile
+#pragma unroll
+      for (int ks = 0; ks < HK; ks++) {
+#pragma unroll
+        for (int ct = 0; ct < CT; ct++) {
+          const double b = xs[((HK + ks) * 4 + t) * XP + ct * 8 + g];
+          dmma_rhs(acc[0][ct][0], acc[0][ct][1], -aB[0][ks], b);
+          dmma_rhs(acc[1][ct][0], acc[1][ct][1], -aB[1][ks], b);
         }
       }
       __syncthreads();  // xs is rewritten for the next tile

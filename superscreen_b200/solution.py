@@ -197,7 +197,13 @@ def _normalize_positions(positions, zs, dtype):
             zs = zs.item() * np.ones(positions.shape[0], dtype=dtype)
     if not isinstance(zs, np.ndarray):
         raise ValueError(f"Expected zs to be an ndarray, but got {type(zs)}.")
-    return np.ascontiguousarray(positions, dtype=np.float64), np.ascontiguousarray(zs, dtype=np.float64)
+    # (views where possible: a million-point grid is not copied just to be split into columns)
+    return np.asarray(positions, dtype=np.float64), np.asarray(zs, dtype=np.float64)
+
+
+# targets per pipelined chunk of a field evaluation: one full wave of the pair-sum kernel (148 SMs x 6 resident
+# CTAs x 512 targets); smaller launches would split their sources and pay a reduction pass
+_EVAL_CHUNK = 148 * 6 * 512
 
 
 def biot_savart_2d(x, y, z, *, positions, current_densities, z0: float = 0, areas=None, length_units: str = "um",
@@ -216,11 +222,7 @@ def biot_savart_2d(x, y, z, *, positions, current_densities, z0: float = 0, area
     to_amp_per_meter = _u.conversion_factor(f"({current_units}) / ({length_units})", "A / m")
     x, y, z = np.atleast_1d(x, y, z)
     dev = torch.device(f"cuda:{torch.cuda.current_device()}")
-    ev = np.empty((len(x), 3), dtype=np.float64)  # filled column by column: no (3, m) temporary + transpose
-    np.multiply(x, to_meter, out=ev[:, 0])
-    np.multiply(y, to_meter, out=ev[:, 1])
-    np.multiply(z, to_meter, out=ev[:, 2])  # (a length-1 z broadcasts)
-    m = len(ev)
+    m = len(x)
     with torch.cuda.device(dev):
         src_key = ("sources", str(dev))
         src = None if device_tensors is None else device_tensors.get(src_key)
@@ -236,15 +238,33 @@ def biot_savart_2d(x, y, z, *, positions, current_densities, z0: float = 0, area
                 device_tensors[src_key] = src
         pos_d, ar_d, J_d = src
         n = int(pos_d.shape[0])
-        # keep the uploads referenced until the result has been read back (stream-ordered use)
-        ev_d = torch.as_tensor(ev).to(dev)
-        out = torch.empty((m, 3) if vector else (m,), dtype=torch.float64, device=dev)
-        _lib.check(L.scb_biot_savart(2 if vector else 1, m, _lib.ptr(ev_d), n, _lib.ptr(pos_d), _lib.ptr(ar_d),
-                                     _lib.ptr(J_d), 0.0, _MU0_BIOT_SAVART / (4 * np.pi), 1, _lib.ptr(out),
-                                     _lib.stream_ptr()))
-        from .solver.solve import _to_host
-
-        return _to_host(out)
+        if m == 0:
+            return np.empty((0, 3) if vector else (0,), dtype=np.float64)
+        # Targets go through PINNED staging in chunks: the host scales chunk k + 1 into its staging block
+        # (column by column: no (3, m) temporary) while the GPU evaluates chunk k, and every chunk's result
+        # is copied back behind its kernel -- one synchronisation at the end, the host preparation and the
+        # transfers of a million-point grid disappear behind the pair sums.
+        chunk = m if m <= _EVAL_CHUNK else _EVAL_CHUNK
+        ev_pin = torch.empty((m, 3), dtype=torch.float64, pin_memory=True)
+        out_pin = torch.empty((m, 3) if vector else (m,), dtype=torch.float64, pin_memory=True)
+        ev = ev_pin.numpy()
+        zb = np.broadcast_to(z, (m,))  # (a length-1 z broadcasts)
+        stream = torch.cuda.current_stream(dev)
+        keep = []  # device blocks stay referenced until the final synchronisation (stream-ordered use)
+        for lo in range(0, m, chunk):
+            hi = min(m, lo + chunk)
+            np.multiply(x[lo:hi], to_meter, out=ev[lo:hi, 0])
+            np.multiply(y[lo:hi], to_meter, out=ev[lo:hi, 1])
+            np.multiply(zb[lo:hi], to_meter, out=ev[lo:hi, 2])
+            ev_d = ev_pin[lo:hi].to(dev, non_blocking=True)
+            out_d = torch.empty((hi - lo, 3) if vector else (hi - lo,), dtype=torch.float64, device=dev)
+            _lib.check(L.scb_biot_savart(2 if vector else 1, hi - lo, _lib.ptr(ev_d), n, _lib.ptr(pos_d), _lib.ptr(ar_d),
+                                         _lib.ptr(J_d), 0.0, _MU0_BIOT_SAVART / (4 * np.pi), 1, _lib.ptr(out_d),
+                                         _lib.stream_ptr()))
+            out_pin[lo:hi].copy_(out_d, non_blocking=True)
+            keep.append((ev_d, out_d))
+        stream.synchronize()
+        return out_pin.numpy()
 
 
 class _FluxoidGeometry(NamedTuple):
