@@ -151,6 +151,18 @@ def launch_count() -> int:
 
 
 _NVTX = os.environ.get("SCB_NVTX", "0") not in ("", "0")
+# SCB_HOST_TIMING=1: host wall time per range name (no device synchronisation: enqueue cost, not kernel time)
+_HOST_TIMING = os.environ.get("SCB_HOST_TIMING", "0") not in ("", "0")
+host_times: dict = {}
+
+
+def host_timing_report(reset: bool = True) -> str:
+    """Table of the accumulated host times of the ``nvtx_range`` sections (``SCB_HOST_TIMING=1``)."""
+    lines = [f"{name:<44s} {n:6d} x {1e3 * t / max(n, 1):9.3f} ms = {1e3 * t:9.3f} ms"
+             for name, (n, t) in sorted(host_times.items(), key=lambda kv: -kv[1][1])]
+    if reset:
+        host_times.clear()
+    return "\n".join(lines)
 
 
 class nvtx_range:
@@ -165,9 +177,19 @@ class nvtx_range:
             import torch
 
             torch.cuda.nvtx.range_push(self.name)
+        if _HOST_TIMING:
+            import time
+
+            self._t0 = time.perf_counter()
         return self
 
     def __exit__(self, *exc):
+        if _HOST_TIMING:
+            import time
+
+            key = self.name.split("[")[0]
+            n, t = host_times.get(key, (0, 0.0))
+            host_times[key] = (n + 1, t + time.perf_counter() - self._t0)
         if _NVTX:
             import torch
 

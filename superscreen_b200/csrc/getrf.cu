@@ -1876,11 +1876,166 @@ extern "C" int scb_getrf_piv(int64_t n_pad, double* M, double* dinv, int32_t* pi
   return getrf_piv_impl(n_pad, M, dinv, piv, perm, info, stream);
 }
 
+// ---------------------------------------------------------------------------------------
+// CUDA-graph replay of a factorization.  The launch sequence of getrf_impl (hundreds of small kernels,
+// event records and waits over two or three streams) depends only on (n_pad, sym) and its pointer
+// arguments.  A small film factors in a few milliseconds of latency-bound kernels, and enqueueing that
+// sequence costs the host about as long as the GPU needs to run it -- several independent films of one
+// model (C3 / C4: one stream per film) then start one after the other instead of together.  The second
+// time a (n_pad, M, dinv, info, sym) combination is seen (the caching allocator of the host side hands
+// the same blocks back in a steady-state loop) the sequence is captured once into a graph and replayed
+// from then on with a single cudaGraphLaunch; the fork / join structure over the helper streams
+// becomes the branches of the graph.  Identical kernels, identical arguments: bit-identical factors.
+// SCB_LU_GRAPH=0 disables it; SCB_LU_GRAPH_MAX_N (default 12288) bounds the matrix size -- large
+// factorizations are not latency-bound and rely on stream priorities for their look-ahead.
+// ---------------------------------------------------------------------------------------
+namespace {
+struct LuGraphKey {
+  int dev;
+  int64_t n_pad;
+  double* M;
+  double* dinv;
+  int32_t* info;
+  bool sym;
+  bool operator<(const LuGraphKey& o) const {
+    if (dev != o.dev) return dev < o.dev;
+    if (n_pad != o.n_pad) return n_pad < o.n_pad;
+    if (M != o.M) return M < o.M;
+    if (dinv != o.dinv) return dinv < o.dinv;
+    if (info != o.info) return info < o.info;
+    return sym < o.sym;
+  }
+};
+struct LuGraphEntry {
+  cudaGraphExec_t exec = nullptr;
+  int sightings = 0;
+  int nodes = 0;  // kernel launches inside the graph (for scb_launch_count)
+  uint64_t last_use = 0;
+};
+std::map<LuGraphKey, LuGraphEntry> g_lu_graphs;
+std::mutex g_lu_graphs_mutex;
+int g_lu_graph_enabled = -1;
+int64_t g_lu_graph_max_n = 12288;
+constexpr size_t kMaxLuGraphs = 96;
+
+uint64_t g_lu_graph_clock = 0;
+
+// table full: forget the keys that were seen once and never again; if every entry holds a graph, drop
+// the least recently used one
+void lu_graphs_evict_locked() {
+  bool dropped = false;
+  for (auto it = g_lu_graphs.begin(); it != g_lu_graphs.end();) {
+    if (!it->second.exec) {
+      it = g_lu_graphs.erase(it);
+      dropped = true;
+    } else {
+      ++it;
+    }
+  }
+  if (dropped || g_lu_graphs.empty()) return;
+  auto lru = g_lu_graphs.begin();
+  for (auto it = g_lu_graphs.begin(); it != g_lu_graphs.end(); ++it)
+    if (it->second.last_use < lru->second.last_use) lru = it;
+  cudaGraphExecDestroy(lru->second.exec);
+  g_lu_graphs.erase(lru);
+}
+}  // namespace
+
+static int getrf_graphed(int64_t n_pad, double* M, double* dinv, int32_t* info, scb_stream_t stream, bool sym) {
+  if (g_lu_graph_enabled < 0) {
+    int en = 1;
+    if (const char* e = getenv("SCB_LU_GRAPH")) en = atoi(e);
+    if (getenv("SCB_LU_TRACE")) en = 0;
+    if (const char* e = getenv("SCB_LU_GRAPH_MAX_N")) g_lu_graph_max_n = atoll(e);
+    g_lu_graph_enabled = en;
+  }
+  if (!g_lu_graph_enabled || n_pad > g_lu_graph_max_n || n_pad <= 0 || n_pad % NB != 0)
+    return getrf_impl(n_pad, M, dinv, info, stream, sym);
+  cudaStream_t s = (cudaStream_t)stream;
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(s, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone) {
+    cudaGetLastError();
+    return getrf_impl(n_pad, M, dinv, info, stream, sym);  // the caller is capturing: just take part in it
+  }
+  int dev = 0;
+  SCB_CUDA(cudaGetDevice(&dev));
+  const LuGraphKey key{dev, n_pad, M, dinv, info, sym};
+  cudaGraphExec_t exec = nullptr;
+  int nodes = 0;
+  bool capture = false;
+  {
+    std::lock_guard<std::mutex> lock(g_lu_graphs_mutex);
+    if (g_lu_graphs.size() >= kMaxLuGraphs && g_lu_graphs.find(key) == g_lu_graphs.end()) lu_graphs_evict_locked();
+    LuGraphEntry& e = g_lu_graphs[key];
+    e.sightings++;
+    e.last_use = ++g_lu_graph_clock;
+    exec = e.exec;
+    nodes = e.nodes;
+    capture = exec == nullptr && e.sightings >= 2;
+  }
+  if (exec) {
+    SCB_CUDA(cudaGraphLaunch(exec, s));
+    scb::count_launch(nodes);
+    return SCB_OK;
+  }
+  if (!capture) return getrf_impl(n_pad, M, dinv, info, stream, sym);
+  // Capture the sequence (nothing runs), instantiate, launch.  The capture runs on a stream of the
+  // library's own (one per device, under a lock): the caller's stream may be the legacy default stream,
+  // which cannot be captured, and is never put into capture mode.
+  static std::mutex capture_mutex;
+  static cudaStream_t capture_streams[64] = {};
+  std::lock_guard<std::mutex> capture_lock(capture_mutex);
+  cudaStream_t& cs = capture_streams[dev & 63];
+  if (cs == nullptr && cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking) != cudaSuccess) {
+    cudaGetLastError();
+    cs = nullptr;
+    return getrf_impl(n_pad, M, dinv, info, stream, sym);
+  }
+  const int64_t before = scb_launch_count();
+  if (cudaStreamBeginCapture(cs, cudaStreamCaptureModeRelaxed) != cudaSuccess) {
+    cudaGetLastError();
+    return getrf_impl(n_pad, M, dinv, info, stream, sym);
+  }
+  const int rc = getrf_impl(n_pad, M, dinv, info, (scb_stream_t)cs, sym);
+  cudaGraph_t graph = nullptr;
+  const cudaError_t ce = cudaStreamEndCapture(cs, &graph);
+  const int captured = (int)(scb_launch_count() - before);
+  scb::count_launch(-captured);  // nothing was launched yet
+  if (rc != SCB_OK || ce != cudaSuccess || graph == nullptr) {
+    cudaGetLastError();
+    if (graph) cudaGraphDestroy(graph);
+    g_lu_graph_enabled = 0;  // do not try again in this process
+    return getrf_impl(n_pad, M, dinv, info, stream, sym);
+  }
+  cudaGraphExec_t new_exec = nullptr;
+  const cudaError_t ie = cudaGraphInstantiate(&new_exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (ie != cudaSuccess || new_exec == nullptr) {
+    cudaGetLastError();
+    g_lu_graph_enabled = 0;
+    return getrf_impl(n_pad, M, dinv, info, stream, sym);
+  }
+  {
+    std::lock_guard<std::mutex> lock(g_lu_graphs_mutex);
+    LuGraphEntry& e = g_lu_graphs[key];
+    if (e.exec) {  // (another thread was faster)
+      cudaGraphExecDestroy(new_exec);
+      new_exec = e.exec;
+    } else {
+      e.exec = new_exec;
+      e.nodes = captured;
+    }
+  }
+  SCB_CUDA(cudaGraphLaunch(new_exec, s));
+  scb::count_launch(captured);
+  return SCB_OK;
+}
+
 extern "C" int scb_getrf_nopiv(int64_t n_pad, double* M, double* dinv, int32_t* info, scb_stream_t stream) {
-  return getrf_impl(n_pad, M, dinv, info, stream, false);
+  return getrf_graphed(n_pad, M, dinv, info, stream, false);
 }
 
 extern "C" int scb_getrf_sym_nopiv(int64_t n_pad, double* M, double* dinv, int32_t* info,
                                    scb_stream_t stream) {
-  return getrf_impl(n_pad, M, dinv, info, stream, true);
+  return getrf_graphed(n_pad, M, dinv, info, stream, true);
 }

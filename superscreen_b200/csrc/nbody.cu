@@ -228,21 +228,33 @@ __global__ void __launch_bounds__(256) nbody_kernel(NbodyParams p) {
   }
 }
 
-// adds the per-split partial sums of a target in split order and stores the final value(s)
+// adds the per-split partial sums of a target in split order and stores the final value(s).
+// A group of NACC consecutive lanes owns one target (lane a of the group adds accumulator a over the
+// splits: coalesced reads, NACC times more loads in flight than one thread per target), the group's
+// totals meet in the lane that stores them through one shared-memory row per target.
 template <int KIND, int NR>
-__global__ void nbody_reduce_kernel(NbodyParams p, int nsplit) {
+__global__ void __launch_bounds__(128) nbody_reduce_kernel(NbodyParams p, int nsplit) {
   constexpr int NACC = Traits<KIND, NR>::nacc;
-  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (i >= p.m) return;
-  double acc[NACC];
-#pragma unroll
-  for (int a = 0; a < NACC; a++) acc[a] = 0.0;
-  for (int y = 0; y < nsplit; y++) {
-    const double* o = p.partial + ((int64_t)y * p.m + i) * NACC;
-#pragma unroll
-    for (int a = 0; a < NACC; a++) acc[a] += o[a];
+  constexpr int TPB = 128 / NACC;  // targets per CTA (NACC in {1, 2, 4, 8, 16})
+  static_assert(128 % NACC == 0, "accumulator count must divide the CTA size");
+  __shared__ double tot[TPB][NACC + 1];
+  const int a = threadIdx.x % NACC, t = threadIdx.x / NACC;
+  const int64_t i = blockIdx.x * (int64_t)TPB + t;
+  if (i < p.m) {
+    const double* o = p.partial + i * NACC + a;
+    const int64_t stride = p.m * NACC;
+    double s0 = 0.0;
+#pragma unroll 8
+    for (int y = 0; y < nsplit; y++) s0 += o[y * stride];  // split order: same sum as before
+    tot[t][a] = s0;
   }
-  nbody_store<KIND, NR>(p, i, acc);
+  __syncthreads();
+  if (i < p.m && a == 0) {
+    double acc[NACC];
+#pragma unroll
+    for (int q = 0; q < NACC; q++) acc[q] = tot[t][q];
+    nbody_store<KIND, NR>(p, i, acc);
+  }
 }
 
 static bool g_pool_set[64] = {};
@@ -285,7 +297,7 @@ static int launch_nbody(NbodyParams p, cudaStream_t s) {
   nbody_kernel<KIND, NR><<<dim3((unsigned)ctas_x, (unsigned)split), 256, 0, s>>>(p);
   SCB_LAUNCH_CHECK();
   if (split > 1) {
-    nbody_reduce_kernel<KIND, NR><<<(unsigned)ceil_div(p.m, 128), 128, 0, s>>>(p, (int)split);
+    nbody_reduce_kernel<KIND, NR><<<(unsigned)ceil_div(p.m, 128 / NACC), 128, 0, s>>>(p, (int)split);
     SCB_LAUNCH_CHECK();
     SCB_CUDA(cudaFreeAsync(p.partial, s));
   }

@@ -370,10 +370,17 @@ class Device:
         return {name: mesh.stats() for name, mesh in self.meshes.items()}
 
     def holes_by_film(self) -> Dict[str, List[Polygon]]:
+        # memoised on the geometry (F x H point-in-polygon tests; asked for several times per solve)
+        key = (tuple((f.name, f.layer, f.points.tobytes()) for f in self.films.values()),
+               tuple((h.name, h.layer, h.points.tobytes()) for h in self.holes.values()))
+        hit = self.__dict__.get("_holes_by_film_cache")
+        if hit is not None and hit[0] == key:
+            return {film: [self.holes[h] for h in names] for film, names in hit[1].items()}
         by_layer = self.polygons_by_layer("hole")
         out = {}
         for film in self.films.values():
             out[film.name] = [h for h in by_layer[film.layer] if film.contains_points(h.points).all()]
+        self.__dict__["_holes_by_film_cache"] = (key, {film: [h.name for h in hs] for film, hs in out.items()})
         return out
 
     def copy(self, with_mesh: bool = True, copy_mesh: bool = False) -> "Device":
@@ -519,13 +526,25 @@ class Device:
         given explicitly."""
         from .solver import factorize_model, solve_batch
 
+        from . import _lib
+
         holes = self.holes
         hole_names = list(holes)
-        for hole_name, polygon in hole_polygon_mapping.items():
-            if hole_name not in holes:
-                raise ValueError(f"Hole '{hole_name}' does not exist in the device.")
-            if not points_in_polygon(polygon, holes[hole_name].points).all():
-                raise ValueError(f"Hole '{hole_name}' is not completely contained within the given polygon.")
+        with _lib.nvtx_range("scb.mim.validate"):
+            # (the containment test of a given (polygon, hole) pair is remembered: the matrix is usually
+            #  evaluated many times for one device -- parameter sweeps, the iterates of a fluxoid solve)
+            checked = self.__dict__.setdefault("_mim_checked", {})
+            for hole_name, polygon in hole_polygon_mapping.items():
+                if hole_name not in holes:
+                    raise ValueError(f"Hole '{hole_name}' does not exist in the device.")
+                key = (hole_name, np.asarray(polygon, dtype=float).tobytes(), holes[hole_name].points.tobytes())
+                ok = checked.get(key)
+                if ok is None:
+                    if len(checked) > 256:
+                        checked.clear()
+                    ok = checked[key] = bool(points_in_polygon(polygon, holes[hole_name].points).all())
+                if not ok:
+                    raise ValueError(f"Hole '{hole_name}' is not completely contained within the given polygon.")
         n_holes = len(hole_polygon_mapping)
         iterations = solve_kwargs.get("iterations", 1)
         I_circ_A = _u.to_quantity("1 mA", "A").to("A").magnitude
@@ -537,26 +556,29 @@ class Device:
             sl = slice(-1, None)
         M = np.zeros((n_iter, n_holes, n_holes))
         films_by_hole = {h.name: film for film, hs in self.holes_by_film().items() for h in hs}
-        model = factorize_model(device=self, current_units="mA", comm=comm)
+        with _lib.nvtx_range("scb.mim.factorize_model"):
+            model = factorize_model(device=self, current_units="mA", comm=comm)
         # Multi-rank: every rank keeps only its own films' solutions (no replication of the results),
         # evaluates the fluxoid rows of the holes in those films, and the small matrix is summed over
         # the ranks -- M[i, j] only needs film(i)'s solution for the driven hole j.
         sharded = comm is not None and comm.world > 1
-        batch = solve_batch(
-            model=model, applied_fields=[solve_kwargs.get("applied_field")] * len(hole_names),
-            circulating_currents=[{name: 1.0} for name in hole_names],
-            field_units=solve_kwargs.get("field_units", "mT"), iterations=solve_kwargs.get("iterations", 0),
-            check_inversion=solve_kwargs.get("check_inversion", False), last_only=not all_iterations,
-            gather=not sharded)
+        with _lib.nvtx_range("scb.mim.solve_batch"):
+            batch = solve_batch(
+                model=model, applied_fields=[solve_kwargs.get("applied_field")] * len(hole_names),
+                circulating_currents=[{name: 1.0} for name in hole_names],
+                field_units=solve_kwargs.get("field_units", "mT"), iterations=solve_kwargs.get("iterations", 0),
+                check_inversion=solve_kwargs.get("check_inversion", False), last_only=not all_iterations,
+                gather=not sharded)
         to_units = _u.conversion_factor("H", units)
-        for j, hole_name in enumerate(hole_names):
-            for nn, solution in enumerate(batch[j][sl]):
-                for i, name in enumerate(hole_names):
-                    if films_by_hole[name] not in solution.film_solutions:
-                        continue  # another rank's film
-                    fluxoid = solution.polygon_fluxoid(hole_polygon_mapping[name], film=films_by_hole[name],
-                                                       units="Phi_0", with_units=False)
-                    M[nn, i, j] = sum(fluxoid) * _u.PHI_0 / I_circ_A * to_units
+        with _lib.nvtx_range("scb.mim.fluxoids"):
+            for j, hole_name in enumerate(hole_names):
+                for nn, solution in enumerate(batch[j][sl]):
+                    for i, name in enumerate(hole_names):
+                        if films_by_hole[name] not in solution.film_solutions:
+                            continue  # another rank's film
+                        fluxoid = solution.polygon_fluxoid(hole_polygon_mapping[name], film=films_by_hole[name],
+                                                           units="Phi_0", with_units=False)
+                        M[nn, i, j] = sum(fluxoid) * _u.PHI_0 / I_circ_A * to_units
         if sharded:
             import torch
 

@@ -421,25 +421,40 @@ def solve_batch(*, model: FactorizedModel, applied_fields: Sequence[Optional[Cal
     current_units = model.current_units
     length_units = device.length_units
     field_conversion = field_conversion_factor(field_units, current_units, length_units=length_units).magnitude
-    funcs = [f or ConstantField(0) for f in applied_fields]
+    zero_field = ConstantField(0)
+    funcs = [f or zero_field for f in applied_fields]
     owned = _owned_films(model)
     film_names = [f for f in device.films if gather or f in owned]
-    per_b = [_evaluate_applied_field(f, device, model.film_info, device.meshes, field_conversion, films=film_names)
-             for f in funcs]
-    host_fields = {name: np.stack([h[name] for h in per_b], axis=0) for name in film_names}  # (B, n) per film
-    dev_fields = {}
-    circ_by_film = {}
-    for name in film_names:
-        if name not in owned:
-            continue
-        dev = device.meshes[name]._data.device
-        # rows are contiguous on the host (fast stack + one H2D copy); the (n, nrhs) layout is made on the device
-        dev_fields[name] = torch.as_tensor(host_fields[name]).to(dev).t().contiguous()
-        circ_by_film[name] = {
-            hole: torch.tensor([float(cc.get(hole, 0.0)) for cc in circulating_currents], dtype=torch.float64,
-                               device=dev)
-            for hole in model.film_info[name].hole_indices
-        }
+    with _lib.nvtx_range("scb.solve_batch.fields"):
+        # (a field function that appears several times in the batch is evaluated once)
+        evaluated = {}
+        per_b = []
+        for f in funcs:
+            hit = evaluated.get(id(f))
+            if hit is None:
+                hit = evaluated[id(f)] = _evaluate_applied_field(f, device, model.film_info, device.meshes,
+                                                                 field_conversion, films=film_names)
+            per_b.append(hit)
+        host_fields = {name: np.stack([h[name] for h in per_b], axis=0) for name in film_names}  # (B, n) per film
+        dev_fields = {}
+        circ_by_film = {}
+        for name in film_names:
+            if name not in owned:
+                continue
+            dev = device.meshes[name]._data.device
+            # rows are contiguous on the host (fast stack + one H2D copy); the (n, nrhs) layout is made on the device
+            if not host_fields[name].any():
+                dev_fields[name] = torch.zeros(host_fields[name].shape[::-1], dtype=torch.float64, device=dev)
+            else:
+                dev_fields[name] = torch.as_tensor(host_fields[name]).to(dev).t().contiguous()
+            holes_of_film = list(model.film_info[name].hole_indices)
+            if holes_of_film:  # one upload for all the holes of the film
+                table = torch.as_tensor(np.array(
+                    [[float(cc.get(hole, 0.0)) for cc in circulating_currents] for hole in holes_of_film],
+                    dtype=np.float64)).to(dev)
+                circ_by_film[name] = {hole: table[k] for k, hole in enumerate(holes_of_film)}
+            else:
+                circ_by_film[name] = {}
     vortex_flux = _u.PHI_0 / _u.MU_0 * _u.conversion_factor("A * m", f"({current_units}) * ({length_units})")
     host = _run(model, dev_fields, circ_by_film, vortex_flux, iterations, check_inversion, field_conversion,
                 batch=B, last_only=last_only, gather=gather)
@@ -447,8 +462,9 @@ def solve_batch(*, model: FactorizedModel, applied_fields: Sequence[Optional[Cal
                         circulating_currents=dict(circulating_currents[b]),
                         terminal_currents=model.terminal_currents, vortices=model.vortices, solver=_solver)
                    for b in range(B)]
-    per_iter_solutions = _solutions_from_host(device, host, film_names, host_fields, field_conversion, kwargs_list,
-                                              batched=True)
+    with _lib.nvtx_range("scb.solve_batch.solutions"):
+        per_iter_solutions = _solutions_from_host(device, host, film_names, host_fields, field_conversion,
+                                                  kwargs_list, batched=True)
     return [[it[b] for it in per_iter_solutions] for b in range(B)]
 
 

@@ -166,28 +166,44 @@ def factorize_linear_systems(device: Device, film_info_dict: Dict[str, FilmInfo]
             # For a constant Lambda, -A is diagonally similar (D = W^1/2) to a symmetric matrix:
             # factor that one with the symmetric LU at half the flops.
             Lam = info.lambda_info.Lambda
+            # index sets uploaded once per (device, film, mesh): `geo` lives in the device-level geometry
+            # cache of make_film_info, so repeated factorizations of one device (one model per
+            # mutual-inductance call, Lambda sweeps) re-use the device copies
+            geo = info.dev.get("_geo")
+            if geo is None:
+                geo = {}
+
+            def cached(key, make):
+                hit = geo.get(key)
+                if hit is None:
+                    hit = geo[key] = make()
+                return hit
+
             sym_full = None
-            if use_symmetric() and T is None and float(Lam.max()) == float(Lam.min()):
-                sym_full = torch.sqrt(d.t["vertex_areas"])
+            if use_symmetric() and T is None and (info.dev.get("Lambda_constant")
+                                                  or float(Lam.max()) == float(Lam.min())):
+                sym_full = cached(("sqrt_w", str(d.device)), lambda: torch.sqrt(d.t["vertex_areas"]))
             hole_systems[film_name] = {}
             for hole_name, indices in info.hole_indices.items():
                 hole_systems[film_name][hole_name] = LinearSystem(
                     indices=indices, film_info=info, grad_Lambda_term=T if T is not None else 0.0,
-                    indices_dev=torch.as_tensor(indices).to(d.device))
-            def factor(indices):
+                    indices_dev=cached(("hole_ix", hole_name, str(d.device)),
+                                       lambda: torch.as_tensor(indices).to(d.device)))
+            def factor(indices, tag):
                 indices = np.ascontiguousarray(indices, dtype=np.int64)
                 n_int = len(indices)
                 if n_int == 0:
                     raise ValueError(f"Film {film_name!r} has no interior mesh vertices.")
                 n_pad = -(-n_int // LU_BLOCK) * LU_BLOCK
                 # every buffer is allocated on the caller's stream; the kernels may run on a side stream
-                ix_dev = torch.as_tensor(indices).to(d.device)
+                ix_dev = cached(("ix", tag, str(d.device)), lambda: torch.as_tensor(indices).to(d.device))
                 M = torch.empty(n_pad, n_pad, dtype=torch.float64, device=d.device)
                 pos = torch.empty(d.n, dtype=torch.int32, device=d.device)
                 margin = torch.empty(n_int, dtype=torch.float64, device=d.device)
                 dinv = torch.empty(int(L.scb_getrf_dinv_bytes(n_pad)) // 8, dtype=torch.float64, device=d.device)
                 lu_info = torch.zeros(1, dtype=torch.int32, device=d.device)
-                sym_scale = None if sym_full is None else sym_full[ix_dev].contiguous()
+                sym_scale = None if sym_full is None else cached(
+                    ("sym_scale", tag, str(d.device)), lambda: sym_full[ix_dev].contiguous())
                 side = side_streams[len(pending) % len(side_streams)] if side_streams else None
                 if side is not None:
                     side.wait_stream(torch.cuda.current_stream(d.device))
@@ -226,20 +242,22 @@ def factorize_linear_systems(device: Device, film_info_dict: Dict[str, FilmInfo]
             interior = info.interior_indices
             interior_no_holes = interior
             if info.hole_indices:
-                interior_no_holes = np.setdiff1d(interior, np.concatenate(list(info.hole_indices.values())))
+                interior_no_holes = cached("interior_no_holes", lambda: np.setdiff1d(
+                    interior, np.concatenate(list(info.hole_indices.values()))))
             # (for terminal films the boundary vertices are already excluded from `interior`,
             #  reference solve_film.py:273-274)
-            film_systems[film_name] = factor(interior_no_holes)
+            film_systems[film_name] = factor(interior_no_holes, "no_holes")
             if film_name in device.terminals:
                 # reference solve_film.py:220-263.  The reference factors the system without holes
                 # twice (as the film system and as film_without_boundary_or_holes); once here.
                 boundary = np.ascontiguousarray(info.boundary_indices, dtype=np.int64)
-                with_holes = factor(interior) if info.hole_indices else film_systems[film_name]
+                with_holes = factor(interior, "interior") if info.hole_indices else film_systems[film_name]
                 terminal_systems[film_name] = TerminalSystems(
                     film=film_name,
                     boundary=LinearSystem(indices=boundary, film_info=info,
                                           grad_Lambda_term=T if T is not None else 0.0,
-                                          indices_dev=torch.as_tensor(boundary).to(d.device)),
+                                          indices_dev=cached(("boundary_ix", str(d.device)),
+                                                             lambda: torch.as_tensor(boundary).to(d.device))),
                     holes=hole_systems[film_name],
                     film_without_boundary=with_holes,
                     film_without_boundary_or_holes=film_systems[film_name] if info.hole_indices else None,
@@ -249,9 +267,23 @@ def factorize_linear_systems(device: Device, film_info_dict: Dict[str, FilmInfo]
     for side in {id(p[3]): p[3] for p in pending if p[3] is not None}.values():
         with torch.cuda.device(side.device):
             torch.cuda.current_stream(side.device).wait_stream(side)
-    for film_name, system, lu_info, _, _keepalive in pending:
-        flag = int(lu_info.item())
-        mm = float(system.margin.min().item())
+    # (one download for the flags and margins of all systems instead of two blocking reads per system)
+    flags_host, margins_host = [], []
+    if pending:
+        by_dev = {}
+        for k, p in enumerate(pending):
+            by_dev.setdefault(p[2].device, []).append(k)
+        flags_host = [0] * len(pending)
+        margins_host = [0.0] * len(pending)
+        for dev_k, ks in by_dev.items():
+            packed = torch.stack([pending[k][2][0].to(torch.float64) for k in ks]
+                                 + [pending[k][1].margin.min() for k in ks]).cpu().numpy()
+            for j, k in enumerate(ks):
+                flags_host[k] = int(packed[j])
+                margins_host[k] = float(packed[len(ks) + j])
+    for k, (film_name, system, lu_info, _, _keepalive) in enumerate(pending):
+        flag = flags_host[k]
+        mm = margins_host[k]
         if flag != 0:
             raise np.linalg.LinAlgError(
                 f"Film {film_name!r}: zero or non-finite pivot at row {flag - 1} of the LU factorization."

@@ -30,11 +30,22 @@ class LambdaInfo:
     Lambda_str = "Λ"
 
     def __init__(self, *, film: str, Lambda: np.ndarray, london_lambda: Optional[np.ndarray] = None,
-                 thickness: Optional[float] = None):
+                 thickness: Optional[float] = None, _constants: Optional[Tuple[float, Optional[float]]] = None):
         self.film = film
         self.Lambda = Lambda
         self.london_lambda = london_lambda
         self.thickness = thickness
+        if _constants is not None:
+            # Lambda (and london_lambda) are filled arrays of these scalars: the checks below on two numbers
+            # instead of several passes over (n, 1) arrays
+            lam, lon = _constants
+            self.inhomogeneous = False
+            if lon is not None:
+                assert thickness is not None
+                assert np.allclose(lam, lon**2 / thickness)
+            if lam < 0:
+                raise ValueError(f"Negative Lambda in film {film!r}.")
+            return
         self.inhomogeneous = bool(
             np.ptp(self.Lambda) / max(np.min(np.abs(self.Lambda)), np.finfo(float).eps) > 1e-6
         )
@@ -133,14 +144,23 @@ def make_film_info(*, device: Device, vortices: Sequence, circulating_currents: 
         london_lambda = layer.london_lambda
         d = layer.thickness
         x, y = mesh.sites[:, 0], mesh.sites[:, 1]
-        Lambda = _evaluate(layer.Lambda, x, y).astype(np.float64)[:, np.newaxis]
+        layer_Lambda = layer.Lambda
+        constants = None
+        if isinstance(layer_Lambda, numbers.Real) and (london_lambda is None or isinstance(london_lambda, numbers.Real)):
+            constants = (float(layer_Lambda), None if london_lambda is None else float(london_lambda))
+            Lambda = np.full((len(x), 1), constants[0], dtype=np.float64)
+        else:
+            Lambda = _evaluate(layer_Lambda, x, y).astype(np.float64)[:, np.newaxis]
         if london_lambda is not None:
             if isinstance(london_lambda, numbers.Real) and london_lambda <= d:
                 logger.info(
                     f"Layer {name!r}: The film thickness, d = {d:.4f}, is greater than or equal to the "
                     f"London penetration depth; the thin-film assumption may not be valid."
                 )
-            london_lambda = _evaluate(london_lambda, x, y)[:, np.newaxis]
+            if constants is not None:
+                london_lambda = np.full((len(x), 1), constants[1], dtype=np.float64)
+            else:
+                london_lambda = _evaluate(london_lambda, x, y)[:, np.newaxis]
         # index sets (reference solver/utils.py:271-304) depend only on the mesh and the polygons:
         # memoised per device, so that repeated factorizations (Lambda sweeps, one model per
         # mutual-inductance call) do not redo the point-in-polygon tests
@@ -150,6 +170,7 @@ def make_film_info(*, device: Device, vortices: Sequence, circulating_currents: 
         hit = cache.get(name)
         if hit is not None and hit[0] == geo_key and hit[1] is mesh:
             hole_indices, in_hole, boundary_indices, interior_indices = hit[2]
+            derived = hit[3]
         else:
             hole_indices = {
                 hole.name: hole.contains_points(mesh.sites, index=True).astype(np.int64)
@@ -165,9 +186,11 @@ def make_film_info(*, device: Device, vortices: Sequence, circulating_currents: 
             keep = film.contains_points(mesh.sites).copy()
             keep[boundary_indices] = False
             interior_indices = np.where(keep)[0].astype(np.int64)  # == setdiff1d(in film, boundary), ascending
-            cache[name] = (geo_key, mesh, (hole_indices, in_hole, boundary_indices, interior_indices))
+            derived = {}  # host / device arrays derived from the index sets (factorize_linear_systems)
+            cache[name] = (geo_key, mesh, (hole_indices, in_hole, boundary_indices, interior_indices), derived)
         circ = {h: c for h, c in circulating_currents.items() if h in hole_indices}
-        lambda_info = LambdaInfo(film=name, Lambda=Lambda, london_lambda=london_lambda, thickness=layer.thickness)
+        lambda_info = LambdaInfo(film=name, Lambda=Lambda, london_lambda=london_lambda, thickness=layer.thickness,
+                                 _constants=constants)
         info = FilmInfo(
             name=name, layer=layer.name, lambda_info=lambda_info, vortices=tuple(vortices_by_film[name]),
             interior_indices=interior_indices, boundary_indices=boundary_indices, hole_indices=hole_indices,
@@ -175,7 +198,15 @@ def make_film_info(*, device: Device, vortices: Sequence, circulating_currents: 
             terminal_currents=terminal_currents.get(name),
         )
         dev = mesh._data.device
-        info.dev["Lambda"] = torch.as_tensor(np.ascontiguousarray(Lambda[:, 0])).to(dev)
+        lam0 = float(Lambda[0, 0]) if len(Lambda) else 0.0
+        if len(Lambda) and (constants is not None or float(Lambda.min()) == lam0 == float(Lambda.max())):
+            # constant Lambda: filled on the device (no pageable host-to-device copy per factorization)
+            info.dev["Lambda"] = torch.full((len(Lambda),), lam0, dtype=torch.float64, device=dev)
+            info.dev["Lambda_constant"] = True
+        else:
+            info.dev["Lambda"] = torch.as_tensor(np.ascontiguousarray(Lambda[:, 0])).to(dev)
+            info.dev["Lambda_constant"] = False
+        info.dev["_geo"] = derived
         film_info[name] = info
     return film_info
 
