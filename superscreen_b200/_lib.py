@@ -141,9 +141,29 @@ def ptr(t) -> Optional[int]:
 
 
 def stream_ptr() -> int:
+    """Raw handle of torch's current stream on the current device (called before every launch: the direct
+    binding, not ``torch.cuda.current_stream()``, which resolves and wraps the stream in Python objects)."""
     import torch
 
-    return torch.cuda.current_stream().cuda_stream
+    try:
+        return torch._C._cuda_getCurrentRawStream(torch._C._cuda_getDevice())
+    except AttributeError:  # (private binding moved: fall back to the public API)
+        return torch.cuda.current_stream().cuda_stream
+
+
+_FILM_STREAMS: dict = {}
+
+
+def film_streams(dev, n: int):
+    """``n`` side streams of device ``dev`` for independent films (factorizations, the solves of one Jacobi
+    step).  One persistent set per device: a stream's first launch costs milliseconds of driver set-up, and
+    ``torch.cuda.Stream()`` per call walks through torch's whole pool of 32 before it re-uses one."""
+    import torch
+
+    pool = _FILM_STREAMS.setdefault(str(dev), [])
+    while len(pool) < n:
+        pool.append(torch.cuda.Stream(device=dev))
+    return pool[:n]
 
 
 def launch_count() -> int:

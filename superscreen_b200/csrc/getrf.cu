@@ -378,6 +378,197 @@ trsm_sym_kernel(double* __restrict__ M, int64_t ld, int64_t o, const double* __r
 }
 
 // ---------------------------------------------------------------------------------------
+// Latency variants of the two GEMM kernels for the launches that sit on the per-block critical chain
+// (the tiles inside an outer panel's diagonal square: at most 14 panel tiles and 56 update tiles of
+// 128 x 64, i.e. far fewer CTAs than SMs, each of them a K = 128 pass that the full-size kernels run as
+// one un-overlapped load -> DMMA -> store sequence per CTA).  Same arithmetic, finer tiles:
+//   * update_lat_kernel: C tiles of 64 x 32 (four per tile of update_kernel_t, 128 threads, warp tile
+//     16 x 32), the packed operand chunks streamed through a 4-stage cp.async ring;
+//   * trsm_sym_lat_kernel: 16 rows of a 64-row panel tile per CTA (row split: a CTA reads and overwrites
+//     only its own rows, so the in-place update stays race-free), operands by cp.async in one commit
+//     group per k chunk.
+// Every accumulator sees the same fragments in the same k order as in the full-size kernels: the factors
+// are bit-identical (checked by tests/test_gpu_round2.py::test_lu_latency_kernels_bit_identical).
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_pending(int pending) {
+  switch (pending) {
+    case 0: asm volatile("cp.async.wait_group 0;\n" ::: "memory"); break;
+    case 1: asm volatile("cp.async.wait_group 1;\n" ::: "memory"); break;
+    case 2: asm volatile("cp.async.wait_group 2;\n" ::: "memory"); break;
+    default: asm volatile("cp.async.wait_group 3;\n" ::: "memory"); break;
+  }
+}
+
+constexpr int LAT_STAGES = 4;
+constexpr int LAT_A = (A_CHUNK / 2);  // doubles of half an A chunk: 8 row blocks x 8 k4 steps x 32 lanes
+constexpr int LAT_B = (B_CHUNK / 2);  // doubles of half a B chunk: 8 k4 steps x 4 column blocks x 32 lanes
+constexpr int kUpdLatSmem = LAT_STAGES * (LAT_A + LAT_B) * (int)sizeof(double);  // 96 KB
+
+template <bool TRI>
+__global__ void __launch_bounds__(128)
+update_lat_kernel(double* __restrict__ M, int64_t ld, int64_t row0, int64_t col0, const double* __restrict__ Lpack,
+                  const double* __restrict__ Upack, int tile_chunks, int chunk0, int nchunks) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double* As = reinterpret_cast<double*>(smem_raw);  // [stage][8 rb][8 s][32]
+  double* Bs = As + LAT_STAGES * LAT_A;               // [stage][8 s][4 nb][32]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int ty = blockIdx.y, tx = blockIdx.x;  // 64-row / 32-column tile
+  const int by = ty >> 1, bx = tx >> 1;        // the 128 x 64 tile of update_kernel_t it belongs to
+  if (TRI && bx > 2 * by + 1) return;          // same element set as update_kernel_t<true>
+  const double* Ltile = Lpack + ((row0 >> 7) + by) * ((int64_t)tile_chunks * A_CHUNK) + (int64_t)chunk0 * A_CHUNK +
+                        (ty & 1) * LAT_A;
+  const double* Utile = Upack + ((col0 >> 6) + bx) * ((int64_t)tile_chunks * B_CHUNK) + (int64_t)chunk0 * B_CHUNK +
+                        (tx & 1) * 4 * 32;
+  auto issue = [&](int c) {
+    double* a = As + (c % LAT_STAGES) * LAT_A;
+    double* b = Bs + (c % LAT_STAGES) * LAT_B;
+    const double* ga = Ltile + (int64_t)c * A_CHUNK;
+    const double* gb = Utile + (int64_t)c * B_CHUNK;
+#pragma unroll
+    for (int q = 0; q < LAT_A / 2 / 128; q++) {  // 8 granules of 16 bytes per thread
+      const int idx = q * 128 + tid;
+      cp_async16(a + 2 * idx, ga + 2 * idx);
+    }
+#pragma unroll
+    for (int q = 0; q < LAT_B / 2 / 128; q++) {  // 4 per thread: 8 segments (one per k4 step) of 1 KB
+      const int idx = q * 128 + tid;
+      const int sseg = idx >> 6, w2 = (idx & 63) * 2;
+      cp_async16(b + sseg * 128 + w2, gb + sseg * 256 + w2);
+    }
+    cp_async_commit();
+  };
+  const int pre = nchunks < LAT_STAGES ? nchunks : LAT_STAGES;
+  for (int c = 0; c < pre; c++) issue(c);
+
+  double acc[2][4][2];
+  double* Cbase = M + (row0 + (int64_t)ty * 64 + warp * 16 + g) * ld + col0 + (int64_t)tx * 32 + 2 * t;
+#pragma unroll
+  for (int i = 0; i < 2; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const double2 v = *reinterpret_cast<const double2*>(Cbase + (int64_t)(i * 8) * ld + j * 8);
+      acc[i][j][0] = v.x;
+      acc[i][j][1] = v.y;
+    }
+#pragma unroll 1
+  for (int c = 0; c < nchunks; c++) {
+    const int issued = (c + LAT_STAGES) < nchunks ? (c + LAT_STAGES) : nchunks;
+    cp_async_wait_pending(issued - c - 1);
+    __syncthreads();
+    const double* a_s = As + (c % LAT_STAGES) * LAT_A + (warp * 2 * 8) * 32 + lane;
+    const double* b_s = Bs + (c % LAT_STAGES) * LAT_B + lane;
+#pragma unroll
+    for (int sk = 0; sk < 8; sk++) {
+      double a[2], b[4];
+#pragma unroll
+      for (int i = 0; i < 2; i++) a[i] = a_s[(i * 8 + sk) * 32];
+#pragma unroll
+      for (int j = 0; j < 4; j++) b[j] = b_s[(sk * 4 + j) * 32];
+#pragma unroll
+      for (int i = 0; i < 2; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) dmma(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+    }
+    if (c + LAT_STAGES < nchunks) {
+      __syncthreads();  // every warp has read the stage that is refilled now
+      issue(c + LAT_STAGES);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 2; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+      *reinterpret_cast<double2*>(Cbase + (int64_t)(i * 8) * ld + j * 8) = make_double2(acc[i][j][0], acc[i][j][1]);
+}
+
+constexpr int LT_ALD = NB + 4;  // 132: row stride of the shared A rows / inv(U) rows (== 4 mod 16: conflict-free)
+constexpr int kTrsmLatSmem = (16 * LT_ALD + NB * LT_ALD) * (int)sizeof(double);  // 152 KB
+
+__global__ void __launch_bounds__(128)
+trsm_sym_lat_kernel(double* __restrict__ M, int64_t ld, int64_t o, const double* __restrict__ invU,
+                    double* __restrict__ Lpack, double* __restrict__ Upack, int tile_chunks, int chunk0, int tile0) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double* As = reinterpret_cast<double*>(smem_raw);  // [16][132]   rows of A21
+  double* Bs = As + 16 * LT_ALD;                      // [128][132]  inv(U11) (upper triangle by 32-blocks)
+  __shared__ double dU[NB];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int64_t o2 = o + NB;
+  const int tile = tile0 + (int)(blockIdx.x >> 2);  // 64-row tile below the diagonal block
+  const int q = blockIdx.x & 3;                      // 16-row quarter of it
+  double* Atile = M + (o2 + (int64_t)tile * 64) * ld + o;
+  const double* Arows = Atile + (int64_t)(q * 16) * ld;
+  dU[tid] = M[(o + tid) * ld + o + tid];
+  // one commit group per k chunk c: columns 32c .. 32c+31 of the 16 A rows, rows 32c .. 32c+31 of inv(U)
+  // right of their diagonal 32-block (the rest of inv(U) is structurally zero)
+#pragma unroll
+  for (int c = 0; c < NCHUNK; c++) {
+#pragma unroll
+    for (int k = 0; k < 2; k++) {  // A: 16 rows x 16 granules
+      const int idx = k * 128 + tid;
+      const int r = idx >> 4, cc = c * KC + (idx & 15) * 2;
+      cp_async16(As + r * LT_ALD + cc, Arows + (int64_t)r * ld + cc);
+    }
+    const int gran_per_row = (NB - c * KC) / 2;  // 64, 48, 32, 16
+    for (int idx = tid; idx < KC * gran_per_row; idx += 128) {
+      const int r = c * KC + idx / gran_per_row, cc = c * KC + (idx % gran_per_row) * 2;
+      cp_async16(Bs + r * LT_ALD + cc, invU + r * NB + cc);
+    }
+    cp_async_commit();
+  }
+  const int wn = warp;  // column group: k index 32 wn .. 32 wn + 31 of the result
+  double acc[2][4][2];
+#pragma unroll
+  for (int i = 0; i < 2; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+#pragma unroll 1
+  for (int c = 0; c < NCHUNK; c++) {
+    cp_async_wait_pending(NCHUNK - 1 - c);
+    __syncthreads();
+    if (c > wn) continue;  // structurally zero block of inv(U)
+#pragma unroll
+    for (int sk = 0; sk < 8; sk++) {
+      double a[2], b[4];
+#pragma unroll
+      for (int i = 0; i < 2; i++) a[i] = As[(i * 8 + g) * LT_ALD + c * KC + sk * 4 + t];
+#pragma unroll
+      for (int j = 0; j < 4; j++) b[j] = Bs[(c * KC + sk * 4 + t) * LT_ALD + wn * 32 + j * 8 + g];
+#pragma unroll
+      for (int i = 0; i < 2; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) dmma(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+    }
+  }
+  __syncthreads();  // (all reads of this CTA's rows are complete before any of them is overwritten)
+  double* PL = Lpack + ((o2 >> 7) + (tile >> 1)) * ((int64_t)tile_chunks * A_CHUNK) + (int64_t)chunk0 * A_CHUNK;
+  double* PU = Upack + ((o2 >> 6) + tile) * ((int64_t)tile_chunks * B_CHUNK) + (int64_t)chunk0 * B_CHUNK;
+  const int rbase = (tile & 1) * 64;
+  double* Urow0 = M + o * ld + o2 + (int64_t)tile * 64;
+#pragma unroll
+  for (int i = 0; i < 2; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const int r = q * 16 + i * 8 + g;        // row inside the 64-row tile
+      const int cc = wn * 32 + j * 8 + 2 * t;  // k index 0..127
+      const double v0 = acc[i][j][0], v1 = acc[i][j][1];
+      *reinterpret_cast<double2*>(Atile + (int64_t)r * ld + cc) = make_double2(v0, v1);
+      PL[lpack_index(rbase + r, cc)] = -v0;
+      PL[lpack_index(rbase + r, cc + 1)] = -v1;
+      const double u0 = dU[cc] * v0, u1 = dU[cc + 1] * v1;
+      PU[upack_index(cc, r)] = u0;
+      PU[upack_index(cc + 1, r)] = u1;
+      Urow0[(int64_t)cc * ld + r] = u0;
+      Urow0[(int64_t)(cc + 1) * ld + r] = u1;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
 // 1. diagonal block: LU (no pivoting) + explicit inverses of both factors in ONE sweep.
 //    The 128x128 block lives in REGISTERS, distributed 2-D cyclically over 512 threads
 //    (thread (ti, tj) = (warp, lane) owns rows ti + 16a, a < 8, and columns tj + 32b, b < 4).
@@ -1352,6 +1543,7 @@ static int g_inner_la = 0;     // split panels: block-level look-ahead inside th
 static int g_tail_q = 0;       // outer-panel width (in 128-blocks) used for the last g_tail_blocks blocks (0: same q)
 static int g_tail_blocks = 0;
 static int g_band = 16;        // raster order of the update kernel: row tiles per band (SCB_LU_BAND=0: hardware order)
+static int g_lat = 3;          // latency variants of the GEMM kernels on the per-block chain: bit 0 in-square panel solve + K = 128 update, bit 1 the K = 1024 update of the next panel's square (SCB_LU_LAT=0: off)
 
 }  // namespace scb
 
@@ -1449,6 +1641,10 @@ static int getrf_impl(int64_t n_pad, double* M, double* dinv, int32_t* info, scb
     if (const char* e = getenv("SCB_LU_TAIL_Q")) g_tail_q = atoi(e);
     if (const char* e = getenv("SCB_LU_TAIL_BLOCKS")) g_tail_blocks = atoi(e);
     if (const char* e = getenv("SCB_LU_BAND")) g_band = atoi(e);
+    if (const char* e = getenv("SCB_LU_LAT")) g_lat = atoi(e);
+    SCB_CUDA(cudaFuncSetAttribute(update_lat_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUpdLatSmem));
+    SCB_CUDA(cudaFuncSetAttribute(update_lat_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUpdLatSmem));
+    SCB_CUDA(cudaFuncSetAttribute(trsm_sym_lat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTrsmLatSmem));
     g_attr_set[dev & 63] = true;
   }
   LuStreams* lsp;
@@ -1545,8 +1741,12 @@ static int getrf_impl(int64_t n_pad, double* M, double* dinv, int32_t* info, scb
         cudaEvent_t e_d = ls.event(ev++);
         SCB_CUDA(cudaEventRecord(e_d, st));
         if (inner_rem > 0) {
-          trsm_sym_kernel<<<2 * inner_rem, 256, trsm_smem, st>>>(M, n_pad, o, invU, Lpack, Upack, tile_chunks,
-                                                                 i * NCHUNK, 0);
+          if (g_lat)
+            trsm_sym_lat_kernel<<<8 * inner_rem, 128, kTrsmLatSmem, st>>>(M, n_pad, o, invU, Lpack, Upack,
+                                                                         tile_chunks, i * NCHUNK, 0);
+          else
+            trsm_sym_kernel<<<2 * inner_rem, 256, trsm_smem, st>>>(M, n_pad, o, invU, Lpack, Upack, tile_chunks,
+                                                                   i * NCHUNK, 0);
           SCB_LAUNCH_CHECK();
         }
         cudaEvent_t e_t = ls.event(ev++);
@@ -1579,6 +1779,10 @@ static int getrf_impl(int64_t n_pad, double* M, double* dinv, int32_t* info, scb
               e_sq_prev = ls.event(ev++);
               SCB_CUDA(cudaEventRecord(e_sq_prev, sq));
             }
+          } else if (g_lat) {
+            update_lat_kernel<true><<<dim3(4 * inner_rem, 2 * inner_rem), 128, kUpdLatSmem, st>>>(
+                M, n_pad, r1, r1, Lpack, Upack, tile_chunks, i * NCHUNK, NCHUNK);
+            SCB_LAUNCH_CHECK();
           } else {
             update_kernel_t<true><<<dim3(2 * inner_rem, inner_rem), 256, upd_smem, st>>>(
                 M, n_pad, r1, r1, Lpack, Upack, tile_chunks, i * NCHUNK, NCHUNK, g_band);
@@ -1730,8 +1934,12 @@ static int getrf_impl(int64_t n_pad, double* M, double* dinv, int32_t* info, scb
       // symmetric, split panels: the square of panel P+1 first -- its factorization (a latency-bound
       // chain) starts as soon as these 72 tiles are done and runs concurrently with the update of
       // the rows below the square, which only the second (rows-below) stream of the panel waits for
-      update_kernel_t<true><<<dim3(2 * ntp, ntp), 256, upd_smem, s>>>(M, n_pad, e0, e0, Lpack, Upack, tile_chunks, 0,
-                                                                       nchunks, g_band);
+      if (g_lat & 2)  // the square of the next panel (on the chain as well): 64 x 32 tiles over all SMs
+        update_lat_kernel<true><<<dim3(4 * ntp, 2 * ntp), 128, kUpdLatSmem, s>>>(M, n_pad, e0, e0, Lpack, Upack,
+                                                                                tile_chunks, 0, nchunks);
+      else
+        update_kernel_t<true><<<dim3(2 * ntp, ntp), 256, upd_smem, s>>>(M, n_pad, e0, e0, Lpack, Upack, tile_chunks, 0,
+                                                                         nchunks, g_band);
       SCB_LAUNCH_CHECK();
       if (nt1 > 0) {
         cudaEvent_t e_sq = ls.event(ev++);

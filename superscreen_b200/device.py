@@ -557,7 +557,7 @@ class Device:
         M = np.zeros((n_iter, n_holes, n_holes))
         films_by_hole = {h.name: film for film, hs in self.holes_by_film().items() for h in hs}
         with _lib.nvtx_range("scb.mim.factorize_model"):
-            model = factorize_model(device=self, current_units="mA", comm=comm)
+            model = factorize_model(device=self, current_units="mA", comm=comm, _defer_checks=True)
         # Multi-rank: every rank keeps only its own films' solutions (no replication of the results),
         # evaluates the fluxoid rows of the holes in those films, and the small matrix is summed over
         # the ranks -- M[i, j] only needs film(i)'s solution for the driven hole j.

@@ -11,7 +11,7 @@ import copy
 import itertools
 import logging
 import os
-from dataclasses import dataclass
+from dataclasses import dataclass, field
 from typing import Callable, Dict, List, Optional, Sequence, Union
 
 import numpy as np
@@ -76,6 +76,14 @@ class FactorizedModel:
     vortices: Union[Sequence[Vortex], Dict[str, Sequence[Vortex]]]
     current_units: str
     comm: object = None  # parallel.Comm: film -> owner rank (None = single process)
+    # read-backs of the factorization flags that have not happened yet (factorize_model(_defer_checks=True))
+    _deferred_checks: list = field(default_factory=list, repr=False, compare=False)
+
+    def finish_checks(self) -> None:
+        """Reads back the singularity flags of factorizations that were enqueued without waiting for them
+        (raises ``LinAlgError`` exactly as ``factorize_model`` would have); a no-op otherwise."""
+        while self._deferred_checks:
+            self._deferred_checks.pop(0)()
 
     def set_circulating_currents(self, circulating_currents: Dict[str, float]) -> None:
         diff = set(circulating_currents) - set(self.device.holes)
@@ -119,9 +127,12 @@ class FactorizedModel:
 
 
 def factorize_model(*, device: Device, current_units: str, terminal_currents=None, circulating_currents=None,
-                    vortices: Optional[Sequence[Vortex]] = None, comm=None) -> FactorizedModel:
+                    vortices: Optional[Sequence[Vortex]] = None, comm=None,
+                    _defer_checks: bool = False) -> FactorizedModel:
     """reference solver/solve.py:223-287.  With a multi-rank ``comm`` (``parallel.DistComm``) each
-    rank assembles and factorizes only the films it owns (one film factorization per GPU)."""
+    rank assembles and factorizes only the films it owns (one film factorization per GPU).
+    ``_defer_checks`` (internal: callers that solve right away) returns while the GPU is still factoring;
+    the zero-pivot flags are then read by ``FactorizedModel.finish_checks()`` / at the end of the solve."""
     ureg = device.ureg
     circulating_currents = currents_to_floats(circulating_currents or {}, ureg, current_units)
     terminal_currents = {
@@ -142,10 +153,36 @@ def factorize_model(*, device: Device, current_units: str, terminal_currents=Non
     comm = comm or Comm()
     owners = film_owners(list(device.films), comm)
     owned = {f for f, r in owners.items() if r == comm.rank}
+    deferred = [] if _defer_checks else None
     with _lib.nvtx_range("scb.factorize_linear_systems"):
-        film_systems, hole_systems, terminal_systems = factorize_linear_systems(device, film_info, owned=owned)
+        film_systems, hole_systems, terminal_systems = factorize_linear_systems(device, film_info, owned=owned,
+                                                                                deferred=deferred)
     return FactorizedModel(device, film_info, film_systems, hole_systems, terminal_systems, terminal_currents,
-                           circulating_currents, vortices, current_units, comm)
+                           circulating_currents, vortices, current_units, comm, deferred or [])
+
+
+_UPLOAD_STREAMS: dict = {}
+
+
+def _upload(host_array, dev):
+    """Host array -> device tensor through a dedicated copy stream.  A pageable host-to-device copy is
+    ordered behind everything already queued on its stream and blocks the host until it has run; issued on
+    the compute stream right after ``factorize_model(_defer_checks=True)`` it would make the host wait for
+    the whole factorization.  On the (otherwise idle) copy stream it completes at once; the compute stream
+    then waits for it with an event."""
+    import torch
+
+    if dev.type != "cuda" or os.environ.get("SCB_UPLOAD_STREAM", "1") == "0":
+        return torch.as_tensor(host_array).to(dev)
+    st = _UPLOAD_STREAMS.get(dev)
+    if st is None:
+        st = _UPLOAD_STREAMS[dev] = torch.cuda.Stream(device=dev)
+    with torch.cuda.stream(st):
+        t = torch.as_tensor(host_array).to(dev)
+    cur = torch.cuda.current_stream(dev)
+    cur.wait_stream(st)
+    t.record_stream(cur)
+    return t
 
 
 def _to_host(t) -> np.ndarray:
@@ -251,12 +288,15 @@ def _run(model: "FactorizedModel", applied_fields, circ_by_film, vortex_flux, it
     iterates = [n_solutions - 1] if last_only else list(range(n_solutions))
 
     hole_states = {}  # hole boundary values + their effective field: constant over the iterations
+    n_solves = {}     # per film: number of the iterate being solved (the driver solves every film once per iterate)
 
     def solve_fn(name, other):
         with _lib.nvtx_range(f"scb.solve_film[{name}]"):
             return _solve_fn(name, other)
 
     def _solve_fn(name, other):
+        it = n_solves.get(name, 0)
+        n_solves[name] = it + 1
         circ = None if circ_by_film is None else circ_by_film[name]
         if name not in hole_states:
             info = film_info[name]
@@ -267,7 +307,8 @@ def _run(model: "FactorizedModel", applied_fields, circ_by_film, vortex_flux, it
             film_info=film_info[name], film_system=model.film_systems[name],
             hole_systems=model.hole_systems[name], applied_field=applied_fields[name], vortex_flux=vortex_flux,
             field_from_other_films=other, check_inversion=check_inversion, circulating_currents=circ,
-            terminal_systems=model.terminal_systems.get(name), device=device, hole_state=hole_states[name])
+            terminal_systems=model.terminal_systems.get(name), device=device, hole_state=hole_states[name],
+            want_self_field=it in iterates)  # (the self field of an iterate that is not stored is never used)
 
     inv4pi = 1.0 / (4.0 * np.pi)
 
@@ -293,7 +334,7 @@ def _run(model: "FactorizedModel", applied_fields, circ_by_film, vortex_flux, it
     side = {}
     n_side = int(os.environ.get("SCB_FILM_STREAMS", "8"))
     if len(mine) > 1 and n_side > 0:
-        pool = [torch.cuda.Stream(device=dev) for _ in range(min(len(mine), n_side))]
+        pool = _lib.film_streams(dev, min(len(mine), n_side))
         side = {f: pool[k % len(pool)] for k, f in enumerate(mine)}
 
     @contextlib.contextmanager
@@ -320,6 +361,7 @@ def _run(model: "FactorizedModel", applied_fields, circ_by_film, vortex_flux, it
             run_film_iterations(layout, comm, solve_fn, coupling_fn, iterations, film_scope=film_scope, join=join,
                                 on_result=packer.put, j_like=j_like)
         packer.scale_fields(1.0 / field_conversion)
+        model.finish_checks()  # (factorizations enqueued without waiting: their zero-pivot flags, now)
         with _lib.nvtx_range("scb.results_to_host"):
             return packer.to_host(gather, to_numpy=_to_host)
 
@@ -331,7 +373,7 @@ def _check_model_args(device, model, terminal_currents, circulating_currents, vo
             raise ValueError("Either a model or a device must be provided.")
         logger.info("Factorizing model.")
         model = factorize_model(device=device, current_units=current_units, terminal_currents=terminal_currents,
-                                circulating_currents=circulating_currents, vortices=vortices)
+                                circulating_currents=circulating_currents, vortices=vortices, _defer_checks=True)
     else:
         if (device is not None or terminal_currents is not None or circulating_currents is not None
                 or vortices is not None):
@@ -364,8 +406,7 @@ def solve(device: Optional[Device] = None, *, model: Optional[FactorizedModel] =
     field_conversion = field_conversion_factor(field_units, current_units, length_units=length_units).magnitude
     host_fields = _evaluate_applied_field(applied_field, device, model.film_info, device.meshes, field_conversion)
     owned = _owned_films(model)
-    applied_fields = {f: torch.as_tensor(h).to(device.meshes[f]._data.device) for f, h in host_fields.items()
-                      if f in owned}
+    applied_fields = {f: _upload(h, device.meshes[f]._data.device) for f, h in host_fields.items() if f in owned}
     # Phi_0 / mu_0 in [current_units * length_units]  (reference solve.py:441)
     vortex_flux = _u.PHI_0 / _u.MU_0 * _u.conversion_factor("A * m", f"({current_units}) * ({length_units})")
     solution_kwargs = dict(applied_field_func=applied_field, field_units=field_units, current_units=current_units,
@@ -446,12 +487,12 @@ def solve_batch(*, model: FactorizedModel, applied_fields: Sequence[Optional[Cal
             if not host_fields[name].any():
                 dev_fields[name] = torch.zeros(host_fields[name].shape[::-1], dtype=torch.float64, device=dev)
             else:
-                dev_fields[name] = torch.as_tensor(host_fields[name]).to(dev).t().contiguous()
+                dev_fields[name] = _upload(host_fields[name], dev).t().contiguous()
             holes_of_film = list(model.film_info[name].hole_indices)
             if holes_of_film:  # one upload for all the holes of the film
-                table = torch.as_tensor(np.array(
+                table = _upload(np.array(
                     [[float(cc.get(hole, 0.0)) for cc in circulating_currents] for hole in holes_of_film],
-                    dtype=np.float64)).to(dev)
+                    dtype=np.float64), dev)
                 circ_by_film[name] = {hole: table[k] for k, hole in enumerate(holes_of_film)}
             else:
                 circ_by_film[name] = {}

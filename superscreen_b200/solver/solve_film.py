@@ -135,9 +135,15 @@ def assemble_negA(info: FilmInfo, ix_dev, n_int: int, n_pad: int, T=None, out=No
     return M, margin
 
 
-def factorize_linear_systems(device: Device, film_info_dict: Dict[str, FilmInfo], owned=None):
+def factorize_linear_systems(device: Device, film_info_dict: Dict[str, FilmInfo], owned=None, deferred=None):
     """reference solver/solve_film.py:151-282 (films without terminals).  ``owned`` restricts the
-    (expensive) assembly + LU to the films this rank owns (multi-GPU film sharding)."""
+    (expensive) assembly + LU to the films this rank owns (multi-GPU film sharding).
+
+    ``deferred``: an optional list.  The singularity flags of the factorizations are normally read back
+    (one blocking download) before this function returns.  If a list is given and no system needs its
+    dominance margin for a decision (symmetric or pivoted factorizations), the read-back is appended to it
+    as a callable instead and the function returns while the GPU is still factoring: the caller enqueues
+    the solves behind it and calls the check before it trusts the results (``FactorizedModel.finish_checks``)."""
     torch = _torch()
     L = _lib.lib()
     film_systems: Dict[str, LinearSystem] = {}
@@ -149,7 +155,7 @@ def factorize_linear_systems(device: Device, film_info_dict: Dict[str, FilmInfo]
     side_streams = []  # several systems: factor them concurrently (small LUs are latency-bound)
     if n_side > 0 and (n_owned > 1 or any(f in device.terminals for f in film_info_dict)):
         dev0 = next(iter(film_info_dict.values())).mesh._data.device
-        side_streams = [torch.cuda.Stream(device=dev0) for _ in range(min(n_side, max(n_owned, 2)))]
+        side_streams = _lib.film_streams(dev0, min(n_side, max(n_owned, 2)))
     for film_name, info in film_info_dict.items():
         if owned is not None and film_name not in owned:
             hole_systems[film_name] = {}
@@ -267,40 +273,53 @@ def factorize_linear_systems(device: Device, film_info_dict: Dict[str, FilmInfo]
     for side in {id(p[3]): p[3] for p in pending if p[3] is not None}.values():
         with torch.cuda.device(side.device):
             torch.cuda.current_stream(side.device).wait_stream(side)
-    # (one download for the flags and margins of all systems instead of two blocking reads per system)
-    flags_host, margins_host = [], []
-    if pending:
+    # The dominance margin decides something only for a general, unpivoted system (SCB_PIVOT=0).  The
+    # symmetrised constant-Lambda system is definite -- elimination without pivoting is stable on it whether
+    # or not its rows are dominant -- and a pivoted system is safe by construction.
+    needs_margin = [system.sym_scale is None and system.piv is None for _, system, _, _, _ in pending]
+
+    def finish_checks():
+        # one download for the flags (and margins) of all systems instead of two blocking reads per system
+        if not pending:
+            return
         by_dev = {}
         for k, p in enumerate(pending):
             by_dev.setdefault(p[2].device, []).append(k)
         flags_host = [0] * len(pending)
-        margins_host = [0.0] * len(pending)
+        margins_host = [None] * len(pending)
         for dev_k, ks in by_dev.items():
-            packed = torch.stack([pending[k][2][0].to(torch.float64) for k in ks]
-                                 + [pending[k][1].margin.min() for k in ks]).cpu().numpy()
+            km = [k for k in ks if needs_margin[k]]
+            with torch.cuda.device(dev_k):
+                packed = torch.stack([pending[k][2][0].to(torch.float64) for k in ks]
+                                     + [pending[k][1].margin.min() for k in km]).cpu().numpy()
             for j, k in enumerate(ks):
                 flags_host[k] = int(packed[j])
+            for j, k in enumerate(km):
                 margins_host[k] = float(packed[len(ks) + j])
-    for k, (film_name, system, lu_info, _, _keepalive) in enumerate(pending):
-        flag = flags_host[k]
-        mm = margins_host[k]
-        if flag != 0:
-            raise np.linalg.LinAlgError(
-                f"Film {film_name!r}: zero or non-finite pivot at row {flag - 1} of the LU factorization."
-            )
-        if system.piv is not None:
-            # partial pivoting: padding rows must not have been interchanged with real ones
-            logger.info(f"Film {film_name!r}: factored with partial pivoting (margin lower bound {mm:.3e}).")
-        elif mm <= 0:
-            # dominance can fail for non-Delaunay (smoothed) meshes or strongly
-            # inhomogeneous Lambda.  The unpivoted factors are then used as a preconditioner:
-            # every solve is iteratively refined against the matrix-free operator and the
-            # final residual is checked (see solve_film_device).
-            system.refine = True
-            logger.info(
-                f"Film {film_name!r}: system matrix is not provably row-diagonally dominant "
-                f"(margin lower bound {mm:.3e}); solves will use iterative refinement."
-            )
+        for k, (film_name, system, lu_info, _, _keepalive) in enumerate(pending):
+            flag = flags_host[k]
+            mm = margins_host[k]
+            if flag != 0:
+                raise np.linalg.LinAlgError(
+                    f"Film {film_name!r}: zero or non-finite pivot at row {flag - 1} of the LU factorization."
+                )
+            if system.piv is not None:
+                logger.info(f"Film {film_name!r}: factored with partial pivoting.")
+            elif mm is not None and mm <= 0:
+                # dominance can fail for non-Delaunay (smoothed) meshes or strongly
+                # inhomogeneous Lambda.  The unpivoted factors are then used as a preconditioner:
+                # every solve is iteratively refined against the matrix-free operator and the
+                # final residual is checked (see solve_film_device).
+                system.refine = True
+                logger.info(
+                    f"Film {film_name!r}: system matrix is not provably row-diagonally dominant "
+                    f"(margin lower bound {mm:.3e}); solves will use iterative refinement."
+                )
+
+    if deferred is not None and not any(needs_margin):
+        deferred.append(finish_checks)
+    else:
+        finish_checks()
     return film_systems, hole_systems, terminal_systems
 
 
@@ -404,9 +423,11 @@ def hole_boundary_state(film_info: FilmInfo, hole_systems: Dict[str, LinearSyste
 def solve_film_device(*, film_info: FilmInfo, film_system: LinearSystem, hole_systems: Dict[str, LinearSystem],
                       applied_field, vortex_flux: float, field_from_other_films=None,
                       check_inversion: bool = False, circulating_currents=None, terminal_systems=None,
-                      device: Optional[Device] = None, hole_state=None):
+                      device: Optional[Device] = None, hole_state=None, want_self_field: bool = True):
     """Device-side body of ``solve_film`` (reference solve_film.py:483-565): all arguments and
-    results are device tensors in solver units.
+    results are device tensors in solver units.  ``want_self_field=False`` skips the screening mat-vec
+    ``Q @ (w g)`` (an output only: the next Jacobi step needs ``J``, not the self field) and returns
+    ``None`` in its place.
 
     ``applied_field`` is ``(n,)`` or, for a batch of B right-hand sides sharing the factorization,
     ``(n, B)``; ``circulating_currents`` (default: ``film_info.circulating_currents``) maps hole
@@ -525,7 +546,9 @@ def solve_film_device(*, film_info: FilmInfo, film_system: LinearSystem, hole_sy
         _lib.check(L.scb_current_density(d.n, _lib.ptr(d.t["op_indptr"]), _lib.ptr(d.t["op_indices"]),
                                          _lib.ptr(d.t["gradient_x"]), _lib.ptr(d.t["gradient_y"]), nrhs, _lib.ptr(g),
                                          _lib.ptr(J), _lib.stream_ptr()))
-        if transport:
+        if not want_self_field:
+            self_field = None
+        elif transport:
             # _biot_savart_within_film on per-triangle current densities (solve_film.py:557-562)
             J_tri = torch.stack([spmv(d, "gtri_y", g), spmv(d, "gtri_x", g, alpha=-1.0)], dim=1).contiguous()
             self_field = torch.empty(d.n, dtype=torch.float64, device=d.device)

@@ -2,6 +2,8 @@
 coupling against scipy / the CPU oracle (not against other kernels of this repo), the BASELINE
 configurations closer to their full sizes, and the full-size C2 film against the oracle together
 with bit-reproducibility of the symmetric factorization at 20k vertices."""
+import os
+
 import numpy as np
 import pytest
 
@@ -495,3 +497,30 @@ def test_factorized_model_hdf5_layout_roundtrip(sc):
     assert set(store.keys()) == {"device", "0"}
     c = sc.Solution.load_solutions(store)[0].film_solutions["ring"]
     assert np.array_equal(c.stream, a.stream)
+
+
+@pytest.mark.gpu
+def test_lu_latency_kernels_and_graph_replay_bit_identical():
+    """The fine-tile kernels on the per-block chain (update_lat_kernel, trsm_sym_lat_kernel; SCB_LU_LAT) and
+    the CUDA-graph replay of a repeated factorization (SCB_LU_GRAPH) only re-schedule the arithmetic of the
+    full-size kernels: the factors and block inverses must agree bit for bit with both switched off."""
+    import json
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+    def hashes(**env):
+        e = dict(os.environ, **{k: str(v) for k, v in env.items()})
+        r = subprocess.run([sys.executable, os.path.join(root, "tools", "lu_factor_hash.py"), "1500", "5300"],
+                           capture_output=True, text=True, env=e, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        return json.loads(r.stdout.strip().splitlines()[-1])
+
+    base = hashes(SCB_LU_LAT=0, SCB_LU_GRAPH=0)
+    for n, hs in base.items():
+        assert len(set(hs)) == 1, f"n={n}: repeated factorizations differ"
+    for env in (dict(SCB_LU_LAT=3, SCB_LU_GRAPH=0), dict(SCB_LU_LAT=1, SCB_LU_GRAPH=1), dict(SCB_LU_LAT=3, SCB_LU_GRAPH=1)):
+        got = hashes(**env)
+        for n in base:
+            assert set(got[n]) == set(base[n]), f"n={n} {env}: factors differ from the full-size kernels"

@@ -17,6 +17,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--tag", default="trace")
 ap.add_argument("--sections", default="film5k,getrs5k,c4,getrf20k")
 ap.add_argument("--warm", type=int, default=2)
+ap.add_argument("--emulate-world", type=int, default=0, help="c4 section: rank 0 of WORLD ranks emulated on one GPU")
 args = ap.parse_args()
 out_dir = os.path.join("gpurun_out", args.tag)
 os.makedirs(out_dir, exist_ok=True)
@@ -108,7 +109,27 @@ if "film5k" in sections or "getrs5k" in sections:
     torch.cuda.empty_cache()
 if "c4" in sections:
     device, polys = configs.c4_ring_array(8, 5000)
-    trace("c4_1gpu", lambda: device.mutual_inductance_matrix(polys, units="pH", iterations=5), warm=args.warm)
+    if args.emulate_world > 1:
+        from superscreen_b200 import parallel
+
+        class EmulatedRankComm(parallel.Comm):
+            def __init__(self, world):
+                self.world, self.rank = world, 0
+
+            def owner(self, index):
+                return index % self.world
+
+            def all_gather_into(self, out, send):
+                out.view(self.world, -1).copy_(send.reshape(1, -1).expand(self.world, -1))
+
+            def all_gather_chunks(self, chunk, sizes):
+                return torch.cat([chunk] * self.world, dim=0)
+
+        comm = EmulatedRankComm(args.emulate_world)
+        trace(f"c4_rank0of{args.emulate_world}",
+              lambda: device.mutual_inductance_matrix(polys, units="pH", iterations=5, comm=comm), warm=args.warm)
+    else:
+        trace("c4_1gpu", lambda: device.mutual_inductance_matrix(polys, units="pH", iterations=5), warm=args.warm)
 if "getrf20k" in sections:
     factor, system, n_int = film_setup(20164)
     trace("film20k_getrf", factor, warm=1)
