@@ -1125,42 +1125,41 @@ __device__ __forceinline__ int ldl64_blocked(double* __restrict__ S, double* __r
     const int k0 = 8 * kb;
     if (kb == 0) SCB_STAMP(8);
     // ---- (A) 8x8 diagonal tile: every lane of warp 0 holds the whole lower triangle in registers
-    //      and runs the same straight-line LDL^T (no shuffles, no divergence); lanes share the stores
+    //      and runs the same straight-line LDL^T (no shuffles).  Every lane also STORES every result --
+    //      the same value to the same address, one wavefront per store: lane-predicated stores made the
+    //      compiler emit dozens of divergent blocks per tile, which cost more than the arithmetic
+    //      (tools/phase_a_bench.cu: 1950 -> 1185 cycles per tile, identical results)
     if (warp == 0) {
       double a[8][8];  // a[r][c], c <= r
 #pragma unroll
       for (int r = 0; r < 8; r++)
 #pragma unroll
         for (int c = 0; c <= r; c++) a[r][c] = S[(k0 + r) * QLD + k0 + c];
-      __syncwarp();  // every lane has read the tile before single lanes overwrite entries of it
+      __syncwarp();  // every lane has read the tile before entries of it are overwritten
 #pragma unroll
       for (int j = 0; j < 8; j++) {
-        // The 8 pivots are a chain of dependent fp64 operations (~25 cycles each): keep it short.
-        // The products a[r][j] a[c][j] do not depend on 1 / d_j, so after the reciprocal (seed + 3
-        // dependent FMAs) every trailing entry, the next pivot included, is ONE FMA away.
+        // The 8 pivots are a chain of dependent fp64 operations: reciprocal (seed + 3 dependent FMAs,
+        // 41 cycles), the multipliers l_r = a_rj / d_j, then every trailing entry is ONE independent FMA
+        // a_rc -= l_r a_cj.
         const double djj = a[j][j];
-        double pr[8][8];
+        const double rjj = fast_rcp_halley(djj);
+        double l[8];
+#pragma unroll
+        for (int r = j + 1; r < 8; r++) l[r] = a[r][j] * rjj;
 #pragma unroll
         for (int r = j + 1; r < 8; r++)
 #pragma unroll
-          for (int c = j + 1; c <= r; c++) pr[r][c] = a[r][j] * a[c][j];
-        const double rjj = fast_rcp_halley(djj);
+          for (int c = j + 1; c <= r; c++) a[r][c] = fma(-l[r], a[c][j], a[r][c]);
+        // column j is final (stores are off the dependency chain)
 #pragma unroll
         for (int r = j + 1; r < 8; r++) {
-#pragma unroll
-          for (int c = j + 1; c <= r; c++) a[r][c] = fma(-pr[r][c], rjj, a[r][c]);
-          // column j of row r is final: store it (off the dependency chain)
-          if (lane == 8 + r) {
-            S[(k0 + r) * QLD + k0 + j] = a[r][j] * rjj;  // L[r][j]
-            S[(k0 + j) * QLD + k0 + r] = a[r][j];        // U[j][r] = d_j L[r][j]
-          }
+          S[(k0 + r) * QLD + k0 + j] = l[r];     // L[r][j]
+          S[(k0 + j) * QLD + k0 + r] = a[r][j];  // U[j][r] = d_j L[r][j]
         }
-        if (lane == j) {
-          dd[k0 + j] = djj;
-          rd[k0 + j] = rjj;
-          S[(k0 + j) * QLD + k0 + j] = djj;
-          if (bad == 0 && !(fabs(djj) > 0.0 && isfinite(djj))) bad = k0 + j + 1;
-        }
+        S[(k0 + j) * QLD + k0 + j] = djj;
+        dd[k0 + j] = djj;
+        rd[k0 + j] = rjj;
+        bad = (bad == 0 && !(fabs(djj) > 0.0 && isfinite(djj))) ? k0 + j + 1 : bad;
       }
     }
     if (kb == 0) SCB_STAMP(9);
