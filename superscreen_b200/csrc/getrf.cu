@@ -844,6 +844,8 @@ __device__ __forceinline__ int sweep64(double (&x)[8][2], double* __restrict__ D
 }
 
 // acc (warp tile 16 x 32, warps 4 x 2) = A[64][QLD] * B[64][QLD]
+// (Skipping the 8 x 8 x 4 products that only add structural zeros of the triangular operands was measured:
+//  no gain -- the phases around these products are bound by global-memory latency and store issue.)
 __device__ __forceinline__ void gemm64(const double* __restrict__ As, const double* __restrict__ Bs,
                                        double (&acc)[2][4][2]) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -1104,8 +1106,8 @@ constexpr int TLD = 36;  // row stride of the 32 x 32 scratch used by the doubli
 
 // (i, j), j <= i, of the e-th tile of a lower-triangular tile grid (row-major enumeration)
 __device__ __forceinline__ void tri_tile(int e, int& i, int& j) {
-  i = 0;
-  while ((i + 1) * (i + 2) / 2 <= e) i++;
+  // e < 28: rows start at 0, 1, 3, 6, 10, 15, 21
+  i = (e >= 1) + (e >= 3) + (e >= 6) + (e >= 10) + (e >= 15) + (e >= 21);
   j = e - i * (i + 1) / 2;
 }
 
@@ -1200,21 +1202,35 @@ __device__ __forceinline__ int ldl64_blocked(double* __restrict__ S, double* __r
     if (kb == 0) SCB_STAMP(11);
     __syncthreads();
     if (kb == 0) SCB_STAMP(12);
-    // ---- (C) trailing lower-triangle tiles: C -= L_panel U_panel ----
+    // ---- (C) trailing lower-triangle tiles: C -= L_panel U_panel, two tiles per warp in flight ----
+    // (Measured alternatives that were slower: four tiles in flight (spills), and letting warp 0 run ahead
+    //  into the next tile factorization while the other warps finish this phase.)
     const int nt = 7 - kb;
     const int ntiles = nt * (nt + 1) / 2;
-    for (int e = warp; e < ntiles; e += 8) {
-      int ti, tj;
-      tri_tile(e, ti, tj);
+#pragma unroll 1
+    for (int e0 = warp; e0 < ntiles; e0 += 16) {
+      const bool two = e0 + 8 < ntiles;
+      int ti, tj, ui = 0, uj = 0;
+      tri_tile(e0, ti, tj);
+      if (two) tri_tile(e0 + 8, ui, uj);
       const int R0 = k0 + 8 + 8 * ti, C0 = k0 + 8 + 8 * tj;
-      double2 c = *reinterpret_cast<const double2*>(&S[(R0 + g) * QLD + C0 + 2 * t]);
+      const int R1 = k0 + 8 + 8 * ui, C1 = k0 + 8 + 8 * uj;
+      double2 c0 = *reinterpret_cast<const double2*>(&S[(R0 + g) * QLD + C0 + 2 * t]);
+      double2 c1 = make_double2(0.0, 0.0);
+      if (two) c1 = *reinterpret_cast<const double2*>(&S[(R1 + g) * QLD + C1 + 2 * t]);
 #pragma unroll
       for (int ks = 0; ks < 2; ks++) {
-        const double av = -S[(R0 + g) * QLD + k0 + ks * 4 + t];
-        const double bv = S[(k0 + ks * 4 + t) * QLD + C0 + g];
-        dmma(c.x, c.y, av, bv);
+        const double av0 = -S[(R0 + g) * QLD + k0 + ks * 4 + t];
+        const double bv0 = S[(k0 + ks * 4 + t) * QLD + C0 + g];
+        dmma(c0.x, c0.y, av0, bv0);
+        if (two) {
+          const double av1 = -S[(R1 + g) * QLD + k0 + ks * 4 + t];
+          const double bv1 = S[(k0 + ks * 4 + t) * QLD + C1 + g];
+          dmma(c1.x, c1.y, av1, bv1);
+        }
       }
-      *reinterpret_cast<double2*>(&S[(R0 + g) * QLD + C0 + 2 * t]) = c;
+      *reinterpret_cast<double2*>(&S[(R0 + g) * QLD + C0 + 2 * t]) = c0;
+      if (two) *reinterpret_cast<double2*>(&S[(R1 + g) * QLD + C1 + 2 * t]) = c1;
     }
     if (kb == 0) SCB_STAMP(13);
     __syncthreads();
