@@ -425,7 +425,7 @@ def run_b200_arm(args):
         sol = sc.solve(device, applied_field=sc.ConstantField(1.0), field_units="mT", current_units="uA")[0]
         return sol.film_solutions["film"]
 
-    for _ in range(min(args.warmup, 2)):
+    for _ in range(args.warmup):  # (W untimed calls here as well: first uses of streams / pools are warm-up)
         e2e_step()
     barrier()
     e2e_times = []

@@ -209,7 +209,13 @@ int64_t scb_getrf_dinv_bytes(int64_t n_pad);
  * factorization of the next outer panel runs on an internal high-priority stream concurrently
  * with the trailing update (look-ahead) and is joined back into `stream` before returning.
  * On return M holds L (unit lower) and U; dinv holds inv(L_kk), inv(U_kk) of every 128x128
- * diagonal block.  info (device int32[1]) <- 0, or 1 + index of the first zero/non-finite pivot. */
+ * diagonal block.  info (device int32[1]) <- 0, or 1 + index of the first zero/non-finite pivot.
+ * Repeated calls with the same (n_pad, M, dinv, info) -- a steady-state loop over a device whose buffers
+ * come from a caching allocator -- are captured into a CUDA graph at the second call (on a stream of the
+ * library) and replayed with one cudaGraphLaunch into `stream` from then on: small films are latency-bound and
+ * enqueueing their few hundred launches costs the host as long as the GPU needs to run them.  Identical
+ * kernels and arguments, bit-identical factors.  n_pad <= SCB_LU_GRAPH_MAX_N (12288) only; SCB_LU_GRAPH=0
+ * disables it.  A call made while `stream` is itself being captured simply takes part in that capture. */
 int scb_getrf_nopiv(int64_t n_pad, double* M, double* dinv, int32_t* info, scb_stream_t stream);
 
 /* Same for a SYMMETRIC matrix (the symmetrised system of scb_system_assemble): only the lower

@@ -153,7 +153,7 @@ def factorize_model(*, device: Device, current_units: str, terminal_currents=Non
     comm = comm or Comm()
     owners = film_owners(list(device.films), comm)
     owned = {f for f, r in owners.items() if r == comm.rank}
-    deferred = [] if _defer_checks else None
+    deferred = [] if (_defer_checks and os.environ.get("SCB_DEFER_CHECKS", "1") != "0") else None
     with _lib.nvtx_range("scb.factorize_linear_systems"):
         film_systems, hole_systems, terminal_systems = factorize_linear_systems(device, film_info, owned=owned,
                                                                                 deferred=deferred)

@@ -524,3 +524,27 @@ def test_lu_latency_kernels_and_graph_replay_bit_identical():
         got = hashes(**env)
         for n in base:
             assert set(got[n]) == set(base[n]), f"n={n} {env}: factors differ from the full-size kernels"
+
+
+@pytest.mark.gpu
+def test_deferred_factorization_check_raises_from_solve(sc):
+    """`solve(device, ...)` / `mutual_inductance_matrix` enqueue the solve behind a factorization that is still
+    running and read its zero-pivot flag only before the results are trusted: a broken system must still end
+    in LinAlgError (as from `factorize_model`, which checks before it returns), never in a silent result."""
+    from superscreen_b200.geometry import box
+    from superscreen_b200.synthetic import square_mesh
+
+    sites, elements = square_mesh(10.0, 900, seed=2)
+    device = sc.Device("sq", layers=[sc.Layer("layer", Lambda=float("nan"), z0=0.0)],
+                       films=[sc.Polygon("film", layer="layer", points=box(10.0, points=4))])
+    device.set_meshes({"film": (sites, elements)})
+    with pytest.raises(np.linalg.LinAlgError):
+        sc.factorize_model(device=device, current_units="uA")
+    with pytest.raises(np.linalg.LinAlgError):
+        sc.solve(device, applied_field=sc.ConstantField(1.0))
+    # and a healthy device right after it is unaffected
+    good = sc.Device("sq", layers=[sc.Layer("layer", Lambda=0.5, z0=0.0)],
+                     films=[sc.Polygon("film", layer="layer", points=box(10.0, points=4))])
+    good.set_meshes({"film": (sites, elements)})
+    sol = sc.solve(good, applied_field=sc.ConstantField(1.0))[0]
+    assert np.isfinite(sol.film_solutions["film"].stream).all()

@@ -9,8 +9,10 @@ for p in $parts; do case $p in
 launches)
   $NCU --metrics gpu__time_duration.sum -c 4000 --csv --log-file $out/bench_launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-sharded > $out/bench_under_ncu.log 2>&1 ;;
 lu)
-  $NCU --set full --kernel-name-base mangled -k regex:update_kernel_tILb1 -c 18 -f -o $out/lu_update_tri python tools/run_stage.py --stage getrf --n 20164 --sym 1 > $out/lu_update_tri.log 2>&1; raw $out/lu_update_tri.ncu-rep
-  $NCU --set full -k regex:diag_kernel_symb -s 20 -c 1 -f -o $out/lu_diag python tools/run_stage.py --stage getrf --n 20164 --sym 1 > $out/lu_diag.log 2>&1; raw $out/lu_diag.ncu-rep ;;
+  $NCU --set full --kernel-name-base mangled -k regex:update_kernel_tILb1 -c 2 -f -o $out/lu_update_tri python tools/run_stage.py --stage getrf --n 20164 --sym 1 > $out/lu_update_tri.log 2>&1; raw $out/lu_update_tri.ncu-rep
+  $NCU --set full -k regex:diag_kernel_symb -s 20 -c 1 -f -o $out/lu_diag python tools/run_stage.py --stage getrf --n 5300 --sym 1 > $out/lu_diag.log 2>&1; raw $out/lu_diag.ncu-rep
+  $NCU --set full -k regex:update_lat_kernel -s 2 -c 1 -f -o $out/lu_update_lat python tools/run_stage.py --stage getrf --n 5300 --sym 1 > $out/lu_update_lat.log 2>&1; raw $out/lu_update_lat.ncu-rep
+  $NCU --set full -k regex:trsm_sym_lat_kernel -s 2 -c 1 -f -o $out/lu_trsm_lat python tools/run_stage.py --stage getrf --n 5300 --sym 1 > $out/lu_trsm_lat.log 2>&1; raw $out/lu_trsm_lat.ncu-rep ;;
 assemble)
   $NCU --set full -k regex:assemble_dense -c 1 -f -o $out/assemble_dense python tools/run_stage.py --stage getrf --n 20164 --sym 1 > $out/assemble.log 2>&1; raw $out/assemble_dense.ncu-rep ;;
 nbody)
@@ -24,4 +26,5 @@ sanitize)
   done ;;
 esac; done
 rm -f $out/*.ncu-rep
+python tools/ncu_summary.py $out/lu_diag.raw.csv $out/lu_update_lat.raw.csv $out/lu_trsm_lat.raw.csv > $out/lat_kernels_ncu.txt 2>/dev/null
 ls -la $out
