@@ -277,6 +277,10 @@ class _FluxoidGeometry(NamedTuple):
     valid: np.ndarray         # (q,) polygon point lies in the film and in the mesh
     dl: np.ndarray            # (q - 1, 2) polygon edge vectors
     Lambda_poly: np.ndarray   # (q,) Lambda at the polygon points
+    # the supercurrent integral as ONE linear functional of the mesh values of J:
+    # trapezoid_q(Lambda_q * sum_c J_poly[q, c] dl[q, c]) = sum_m J_coef[m] . J[J_idx[m]]
+    J_idx: np.ndarray         # (3 (q - 1),) mesh vertices (corners of the triangles under the polygon points)
+    J_coef: np.ndarray        # (3 (q - 1), 2) trapezoid weight * Lambda * barycentric weight * edge vector
 
 
 _FLUXOID_GEOMETRY: Dict[tuple, Any] = {}
@@ -304,8 +308,20 @@ def _fluxoid_geometry(device: Device, film: str, mesh, polygon_coords) -> _Fluxo
         Lambda_poly = np.asarray(Lambda(points[:, 0], points[:, 1]), dtype=float) * np.ones(len(points))
     else:
         Lambda_poly = float(Lambda) * np.ones(len(points))
-    geo = _FluxoidGeometry(ix=ix, w_ix=mesh.vertex_areas[ix], tri_vertices=mesh.elements[tri], bary=w,
-                           valid=valid, dl=np.diff(points, axis=0), Lambda_poly=Lambda_poly)
+    dl = np.diff(points, axis=0)
+    tri_vertices = mesh.elements[tri]
+    nq = len(points) - 1  # samples of the trapezoid rule (reference solution.py:556-557 drops the last point)
+    trap = np.ones(nq)
+    if nq >= 2:
+        trap[0] = trap[-1] = 0.5
+    else:
+        trap[:] = 0.0  # (np.trapezoid of a single sample is 0)
+    per_point = trap * Lambda_poly[:-1] * valid[:-1]                                   # (nq,)
+    J_coef = (per_point[:, None, None] * w[:-1, :, None] * dl[:, None, :]).reshape(-1, 2)  # (3 nq, 2)
+    J_coef = np.where(np.isfinite(J_coef), J_coef, 0.0)  # (barycentric weights of points outside the mesh)
+    J_idx = np.where(valid[:-1, None], tri_vertices[:-1], 0).reshape(-1)
+    geo = _FluxoidGeometry(ix=ix, w_ix=mesh.vertex_areas[ix], tri_vertices=tri_vertices, bary=w,
+                           valid=valid, dl=dl, Lambda_poly=Lambda_poly, J_idx=J_idx, J_coef=J_coef)
     if len(_FLUXOID_GEOMETRY) > 256:
         _FLUXOID_GEOMETRY.clear()
     _FLUXOID_GEOMETRY[key] = (mesh, Lambda, geo)
@@ -474,19 +490,36 @@ class Solution:
         mesh = device.meshes[film]
         geo = _fluxoid_geometry(device, film, mesh, polygon_coords)
         fs = self.film_solutions[film]
-        flux = np.einsum("i, i ->", fs.total_field[geo.ix], geo.w_ix)
-        flux_units = f"({self.field_units}) * ({device.length_units}) ** 2"
-        flux_part = flux * _flux_conversion(flux_units, units)
-        J_units = f"({self.current_units}) / ({device.length_units})"
-        # J at the polygon vertices: linear interpolation on the mesh, zero outside the film / mesh
-        # (interp_current_density, reference solution.py:278-319, on cached barycentric weights)
-        J_poly = np.einsum("qk,qkc->qc", geo.bary, fs.current_density[geo.tri_vertices])
-        J_poly[~geo.valid] = 0
-        J_poly[~np.isfinite(J_poly).all(axis=1)] = 0
-        int_J = np.trapezoid(geo.Lambda_poly[:-1] * np.sum(J_poly[:-1] * geo.dl, axis=1))
-        # mu_0 * [J_units * length^2]
-        si = _u.MU_0 * int_J * _u.conversion_factor(f"({J_units}) * ({device.length_units}) ** 2", "A * m")
-        supercurrent_part = si * _u.conversion_factor("Wb", units)
+        # flux part: total field (applied + self + other films, in that order) over the enclosed vertex areas
+        if fs._total_field is not None:
+            field_ix = fs._total_field[geo.ix]
+        else:  # (no (n,) temporaries for a solution whose total field has not been asked for)
+            field_ix = fs.applied_field[geo.ix] + fs.self_field[geo.ix]
+            if fs.field_from_other_films is not None:
+                field_ix = field_ix + fs.field_from_other_films[geo.ix]
+        flux = float(np.dot(field_ix, geo.w_ix))
+        conv = self.__dict__.get("_fluxoid_conversions", {}).get(units)
+        if conv is None:
+            flux_units = f"({self.field_units}) * ({device.length_units}) ** 2"
+            J_units = f"({self.current_units}) / ({device.length_units})"
+            conv = (_flux_conversion(flux_units, units),
+                    _u.MU_0 * _u.conversion_factor(f"({J_units}) * ({device.length_units}) ** 2", "A * m")
+                    * _u.conversion_factor("Wb", units))
+            self.__dict__.setdefault("_fluxoid_conversions", {})[units] = conv
+        flux_part = flux * conv[0]
+        # supercurrent part: J at the polygon vertices (linear interpolation on the mesh, zero outside the film /
+        # mesh: interp_current_density, reference solution.py:278-319), Lambda J . dl, trapezoid rule -- one
+        # cached linear functional of the mesh values of J
+        J_corner = fs.current_density[geo.J_idx]
+        if np.isfinite(J_corner).all():
+            int_J = float(np.einsum("mc,mc->", geo.J_coef, J_corner))
+        else:  # the reference zeroes polygon points whose interpolated J is not finite
+            J_poly = np.einsum("qk,qkc->qc", geo.bary, fs.current_density[geo.tri_vertices])
+            J_poly[~geo.valid] = 0
+            J_poly[~np.isfinite(J_poly).all(axis=1)] = 0
+            int_J = np.trapezoid(geo.Lambda_poly[:-1] * np.sum(J_poly[:-1] * geo.dl, axis=1))
+        # mu_0 * [J_units * length^2] -> units
+        supercurrent_part = int_J * conv[1]
         if with_units:
             return Fluxoid(_u.Quantity(flux_part, units), _u.Quantity(supercurrent_part, units))
         return Fluxoid(flux_part, supercurrent_part)

@@ -115,6 +115,7 @@ class FactorizedModel:
         """reference solver/solve.py:102-132 (same groups, datasets and attributes; ``superscreen_b200.io``)"""
         from .. import io as _io
 
+        self.finish_checks()
         _io.model_to_hdf5(self, h5group)
 
     @staticmethod
@@ -479,6 +480,16 @@ def solve_batch(*, model: FactorizedModel, applied_fields: Sequence[Optional[Cal
         host_fields = {name: np.stack([h[name] for h in per_b], axis=0) for name in film_names}  # (B, n) per film
         dev_fields = {}
         circ_by_film = {}
+        # the circulating currents of all holes of all owned films: ONE table, one upload per device
+        hole_rows, tables = {}, {}
+        for name in film_names:
+            if name in owned:
+                dev = device.meshes[name]._data.device
+                for hole in model.film_info[name].hole_indices:
+                    hole_rows.setdefault(dev, []).append((name, hole))
+        for dev, rows in hole_rows.items():
+            tables[dev] = _upload(np.array([[float(cc.get(hole, 0.0)) for cc in circulating_currents]
+                                            for _, hole in rows], dtype=np.float64), dev)
         for name in film_names:
             if name not in owned:
                 continue
@@ -488,14 +499,8 @@ def solve_batch(*, model: FactorizedModel, applied_fields: Sequence[Optional[Cal
                 dev_fields[name] = torch.zeros(host_fields[name].shape[::-1], dtype=torch.float64, device=dev)
             else:
                 dev_fields[name] = _upload(host_fields[name], dev).t().contiguous()
-            holes_of_film = list(model.film_info[name].hole_indices)
-            if holes_of_film:  # one upload for all the holes of the film
-                table = _upload(np.array(
-                    [[float(cc.get(hole, 0.0)) for cc in circulating_currents] for hole in holes_of_film],
-                    dtype=np.float64), dev)
-                circ_by_film[name] = {hole: table[k] for k, hole in enumerate(holes_of_film)}
-            else:
-                circ_by_film[name] = {}
+            circ_by_film[name] = {hole: tables[dev][k] for k, (film, hole) in enumerate(hole_rows.get(dev, []))
+                                  if film == name}
     vortex_flux = _u.PHI_0 / _u.MU_0 * _u.conversion_factor("A * m", f"({current_units}) * ({length_units})")
     host = _run(model, dev_fields, circ_by_film, vortex_flux, iterations, check_inversion, field_conversion,
                 batch=B, last_only=last_only, gather=gather)
