@@ -86,6 +86,19 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
       "l"(src), "r"(bytes), "r"(smem_u32(bar))
       : "memory");
 }
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_pending(int pending) {
+  switch (pending) {
+    case 0: asm volatile("cp.async.wait_group 0;\n" ::: "memory"); break;
+    case 1: asm volatile("cp.async.wait_group 1;\n" ::: "memory"); break;
+    case 2: asm volatile("cp.async.wait_group 2;\n" ::: "memory"); break;
+    default: asm volatile("cp.async.wait_group 3;\n" ::: "memory"); break;
+  }
+}
+
 __device__ __forceinline__ void fence_barrier_init() {
   asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
 }
@@ -244,34 +257,55 @@ __device__ __forceinline__ void gemm_k128(const double* __restrict__ A, int64_t 
   for (int i = 0; i < 4; i++)
 #pragma unroll
     for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
-#pragma unroll 1
-  for (int c = 0; c < NCHUNK; c++) {
-    __syncthreads();
-    // A chunk: TM rows x 32 k  (16 double2 per row)
+  // The operands of chunk c + 1 are on their way while chunk c feeds the tensor cores (one round trip to
+  // L2 / HBM per CTA instead of four back to back): the A rows through registers, the B rows (the block
+  // inverse, shared by all CTAs of the launch) by cp.async into the second of two shared buffers.  Same
+  // fragments, same k order: bit-identical results.  Bs points to 2 x KC x TB_LD doubles.
+  constexpr int QA = TM * 16 / 256;        // double2 of an A chunk per thread
+  constexpr int QB = KC * (TN / 2) / 256;  // 16-byte granules of a B chunk per thread
+  double2 ra[QA];
+  auto fetch_a = [&](int c) {
 #pragma unroll
-    for (int q = 0; q < TM * 16 / 256; q++) {
+    for (int q = 0; q < QA; q++) {
       const int idx = q * 256 + tid;
       const int r = idx >> 4, kk = (idx & 15) * 2;
-      *reinterpret_cast<double2*>(&As[r * TA_LD + kk]) =
-          *reinterpret_cast<const double2*>(A + (int64_t)r * lda + c * KC + kk);
+      ra[q] = *reinterpret_cast<const double2*>(A + (int64_t)r * lda + c * KC + kk);
     }
-    // B chunk: 32 k rows x TN cols  (TN/2 double2 per row)
+  };
+  auto issue_b = [&](int c) {
+    double* dst = Bs + (c & 1) * (KC * TB_LD);
 #pragma unroll
-    for (int q = 0; q < KC * (TN / 2) / 256; q++) {
+    for (int q = 0; q < QB; q++) {
       const int idx = q * 256 + tid;
       const int kr = idx / (TN / 2), cc = (idx % (TN / 2)) * 2;
-      *reinterpret_cast<double2*>(&Bs[kr * TB_LD + cc]) =
-          *reinterpret_cast<const double2*>(B + (int64_t)(c * KC + kr) * ldb + cc);
+      cp_async16(dst + kr * TB_LD + cc, B + (int64_t)(c * KC + kr) * ldb + cc);
     }
+    cp_async_commit();
+  };
+  issue_b(0);
+  fetch_a(0);
+#pragma unroll 1
+  for (int c = 0; c < NCHUNK; c++) {
+    __syncthreads();  // the previous chunk has been consumed: As and the other B buffer are free
+#pragma unroll
+    for (int q = 0; q < QA; q++) {
+      const int idx = q * 256 + tid;
+      const int r = idx >> 4, kk = (idx & 15) * 2;
+      *reinterpret_cast<double2*>(&As[r * TA_LD + kk]) = ra[q];
+    }
+    if (c + 1 < NCHUNK) issue_b(c + 1);
+    cp_async_wait_pending(c + 1 < NCHUNK ? 1 : 0);
     __syncthreads();
+    if (c + 1 < NCHUNK) fetch_a(c + 1);
     if ((TRI == 1 && c > wn) || (TRI == 2 && c > wm)) continue;  // structurally zero block
+    const double* Bc = Bs + (c & 1) * (KC * TB_LD);
 #pragma unroll
     for (int s = 0; s < 8; s++) {
       double a[4], b[4];
 #pragma unroll
       for (int i = 0; i < 4; i++) a[i] = As[(wm * 32 + i * 8 + g) * TA_LD + s * 4 + t];
 #pragma unroll
-      for (int j = 0; j < 4; j++) b[j] = Bs[(s * 4 + t) * TB_LD + wn * 32 + j * 8 + g];
+      for (int j = 0; j < 4; j++) b[j] = Bc[(s * 4 + t) * TB_LD + wn * 32 + j * 8 + g];
 #pragma unroll
       for (int i = 0; i < 4; i++)
 #pragma unroll
@@ -280,9 +314,9 @@ __device__ __forceinline__ void gemm_k128(const double* __restrict__ A, int64_t 
   }
 }
 
-constexpr int kTrsmSmemDoubles = 128 * TA_LD + KC * (64 + 4) > 64 * TA_LD + KC * (128 + 4)
-                                     ? 128 * TA_LD + KC * (64 + 4)
-                                     : 64 * TA_LD + KC * (128 + 4);
+constexpr int kTrsmSmemDoubles = 128 * TA_LD + 2 * KC * (64 + 4) > 64 * TA_LD + 2 * KC * (128 + 4)
+                                     ? 128 * TA_LD + 2 * KC * (64 + 4)
+                                     : 64 * TA_LD + 2 * KC * (128 + 4);  // A chunk + two B chunk buffers
 
 __global__ void __launch_bounds__(256)
 trsm_kernel(double* __restrict__ M, int64_t ld, int64_t o, int ncol, const double* __restrict__ invL,
@@ -390,19 +424,6 @@ trsm_sym_kernel(double* __restrict__ M, int64_t ld, int64_t o, const double* __r
 // Every accumulator sees the same fragments in the same k order as in the full-size kernels: the factors
 // are bit-identical (checked by tests/test_gpu_round2.py::test_lu_latency_kernels_bit_identical).
 // ---------------------------------------------------------------------------------------
-__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_u32(dst)), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_pending(int pending) {
-  switch (pending) {
-    case 0: asm volatile("cp.async.wait_group 0;\n" ::: "memory"); break;
-    case 1: asm volatile("cp.async.wait_group 1;\n" ::: "memory"); break;
-    case 2: asm volatile("cp.async.wait_group 2;\n" ::: "memory"); break;
-    default: asm volatile("cp.async.wait_group 3;\n" ::: "memory"); break;
-  }
-}
-
 constexpr int LAT_STAGES = 4;
 constexpr int LAT_A = (A_CHUNK / 2);  // doubles of half an A chunk: 8 row blocks x 8 k4 steps x 32 lanes
 constexpr int LAT_B = (B_CHUNK / 2);  // doubles of half a B chunk: 8 k4 steps x 4 column blocks x 32 lanes
