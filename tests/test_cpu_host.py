@@ -262,3 +262,73 @@ def test_meshgen_host_geometry_helpers():
     if not torch.cuda.is_available():
         with pytest.raises(_lib.SCBError):
             meshgen.generate_mesh(ell, min_points=100)
+
+
+def test_polygon_fluxoid_functional_and_geometry_caches():
+    """`Solution.polygon_fluxoid` evaluates the supercurrent integral through a cached linear functional of
+    the mesh currents: it must agree with the direct formula of the reference (solution.py:484-563:
+    interpolate J at the polygon points, Lambda J . dl, trapezoid rule; flux = total field over the enclosed
+    vertex areas) -- also when J is not finite somewhere (fallback path); `Device.holes_by_film` is memoised
+    on the geometry and must follow a changed polygon."""
+    from types import SimpleNamespace
+
+    from superscreen_b200.solution import FilmSolution, Solution, _barycentric, _locate
+    from superscreen_b200 import units as _u
+
+    sites, elements = disk_mesh(3.0, 900, seed=4)
+    # vertex areas: a third of the incident triangle areas (what Mesh.vertex_areas holds)
+    p = sites[elements]
+    tri_area = 0.5 * np.abs((p[:, 1, 0] - p[:, 0, 0]) * (p[:, 2, 1] - p[:, 0, 1])
+                            - (p[:, 1, 1] - p[:, 0, 1]) * (p[:, 2, 0] - p[:, 0, 0]))
+    w = np.zeros(len(sites))
+    np.add.at(w, elements.ravel(), np.repeat(tri_area / 3.0, 3))
+    device = sc.Device("d", layers=[sc.Layer("l", Lambda=0.7, z0=0.0)],
+                       films=[sc.Polygon("film", layer="l", points=circle(3.0, 80))],
+                       holes=[sc.Polygon("hole", layer="l", points=circle(0.5, 40))])
+    device.meshes = {"film": SimpleNamespace(sites=sites, elements=elements, vertex_areas=w)}
+    rng = np.random.default_rng(1)
+    n = len(sites)
+    fs = FilmSolution(stream=rng.standard_normal(n), current_density=rng.standard_normal((n, 2)),
+                      applied_field=rng.standard_normal(n), self_field=rng.standard_normal(n),
+                      field_from_other_films=rng.standard_normal(n))
+    sol = Solution(device=device, film_solutions={"film": fs}, applied_field_func=sc.ConstantField(0.0),
+                   field_units="mT", current_units="uA", _device_is_copy=True)
+    polygon = circle(1.5, 101)
+
+    def direct(film_solution):
+        poly = sc.Polygon(points=polygon)
+        pts = poly.points
+        ix = np.where(poly.contains_points(sites))[0]
+        total = film_solution.applied_field + film_solution.self_field + film_solution.field_from_other_films
+        flux = np.sum(total[ix] * w[ix])
+        ok, tri, bw = _locate(sites, elements, pts, 16)
+        J = np.einsum("qk,qkc->qc", bw, film_solution.current_density[elements[tri]])
+        J[~(ok & device.films["film"].contains_points(pts))] = 0
+        J[~np.isfinite(J).all(axis=1)] = 0
+        int_J = np.trapezoid(0.7 * np.sum(J[:-1] * np.diff(pts, axis=0), axis=1))
+        to_phi0 = _u.conversion_factor("mT * um ** 2", "Phi_0")
+        si = _u.MU_0 * int_J * _u.conversion_factor("(uA / um) * um ** 2", "A * m") * _u.conversion_factor("Wb", "Phi_0")
+        return flux * to_phi0, si
+
+    got = sol.polygon_fluxoid(polygon, film="film", units="Phi_0", with_units=False)
+    ref = direct(fs)
+    assert abs(got.flux_part - ref[0]) <= 1e-12 * abs(ref[0])
+    assert abs(got.supercurrent_part - ref[1]) <= 1e-12 * abs(ref[1])
+    again = sol.polygon_fluxoid(polygon, film="film", units="Phi_0", with_units=False)  # cached geometry + conversions
+    assert again.flux_part == got.flux_part and again.supercurrent_part == got.supercurrent_part
+    # a non-finite current density at one corner takes the reference's zeroing path
+    bad = FilmSolution(stream=fs.stream, current_density=fs.current_density.copy(), applied_field=fs.applied_field,
+                       self_field=fs.self_field, field_from_other_films=fs.field_from_other_films)
+    ok, tri, _ = _locate(sites, elements, sc.Polygon(points=polygon).points, 16)
+    bad.current_density[elements[tri[3], 0]] = np.nan
+    sol_bad = Solution(device=device, film_solutions={"film": bad}, applied_field_func=sc.ConstantField(0.0),
+                       field_units="mT", current_units="uA", _device_is_copy=True)
+    got_bad = sol_bad.polygon_fluxoid(polygon, film="film", units="Phi_0", with_units=False)
+    ref_bad = direct(bad)
+    assert np.isfinite(got_bad.supercurrent_part)
+    assert abs(got_bad.supercurrent_part - ref_bad[1]) <= 1e-12 * abs(ref_bad[1])
+    # holes_by_film: memoised on the geometry, follows a moved hole
+    assert [h.name for h in device.holes_by_film()["film"]] == ["hole"]
+    assert [h.name for h in device.holes_by_film()["film"]] == ["hole"]
+    device.holes["hole"] = sc.Polygon("hole", layer="l", points=circle(0.5, 40) + np.array([10.0, 0.0]))  # outside
+    assert device.holes_by_film()["film"] == []
