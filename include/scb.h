@@ -267,6 +267,15 @@ int scb_solve_stream(int64_t n, int64_t nrhs, const int32_t* pos, const double* 
                      const double* g0, double* g, scb_stream_t stream);
 int scb_current_density(int64_t n, const int32_t* op_indptr, const int32_t* op_indices, const double* gradient_x,
                         const double* gradient_y, int64_t nrhs, const double* g, double* J, scb_stream_t stream);
+/* The whole device-side body of one film solve in a single call (solver/solve_film.py:526-531,545,556-559):
+ * scb_solve_rhs -> scb_getrs_nopiv -> scb_solve_stream -> scb_current_density with the arguments of those
+ * entry points (B is the [n_pad, nrhs] workspace of the triangular solves).  A Jacobi step of a small film is
+ * latency-bound; one foreign call instead of four shortens the host side of it. */
+int scb_solve_step(int64_t n, int64_t n_int, int64_t n_pad, int64_t nrhs, const int64_t* rhs_ix,
+                   const double* applied, const double* other, const double* ha_eff, const double* scale,
+                   const double* LU, const double* dinv, double* B, const int32_t* pos, const double* g0, double* g,
+                   const int32_t* op_indptr, const int32_t* op_indices, const double* gradient_x,
+                   const double* gradient_y, double* J, scb_stream_t stream);
 
 /* ------------------------------------------------------------------------------------
  * Biot-Savart family (K15-K18, rows a14, a15, a17, a18)

@@ -60,6 +60,7 @@ EXPORTS = {
     "scb_solve_rhs": (c_int, [c_int64, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "scb_solve_stream": (c_int, [c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "scb_current_density": (c_int, [c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
+    "scb_solve_step": (c_int, [c_int64, c_int64, c_int64, c_int64] + [c_void_p] * 17),
     "scb_biot_savart": (c_int, [c_int, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_double, c_double, c_int64, c_void_p, c_void_p]),
     "scb_film_coupling": (c_int, [c_int64, c_void_p, c_double, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_int64,
                                   c_double, c_int64, c_void_p, c_void_p]),

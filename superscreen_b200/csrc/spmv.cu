@@ -117,3 +117,14 @@ extern "C" int scb_spmv(int64_t nrows, const int32_t* indptr, const int32_t* ind
   SCB_LAUNCH_CHECK();
   return SCB_OK;
 }
+
+extern "C" int scb_solve_step(int64_t n, int64_t n_int, int64_t n_pad, int64_t nrhs, const int64_t* rhs_ix,
+                              const double* applied, const double* other, const double* ha_eff, const double* scale,
+                              const double* LU, const double* dinv, double* B, const int32_t* pos, const double* g0,
+                              double* g, const int32_t* op_indptr, const int32_t* op_indices,
+                              const double* gradient_x, const double* gradient_y, double* J, scb_stream_t stream) {
+  if (int rc = scb_solve_rhs(n_int, n_pad, rhs_ix, nrhs, applied, other, ha_eff, scale, B, stream)) return rc;
+  if (int rc = scb_getrs_nopiv(n_pad, LU, dinv, nrhs, B, stream)) return rc;
+  if (int rc = scb_solve_stream(n, nrhs, pos, B, scale, g0, g, stream)) return rc;
+  return scb_current_density(n, op_indptr, op_indices, gradient_x, gradient_y, nrhs, g, J, stream);
+}

@@ -580,9 +580,9 @@ class Solution:
                     current_densities=self.film_solutions[name].current_density, z0=layer.z0,
                     length_units=device.length_units, current_units=self.current_units, vector=vector,
                     device_tensors=self._source_cache(name))
-            fields[name] = convert_field(field_from_film, units, old_units="tesla", with_units=with_units)
+            fields[name] = _convert_owned(field_from_film, units, "tesla", with_units)
         if return_sum:
-            return sum(fields.values())
+            return _sum_owned(fields, with_units)
         return fields
 
     def field_at_position(self, positions, *, zs=None, interp_method: str = "linear", units: Optional[str] = None,
@@ -619,10 +619,10 @@ class Solution:
             Hz_applied[mask] = np.squeeze(
                 self.applied_field_func(positions[mask, 0], positions[mask, 1], zs[mask, np.newaxis]))
         fields["applied_field"] = np.atleast_1d(Hz_applied).squeeze()
-        for key, f in fields.items():
-            fields[key] = convert_field(f, units, old_units=self.field_units, with_units=with_units)
+        for key, f in fields.items():  # (the applied field may be an array of the user's own function)
+            fields[key] = _convert_owned(f, units, self.field_units, with_units, owned=key != "applied_field")
         if return_sum:
-            return sum(fields.values())
+            return _sum_owned(fields, with_units, not_owned=("applied_field",))
         return fields
 
     def vector_potential_at_position(self, positions, *, zs=None, units: Optional[str] = None,
@@ -662,6 +662,44 @@ class Solution:
         if return_sum:
             return sum(out.values())
         return out
+
+
+_FIELD_FACTORS: Dict[tuple, float] = {}
+
+
+def _convert_owned(value, new_units: str, old_units: str, with_units: bool, owned: bool = True):
+    """``convert_field`` for an array this module has just produced itself (a million-point field evaluation
+    makes half a dozen such passes): the factor is looked up once per unit pair, a factor of one costs nothing
+    and the scaling is done in place."""
+    from .solver.utils import convert_field
+
+    key = (str(old_units), str(new_units))
+    factor = _FIELD_FACTORS.get(key)
+    if factor is None:
+        factor = _FIELD_FACTORS[key] = float(convert_field(1.0, new_units, old_units=old_units, with_units=False))
+    if factor != 1.0:
+        if owned and isinstance(value, np.ndarray) and value.flags.writeable and value.dtype == np.float64:
+            np.multiply(value, factor, out=value)
+        else:
+            value = value * factor
+    return _u.Quantity(value, new_units) if with_units else value
+
+
+def _sum_owned(fields: Dict[str, Any], with_units: bool, not_owned: Sequence[str] = ()):
+    """Sum of the per-source fields (reference: ``sum(fields.values())``), accumulated in place in the first
+    array (which this module produced itself; entries named in ``not_owned`` are never written to)."""
+    if with_units:
+        return sum(fields.values())
+    total = None
+    for key, f in fields.items():
+        if total is None:
+            own = key not in not_owned and isinstance(f, np.ndarray) and f.flags.writeable and f.dtype == np.float64
+            total = f if own else np.array(f, dtype=np.float64)
+        elif np.shape(f) == total.shape or np.ndim(f) == 0:
+            np.add(total, f, out=total)
+        else:
+            total = total + f
+    return 0 if total is None else total
 
 
 def _flux_conversion(old: str, new: str) -> float:

@@ -461,12 +461,24 @@ def solve_film_device(*, film_info: FilmInfo, film_system: LinearSystem, hole_sy
             other_c = None if field_from_other_films is None else field_from_other_films.contiguous()
             s = _lib.stream_ptr()
             rhs_ix = film_system.indices_dev if film_system.rhs_indices_dev is None else film_system.rhs_indices_dev
+            g = torch.empty_like(applied_c)
+            if not info.vortices:
+                # right-hand side, triangular solves, stream function and current density in ONE foreign call
+                J = torch.empty((d.n, nrhs, 2) if batched else (d.n, 2), dtype=torch.float64, device=d.device)
+                _lib.check(L.scb_solve_step(
+                    d.n, n_int, n_pad, nrhs, _lib.ptr(rhs_ix), _lib.ptr(applied_c), _lib.ptr(other_c),
+                    _lib.ptr(Ha_eff), _lib.ptr(film_system.sym_scale), _lib.ptr(film_system.lu),
+                    _lib.ptr(film_system.dinv), _lib.ptr(B), _lib.ptr(film_system.pos), _lib.ptr(g0), _lib.ptr(g),
+                    _lib.ptr(d.t["op_indptr"]), _lib.ptr(d.t["op_indices"]), _lib.ptr(d.t["gradient_x"]),
+                    _lib.ptr(d.t["gradient_y"]), _lib.ptr(J), s))
+                if not want_self_field:
+                    return g, J, None
+                return g, J, apply_operator(info, g, src_idx=None, with_sparse=False)
             _lib.check(L.scb_solve_rhs(n_int, n_pad, _lib.ptr(rhs_ix), nrhs, _lib.ptr(applied_c),
                                        _lib.ptr(other_c), _lib.ptr(Ha_eff), _lib.ptr(film_system.sym_scale),
                                        _lib.ptr(B), s))
             _lib.check(L.scb_getrs_nopiv(n_pad, _lib.ptr(film_system.lu), _lib.ptr(film_system.dinv), nrhs,
                                          _lib.ptr(B), s))
-            g = torch.empty_like(applied_c)
             _lib.check(L.scb_solve_stream(d.n, nrhs, _lib.ptr(film_system.pos), _lib.ptr(B),
                                           _lib.ptr(film_system.sym_scale), _lib.ptr(g0), _lib.ptr(g), s))
         else:
