@@ -1579,7 +1579,7 @@ static int g_inner_la = 0;     // split panels: block-level look-ahead inside th
 static int g_tail_q = 0;       // outer-panel width (in 128-blocks) used for the last g_tail_blocks blocks (0: same q)
 static int g_tail_blocks = 0;
 static int g_band = 16;        // raster order of the update kernel: row tiles per band (SCB_LU_BAND=0: hardware order)
-static int g_lat = 3;          // latency variants of the GEMM kernels on the per-block chain: bit 0 in-square panel solve + K = 128 update, bit 1 the K = 1024 update of the next panel's square (SCB_LU_LAT=0: off)
+static int g_lat = 3;          // latency variants of the GEMM kernels on the per-block chain: bit 0 in-square panel solve + K = 128 update, bit 1 the K = 1024 update of the next panel's square, bit 2 (off: measured slower, 5.3k film 3.57 -> 3.69 ms, 20k 80.1 -> 80.5 ms) that update split so that its first block column releases the chain (SCB_LU_LAT=0: all off)
 
 }  // namespace scb
 
@@ -1745,7 +1745,9 @@ static int getrf_impl(int64_t n_pad, double* M, double* dinv, int32_t* info, scb
 
   // factorization of outer panel P (inner blocks kb .. kb+q_eff-1) on stream st, packs -> set (P & 1)
   // rest_ready: event after which the rows below the panel's square are up to date (split panels)
-  auto factor_panel = [&](int64_t P, cudaStream_t st, cudaEvent_t rest_ready) -> int {
+  // sq_ready: event after which the part of the panel's square right of its first block column is up to date
+  // (split square update, see below); nullptr: everything was ready when `st` was released
+  auto factor_panel = [&](int64_t P, cudaStream_t st, cudaEvent_t rest_ready, cudaEvent_t sq_ready) -> int {
     if (P >= np) return SCB_OK;
     const int64_t kb = pk[P];
     const int q_eff = pq[P];
@@ -1797,6 +1799,7 @@ static int getrf_impl(int64_t n_pad, double* M, double* dinv, int32_t* info, scb
           // Inside the square (the latency-critical chain): eager right-looking updates, K = 128 -- every
           // launch is short (4 k-chunks per CTA) and the next diagonal block is ready right after it.
           const int64_t r1 = (kb + i + 1) * NB;
+          if (i == 0 && sq_ready) SCB_CUDA(cudaStreamWaitEvent(st, sq_ready, 0));  // (split square update)
           if (inner_la) {
             // Block-level look-ahead: the chain updates only the block column it factors next (2 x inner_rem
             // CTAs, so it never queues behind its own wide launches for SM slots held by bulk CTAs); the
@@ -1947,7 +1950,7 @@ static int getrf_impl(int64_t n_pad, double* M, double* dinv, int32_t* info, scb
     SCB_CUDA(cudaEventRecord(e0, s));
     SCB_CUDA(cudaStreamWaitEvent(sp, e0, 0));
   }
-  if (int rc = factor_panel(0, sp, nullptr)) return rc;
+  if (int rc = factor_panel(0, sp, nullptr, nullptr)) return rc;
   stamp("chain_end", 0, sp);
   for (int64_t P = 0; P < np; P++) {
     const int64_t kb = pk[P];
@@ -1965,22 +1968,46 @@ static int getrf_impl(int64_t n_pad, double* M, double* dinv, int32_t* info, scb
     }
     // A: the L-shaped strip that panel P+1 lives in (rows e0..e1 x all columns, rows below x cols e0..e1)
     const int nt0 = (int)((n_pad - e0) / NB), ntp = (int)((e1 - e0) / NB), nt1 = (int)((n_pad - e1) / NB);
-    cudaEvent_t rest_ready = nullptr;
+    cudaEvent_t rest_ready = nullptr, sq_ready = nullptr;
     if (sym && split) {
       // symmetric, split panels: the square of panel P+1 first -- its factorization (a latency-bound
       // chain) starts as soon as these 72 tiles are done and runs concurrently with the update of
       // the rows below the square, which only the second (rows-below) stream of the panel waits for
-      if (g_lat & 2)  // the square of the next panel (on the chain as well): 64 x 32 tiles over all SMs
-        update_lat_kernel<true><<<dim3(4 * ntp, 2 * ntp), 128, kUpdLatSmem, s>>>(M, n_pad, e0, e0, Lpack, Upack,
-                                                                                tile_chunks, 0, nchunks);
-      else
-        update_kernel_t<true><<<dim3(2 * ntp, ntp), 256, upd_smem, s>>>(M, n_pad, e0, e0, Lpack, Upack, tile_chunks, 0,
-                                                                         nchunks, g_band);
-      SCB_LAUNCH_CHECK();
-      if (nt1 > 0) {
+      bool chain_released = false;
+      if ((g_lat & 6) == 6 && ntp > 1 && nt1 > 0) {
+        // Split square (SCB_LU_LAT=7; off by default, measured slower: the released diagonal block then shares the
+        // GPU with the rest of the square): the first diagonal block of the next panel and its panel solve need only the FIRST block
+        // column of the square (K = 1024 over 8 row tiles: ~17 us instead of ~44 for the whole square) -- the
+        // chain is released behind it; the rest of the square (a triangular region again) is updated beside the
+        // first diagonal block and awaited before the chain's first in-square update.  Same element set, one
+        // K = 1024 pass per element: bit-identical.
+        update_lat_kernel<false><<<dim3(4, 2 * ntp), 128, kUpdLatSmem, s>>>(M, n_pad, e0, e0, Lpack, Upack, tile_chunks,
+                                                                           0, nchunks);
+        SCB_LAUNCH_CHECK();
         cudaEvent_t e_sq = ls.event(ev++);
         SCB_CUDA(cudaEventRecord(e_sq, s));
         SCB_CUDA(cudaStreamWaitEvent(sp, e_sq, 0));
+        chain_released = true;
+        update_lat_kernel<true><<<dim3(4 * (ntp - 1), 2 * (ntp - 1)), 128, kUpdLatSmem, s>>>(
+            M, n_pad, e0 + NB, e0 + NB, Lpack, Upack, tile_chunks, 0, nchunks);
+        SCB_LAUNCH_CHECK();
+        sq_ready = ls.event(ev++);
+        SCB_CUDA(cudaEventRecord(sq_ready, s));
+      } else if (g_lat & 2) {  // the square of the next panel (on the chain as well): 64 x 32 tiles over all SMs
+        update_lat_kernel<true><<<dim3(4 * ntp, 2 * ntp), 128, kUpdLatSmem, s>>>(M, n_pad, e0, e0, Lpack, Upack,
+                                                                                tile_chunks, 0, nchunks);
+        SCB_LAUNCH_CHECK();
+      } else {
+        update_kernel_t<true><<<dim3(2 * ntp, ntp), 256, upd_smem, s>>>(M, n_pad, e0, e0, Lpack, Upack, tile_chunks, 0,
+                                                                         nchunks, g_band);
+        SCB_LAUNCH_CHECK();
+      }
+      if (nt1 > 0) {
+        if (!chain_released) {
+          cudaEvent_t e_sq = ls.event(ev++);
+          SCB_CUDA(cudaEventRecord(e_sq, s));
+          SCB_CUDA(cudaStreamWaitEvent(sp, e_sq, 0));
+        }
         update_kernel_t<false><<<dim3(2 * ntp, nt1), 256, upd_smem, s>>>(M, n_pad, e1, e0, Lpack, Upack, tile_chunks, 0,
                                                                           nchunks, g_band);
         SCB_LAUNCH_CHECK();
@@ -2009,7 +2036,7 @@ static int getrf_impl(int64_t n_pad, double* M, double* dinv, int32_t* info, scb
       SCB_CUDA(cudaEventRecord(e, s));
       SCB_CUDA(cudaStreamWaitEvent(sp, e, 0));
     }
-    if (int rc = factor_panel(P + 1, sp, rest_ready)) return rc;
+    if (int rc = factor_panel(P + 1, sp, rest_ready, sq_ready)) return rc;
     stamp("chain_end", P + 1, sp);
     // B: the rest of the trailing block, concurrently with the factorization of panel P+1
     if (nt1 > 0) {

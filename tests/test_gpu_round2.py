@@ -520,7 +520,8 @@ def test_lu_latency_kernels_and_graph_replay_bit_identical():
     base = hashes(SCB_LU_LAT=0, SCB_LU_GRAPH=0)
     for n, hs in base.items():
         assert len(set(hs)) == 1, f"n={n}: repeated factorizations differ"
-    for env in (dict(SCB_LU_LAT=3, SCB_LU_GRAPH=0), dict(SCB_LU_LAT=1, SCB_LU_GRAPH=1), dict(SCB_LU_LAT=3, SCB_LU_GRAPH=1)):
+    for env in (dict(SCB_LU_LAT=3, SCB_LU_GRAPH=0), dict(SCB_LU_LAT=1, SCB_LU_GRAPH=1), dict(SCB_LU_LAT=7, SCB_LU_GRAPH=0),
+                dict(SCB_LU_LAT=7, SCB_LU_GRAPH=1)):
         got = hashes(**env)
         for n in base:
             assert set(got[n]) == set(base[n]), f"n={n} {env}: factors differ from the full-size kernels"
