@@ -17,12 +17,13 @@ for line in out.splitlines():
 groups = [("DMMA", r"^DMMA"), ("DFMA", r"^DFMA"), ("DADD/DMUL", r"^(DADD|DMUL)"), ("DSETP", r"^DSETP"), ("MUFU.RSQ64H", r"^MUFU\.RSQ64H"),
           ("MUFU.RCP64H", r"^MUFU\.RCP64H"), ("UBLKCP", r"^UBLKCP"), ("SYNCS", r"^SYNCS"), ("LDG", r"^LDG"), ("STG", r"^STG"),
           ("LDS", r"^LDS"), ("STS", r"^STS"), ("SHFL", r"^SHFL"), ("BAR", r"^BAR"), ("ATOM/RED", r"^(ATOM|RED|ATOMG)"),
-          ("CCTL/PREF", r"^(CCTL|LDGDEPBAR|PREFETCH)"), ("UTMALDG", r"^UTMALDG"), ("UTCxMMA", r"^UTC"), ("LDTM", r"^LDTM"), ("total", r".")]
+          ("LDGSTS", r"^LDGSTS"), ("CCTL/PREF", r"^(CCTL|LDGDEPBAR|PREFETCH)"), ("UTMALDG", r"^UTMALDG"), ("UTCxMMA", r"^UTC"), ("LDTM", r"^LDTM"), ("total", r".")]
 lines = ["# cuobjdump -sass superscreen_b200/libsc_b200.so : opcode counts per kernel (static instruction counts)",
          f"# cubin architectures: {sorted(arch)}",
          "# fp64 tensor cores on sm_100a are reached through mma.sync.m8n8k4.f64 -> SASS DMMA (there is no fp64 tcgen05 kind:",
          "# UTC*MMA / LDTM / UTMALDG are expected to be 0); TMA appears as 1-D bulk copies cp.async.bulk -> UBLKCP + mbarrier SYNCS",
-         "# (the LU operands are pre-packed fragment-major by the panel-solve kernels, so no tensor-map TMA is needed).",
+         "# (the LU operands are pre-packed fragment-major by the panel-solve kernels, so no tensor-map TMA is needed);",
+         "# cp.async (the fine-tile latency kernels and the pipelined panel solves of the LU) appears as LDGSTS.",
          "", "kernel".ljust(64) + "".join(g[0].rjust(12) for g in groups)]
 tot = collections.Counter()
 for name, cnt in kernels.items():
