@@ -299,25 +299,33 @@ trsm_sweep_dmma_kernel(const double* __restrict__ F, int64_t ld, const double* _
         }
       }
       __syncthreads();
+      // The two k halves of the tile accumulate into separate registers (acc / acc2): on the critical tile of a
+      // block step (x_j just published) the dependent DMMA chain per accumulator is 16 long instead of 32.
+      double acc2[2][CT][2];
+#pragma unroll
+      for (int rt = 0; rt < 2; rt++)
+#pragma unroll
+        for (int ct = 0; ct < CT; ct++) acc2[rt][ct][0] = acc2[rt][ct][1] = 0.0;
 #pragma unroll
       for (int ks = 0; ks < HK; ks++) {
 #pragma unroll
         for (int ct = 0; ct < CT; ct++) {
           const double b = xs[(ks * 4 + t) * XP + ct * 8 + g];
+          const double b2 = xs[((HK + ks) * 4 + t) * XP + ct * 8 + g];
           dmma_rhs(acc[0][ct][0], acc[0][ct][1], -aA[0][ks], b);
           dmma_rhs(acc[1][ct][0], acc[1][ct][1], -aA[1][ks], b);
+          dmma_rhs(acc2[0][ct][0], acc2[0][ct][1], -aB[0][ks], b2);
+          dmma_rhs(acc2[1][ct][0], acc2[1][ct][1], -aB[1][ks], b2);
         }
       }
-      if (q + 1 < p) load_half(aA, lower ? q + 1 : nb - 2 - q, 0);  // first half of the next tile
 #pragma unroll
-      for (int ks = 0; ks < HK; ks++) {
+      for (int rt = 0; rt < 2; rt++)
 #pragma unroll
         for (int ct = 0; ct < CT; ct++) {
-          const double b = xs[((HK + ks) * 4 + t) * XP + ct * 8 + g];
-          dmma_rhs(acc[0][ct][0], acc[0][ct][1], -aB[0][ks], b);
-          dmma_rhs(acc[1][ct][0], acc[1][ct][1], -aB[1][ks], b);
+          acc[rt][ct][0] += acc2[rt][ct][0];
+          acc[rt][ct][1] += acc2[rt][ct][1];
         }
-      }
+      if (q + 1 < p) load_half(aA, lower ? q + 1 : nb - 2 - q, 0);  // first half of the next tile
       __syncthreads();  // xs is rewritten for the next tile
     }
     // finish: x_i = inv(F_ii) acc_i, A fragments from the shared copy of the inverse
@@ -328,23 +336,34 @@ trsm_sweep_dmma_kernel(const double* __restrict__ F, int64_t ld, const double* _
 #pragma unroll
         for (int e = 0; e < 2; e++) xs[(warp * 16 + rt * 8 + g) * XP + ct * 8 + 2 * t + e] = acc[rt][ct][e];
     __syncthreads();
-    double out[2][CT][2];
+    double out[2][CT][2], out2[2][CT][2];  // (even / odd k4 steps: two dependent chains of 16 instead of one of 32)
 #pragma unroll
     for (int rt = 0; rt < 2; rt++)
 #pragma unroll
-      for (int ct = 0; ct < CT; ct++) out[rt][ct][0] = out[rt][ct][1] = 0.0;
+      for (int ct = 0; ct < CT; ct++) out[rt][ct][0] = out[rt][ct][1] = out2[rt][ct][0] = out2[rt][ct][1] = 0.0;
     const double* D0 = dsm + (warp * 16 + g) * DLDS + t;
     const double* D1 = D0 + 8 * DLDS;
-#pragma unroll 8
-    for (int ks = 0; ks < NB / 4; ks++) {
+#pragma unroll 4
+    for (int ks = 0; ks < NB / 4; ks += 2) {
       const double a0 = D0[ks * 4], a1 = D1[ks * 4];
+      const double c0 = D0[(ks + 1) * 4], c1 = D1[(ks + 1) * 4];
 #pragma unroll
       for (int ct = 0; ct < CT; ct++) {
         const double b = xs[(ks * 4 + t) * XP + ct * 8 + g];
+        const double b2 = xs[((ks + 1) * 4 + t) * XP + ct * 8 + g];
         dmma_rhs(out[0][ct][0], out[0][ct][1], a0, b);
         dmma_rhs(out[1][ct][0], out[1][ct][1], a1, b);
+        dmma_rhs(out2[0][ct][0], out2[0][ct][1], c0, b2);
+        dmma_rhs(out2[1][ct][0], out2[1][ct][1], c1, b2);
       }
     }
+#pragma unroll
+    for (int rt = 0; rt < 2; rt++)
+#pragma unroll
+      for (int ct = 0; ct < CT; ct++) {
+        out[rt][ct][0] += out2[rt][ct][0];
+        out[rt][ct][1] += out2[rt][ct][1];
+      }
 #pragma unroll
     for (int rt = 0; rt < 2; rt++)
 #pragma unroll
