@@ -549,3 +549,82 @@ def test_deferred_factorization_check_raises_from_solve(sc):
     good.set_meshes({"film": (sites, elements)})
     sol = sc.solve(good, applied_field=sc.ConstantField(1.0))[0]
     assert np.isfinite(sol.film_solutions["film"].stream).all()
+
+
+@pytest.mark.gpu
+def test_solve_step_matches_the_separate_entry_points(sc):
+    """`scb_solve_step` (one foreign call per film solve) is scb_solve_rhs -> scb_getrs_nopiv -> scb_solve_stream
+    -> scb_current_density: bit-identical stream function and current density, batched right-hand sides."""
+    import torch
+
+    from superscreen_b200 import _lib, configs
+    from superscreen_b200.solver.solve_film import hole_boundary_state
+
+    L = _lib.lib()
+    device, _ = configs.c1_ring(1500)
+    model = sc.factorize_model(device=device, current_units="uA", circulating_currents={"ring_hole": "1 mA"})
+    info, fsys = model.film_info["ring"], model.film_systems["ring"]
+    d = info.mesh._data
+    nrhs = 3
+    rng = np.random.default_rng(0)
+    applied = torch.as_tensor(rng.standard_normal((d.n, nrhs))).to(d.device).contiguous()
+    other = torch.as_tensor(rng.standard_normal((d.n, nrhs))).to(d.device).contiguous()
+    circ = {"ring_hole": torch.tensor([1.0, 0.0, -2.0], dtype=torch.float64, device=d.device)}
+    g0, ha_eff = hole_boundary_state(info, model.hole_systems["ring"], circ, applied)
+    n_int, n_pad = len(fsys.indices), fsys.n_pad
+    s = _lib.stream_ptr()
+    p = _lib.ptr
+    # separate entry points
+    B = torch.empty((n_pad, nrhs), dtype=torch.float64, device=d.device)
+    _lib.check(L.scb_solve_rhs(n_int, n_pad, p(fsys.indices_dev), nrhs, p(applied), p(other), p(ha_eff),
+                               p(fsys.sym_scale), p(B), s))
+    _lib.check(L.scb_getrs_nopiv(n_pad, p(fsys.lu), p(fsys.dinv), nrhs, p(B), s))
+    g_a = torch.empty_like(applied)
+    _lib.check(L.scb_solve_stream(d.n, nrhs, p(fsys.pos), p(B), p(fsys.sym_scale), p(g0), p(g_a), s))
+    J_a = torch.empty((d.n, nrhs, 2), dtype=torch.float64, device=d.device)
+    _lib.check(L.scb_current_density(d.n, p(d.t["op_indptr"]), p(d.t["op_indices"]), p(d.t["gradient_x"]),
+                                     p(d.t["gradient_y"]), nrhs, p(g_a), p(J_a), s))
+    # one call
+    B2 = torch.empty_like(B)
+    g_b = torch.empty_like(applied)
+    J_b = torch.empty_like(J_a)
+    _lib.check(L.scb_solve_step(d.n, n_int, n_pad, nrhs, p(fsys.indices_dev), p(applied), p(other), p(ha_eff),
+                                p(fsys.sym_scale), p(fsys.lu), p(fsys.dinv), p(B2), p(fsys.pos), p(g0), p(g_b),
+                                p(d.t["op_indptr"]), p(d.t["op_indices"]), p(d.t["gradient_x"]),
+                                p(d.t["gradient_y"]), p(J_b), s))
+    torch.cuda.synchronize()
+    assert torch.isfinite(g_a).all() and float(g_a.abs().max()) > 0
+    assert torch.equal(g_a, g_b) and torch.equal(J_a, J_b)
+
+
+@pytest.mark.gpu
+def test_graph_replayed_mutual_inductance_and_untouched_user_arrays(sc):
+    """Repeated `mutual_inductance_matrix` calls on one device go from direct launches to graph capture to
+    graph replay of the factorizations (and through the per-device geometry caches): every call must return the
+    same matrix bit for bit.  And `field_at_position` converts and sums its fields in place: never in an array
+    that belongs to the user's applied-field function."""
+    from superscreen_b200 import configs
+
+    device, polys = configs.c4_ring_array(2, 1500)
+    Ms = [np.array(device.mutual_inductance_matrix(polys, units="pH", iterations=2)) for _ in range(4)]
+    for M in Ms[1:]:
+        assert np.array_equal(M, Ms[0])
+    assert np.isfinite(Ms[0]).all() and abs(Ms[0][0, 0]) > 10 * abs(Ms[0][0, 1]) > 0
+
+    held = {}
+
+    def applied(x, y, z):  # hands out the same array on every call
+        if "a" not in held or held["a"].shape != np.shape(x):
+            held["a"] = 0.25 + 0.01 * np.asarray(x, dtype=np.float64)
+            held["copy"] = held["a"].copy()
+        return held["a"]
+
+    sol = sc.solve(device, applied_field=applied, field_units="mT", current_units="uA")[0]
+    pos = np.column_stack([np.linspace(-3.0, 15.0, 257), np.linspace(-2.0, 2.0, 257), np.full(257, 1.5)])
+    held.clear()
+    f_mT = sol.field_at_position(pos, units="mT", with_units=False)
+    f_uT = sol.field_at_position(pos, units="uT", with_units=False)
+    assert np.array_equal(held["a"], held["copy"]), "the applied-field array of the user was modified"
+    assert np.allclose(f_uT, 1e3 * f_mT, rtol=1e-13, atol=0)
+    parts = sol.field_at_position(pos, units="mT", with_units=False, return_sum=False)
+    assert np.allclose(sum(parts.values()), f_mT, rtol=1e-13, atol=1e-300)
