@@ -517,10 +517,12 @@ class Device:
             raise ValueError("The device does not have a mesh.")
         return boundary_vertices_ccw(self.meshes[film].elements)
 
-    def mutual_inductance_matrix(self, hole_polygon_mapping: Dict[str, np.ndarray], units: str = "pH",
-                                 all_iterations: bool = False, comm=None, **solve_kwargs):
-        """reference device/device.py:538-648.  ``hole_polygon_mapping`` is required (the default
-        shapely-buffered polygons of fluxoid.py:12-52 are out of scope).  The reference solves once
+    def mutual_inductance_matrix(self, hole_polygon_mapping: Optional[Dict[str, np.ndarray]] = None,
+                                 units: str = "pH", all_iterations: bool = False, comm=None, **solve_kwargs):
+        """reference device/device.py:538-648.  Without ``hole_polygon_mapping`` the polygons come from
+        ``fluxoid.make_fluxoid_polygons`` as in the reference (device.py:592-595; the holes are grown by half
+        the distance to the nearest other polygon -- by scaling about the centroid here, by a shapely buffer
+        there: identical for circular holes, pass explicit polygons for parity runs).  The reference solves once
         per driven hole against one factorization; here all columns are one batched solve
         (``solve_batch``).  As in the reference, ``iterations`` is forwarded to the solver only if
         given explicitly."""
@@ -528,6 +530,10 @@ class Device:
 
         from . import _lib
 
+        if hole_polygon_mapping is None:
+            from .fluxoid import make_fluxoid_polygons
+
+            hole_polygon_mapping = make_fluxoid_polygons(self)
         holes = self.holes
         hole_names = list(holes)
         with _lib.nvtx_range("scb.mim.validate"):

@@ -332,3 +332,26 @@ def test_polygon_fluxoid_functional_and_geometry_caches():
     assert [h.name for h in device.holes_by_film()["film"]] == ["hole"]
     device.holes["hole"] = sc.Polygon("hole", layer="l", points=circle(0.5, 40) + np.array([10.0, 0.0]))  # outside
     assert device.holes_by_film()["film"] == []
+
+
+def test_default_fluxoid_polygons_of_a_ring():
+    """`make_fluxoid_polygons` (the default of `Device.mutual_inductance_matrix` / `find_fluxoid_solution`, reference
+    fluxoid.py:12-52): a hole is grown by half the distance to the nearest other polygon of its layer -- for the
+    ring of the reference's tests (hole r = 2 in a film r = 4) the circle of radius 3, counter-clockwise, and it
+    contains the hole and lies in the film."""
+    from superscreen_b200.fluxoid import make_fluxoid_polygons
+
+    device = sc.Device("ring", layers=[sc.Layer("base", Lambda=1.0, z0=0.0)],
+                       films=[sc.Polygon("ring", layer="base", points=circle(4.0, 200))],
+                       holes=[sc.Polygon("hole", layer="base", points=circle(2.0, 200))])
+    polys = make_fluxoid_polygons(device)
+    assert list(polys) == ["hole"]
+    p = polys["hole"]
+    r = np.linalg.norm(p, axis=1)
+    assert np.allclose(r, 3.0, atol=2e-3)
+    area2 = np.sum(p[:-1, 0] * p[1:, 1] - p[1:, 0] * p[:-1, 1]) if np.array_equal(p[0], p[-1]) else \
+        np.sum(p[:, 0] * np.roll(p[:, 1], -1) - np.roll(p[:, 0], -1) * p[:, 1])
+    assert area2 > 0  # counter-clockwise
+    assert points_in_polygon(p, device.holes["hole"].points).all()
+    assert device.films["ring"].contains_points(p).all()
+    assert len(make_fluxoid_polygons(device, holes="hole", interp_points=64)["hole"]) in (64, 65)
