@@ -49,6 +49,18 @@ class Layer:
         self.london_lambda = None
         self.thickness = None
 
+    def to_hdf5(self, h5group) -> None:
+        """reference device/layer.py: attributes name, z0, thickness, london_lambda | Lambda"""
+        from . import io as _io
+
+        _io.layer_to_hdf5(self, h5group)
+
+    @staticmethod
+    def from_hdf5(h5group) -> "Layer":
+        from . import io as _io
+
+        return _io.layer_from_hdf5(h5group)
+
     def copy(self) -> "Layer":
         if self._Lambda is not None:
             return Layer(self.name, Lambda=self._Lambda, z0=self.z0)
@@ -178,6 +190,34 @@ class Polygon:
                                                   convex_hull=convex_hull, **meshpy_kwargs)
         mesh = _Mesh.from_triangulation(points, triangles, build_operators=build_operators and not smooth)
         return mesh.smooth(smooth, build_operators=build_operators) if smooth else mesh
+
+    def to_hdf5(self, h5group) -> None:
+        """reference device/polygon.py: attributes name, layer and the dataset ``points``"""
+        from . import io as _io
+
+        _io.polygon_to_hdf5(self, h5group)
+
+    @staticmethod
+    def from_hdf5(h5group) -> "Polygon":
+        from . import io as _io
+
+        return _io.polygon_from_hdf5(h5group)
+
+    def resample(self, num_points: Optional[int] = None) -> "Polygon":
+        """A copy whose vertices are uniformly distributed in arc length along the boundary (reference
+        device/polygon.py:483-506: shapely ``segmentize`` + ``interpolate(linspace(0, 1, num_points), normalized=True)``,
+        i.e. piecewise-linear interpolation of the closed boundary).  ``num_points=None``: as many as now; a false
+        ``num_points`` returns an unaltered copy."""
+        if num_points is None:
+            num_points = len(self.points)
+        if not num_points:
+            return self.copy()
+        pts = self.points
+        closed = pts if np.allclose(pts[0], pts[-1]) else np.concatenate([pts, pts[:1]])
+        arc = np.concatenate([[0.0], np.cumsum(np.linalg.norm(np.diff(closed, axis=0), axis=1))])
+        t = np.linspace(0.0, 1.0, int(num_points)) * arc[-1]
+        new = np.stack([np.interp(t, arc, closed[:, k]) for k in range(2)], axis=1)
+        return Polygon(self.name, layer=self.layer, points=new)
 
     def copy(self) -> "Polygon":
         # the stored points are already closed and counter-clockwise: skip the constructor's normalisation
@@ -398,6 +438,77 @@ class Device:
             d.meshes = self.meshes
         return d
 
+    # ------------------------------------------------------------ rigid transformations of the whole device
+    def _warn_if_mesh_exist(self, method: str) -> None:
+        if self.meshes:
+            logger.warning(
+                f"Calling device.{method} on a device whose mesh already exists returns a new device with no mesh. "
+                f"Call new_device.make_mesh() to generate the mesh for the new device.")
+
+    @staticmethod
+    def _check_origin(origin) -> None:
+        import numbers
+
+        if not (isinstance(origin, tuple) and len(origin) == 2 and all(isinstance(v, numbers.Real) for v in origin)):
+            raise TypeError("Origin must be a tuple of floats (x, y).")
+
+    def scale(self, xfact: float = 1, yfact: float = 1, origin: Tuple[float, float] = (0, 0)) -> "Device":
+        """reference device/device.py:266-292: a copy (without mesh) scaled about ``origin``; negative factors mirror."""
+        self._check_origin(origin)
+        self._warn_if_mesh_exist("scale()")
+        device = self.copy(with_mesh=False)
+        for polygon in device.get_polygons():
+            polygon.scale(xfact=xfact, yfact=yfact, origin=origin, inplace=True)
+        return device
+
+    def rotate(self, degrees: float, origin: Tuple[float, float] = (0, 0)) -> "Device":
+        """reference device/device.py:294-315: a copy (without mesh) rotated counter-clockwise about ``origin``."""
+        self._check_origin(origin)
+        self._warn_if_mesh_exist("rotate()")
+        device = self.copy(with_mesh=False)
+        for polygon in device.get_polygons():
+            polygon.rotate(degrees, origin=origin, inplace=True)
+        return device
+
+    def mirror_layers(self, about_z: float = 0.0) -> "Device":
+        """reference device/device.py:317-332: a copy (without mesh) with every layer mirrored about ``z = about_z``."""
+        self._warn_if_mesh_exist("mirror_layers()")
+        device = self.copy(with_mesh=False)
+        for layer in device.layers.values():
+            layer.z0 = about_z - layer.z0
+        return device
+
+    def translate(self, dx: float = 0, dy: float = 0, dz: float = 0, inplace: bool = False) -> "Device":
+        """reference device/device.py:334-365.  Polygons (and meshes) move by ``(dx, dy)``, layers by ``dz``.  The
+        reference shifts ``mesh.sites`` in place; here a device-resident mesh is rebuilt from the shifted sites
+        (its operators are translation invariant, its coordinates are not)."""
+        device = self if inplace else self.copy(with_mesh=True, copy_mesh=True)
+        for polygon in device.get_polygons():
+            polygon.translate(dx, dy, inplace=True)
+        if device.meshes and (dx or dy):
+            shift = np.array([[dx, dy]], dtype=float)
+            device.set_meshes({name: (np.asarray(mesh.sites) + shift, np.asarray(mesh.elements))
+                               for name, mesh in device.meshes.items()})
+        if dz:
+            for layer in device.layers.values():
+                layer.z0 += dz
+        return device
+
+    def translation(self, dx: float, dy: float, dz: float = 0):
+        """Context manager: the device is translated inside the block and moved back afterwards
+        (reference device/device.py:367-381)."""
+        from contextlib import contextmanager
+
+        @contextmanager
+        def moved():
+            try:
+                self.translate(dx, dy, dz=dz, inplace=True)
+                yield
+            finally:
+                self.translate(-dx, -dy, dz=-dz, inplace=True)
+
+        return moved()
+
     def to_hdf5(self, path_or_group, save_mesh: bool = True, compress: bool = True) -> None:
         """reference device/device.py:936-977"""
         from . import io as _io
@@ -518,11 +629,13 @@ class Device:
         return boundary_vertices_ccw(self.meshes[film].elements)
 
     def mutual_inductance_matrix(self, hole_polygon_mapping: Optional[Dict[str, np.ndarray]] = None,
-                                 units: str = "pH", all_iterations: bool = False, comm=None, **solve_kwargs):
+                                 units: str = "pH", all_iterations: bool = False, progress_bar: bool = False,
+                                 comm=None, **solve_kwargs):
         """reference device/device.py:538-648.  Without ``hole_polygon_mapping`` the polygons come from
         ``fluxoid.make_fluxoid_polygons`` as in the reference (device.py:592-595; the holes are grown by half
         the distance to the nearest other polygon -- by scaling about the centroid here, by a shapely buffer
-        there: identical for circular holes, pass explicit polygons for parity runs).  The reference solves once
+        there: identical for circular holes, pass explicit polygons for parity runs).  ``progress_bar`` is accepted
+        for compatibility (there is no per-hole loop to show progress of).  The reference solves once
         per driven hole against one factorization; here all columns are one batched solve
         (``solve_batch``).  As in the reference, ``iterations`` is forwarded to the solver only if
         given explicitly."""

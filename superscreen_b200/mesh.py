@@ -348,5 +348,18 @@ class Mesh:
     def closest_site(self, xy) -> int:
         return int(np.argmin(np.linalg.norm(self.sites - np.atleast_2d(xy), axis=1)))
 
+    def to_hdf5(self, h5group, compress: bool = True) -> None:
+        """reference device/mesh.py:250-275 (``sites``, ``elements``; the derived arrays too if not ``compress``)"""
+        from . import io as _io
+
+        _io.mesh_to_hdf5(self, h5group, compress=compress)
+
+    @staticmethod
+    def from_hdf5(h5group) -> "Mesh":
+        """reference device/mesh.py:277-293; the device-resident operators are rebuilt from the triangulation."""
+        from . import io as _io
+
+        return _io.mesh_from_hdf5(h5group)
+
     def copy(self) -> "Mesh":
         return self

@@ -479,6 +479,33 @@ class Solution:
         return self.film_solutions == other.film_solutions
 
     # ---------------------------------------------------------------- fluxoid
+    def polygon_flux(self, name: str, units: Optional[str] = None, with_units: bool = True):
+        """Flux ``sum(mu_0 H_z w)`` through the polygon ``name`` of the device (a film, a hole or an abstract
+        region), over the vertex areas of the film mesh that contains it (reference solution.py:430-482)."""
+        from .solver.utils import convert_field
+
+        device = self.device
+        polygons = {p.name: p for p in device.get_polygons(include_terminals=False)}
+        if name not in polygons:
+            raise ValueError(f"Unknown polygon: {name!r}.")
+        new_units = units or f"({self.field_units}) * ({device.length_units}) ** 2"
+        polygon = polygons[name]
+        if name in device.films:
+            film_name = name
+        else:
+            film_name = None
+            for film in device.films.values():
+                film_name = film.name  # (the reference falls through to the last film if none contains it)
+                if film.layer == polygon.layer and film.contains_points(polygon.points).all():
+                    break
+        mesh = device.meshes[film_name]
+        ix = polygon.contains_points(mesh.sites, index=True)
+        field_mT = convert_field(self.film_solutions[film_name].total_field[ix], "mT", old_units=self.field_units,
+                                 with_units=False)
+        flux = float(np.dot(field_mT, mesh.vertex_areas[ix]))
+        flux = flux * _flux_conversion(f"mT * ({device.length_units}) ** 2", str(new_units))
+        return _u.Quantity(flux, str(new_units)) if with_units else flux
+
     def polygon_fluxoid(self, polygon_coords, *, film: str, interp_method: str = "linear",
                         units: Optional[str] = "Phi_0", with_units: bool = True) -> Fluxoid:
         """reference solution.py:484-563"""

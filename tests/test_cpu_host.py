@@ -355,3 +355,99 @@ def test_default_fluxoid_polygons_of_a_ring():
     assert points_in_polygon(p, device.holes["hole"].points).all()
     assert device.films["ring"].contains_points(p).all()
     assert len(make_fluxoid_polygons(device, holes="hole", interp_points=64)["hole"]) in (64, 65)
+
+
+def test_polygon_flux():
+    """`Solution.polygon_flux` (reference solution.py:430-482): total field times vertex areas over the mesh vertices
+    inside a named polygon of the device, in flux units; unknown names raise ValueError."""
+    from types import SimpleNamespace
+
+    from superscreen_b200.solution import FilmSolution, Solution
+    from superscreen_b200 import units as _u
+
+    sites, elements = disk_mesh(3.0, 700, seed=6)
+    p = sites[elements]
+    tri_area = 0.5 * np.abs((p[:, 1, 0] - p[:, 0, 0]) * (p[:, 2, 1] - p[:, 0, 1])
+                            - (p[:, 1, 1] - p[:, 0, 1]) * (p[:, 2, 0] - p[:, 0, 0]))
+    w = np.zeros(len(sites))
+    np.add.at(w, elements.ravel(), np.repeat(tri_area / 3.0, 3))
+    device = sc.Device("d", layers=[sc.Layer("l", Lambda=0.7, z0=0.0)],
+                       films=[sc.Polygon("film", layer="l", points=circle(3.0, 80))],
+                       holes=[sc.Polygon("hole", layer="l", points=circle(0.8, 40))])
+    device.meshes = {"film": SimpleNamespace(sites=sites, elements=elements, vertex_areas=w)}
+    rng = np.random.default_rng(3)
+    n = len(sites)
+    fs = FilmSolution(stream=np.zeros(n), current_density=np.zeros((n, 2)), applied_field=rng.standard_normal(n),
+                      self_field=rng.standard_normal(n))
+    sol = Solution(device=device, film_solutions={"film": fs}, applied_field_func=sc.ConstantField(0.0),
+                   field_units="uT", current_units="uA", _device_is_copy=True)
+    for name in ("film", "hole"):
+        ix = points_in_polygon(device.get_polygons(include_terminals=False)[[q.name for q in device.get_polygons(
+            include_terminals=False)].index(name)].points, sites)
+        ref_uT_um2 = np.sum(fs.total_field[ix] * w[ix])
+        got = sol.polygon_flux(name, with_units=False)                      # default units: field * length^2
+        assert abs(got - ref_uT_um2) <= 1e-12 * abs(ref_uT_um2)
+        got_phi0 = sol.polygon_flux(name, units="Phi_0", with_units=False)
+        assert abs(got_phi0 - ref_uT_um2 * _u.conversion_factor("uT * um ** 2", "Phi_0")) <= 1e-12 * abs(got_phi0)
+        assert sol.polygon_flux(name, units="Phi_0").magnitude == got_phi0
+    with pytest.raises(ValueError):
+        sol.polygon_flux("nope")
+
+
+def test_polygon_resample_and_hdf5_methods():
+    """`Polygon.resample` (uniform in arc length along the closed boundary, reference device/polygon.py:483-506)
+    and the `to_hdf5` / `from_hdf5` methods of Layer / Polygon (reference group layouts) on an in-memory group."""
+    from superscreen_b200.io import MemoryGroup
+
+    sq = sc.Polygon("sq", layer="l", points=box(2.0, points=4))
+    rs = sq.resample(41)
+    assert rs.name == "sq" and rs.layer == "l"
+    p = rs.points
+    closed = p if np.allclose(p[0], p[-1]) else np.concatenate([p, p[:1]])
+    seg = np.linalg.norm(np.diff(closed, axis=0), axis=1)
+    assert np.allclose(np.abs(closed).max(axis=1), 1.0)          # all points on the boundary of the 2 x 2 box
+    assert np.allclose(seg[seg > 1e-12], 8.0 / 40, atol=1e-12)   # perimeter 8 in 40 equal steps
+    assert np.array_equal(sq.resample(0).points, sq.points) and sq.resample(0) is not sq
+    assert len(sq.resample().points) == len(sq.points)
+    g = MemoryGroup()
+    sq.to_hdf5(g.create_group("poly"))
+    back = sc.Polygon.from_hdf5(g["poly"])
+    assert back.name == "sq" and back.layer == "l" and np.array_equal(back.points, sq.points)
+    layer = sc.Layer("base", london_lambda=0.5, thickness=0.05, z0=0.25)
+    layer.to_hdf5(g.create_group("layer"))
+    lb = sc.Layer.from_hdf5(g["layer"])
+    assert lb.name == "base" and lb.z0 == 0.25 and lb.thickness == 0.05 and lb.london_lambda == 0.5
+    assert np.isclose(lb.Lambda, 0.5**2 / 0.05)
+
+
+def test_device_rigid_transformations():
+    """Device.scale / rotate / mirror_layers / translate / translation (reference device/device.py:256-381) on a
+    device without meshes: new devices with transformed polygons and layers, the original untouched."""
+    device = sc.Device("d", layers=[sc.Layer("a", Lambda=1.0, z0=0.5), sc.Layer("b", Lambda=2.0, z0=-1.0)],
+                       films=[sc.Polygon("film", layer="a", points=box(2.0, points=4)),
+                              sc.Polygon("plate", layer="b", points=box(4.0, points=4))],
+                       holes=[sc.Polygon("hole", layer="a", points=circle(0.3, 24))])
+    orig = {p.name: p.points.copy() for p in device.get_polygons()}
+    moved = device.translate(1.5, -2.0, dz=0.25)
+    assert moved is not device
+    for p in moved.get_polygons():
+        assert np.allclose(p.points, orig[p.name] + np.array([1.5, -2.0]))
+    assert moved.layers["a"].z0 == 0.75 and moved.layers["b"].z0 == -0.75 and device.layers["a"].z0 == 0.5
+    for p in device.get_polygons():
+        assert np.array_equal(p.points, orig[p.name])
+    rot = device.rotate(90.0)
+    assert np.allclose(rot.films["film"].points, orig["film"] @ np.array([[0.0, 1.0], [-1.0, 0.0]]))
+    sca = device.scale(xfact=-2.0, yfact=0.5, origin=(1.0, 0.0))
+    want = (orig["hole"] - [1.0, 0.0]) * [-2.0, 0.5] + [1.0, 0.0]  # (a mirrored polygon is re-oriented counter-clockwise)
+    srt = lambda a: a[np.lexsort((np.round(a[:, 1], 9), np.round(a[:, 0], 9)))]
+    assert np.allclose(srt(np.unique(np.round(sca.holes["hole"].points, 12), axis=0)),
+                       srt(np.unique(np.round(want, 12), axis=0)))
+    with pytest.raises(TypeError):
+        device.rotate(10.0, origin=[0, 0])
+    mir = device.mirror_layers(about_z=1.0)
+    assert mir.layers["a"].z0 == 0.5 and mir.layers["b"].z0 == 2.0
+    with device.translation(3.0, 0.0, dz=1.0):
+        assert np.allclose(device.films["film"].points, orig["film"] + np.array([3.0, 0.0]))
+        assert device.layers["b"].z0 == 0.0
+    assert np.allclose(device.films["film"].points, orig["film"]) and device.layers["b"].z0 == -1.0
+    assert device.translate(1.0, 1.0, inplace=True) is device
