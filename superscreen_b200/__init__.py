@@ -25,3 +25,16 @@ from .solver import (
 from .sources import Constant, ConstantField, Parameter
 
 __version__ = "0.1.0"
+
+
+def version_dict():
+    """Versions of the package and of what it runs on (reference about.py ``version_dict``)."""
+    return io.version_info()
+
+
+def version_table(version_info=None, verbose: bool = False) -> str:
+    """The same as an HTML table (reference about.py ``version_table``; returned as a string -- IPython is not a
+    dependency here)."""
+    info = version_info if version_info is not None else version_dict()
+    rows = "".join(f"<tr><td>{k}</td><td>{v}</td></tr>" for k, v in info.items())
+    return f"<table><tr><th>Software</th><th>Version</th></tr>{rows}</table>"
