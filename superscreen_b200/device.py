@@ -139,14 +139,34 @@ class Polygon:
         o = self._origin(origin)
         return self._mapped((self._points - o) * np.array([xfact, yfact], dtype=float) + o, inplace)
 
-    def union(self, *others) -> "Polygon":
+    def union(self, *others, name: Optional[str] = None) -> "Polygon":
         """Union with other polygons / coordinate arrays (reference device/polygon.py:302-340) as a
         ``CompositePolygon`` (membership tests only, no outline)."""
-        return CompositePolygon(self.name, layer=self.layer, add=[self._points] + _rings_of(others))
+        return CompositePolygon(name or self.name, layer=self.layer, add=[self._points] + _rings_of(others))
 
-    def difference(self, *others) -> "Polygon":
+    def difference(self, *others, symmetric: bool = False, name: Optional[str] = None) -> "Polygon":
         """This polygon minus others (reference device/polygon.py:378-435), as a ``CompositePolygon``."""
-        return CompositePolygon(self.name, layer=self.layer, add=[self._points], sub=_rings_of(others))
+        if symmetric:
+            raise NotImplementedError("The symmetric difference needs polygon clipping (shapely); not available.")
+        return CompositePolygon(name or self.name, layer=self.layer, add=[self._points], sub=_rings_of(others))
+
+    def on_boundary(self, points, radius: float = 1e-3, index: bool = False):
+        """Whether ``points`` lie within ``radius`` of the polygon boundary (reference device/polygon.py:164-190,
+        there via matplotlib's path with a positive / negative radius; here by the distance to the nearest edge)."""
+        pts = np.atleast_2d(np.asarray(points, dtype=float))
+        boundary = np.zeros(len(pts), dtype=bool)
+        for ring in self.rings:
+            a, b = ring[:-1], ring[1:]
+            ab = b - a
+            len2 = np.maximum(np.einsum("ij,ij->i", ab, ab), 1e-300)
+            for s0 in range(0, len(pts), 4096):  # (bounds the points x edges temporaries)
+                q = pts[s0:s0 + 4096]
+                t = np.clip(np.einsum("qej,ej->qe", q[:, None, :] - a[None, :, :], ab) / len2, 0.0, 1.0)
+                d = np.linalg.norm(q[:, None, :] - (a[None, :, :] + t[:, :, None] * ab[None, :, :]), axis=2)
+                boundary[s0:s0 + 4096] |= d.min(axis=1) <= abs(radius)
+        if index:
+            return np.where(boundary)[0]
+        return boundary
 
     @property
     def rings(self) -> List[np.ndarray]:
@@ -272,11 +292,13 @@ class CompositePolygon(Polygon):
             mask &= ~Polygon.contains_points(_ring_polygon(ring), pts)
         return np.where(mask)[0] if index else mask
 
-    def union(self, *others) -> "CompositePolygon":
-        return CompositePolygon(self.name, layer=self.layer, add=self._add + _rings_of(others), sub=self._sub)
+    def union(self, *others, name: Optional[str] = None) -> "CompositePolygon":
+        return CompositePolygon(name or self.name, layer=self.layer, add=self._add + _rings_of(others), sub=self._sub)
 
-    def difference(self, *others) -> "CompositePolygon":
-        return CompositePolygon(self.name, layer=self.layer, add=self._add, sub=self._sub + _rings_of(others))
+    def difference(self, *others, symmetric: bool = False, name: Optional[str] = None) -> "CompositePolygon":
+        if symmetric:
+            raise NotImplementedError("The symmetric difference needs polygon clipping (shapely); not available.")
+        return CompositePolygon(name or self.name, layer=self.layer, add=self._add, sub=self._sub + _rings_of(others))
 
     def copy(self) -> "CompositePolygon":
         return CompositePolygon(self.name, layer=self.layer, add=[r.copy() for r in self._add],
@@ -382,8 +404,12 @@ class Device:
             out[p.layer].append(p)
         return out
 
-    def get_polygons(self, polygon_type: Optional[str] = None, include_terminals: bool = True) -> List[Polygon]:
-        """All polygons of the device, or those of one kind (reference device/device.py:186-219)."""
+    def get_polygons(self, include_terminals: bool = True, polygon_type: Optional[str] = None) -> List[Polygon]:
+        """All polygons of the device (reference ``get_polygons(include_terminals=True)``), or, as an extension,
+        those of one kind (``polygon_type`` = film / hole / abstract / terminal; a string passed positionally is
+        taken as the kind)."""
+        if isinstance(include_terminals, str):
+            include_terminals, polygon_type = True, include_terminals
         kinds = {"film": list(self.films.values()), "hole": list(self.holes.values()),
                  "abstract": list(self.abstract_regions.values()),
                  "terminal": [t for ts in self.terminals.values() for t in ts]}

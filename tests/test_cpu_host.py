@@ -451,3 +451,22 @@ def test_device_rigid_transformations():
         assert device.layers["b"].z0 == 0.0
     assert np.allclose(device.films["film"].points, orig["film"]) and device.layers["b"].z0 == -1.0
     assert device.translate(1.0, 1.0, inplace=True) is device
+
+
+def test_polygon_on_boundary_and_named_set_operations():
+    """Polygon.on_boundary (reference device/polygon.py:164-190) and the `name` argument of union / difference."""
+    sq = sc.Polygon("sq", layer="l", points=box(2.0, points=4))
+    pts = np.array([[1.0, 0.3], [0.9995, -0.2], [0.99, 0.0], [0.0, 0.0], [1.0005, 1.0005], [1.01, 0.0], [-1.0, -1.0]])
+    got = sq.on_boundary(pts, radius=1e-3)
+    assert got.tolist() == [True, True, False, False, True, False, True]
+    assert sq.on_boundary(pts, radius=1e-3, index=True).tolist() == [0, 1, 4, 6]
+    assert sq.on_boundary(pts, radius=0.02).tolist() == [True, True, True, False, True, True, True]
+    hole = sc.Polygon("h", layer="l", points=circle(0.4, 32))
+    ring = sq.difference(hole, name="ring")
+    assert ring.name == "ring" and ring.layer == "l"
+    assert ring.contains_points([[0.8, 0.0], [0.0, 0.0]]).tolist() == [True, False]
+    both = sq.union(sc.Polygon("far", layer="l", points=box(1.0, points=4) + np.array([5.0, 0.0])), name="both")
+    assert both.name == "both" and both.contains_points([[5.0, 0.0], [3.0, 0.0]]).tolist() == [True, False]
+    assert sq.union(hole).name == "sq"
+    with pytest.raises(NotImplementedError):
+        sq.difference(hole, symmetric=True)
