@@ -44,6 +44,7 @@ _BASE = {
 _CONST = {
     "mu_0": (MU_0, _L + _M - 2 * _T - 2 * _I), "mu0": (MU_0, _L + _M - 2 * _T - 2 * _I),
     "Phi_0": (PHI_0, _WB), "Phi0": (PHI_0, _WB),
+    "mu_B": (9.2740100783e-24, _I + 2 * _L), "bohr_magneton": (9.2740100783e-24, _I + 2 * _L),  # A m^2 (CODATA 2018)
     "dimensionless": (1.0, _ZERO),
 }
 _LONG_PREFIX = {"micro": 1e-6, "milli": 1e-3, "nano": 1e-9, "pico": 1e-12, "kilo": 1e3}

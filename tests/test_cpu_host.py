@@ -470,3 +470,29 @@ def test_polygon_on_boundary_and_named_set_operations():
     assert sq.union(hole).name == "sq"
     with pytest.raises(NotImplementedError):
         sq.difference(hole, symmetric=True)
+
+
+def test_applied_field_sources_known_answers():
+    """Known answers of the applied-field sources (these run without the reference): the on-axis field of a z dipole
+    mu_0 m / (2 pi d^3), the flux n Phi_0 / 2 of a monopole through the half space above it, and the total flux
+    n Phi_0 carried by a Pearl vortex."""
+    from scipy.constants import mu_0
+
+    import superscreen_b200.sources as S
+
+    d = 2.5e-6
+    B = S.dipole_field((0.0, 0.0, d), r0=(0, 0, 0), moment=(0, 0, 3e-15))
+    assert np.allclose(B, [0, 0, mu_0 * 3e-15 / (2 * np.pi * d**3)], rtol=1e-14, atol=0)
+    Bz = S.DipoleField(dipole_positions=(0, 0, 0), dipole_moments=(0, 0, 1e8), component="z", length_units="um",
+                       moment_units="mu_B")(np.array([0.0]), np.array([0.0]), np.array([2.5]))
+    assert np.allclose(Bz, mu_0 * 1e8 * 9.2740100783e-24 / (2 * np.pi * d**3), rtol=1e-12)
+    # monopole: integral of mu_0 H_z over the plane z = h above it is n Phi_0 / 2 (half of the solid angle... of 2 n Phi_0)
+    g = np.linspace(-400, 400, 1601)
+    X, Y = np.meshgrid(g, g)
+    hz = S.MonopoleField(r0=(0, 0, 0), nPhi0=3)(X.ravel(), Y.ravel(), np.full(X.size, 1.0))
+    assert abs(hz.sum() * (g[1] - g[0]) ** 2 - 3.0) < 0.02  # n Phi_0 (2 pi / 2 pi), minus what leaves the window
+    xs = np.linspace(-40, 40, 256)  # (an even count puts a sample at k = 0: the grid sum is the zero-frequency term)
+    pv = S.PearlVortexField(r0=(0, 0, 0), Lambda=0.5, nPhi0=2, xs=xs, ys=xs)
+    Xs, Ys = np.meshgrid(xs, xs)
+    total = pv(Xs.ravel(), Ys.ravel(), np.full(Xs.size, 0.3)).sum() * (xs[1] - xs[0]) ** 2
+    assert abs(total - 2.0) < 1e-9
