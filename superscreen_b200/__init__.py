@@ -22,7 +22,8 @@ from .solver import (
     solve,
     solve_batch,
 )
-from .sources import Constant, ConstantField, DipoleField, MonopoleField, Parameter, PearlVortexField, VortexField
+from .sources import (CompositeParameter, Constant, ConstantField, DipoleField, MonopoleField, Parameter,
+                      PearlVortexField, VortexField)
 
 __version__ = "0.1.0"
 

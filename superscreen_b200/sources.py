@@ -26,6 +26,67 @@ class Parameter:
     def __repr__(self):
         return f"Parameter<{getattr(self.func, '__name__', 'f')}({self.kwargs})>"
 
+    # arithmetic between Parameters and real numbers gives a CompositeParameter (reference parameter.py:146-184)
+    def __add__(self, other):
+        return CompositeParameter(self, other, "+")
+
+    def __radd__(self, other):
+        return CompositeParameter(other, self, "+")
+
+    def __sub__(self, other):
+        return CompositeParameter(self, other, "-")
+
+    def __rsub__(self, other):
+        return CompositeParameter(other, self, "-")
+
+    def __mul__(self, other):
+        return CompositeParameter(self, other, "*")
+
+    def __rmul__(self, other):
+        return CompositeParameter(other, self, "*")
+
+    def __truediv__(self, other):
+        return CompositeParameter(self, other, "/")
+
+    def __rtruediv__(self, other):
+        return CompositeParameter(other, self, "/")
+
+    def __pow__(self, other):
+        return CompositeParameter(self, other, "**")
+
+    def __rpow__(self, other):
+        return CompositeParameter(other, self, "**")
+
+
+class CompositeParameter(Parameter):
+    """The result of ``+ - * / **`` between Parameters and / or real numbers: evaluates both sides at the same
+    ``(x, y[, z])`` and combines them (reference parameter.py:200-273), e.g.
+    ``ConstantField(0.1) + DipoleField(...)`` as the applied field of a solve."""
+
+    _OPS = {"+": np.add, "-": np.subtract, "*": np.multiply, "/": np.divide, "**": np.power}
+
+    def __init__(self, left, right, op):
+        import numbers
+
+        for side, what in ((left, "Left"), (right, "Right")):
+            if not isinstance(side, (numbers.Real, Parameter)):
+                raise TypeError(f"{what} must be a number, Parameter, or CompositeParameter, not {type(side)!r}.")
+        if isinstance(left, numbers.Real) and isinstance(right, numbers.Real):
+            raise TypeError("Either left or right must be a Parameter or CompositeParameter.")
+        op = op.strip() if isinstance(op, str) else op
+        if op not in self._OPS:
+            raise ValueError(f"Unknown operator, {op!r}. Valid operators are {list(self._OPS)!r}.")
+        self.left, self.right, self.operator = left, right, op
+        self.func, self.kwargs = None, {}
+
+    def __call__(self, x, y, z=None):
+        lv = self.left(x, y, z) if isinstance(self.left, Parameter) else self.left
+        rv = self.right(x, y, z) if isinstance(self.right, Parameter) else self.right
+        return self._OPS[self.operator](lv, rv)
+
+    def __repr__(self):
+        return f"({self.left!r} {self.operator} {self.right!r})"
+
 
 class Constant(Parameter):
     def __init__(self, value, dimensions: int = 2):

@@ -496,3 +496,25 @@ def test_applied_field_sources_known_answers():
     Xs, Ys = np.meshgrid(xs, xs)
     total = pv(Xs.ravel(), Ys.ravel(), np.full(Xs.size, 0.3)).sum() * (xs[1] - xs[0]) ** 2
     assert abs(total - 2.0) < 1e-9
+
+
+def test_parameter_arithmetic():
+    """Parameters compose with + - * / ** among themselves and with real numbers (reference parameter.py:146-273)."""
+    import superscreen_b200.sources as S
+
+    x, y, z = np.linspace(-1, 1, 7), np.linspace(2, 3, 7), np.full(7, 0.5)
+    c, m = S.ConstantField(0.25), S.MonopoleField(r0=(0, 0, -1.0), nPhi0=2)
+    f = 2 * c + m / 4 - 1
+    assert isinstance(f, S.CompositeParameter) and isinstance(f, S.Parameter)
+    assert np.allclose(f(x, y, z), 2 * c(x, y, z) + m(x, y, z) / 4 - 1)
+    assert np.allclose((c ** 2)(x, y, z), 0.0625) and np.allclose((2 ** c)(x, y, z), 2 ** 0.25)
+    assert np.allclose((1 - c)(x, y, z), 0.75) and np.allclose((1 / c)(x, y, z), 4.0) and np.allclose((c * m)(x, y, z),
+                                                                                                  0.25 * m(x, y, z))
+    lam = S.Parameter(lambda x, y, a=1.0: a * (1 + x**2), a=0.5)  # a 2-D parameter (e.g. Lambda(x, y))
+    assert np.allclose((lam + 1)(x, y), 1 + 0.5 * (1 + x**2))
+    with pytest.raises(TypeError):
+        S.CompositeParameter(1, 2, "+")
+    with pytest.raises(TypeError):
+        c + "a"
+    with pytest.raises(ValueError):
+        S.CompositeParameter(c, 2, "%")
