@@ -518,3 +518,24 @@ def test_parameter_arithmetic():
         c + "a"
     with pytest.raises(ValueError):
         S.CompositeParameter(c, 2, "%")
+
+
+def test_host_section_timing(monkeypatch):
+    """`SCB_HOST_TIMING`: the NVTX ranges of the path also accumulate host wall time per section name (film names in
+    brackets are folded together); off by default and free of cost."""
+    import time
+
+    from superscreen_b200 import _lib
+
+    _lib.host_times.clear()
+    with _lib.nvtx_range("scb.section[a]"):
+        pass
+    assert _lib.host_times == {}
+    monkeypatch.setattr(_lib, "_HOST_TIMING", True)
+    for name in ("scb.section[a]", "scb.section[b]", "scb.other"):
+        with _lib.nvtx_range(name):
+            time.sleep(0.002)
+    assert set(_lib.host_times) == {"scb.section", "scb.other"}
+    assert _lib.host_times["scb.section"][0] == 2 and _lib.host_times["scb.section"][1] >= 0.003
+    report = _lib.host_timing_report()
+    assert "scb.section" in report and "2 x" in report and _lib.host_times == {}
